@@ -1,0 +1,105 @@
+"""Parity of the tcgen05 GEMM (tt_gemm_bf16_tn) and the bf16 operand cast against torch fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a16, b16, bias, residual, alpha, act):
+    c = alpha * (a16.float() @ b16.float().t())
+    if bias is not None:
+        c = c + bias
+    if act == 1:
+        c = torch.relu(c)
+    elif act == 2:
+        c = torch.nn.functional.gelu(c)
+    if residual is not None:
+        c = c + residual
+    return c
+
+
+@pytest.mark.parametrize('M,N,K', [
+    (128, 128, 64), (128, 256, 128), (800, 1024, 1024), (8192, 1024, 1024),
+    (800, 2048, 1024), (800, 1024, 4096), (100, 48, 1024), (77, 5002, 1024),
+    (8192, 3072, 1024), (1, 1024, 1024), (300, 496, 1000), (4096, 4096, 512),
+    (33, 40, 8), (2048, 30265, 1024)])
+def test_gemm_plain(M, N, K):
+    from tell_b200 import ops
+    torch.manual_seed(M * 31 + N * 7 + K)
+    a = torch.randn(M, K, device='cuda').bfloat16()
+    b = torch.randn(N, K, device='cuda').bfloat16()
+    c = ops.gemm_tn(a, b)
+    torch.cuda.synchronize()
+    ref = _ref(a, b, None, None, 1.0, 0)
+    err = (c - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_gemm_epilogue(act):
+    from tell_b200 import ops
+    torch.manual_seed(act)
+    M, N, K = 800, 1024, 1024
+    a = (torch.randn(M, K, device='cuda') / 32).bfloat16()
+    b = torch.randn(N, K, device='cuda').bfloat16()
+    bias = torch.randn(N, device='cuda')
+    res = torch.randn(M, N, device='cuda')
+    c, c16 = ops.gemm_tn(a, b, bias=bias, residual=res, alpha=0.5, act=act, want16=True)
+    ref = _ref(a, b, bias, res, 0.5, act)
+    assert (c - ref).abs().max().item() < 2e-3
+    assert (c16.float() - ref).abs().max().item() < 5e-2
+    # accumulate into C
+    c2 = c.clone()
+    ops.gemm_tn(a, b, out=c2, accumulate=True)
+    ref2 = ref + _ref(a, b, None, None, 1.0, 0)
+    assert (c2 - ref2).abs().max().item() < 4e-3
+
+
+def test_gemm_unaligned_output_and_m_limit():
+    from tell_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 300, 50, 72
+    a = torch.randn(M, K, device='cuda').bfloat16()
+    b = torch.randn(N, K, device='cuda').bfloat16()
+    out = torch.full((M, N), 7.0, device='cuda')
+    lim = torch.tensor([130], dtype=torch.int32, device='cuda')
+    ops.gemm_tn(a, b, out=out, m_limit=lim)
+    ref = _ref(a, b, None, None, 1.0, 0)
+    assert (out[:130] - ref[:130]).abs().max().item() < 2e-3
+    assert (out[130:] == 7.0).all()
+
+
+@pytest.mark.parametrize('transpose', [False, True])
+@pytest.mark.parametrize('split', [0, 1, 2])
+def test_cast(transpose, split):
+    from tell_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(70, 100, device='cuda')
+    y = ops.cast_bf16(x, transpose=transpose, split=split)
+    src = x.t() if transpose else x
+    hi = src.bfloat16()
+    lo = (src - hi.float()).bfloat16()
+    if split == 0:
+        exp = hi
+    elif split == 1:
+        exp = torch.cat([hi, lo, hi], 1)
+    else:
+        exp = torch.cat([hi, hi, lo], 1)
+    assert torch.equal(y, exp)
+
+
+def test_gemm_split_precision():
+    """bf16x3 operands recover ~fp32 accuracy (parity mode)."""
+    from tell_b200 import ops
+    torch.manual_seed(11)
+    M, N, K = 256, 512, 1024
+    x = torch.randn(M, K, device='cuda')
+    w = torch.randn(N, K, device='cuda') / 32
+    a = ops.cast_bf16(x, split=1)
+    b = ops.cast_bf16(w, split=2)
+    c = ops.gemm_tn(a, b)
+    ref = (x.double() @ w.double().t()).float()
+    err = (c - ref).abs().max().item()
+    assert err < 2e-4, err
+    c1 = ops.gemm_tn(ops.cast_bf16(x), ops.cast_bf16(w))
+    assert (c1 - ref).abs().max().item() > err

@@ -1,0 +1,349 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias) + residual
+//
+// Persistent, warp-specialised (one CTA per SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 tiles, 128B swizzle
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma 128xBNx16 (kind::f16, fp32 accum in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       : tcgen05.ld accumulator -> registers -> alpha/bias/act/residual -> HBM
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, the
+// accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmArgs {
+  int M, N, K;
+  float* C;
+  long long ldc;
+  __nv_bfloat16* C16;
+  long long ldc16;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  float alpha;
+  int act;
+  int accumulate;
+  const int* m_limit;
+  int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == TT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == TT_ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int M = g.M;
+  if (g.m_limit != nullptr) M = min(M, __ldg(g.m_limit));
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= g.N) continue;  // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
+        if (g.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+        }
+        if (g.act != TT_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+        }
+        if (!row_ok) continue;
+        const bool full = (col0 + 32 <= g.N) && g.vec_ok;
+        if (full) {
+          if (g.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(g.residual + row * g.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(rp + j);
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+          if (g.C != nullptr) {
+            float4* cp = reinterpret_cast<float4*>(g.C + row * g.ldc + col0);
+            if (g.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = cp[j];
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (g.C16 != nullptr) {
+            uint4* hp = reinterpret_cast<uint4*>(g.C16 + row * g.ldc16 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0);
+              u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2);
+              u.w = *reinterpret_cast<uint32_t*>(&p3);
+              hp[j] = u;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < g.N) {
+              float o = v[j];
+              if (g.residual != nullptr) o += __ldg(g.residual + row * g.ldr + col);
+              if (g.C != nullptr) {
+                float* cp = g.C + row * g.ldc + col;
+                if (g.accumulate) o += *cp;
+                *cp = o;
+              }
+              if (g.C16 != nullptr) g.C16[row * g.ldc16 + col] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm BN=%d, %d B): %s", BN, Cfg::SMEM_BYTES,
+                cudaGetErrorString(e));
+      return TT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  return check_launch("gemm_bf16_tn_kernel");
+}
+
+// Tile-width heuristic: the widest BN that still yields at least one tile per SM; otherwise the
+// width giving the most tiles (small-M decoder GEMMs), never below 32.
+static int pick_bn(int M, int N, int sms) {
+  const int num_m = ceil_div(M, BM);
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && N < bn) continue;
+    if (num_m * ceil_div(N, bn) >= sms) return bn;
+  }
+  // not enough tiles anywhere: prefer 64 unless 32 is needed to get past half the machine
+  if (num_m * ceil_div(N, 64) >= sms / 2 || N <= 32) return N >= 64 ? 64 : 32;
+  return 32;
+}
+
+}  // namespace tt
+
+extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
+  using namespace tt;
+  TT_REQUIRE(p != nullptr, "tt_gemm_bf16_tn: null params");
+  TT_REQUIRE(p->M >= 0 && p->N > 0 && p->K > 0, "tt_gemm_bf16_tn: bad shape M=%d N=%d K=%d", p->M,
+             p->N, p->K);
+  if (p->M == 0) return TT_OK;
+  TT_REQUIRE(p->A && p->B, "tt_gemm_bf16_tn: null operand");
+  TT_REQUIRE(p->C || p->C16, "tt_gemm_bf16_tn: no output buffer");
+  TT_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->lda >= p->K && p->ldb >= p->K,
+             "tt_gemm_bf16_tn: lda/ldb must be multiples of 8 and >= K (lda=%lld ldb=%lld K=%d)",
+             p->lda, p->ldb, p->K);
+  TT_REQUIRE((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
+             "tt_gemm_bf16_tn: operands must be 16-byte aligned");
+  TT_REQUIRE(!(p->accumulate && !p->C), "tt_gemm_bf16_tn: accumulate needs the fp32 output");
+
+  const int sms = num_sms();
+  const int bn = pick_bn(p->M, p->N, sms);
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
+  if (rc != TT_OK) return rc;
+  rc = make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->ldb, BK, bn);
+  if (rc != TT_OK) return rc;
+
+  GemmArgs g;
+  g.M = p->M; g.N = p->N; g.K = p->K;
+  g.C = p->C; g.ldc = p->ldc;
+  g.C16 = reinterpret_cast<__nv_bfloat16*>(p->C16); g.ldc16 = p->ldc16;
+  g.bias = p->bias;
+  g.residual = p->residual; g.ldr = p->ldr;
+  g.alpha = p->alpha; g.act = p->act; g.accumulate = p->accumulate;
+  g.m_limit = p->m_limit;
+  bool vec = true;
+  if (p->C) vec = vec && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0 && (p->ldc % 4 == 0);
+  if (p->C16) vec = vec && (reinterpret_cast<uintptr_t>(p->C16) & 15) == 0 && (p->ldc16 % 8 == 0);
+  if (p->residual)
+    vec = vec && (reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && (p->ldr % 4 == 0);
+  g.vec_ok = vec ? 1 : 0;
+
+  const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
+  const int grid = tiles < sms ? tiles : sms;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256>(tmA, tmB, g, grid, s);
+    case 128: return launch_gemm<128>(tmA, tmB, g, grid, s);
+    case 64: return launch_gemm<64>(tmA, tmB, g, grid, s);
+    default: return launch_gemm<32>(tmA, tmB, g, grid, s);
+  }
+}

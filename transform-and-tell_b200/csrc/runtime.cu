@@ -1,0 +1,94 @@
+// Error plumbing, launch counter and driver-entry-point lookup shared by all ops.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return TT_ERR_CUDA;
+  }
+  count_launch(1);
+  return TT_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return TT_ERR_NO_DEVICE;
+  }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu rows=%llu ld=%llu box=%ux%u",
+              (int)r, ptr, (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)ld_elems, box_inner, box_rows);
+    return TT_ERR_CUDA;
+  }
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" {
+const char* tt_last_error(void) { return tt::g_err; }
+int tt_abi_version(void) { return 1; }
+long long tt_launch_count(void) { return tt::g_launches.load(); }
+void tt_reset_launch_count(void) { tt::g_launches.store(0); }
+}

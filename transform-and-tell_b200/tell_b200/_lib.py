@@ -1,0 +1,67 @@
+"""ctypes binding of libtt_b200.so (the C ABI declared in include/tt_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the
+error is raised.  The product path never routes through oracle/ or a CPU implementation.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtt_b200.so')
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_float = ctypes.c_float
+
+
+class TtError(RuntimeError):
+    pass
+
+
+class TtGemmParams(ctypes.Structure):
+    _fields_ = [('M', c_int), ('N', c_int), ('K', c_int),
+                ('A', c_void_p), ('lda', c_ll),
+                ('B', c_void_p), ('ldb', c_ll),
+                ('C', c_void_p), ('ldc', c_ll),
+                ('C16', c_void_p), ('ldc16', c_ll),
+                ('bias', c_void_p),
+                ('residual', c_void_p), ('ldr', c_ll),
+                ('alpha', c_float), ('act', c_int), ('accumulate', c_int),
+                ('m_limit', c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TtError(
+                'libtt_b200.so not built (%s). Run `python -c "import __graft_entry__ as g; '
+                'g.build()"` or transform-and-tell_b200/csrc/build.py. There is no CPU fallback.'
+                % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.tt_last_error.restype = ctypes.c_char_p
+        _lib.tt_launch_count.restype = c_ll
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().tt_last_error().decode('utf-8', 'replace')
+        raise TtError('%s failed (%d): %s' % (what, rc, msg))
+
+
+def call(name, *args):
+    fn = getattr(lib(), name)
+    check(fn(*args), name)
+
+
+def launch_count():
+    return int(lib().tt_launch_count())
+
+
+def reset_launch_count():
+    lib().tt_reset_launch_count()
