@@ -38,9 +38,14 @@ int tt_abi_version(void);
 /* Number of kernel launches issued by this library in this process (bench `gpu_launches`). */
 long long tt_launch_count(void);
 void tt_reset_launch_count(void);
+/* Dropout masks are a pure function of (seed argument, element index, *step) where `step` is an
+ * optional device-resident counter registered here (NULL = none).  Advancing it inside a captured
+ * CUDA graph gives every replay fresh masks while forward and backward of one step still agree. */
+void tt_set_rng_step_ptr(const unsigned long long* dev_ptr);
+int tt_rng_step_advance(unsigned long long* dev_ptr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * GEMM  C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias[N]) + residual[M,N]
+ * GEMM  C[M,N] = act(alpha * (A[M,K] . B[N,K]^T + bias[N]) + residual[M,N])
  * bf16 operands (both K-contiguous, i.e. nn.Linear's x @ W^T), fp32 accumulation in TMEM
  * (tcgen05.mma), TMA operand staging.  Replaces every F.linear / addmm on the path:
  *   tell/modules/linear.py:8-34 (GehringLinear), tell/modules/attention/multi_head.py:491-518
@@ -62,8 +67,10 @@ typedef struct {
   void* C16;
   long long ldc16;
   const float* bias;
-  const float* residual;
+  const float* residual;   /* fp32 [M,N], optional */
   long long ldr;
+  const void* residual16;  /* bf16 [M,N], optional (ResNet identity branch) */
+  long long ldr16;
   float alpha;
   int act;
   int accumulate;
@@ -77,9 +84,144 @@ int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
  *   split==1 (rep=3): error-compensated operand "A side": [hi | lo | hi] along K
  *   split==2 (rep=3): error-compensated operand "B side": [hi | hi | lo] along K
  * so that A'.B'^T = hi.hi + lo.hi + hi.lo (parity mode, ~2^-16 relative error).
- * ld_dst in elements. */
+ * ld_dst in elements.  seg_stride: distance (elements) between the three K segments; 0 = the
+ * contraction length of this call (cols, or rows when transposed).  A larger value lets several
+ * calls assemble ONE operand whose K axis is a concatenation (e.g. the band projections). */
 int tt_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int rows,
-                 int cols, int transpose, int split, void* stream);
+                 int cols, int transpose, int split, long long seg_stride, void* stream);
+/* out[0] = a[0] * b[0] (device scalars; folds the upstream loss gradient without a host sync). */
+int tt_scalar_mul(const float* a, const float* b, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise decoder-layer kernels (fp32 activations, one warp per row).
+ */
+/* x = res + dropout(h) is written back into h (it is what the backward needs); y = LN(x).
+ * decoder_faces_objects.py:263-266, 283-287, 361-364 (dropout -> residual -> post-LayerNorm).
+ * res may be NULL; mean/rstd [N] saved for tt_ln_bwd.  ldy = row stride of y (concat buffers). */
+int tt_ln_fwd(float* h, const float* res, const float* gamma, const float* beta, float* y,
+              long long ldy, float* mean, float* rstd, int N, int E, float eps, float p_drop,
+              unsigned long long seed, void* stream);
+/* dx = dL/d(pre-norm sum) (goes to the residual); dh = dx * dropmask/(1-p) (goes to the branch);
+ * dgamma/dbeta [E] are ACCUMULATED (atomicAdd) -- zero them first.  Any output may be NULL. */
+int tt_ln_bwd(const float* dy, long long lddy, const float* x, const float* mean,
+              const float* rstd, const float* gamma, float* dx, float* dh, float* dgamma,
+              float* dbeta, int N, int E, float p_drop, unsigned long long seed, void* stream);
+/* nn.GLU over the last dim: h [N,2C] -> out [N,C].  decoder_faces_objects.py:193-195,259-260 */
+int tt_glu_fwd(const float* h, float* out, long long N, int C, void* stream);
+int tt_glu_bwd(const float* dout, const float* h, float* dh, long long N, int C, void* stream);
+/* F.dropout with a counter-based mask: y[i] = x[i] * keep(seed,i)/(1-p).  Calling it again on the
+ * gradient with the same seed is the backward.  decoder_faces_objects.py:106,258 */
+int tt_dropout(const float* x, float* y, long long n, float p, unsigned long long seed,
+               void* stream);
+/* y = a*x + b*y */
+int tt_axpby(const float* x, float* y, long long n, float a, float b, void* stream);
+/* nn.utils.weight_norm (dim=0) of GehringLinear, linear.py:30-34: w[o,:] = g[o] v[o,:]/||v[o,:]|| */
+int tt_wnorm_fwd(const float* v, const float* g, float* w, float* norm, int O, int I,
+                 void* stream);
+int tt_wnorm_bwd(const float* dw, const float* v, const float* g, const float* norm, float* dv,
+                 float* dg, int O, int I, void* stream);
+/* mask[r] = any(isnan(x[r,:])), NaN rows zeroed in place. transformer_faces_objects.py:374-379 */
+int tt_nan_rows(float* x, uint8_t* mask, int R, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DynamicConv1dTBC core, tell/modules/convolutions/dynamic.py:285-336 (_forward_expanded).
+ * x/out [T,B,C]; z = filter logits [T,B,H,K] (z_tb_stride = H*K) or [H,K] broadcast
+ * (z_tb_stride = 0: LightweightConv1dTBC, lightweight.py:88-240); K <= 32, C/H <= 64.
+ * probs [T,B,H,K] (softmax output before DropConnect) is saved for the backward.
+ */
+int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_stride, float* out, float* probs,
+                   int T, int B, int C, int H, int K, int softmax, float p_drop,
+                   unsigned long long seed, void* stream);
+int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float* dx, float* dz,
+                   int T, int B, int C, int H, int K, int softmax, float p_drop,
+                   unsigned long long seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-attention core, tell/modules/attention/multi_head.py:355-466 (static_kv=True path).
+ * q/out [T,B,H*D] (q pre-scaled by D^-0.5), k/v [S,B,H*D]; extended key set is
+ * [k rows ; bias_k row (if bias_k) ; zero row (if zero_row)]; key_padding_mask [B,S] (1 = pad).
+ * ldq/ldkv/ldo: row strides (elements) of q & dq, k/v & dk/dv, out & dout, so that fused
+ * projection outputs ([N,4E] queries, [S*B,2E] key|value) are consumed without copies.
+ * lse [B,H,T] saved for the backward.  dbias_k/dbias_v [H*D] are ACCUMULATED (atomicAdd).
+ * tt_attn_avg_weights accumulates head-averaged probabilities into avg_w [B,T,L] (zero it first).
+ */
+int tt_attn_fwd(const float* q, const float* k, const float* v, const float* bias_k,
+                const float* bias_v, const uint8_t* key_padding_mask, float* out, float* lse,
+                int T, int B, int S, int H, int D, long long ldq, long long ldkv, long long ldo,
+                int zero_row, float p_drop, unsigned long long seed, void* stream);
+int tt_attn_bwd(const float* dout, const float* q, const float* k, const float* v,
+                const float* bias_k, const float* bias_v, const uint8_t* key_padding_mask,
+                const float* out, const float* lse, float* dq, float* dk, float* dv,
+                float* dbias_k, float* dbias_v, int T, int B, int S, int H, int D, long long ldq,
+                long long ldkv, long long ldo, int zero_row, float p_drop,
+                unsigned long long seed, void* stream);
+int tt_attn_avg_weights(const float* q, const float* k, const float* bias_k,
+                        const uint8_t* key_padding_mask, const float* lse, float* avg_w, int T,
+                        int B, int S, int H, int D, long long ldq, long long ldkv, int zero_row,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive softmax / loss, tell/modules/softmax.py:144-222, criteria/adaptive_loss.py:27-73.
+ * cutoffs = {c0, c1, ..., vocab} (n_clusters entries: head + tails).
+ */
+/* adapt_target (softmax.py:144-167) without host syncs: head_target [N]; per tail i an ordered
+ * list of member rows tail_idx[i*N + slot], their local ids tail_local[i*N + slot], and
+ * tail_count[i]; ntokens = #(target != pad_idx) (adaptive_loss.py:64-65). */
+int tt_adaptive_prepare(const long long* target, int N, const int* cutoffs, int n_clusters,
+                        int pad_idx, int* head_target, int* tail_idx, int* tail_local,
+                        int* tail_count, int* ntokens, void* stream);
+/* dst[i,:] = src[idx[i],:] for i < *count_ptr (all `cap` rows when NULL), else 0. */
+int tt_gather_rows(const float* src, const int* idx, const int* count_ptr, float* dst, int cap,
+                   int E, void* stream);
+/* dst[idx[i],:] += src[i,:] for i < *count_ptr (atomicAdd; idx < 0 skipped). */
+int tt_scatter_add_rows(const float* src, const int* idx, const int* count_ptr, float* dst,
+                        int cap, int E, void* stream);
+/* F.cross_entropy(reduction='sum', ignore_index) per row: row_loss [M], lse [M]; rows >= *count_ptr
+ * contribute 0. */
+int tt_ce_fwd(const float* logits, long long ld, const int* target, const int* count_ptr, int M,
+              int V, int ignore_index, float* lse, float* row_loss, void* stream);
+/* in place: logits <- (softmax - onehot) * *scale_ptr ; ignored / inactive rows <- 0. */
+int tt_ce_bwd(float* logits, long long ld, const int* target, const int* count_ptr, int M, int V,
+              int ignore_index, const float* lse, const float* scale_ptr, void* stream);
+/* loss = sum(row_loss)/ln2/ntokens, scale = 1/(ln2*ntokens). transformer_faces_objects.py:85-90 */
+int tt_loss_finalize(const float* row_loss, long long n, const int* ntokens, float* loss,
+                     float* scale, void* stream);
+/* get_log_prob (softmax.py:193-222) + greedy top-1 (transformer_faces_objects.py:443-464).
+ * head [M, c0+n_tails], tails[i] [M, V_i].  Any of log_probs [M,vocab], argmax_id, argmax_lp
+ * may be NULL. */
+int tt_adaptive_logprob(const float* head, long long ld_head, const float* const* tails,
+                        const long long* ld_tails, const int* cutoffs, int n_clusters, int M,
+                        float* log_probs, long long* argmax_id, float* argmax_lp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding front end: adaptive.py:61-76, positional.py:167-268.
+ * ids [B,T] int64; output row n = t*B+b when tbc != 0 (decoder works in T x B x C), else b*T+t.
+ */
+/* out [N, n_bands*E]: token's embedding row in its band's slot, zeros elsewhere. */
+int tt_embed_gather(const long long* ids, int B, int T, int tbc, const int* cutoffs, int n_bands,
+                    const float* const* tables, int E, float* out, void* stream);
+/* grads[band][local,:] += dA[n, band*E:(band+1)*E], skipping local == padding_idx. */
+int tt_embed_scatter_grad(const long long* ids, int B, int T, int tbc, const int* cutoffs,
+                          int n_bands, float* const* grads, int E, int padding_idx,
+                          const float* dA, void* stream);
+/* make_positions (positional.py:231-268) + incremental start_pos (:196-198). */
+int tt_make_positions(const long long* ids, int B, int T, int pad, int left_pad, int start_pos,
+                      int tbc, int* pos, void* stream);
+/* [A,B,C] -> [B,A,C] */
+int tt_transpose01(const float* in, float* out, int A, int B, int C, void* stream);
+
+/* out[c] = scale * sum_r x[r,c] (+ out[c] when accumulate): bias gradients. */
+int tt_colsum(const float* x, long long ld, int M, int N, float* out, float scale, int accumulate,
+              void* stream);
+/* dx = dy * (y > 0): backward of the ReLU fused into fc1's GEMM epilogue. */
+int tt_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
+/* RoBERTa layer mix, transformer_faces_objects.py:355-364: out = sum_l softmax(w)[l] * h_l.
+ * hiddens: bf16, layer l at hiddens + l*layer_stride, n elements each.  bwd: dw [L] (= d bert_weight);
+ * dots [L] is scratch. */
+int tt_layer_mix_fwd(const void* hiddens, long long layer_stride, const float* w, int L,
+                     long long n, float* out, void* stream);
+int tt_layer_mix_bwd(const void* hiddens, long long layer_stride, const float* w,
+                     const float* dout, int L, long long n, float* dots, float* dw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,28 @@ def load():
     _loaded = True
 
 
+def load_model_module():
+    """Makes tell.models.transformer_faces_objects importable (class only; its constructor needs
+    network access, so tests call its `_forward` / `_generate` methods unbound on a stub self)."""
+    load()
+    for n in ['allennlp.models', 'allennlp.models.model', 'allennlp.nn', 'allennlp.nn.initializers',
+              'pycocoevalcap', 'pycocoevalcap.bleu', 'pycocoevalcap.bleu.bleu_scorer']:
+        if n not in sys.modules:
+            _mod(n)
+
+    class Model(nn.Module, _Registrable):
+        def __init__(self, vocab=None):
+            super().__init__()
+
+    sys.modules['allennlp.models.model'].Model = Model
+    sys.modules['allennlp.models'].Model = Model
+    sys.modules['allennlp.nn.initializers'].InitializerApplicator = lambda *a, **k: (lambda m: None)
+    sys.modules['allennlp.nn'].InitializerApplicator = sys.modules['allennlp.nn.initializers'].InitializerApplicator
+    sys.modules['pycocoevalcap.bleu.bleu_scorer'].BleuScorer = object
+    import importlib
+    return importlib.import_module('tell.models.transformer_faces_objects')
+
+
 def build_embedder(vocab_size=50265, embed_dim=1024, cutoff=(5000, 20000), max_pos=512):
     load()
     from tell.modules.token_embedders import (AdaptiveEmbedding,
@@ -108,7 +130,7 @@ def build_decoder(kind='faces_objects', vocab_size=50265, embed_dim=1024, heads=
     if kind == 'faces_objects':
         from tell.models.decoder_faces_objects import DynamicConvFacesObjectsDecoder as D
     elif kind == 'no_image':
-        from tell.models.decoder_flattened_no_image import DynamicConvDecoder as D
+        from tell.models.decoder_flattened_no_image import DynamicConvDecoderNoImage as D
     else:
         raise ValueError(kind)
     dec = D(None, emb, 512, dropout, True, embed_dim, embed_dim, True, 'dynamic', True,

@@ -1,0 +1,374 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (plain PyTorch fp32) of the reference algorithm
+for the caption hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this file; the product (transform-and-tell_b200/) never does.
+
+Parity status: PINNED.  Every function below is checked in tests/test_oracle_cpu.py against
+golden vectors produced by the reference's own, unmodified modules
+(oracle/gen_golden.py imports them from /root/reference via oracle/ref_loader.py; the vectors are
+committed under tests/golden/) and against the reference's only known-answer test
+(tell/modules/token_embedders/tests/test_positional.py:12-32).
+Exceptions, stated in DESIGN.md: the RoBERTa encoder (fairseq, un-vendored) and torchvision's
+Bottleneck are third-party code absent from the reference tree -- their restatements here follow
+the published architectures and are "parity unpinned".
+
+All functions are stateless and take the reference state_dict (Appendix B key names), so the same
+dict feeds the oracle and the CUDA modules.  Citations are relative to the reference repo root.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+LN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------- embeddings
+def make_positions(ids, padding_idx, left_pad):
+    """tell/modules/token_embedders/positional.py:231-268."""
+    mask = ids.ne(padding_idx)
+    T = ids.shape[1]
+    positions = torch.arange(padding_idx + 1, padding_idx + 1 + T).expand_as(ids)
+    if left_pad:
+        positions = positions - (T - mask.long().sum(dim=1, keepdim=True))
+    return torch.where(mask, positions, torch.full_like(ids, padding_idx))
+
+
+def sinusoidal_table(n_embeds, embed_dim, padding_idx):
+    """positional.py:124-164 get_embedding (tensor2tensor layout: sin || cos)."""
+    n_ts = embed_dim // 2
+    increment = math.log(10000.0) / (n_ts - 1)
+    inv = torch.exp(torch.arange(n_ts, dtype=torch.float) * -increment)
+    st = torch.arange(n_embeds, dtype=torch.float).unsqueeze(1) * inv.unsqueeze(0)
+    sig = torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+    if embed_dim % 2 == 1:
+        sig = torch.cat([sig, torch.zeros(n_embeds, 1)], dim=1)
+    if padding_idx is not None:
+        sig[padding_idx, :] = 0
+    return sig
+
+
+def positional_embedding(ids, table, padding_idx=1, left_pad=False, start_pos=0):
+    """positional.py:167-211 forward (start_pos = incremental position)."""
+    pos = make_positions(ids, padding_idx, left_pad)
+    pos = torch.where(pos != padding_idx, pos + start_pos, pos)
+    return table.index_select(0, pos.reshape(-1)).view(ids.shape[0], ids.shape[1], -1)
+
+
+def adaptive_embedding(ids, sd, prefix, cutoffs, embed_dim, scale=True):
+    """adaptive.py:61-76.  cutoffs includes the vocab size as last entry."""
+    out = torch.zeros(ids.shape + (embed_dim,))
+    for i, hi in enumerate(cutoffs):
+        lo = cutoffs[i - 1] if i > 0 else 0
+        mask = (ids >= lo) & (ids < hi)
+        if mask.any():
+            emb = sd[prefix + 'embeddings.%d.0.weight' % i]
+            proj = sd[prefix + 'embeddings.%d.1.weight' % i]
+            # nn.Embedding(..., padding_idx=0): local row 0 receives no gradient
+            out[mask] = F.linear(F.embedding(ids[mask] - lo, emb, padding_idx=0), proj)
+    return (math.sqrt(embed_dim) if scale else 1.0) * out
+
+
+def sum_embedder(ids, sd, cutoffs, embed_dim, start_pos=0, prefix='embedder.'):
+    """sum_text_field_embedder.py:70-118: adaptive + sinusoidal, summed."""
+    a = adaptive_embedding(ids, sd, prefix + 'token_embedder_adaptive.', cutoffs, embed_dim)
+    p = positional_embedding(ids, sd[prefix + 'token_embedder_position.weights'], 1, False,
+                             start_pos)
+    return a + p
+
+
+# ------------------------------------------------------------------------------------- linear
+def gehring_linear(x, sd, prefix):
+    """linear.py:8-34: weight-norm (dim 0) linear."""
+    v, g = sd[prefix + 'weight_v'], sd[prefix + 'weight_g']
+    w = v * (g / v.norm(dim=1, keepdim=True))
+    return F.linear(x, w, sd.get(prefix + 'bias'))
+
+
+# ------------------------------------------------------------------------------------- dynconv
+def dynamic_conv(x, w_filter, K, H, weight_softmax=True):
+    """convolutions/dynamic.py:285-336 in closed form:
+    out[t,b,hR+r] = sum_k softmax_k(W_f x_t)[h,k] * x[t-(K-1)+k, b, hR+r], zero for negative time.
+    The softmax runs over all K taps even when some hit the padding."""
+    T, B, C = x.shape
+    R = C // H
+    z = F.linear(x, w_filter).view(T, B, H, K)
+    p = F.softmax(z, dim=-1) if weight_softmax else z
+    xp = torch.cat([x.new_zeros(K - 1, B, C), x], dim=0)
+    win = xp.unfold(0, K, 1)                       # [T, B, C, K]
+    win = win.view(T, B, H, R, K)
+    return torch.einsum('tbhrk,tbhk->tbhr', win, p).reshape(T, B, C)
+
+
+# ------------------------------------------------------------------------------------- attention
+def multi_head_attention(query, key, key_padding_mask, sd, prefix, H, need_weights=False):
+    """attention/multi_head.py:288-486, static_kv=True / incremental_state=None path."""
+    T, B, E = query.shape
+    d = E // H
+    bias = sd[prefix + 'in_proj_bias']
+    if (prefix + 'in_proj_weight') in sd:
+        w = sd[prefix + 'in_proj_weight']
+        wq, wk, wv = w[:E], w[E:2 * E], w[2 * E:]
+    else:
+        wq, wk, wv = (sd[prefix + 'q_proj_weight'], sd[prefix + 'k_proj_weight'],
+                      sd[prefix + 'v_proj_weight'])
+    q = F.linear(query, wq, bias[:E]) * d ** -0.5
+    S = key.shape[0] if key.shape[2] > 0 else 0
+    bk = sd[prefix + 'bias_k'].repeat(1, B, 1)
+    bv = sd[prefix + 'bias_v'].repeat(1, B, 1)
+    if S > 0:
+        k = torch.cat([F.linear(key, wk, bias[E:2 * E]), bk])
+        v = torch.cat([F.linear(key, wv, bias[2 * E:]), bv])
+        mask = torch.cat([key_padding_mask, key_padding_mask.new_zeros(B, 1)], dim=1)
+    else:
+        k, v = bk, bv
+        mask = key_padding_mask.new_zeros(B, 1)
+    q = q.contiguous().view(T, B * H, d).transpose(0, 1)
+    k = k.contiguous().view(-1, B * H, d).transpose(0, 1)
+    v = v.contiguous().view(-1, B * H, d).transpose(0, 1)
+    k = torch.cat([k, k.new_zeros(B * H, 1, d)], dim=1)          # add_zero_attn
+    v = torch.cat([v, v.new_zeros(B * H, 1, d)], dim=1)
+    mask = torch.cat([mask, mask.new_zeros(B, 1)], dim=1)
+    L = k.shape[1]
+    w = torch.bmm(q, k.transpose(1, 2)).view(B, H, T, L)
+    w = w.masked_fill(mask.bool().unsqueeze(1).unsqueeze(2), float('-inf')).view(B * H, T, L)
+    w = F.softmax(w, dim=-1, dtype=torch.float32)
+    attn = torch.bmm(w, v).transpose(0, 1).contiguous().view(T, B, E)
+    attn = F.linear(attn, sd[prefix + 'out_proj.weight'], sd[prefix + 'out_proj.bias'])
+    weights = w.view(B, H, T, L).sum(dim=1) / H if need_weights else None
+    return attn, weights
+
+
+# ------------------------------------------------------------------------------------- decoder
+def _ln(x, sd, prefix):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + 'weight'], sd[prefix + 'bias'], LN_EPS)
+
+
+def decoder_layer(X, contexts, sd, prefix, K, H, ctx_names, conv_state=None):
+    """models/decoder_faces_objects.py:255-365 (eval / dropout-free); also covers
+    decoder_flattened_no_image.py's layer (ctx_names = ['article']).
+    conv_state: None, or a list [buffer] holding the DynamicConv input buffer
+    (dynamic.py:95-99 incremental semantics)."""
+    residual = X
+    h = gehring_linear(X, sd, prefix + 'linear1.')
+    h = F.glu(h, dim=-1)
+    if conv_state is not None:
+        prev = conv_state[0]
+        if prev is not None:
+            h = torch.cat([prev, h], dim=0)
+        conv_state[0] = h[-K + 1:] if K > 1 else h[:0]
+        o = dynamic_conv(h, sd[prefix + 'conv.weight_linear.weight'], K, H)
+        if prev is not None:
+            o = o[prev.shape[0]:]
+    else:
+        o = dynamic_conv(h, sd[prefix + 'conv.weight_linear.weight'], K, H)
+    h = gehring_linear(o, sd, prefix + 'linear2.')
+    X = _ln(residual + h, sd, prefix + 'conv_layer_norm.')
+    outs, attns = [], {}
+    for name in ctx_names:
+        a, w = multi_head_attention(X, contexts[name], contexts[name + '_mask'], sd,
+                                    prefix + 'context_attns.%s.' % name, H, need_weights=True)
+        outs.append(_ln(X + a, sd, prefix + 'context_attn_lns.%s.' % name))
+        attns[name] = w
+    Xc = torch.cat(outs, dim=-1)
+    X = gehring_linear(Xc, sd, prefix + 'context_fc.')
+    residual = X
+    h = F.relu(gehring_linear(X, sd, prefix + 'fc1.'))
+    h = gehring_linear(h, sd, prefix + 'fc2.')
+    X = _ln(residual + h, sd, prefix + 'final_layer_norm.')
+    return X, attns
+
+
+def decoder_forward(ids, contexts, sd, cfg, incremental_state=None):
+    """decoder_faces_objects.py:95-142.  cfg: dict(embed_dim, heads, kernels, cutoffs (with vocab),
+    ctx_names).  incremental_state: None or dict {'pos': int, 'conv': [[buf] per layer]}.
+    Returns [B,T,E] and per-layer attention dicts."""
+    start = 0
+    if incremental_state is not None:
+        start = incremental_state.setdefault('pos', 0)
+        incremental_state['pos'] = start + ids.shape[1]
+        conv = incremental_state.setdefault('conv', [[None] for _ in cfg['kernels']])
+    X = sum_embedder(ids, sd, cfg['cutoffs'], cfg['embed_dim'], start)
+    X = X.transpose(0, 1)
+    attns = []
+    for i, K in enumerate(cfg['kernels']):
+        X, a = decoder_layer(X, contexts, sd, 'layers.%d.' % i, K, cfg['heads'], cfg['ctx_names'],
+                             conv[i] if incremental_state is not None else None)
+        attns.append(a)
+    return X.transpose(0, 1), attns
+
+
+# ------------------------------------------------------------------------------------- softmax / loss
+def adaptive_logits(X, target, sd, cutoffs, prefix='adaptive_softmax.'):
+    """softmax.py:144-191: (list of logits, list of targets); tied weights."""
+    X = X.contiguous().view(-1, X.shape[-1])
+    target = target.reshape(-1)
+    head_w = torch.cat([sd[prefix + 'head.word_proj.weight'], sd[prefix + 'head.class_proj.weight']])
+    new_target = [target.clone()]
+    logits = [F.linear(X, head_w)]
+    for i in range(len(cutoffs) - 1):
+        mask = (target >= cutoffs[i]) & (target < cutoffs[i + 1])
+        new_target[0][mask] = cutoffs[0] + i
+        if mask.any():
+            idx = mask.nonzero().squeeze(1)
+            new_target.append(target[mask] - cutoffs[i])
+            h = F.linear(X.index_select(0, idx), sd[prefix + 'tail.%d.0.weight' % i])
+            logits.append(F.linear(h, sd[prefix + 'tail.%d.2.weight' % i]))
+        else:
+            new_target.append(None)
+            logits.append(None)
+    return logits, new_target
+
+
+def adaptive_loss(X, target, sd, cutoffs, padding_idx=1):
+    """criteria/adaptive_loss.py:27-73 + transformer_faces_objects.py:82-90.
+    Returns (loss_sum, ntokens, loss = sum / ln2 / ntokens).  ignore_index is applied to the
+    CLUSTER-LOCAL targets, exactly as the reference does."""
+    logits, tgt = adaptive_logits(X, target, sd, cutoffs)
+    loss = X.new_zeros(1)
+    for lg, t in zip(logits, tgt):
+        if t is not None:
+            loss = loss + F.cross_entropy(lg, t, ignore_index=padding_idx, reduction='sum')
+    ntokens = int(target.ne(padding_idx).sum())
+    return loss, ntokens, loss / math.log(2) / ntokens
+
+
+def adaptive_log_prob(X, sd, cutoffs, prefix='adaptive_softmax.'):
+    """softmax.py:193-222 get_log_prob: [B,T,vocab]."""
+    B, T, E = X.shape
+    X2 = X.contiguous().view(-1, E)
+    head_w = torch.cat([sd[prefix + 'head.word_proj.weight'], sd[prefix + 'head.class_proj.weight']])
+    head_lp = F.log_softmax(F.linear(X2, head_w), dim=1)
+    parts = [head_lp[:, :cutoffs[0]]]
+    for i in range(len(cutoffs) - 1):
+        h = F.linear(X2, sd[prefix + 'tail.%d.0.weight' % i])
+        t = F.log_softmax(F.linear(h, sd[prefix + 'tail.%d.2.weight' % i]), dim=1)
+        parts.append(t + head_lp[:, cutoffs[0] + i, None])
+    return torch.cat(parts, dim=1).view(B, T, -1)
+
+
+# ------------------------------------------------------------------------------------- model level
+def nan_mask_(x):
+    """transformer_faces_objects.py:374-379: mask = isnan(x).any(-1); x[mask] = 0 (in place)."""
+    mask = torch.isnan(x).any(dim=-1)
+    x[mask] = 0
+    return mask
+
+
+def build_contexts(image_feats, article_hiddens, bert_weight, article_ids, face_embeds, obj_embeds,
+                   padding_idx=1):
+    """transformer_faces_objects.py:335-395.  image_feats [B,2048,7,7] (ResNet output),
+    article_hiddens: list of 25 [B,S,1024] (RoBERTa all-layer features)."""
+    B = article_ids.shape[0]
+    contexts = {}
+    if image_feats is not None:
+        X_image = image_feats.permute(0, 2, 3, 1).reshape(B, -1, image_feats.shape[1])
+        contexts['image'] = X_image.transpose(0, 1)
+        contexts['image_mask'] = X_image.new_zeros(B, X_image.shape[1]).bool()
+    X_article = torch.stack(article_hiddens, dim=2)                 # [B,S,25,1024]
+    w = F.softmax(bert_weight, dim=0).unsqueeze(0).unsqueeze(1).unsqueeze(3)
+    X_article = (X_article * w).sum(dim=2)
+    contexts['article'] = X_article.transpose(0, 1)
+    contexts['article_mask'] = article_ids == padding_idx
+    if face_embeds is not None:
+        fm = nan_mask_(face_embeds)
+        contexts['faces'] = face_embeds.transpose(0, 1)
+        contexts['faces_mask'] = fm
+    if obj_embeds is not None:
+        om = nan_mask_(obj_embeds)
+        contexts['obj'] = obj_embeds.transpose(0, 1)
+        contexts['obj_mask'] = om
+    return contexts
+
+
+def shift_caption(caption_ids, padding_idx=1):
+    """transformer_faces_objects.py:321-329: inputs = ids[:, :-1], targets = ids[:, 1:]."""
+    target = caption_ids[:, 1:].contiguous()
+    inp = caption_ids[:, :-1].contiguous()
+    return inp, target
+
+
+def greedy_generate(seed_ids, contexts, sd, cfg, gen_len=100, eos=2, padding_idx=1,
+                    early_exit=True):
+    """transformer_faces_objects.py:399-494 _generate with sampling_topk=1 (argmax), written
+    without the active-row compaction but emitting the identical matrices: token_ids [B, 1+n]
+    (seed column first) and log_probs [B, n]; finished rows emit pad (1) with log-prob 0."""
+    B = seed_ids.shape[0]
+    state = {}
+    active = torch.ones(B, dtype=torch.bool)
+    prev = seed_ids[:, 0:1]
+    cols, lps = [prev.clone()], []
+    for _ in range(gen_len):
+        X, _ = decoder_forward(prev, contexts, sd, cfg, state)
+        lp = adaptive_log_prob(X[:, -1:], sd, cfg['cutoffs'])[:, 0]
+        best_lp, best = lp.max(dim=-1)
+        tok = torch.where(active, best, torch.full_like(best, padding_idx))
+        cols.append(tok.unsqueeze(1))
+        lps.append(torch.where(active, best_lp, torch.zeros_like(best_lp)).unsqueeze(1))
+        active = active & (tok != eos)
+        prev = tok.unsqueeze(1)
+        if early_exit and not bool(active.any()):
+            break
+    return torch.cat(cols, dim=1), torch.cat(lps, dim=1)
+
+
+# ------------------------------------------------------------------------------------- encoders
+def resnet152_forward(image, sd, prefix='resnet.', bn_eps=1e-5, blocks=(3, 8, 36, 3)):
+    """models/resnet.py:92-108 (torchvision Bottleneck stack, eval-mode BatchNorm): [B,3,224,224]
+    -> [B,2048,7,7].  Third-party block definition (torchvision 0.6.1): parity unpinned."""
+    def bn(x, p):
+        return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'],
+                            sd[p + 'bias'], False, 0.0, bn_eps)
+    x = F.conv2d(image, sd[prefix + 'conv1.weight'], stride=2, padding=3)
+    x = F.relu(bn(x, prefix + 'bn1.'))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, n in enumerate(blocks):
+        for bi in range(n):
+            p = prefix + 'layer%d.%d.' % (li + 1, bi)
+            stride = 2 if (li > 0 and bi == 0) else 1
+            idn = x
+            o = F.relu(bn(F.conv2d(x, sd[p + 'conv1.weight']), p + 'bn1.'))
+            o = F.relu(bn(F.conv2d(o, sd[p + 'conv2.weight'], stride=stride, padding=1), p + 'bn2.'))
+            o = bn(F.conv2d(o, sd[p + 'conv3.weight']), p + 'bn3.')
+            if (p + 'downsample.0.weight') in sd:
+                idn = bn(F.conv2d(x, sd[p + 'downsample.0.weight'], stride=stride),
+                         p + 'downsample.1.')
+            x = F.relu(o + idn)
+    return x
+
+
+def roberta_forward(ids, sd, n_layers, heads, prefix='roberta.', padding_idx=1, eps=1e-5):
+    """fairseq RoBERTa encoder `extract_features(return_all_hiddens=True)` (call site
+    transformer_faces_objects.py:352-353): learned positions (pad-aware, offset by pad+1),
+    embedding LayerNorm, post-LN encoder layers with GELU; returns n_layers+1 [B,S,E] tensors.
+    Un-vendored third-party model (fairseq @ 2f7e3f3323): parity unpinned; key names follow
+    fairseq's `decoder.sentence_encoder.*` layout."""
+    p = prefix + 'decoder.sentence_encoder.'
+    B, S = ids.shape
+    pad = ids.eq(padding_idx)
+    pos = make_positions(ids, padding_idx, False)
+    x = F.embedding(ids, sd[p + 'embed_tokens.weight']) + F.embedding(pos, sd[p + 'embed_positions.weight'])
+    x = F.layer_norm(x, (x.shape[-1],), sd[p + 'emb_layer_norm.weight'], sd[p + 'emb_layer_norm.bias'], eps)
+    x = x * (~pad).unsqueeze(-1).type_as(x)
+    E = x.shape[-1]
+    d = E // heads
+    hiddens = [x]
+    for i in range(n_layers):
+        lp = p + 'layers.%d.' % i
+        qkv = F.linear(x, sd[lp + 'self_attn.in_proj_weight'], sd[lp + 'self_attn.in_proj_bias'])
+        q, k, v = qkv.chunk(3, dim=-1)
+        q = (q * d ** -0.5).view(B, S, heads, d).transpose(1, 2)
+        k = k.view(B, S, heads, d).transpose(1, 2)
+        v = v.view(B, S, heads, d).transpose(1, 2)
+        w = torch.matmul(q, k.transpose(-1, -2))
+        w = w.masked_fill(pad.view(B, 1, 1, S), float('-inf'))
+        w = F.softmax(w, dim=-1)
+        a = torch.matmul(w, v).transpose(1, 2).reshape(B, S, E)
+        a = F.linear(a, sd[lp + 'self_attn.out_proj.weight'], sd[lp + 'self_attn.out_proj.bias'])
+        x = F.layer_norm(x + a, (E,), sd[lp + 'self_attn_layer_norm.weight'],
+                         sd[lp + 'self_attn_layer_norm.bias'], eps)
+        h = F.gelu(F.linear(x, sd[lp + 'fc1.weight'], sd[lp + 'fc1.bias']))
+        h = F.linear(h, sd[lp + 'fc2.weight'], sd[lp + 'fc2.bias'])
+        x = F.layer_norm(x + h, (E,), sd[lp + 'final_layer_norm.weight'],
+                         sd[lp + 'final_layer_norm.bias'], eps)
+        hiddens.append(x)
+    return hiddens

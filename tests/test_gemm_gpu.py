@@ -6,15 +6,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _ref(a16, b16, bias, residual, alpha, act):
-    c = alpha * (a16.float() @ b16.float().t())
+    # act(alpha * (A.B^T + bias) + residual)
+    c = a16.float() @ b16.float().t()
     if bias is not None:
         c = c + bias
+    c = alpha * c
+    if residual is not None:
+        c = c + residual
     if act == 1:
         c = torch.relu(c)
     elif act == 2:
         c = torch.nn.functional.gelu(c)
-    if residual is not None:
-        c = c + residual
     return c
 
 
@@ -53,6 +55,10 @@ def test_gemm_epilogue(act):
     ops.gemm_tn(a, b, out=c2, accumulate=True)
     ref2 = ref + _ref(a, b, None, None, 1.0, 0)
     assert (c2 - ref2).abs().max().item() < 4e-3
+    # bf16 residual (ResNet identity branch)
+    c3 = ops.gemm_tn(a, b, bias=bias, residual16=res.bfloat16(), act=act)
+    ref3 = _ref(a, b, bias, res.bfloat16().float(), 1.0, act)
+    assert (c3 - ref3).abs().max().item() < 2e-3
 
 
 def test_gemm_unaligned_output_and_m_limit():

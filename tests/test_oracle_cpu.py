@@ -1,0 +1,131 @@
+"""CPU suite: pins the oracle (oracle/restate.py) to golden vectors produced by the reference's
+own modules (oracle/gen_golden.py) and to the reference's known-answer test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+import restate  # noqa: E402
+from tell_b200 import synth  # noqa: E402
+
+SHAPES = dict(B=3, T=9, S=11, F=3, O=4, P=5)
+
+
+def T_(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_make_positions_reference_vectors():
+    """tell/modules/token_embedders/tests/test_positional.py:12-32."""
+    left_in = torch.tensor([[9, 9, 9, 9, 9], [1, 9, 9, 9, 9], [1, 1, 1, 9, 9]])
+    left_out = torch.tensor([[2, 3, 4, 5, 6], [1, 2, 3, 4, 5], [1, 1, 1, 2, 3]])
+    right_in = torch.tensor([[9, 9, 9, 9, 9], [9, 9, 9, 9, 1], [9, 9, 1, 1, 1]])
+    right_out = torch.tensor([[2, 3, 4, 5, 6], [2, 3, 4, 5, 1], [2, 3, 1, 1, 1]])
+    assert torch.equal(restate.make_positions(left_in, 1, True), left_out)
+    assert torch.equal(restate.make_positions(right_in, 1, False), right_out)
+
+
+def test_op_goldens():
+    g = np.load(os.path.join(GOLD, 'ops.npz'))
+    for (T, K) in [(5, 15), (12, 7)]:
+        tag = 'dynconv_T%d_K%d/' % (T, K)
+        y = restate.dynamic_conv(T_(g[tag + 'x']), T_(g[tag + 'w']), K, 4)
+        assert (y - T_(g[tag + 'y'])).abs().max() < 1e-5
+    sd = {k[len('mha_empty/'):]: T_(g[k]) for k in g.files if k.startswith('mha_empty/a.')}
+    q = T_(g['mha_empty/q'])
+    y, w = restate.multi_head_attention(q, torch.zeros(1, 2, 0), torch.zeros(2, 1, dtype=torch.bool),
+                                        sd, 'a.', 4, True)
+    assert (y - T_(g['mha_empty/y'])).abs().max() < 1e-5
+    assert (w - T_(g['mha_empty/w'])).abs().max() < 1e-6
+    assert w.shape == (2, 4, 2)      # bias row + zero row only
+
+
+def test_forward_glue_goldens():
+    g = np.load(os.path.join(GOLD, 'forward_glue.npz'))
+    hid = [T_(h) for h in g['hid']]
+    ctx = restate.build_contexts(T_(g['feats']), hid, T_(g['bert_weight']), T_(g['art']),
+                                 T_(g['faces']).clone(), T_(g['objs']).clone())
+    for k, v in ctx.items():
+        assert torch.allclose(v.float(), T_(g['ctx/' + k]).float(), atol=1e-6), k
+    inp, tgt = restate.shift_caption(T_(g['cap']))
+    assert torch.equal(inp, T_(g['caption_ids'])) and torch.equal(tgt, T_(g['target_ids']))
+
+
+@pytest.mark.parametrize('tag,cfg', [('tiny_faces_objects', synth.CFG_TINY),
+                                     ('tiny_no_image', synth.CFG_TINY_NO_IMAGE)])
+def test_decoder_goldens(tag, cfg):
+    g = np.load(os.path.join(GOLD, 'decoder_%s.npz' % tag))
+    sd = synth.decoder_state_dict(cfg, seed=0, logit_gain=4.0)
+    for k in sd:
+        if sd[k].is_floating_point():
+            sd[k] = sd[k].clone().requires_grad_(True)
+    # re-tie after cloning
+    pre = 'embedder.token_embedder_adaptive.embeddings.'
+    sd['adaptive_softmax.head.word_proj.weight'] = sd[pre + '0.0.weight']
+    for i in range(2):
+        sd['adaptive_softmax.tail.%d.2.weight' % i] = sd[pre + '%d.0.weight' % (i + 1)]
+    cap, ctx = synth.decoder_inputs(cfg, **SHAPES, seed=1234)
+    inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    ocfg = synth.oracle_cfg(cfg)
+    ctx['article'].requires_grad_(True)
+    out, attns = restate.decoder_forward(inp, ctx, sd, ocfg)
+    assert (out.detach() - T_(g['dec_out'])).abs().max() < 2e-5
+    loss_sum, n, loss = restate.adaptive_loss(out, tgt, sd, ocfg['cutoffs'])
+    assert n == int(g['ntokens'][0])
+    assert abs(loss_sum.item() - float(g['loss_sum'][0])) < 1e-3
+    loss.backward()
+    assert (ctx['article'].grad - T_(g['d_article'])).abs().max() < 1e-5
+    for k in g.files:
+        if k.startswith('gfull/'):
+            name = k[len('gfull/'):]
+            assert (sd[name].grad - T_(g[k])).abs().max() < 2e-5, name
+        if k.startswith('gsum/'):
+            name = k[len('gsum/'):]
+            gr = sd[name].grad
+            norm = gr.double().norm().item() if gr is not None else 0.0
+            assert abs(norm - g[k][0]) < 1e-4 * max(1.0, g[k][0]), name
+    if 'attn0/article' in g.files:
+        for nm in ocfg['ctx_names']:
+            assert (attns[0][nm].detach() - T_(g['attn0/' + nm])).abs().max() < 1e-5
+    with torch.no_grad():
+        sdd = {k: v.detach() for k, v in sd.items()}
+        ctxd = {k: v.detach() for k, v in ctx.items()}
+        lp = restate.adaptive_log_prob(out[:, -1:].detach(), sdd, ocfg['cutoffs'])
+        assert (lp - T_(g['log_probs_last'])).abs().max() < 1e-4
+        state, steps = {}, []
+        for t in range(inp.shape[1]):
+            o, _ = restate.decoder_forward(inp[:, t:t + 1], ctxd, sdd, ocfg, state)
+            steps.append(o)
+        assert (torch.cat(steps, 1) - T_(g['dec_out_incremental'])).abs().max() < 2e-5
+        if 'greedy_ids' in g.files:
+            ids, lps = restate.greedy_generate(cap[:, 0:1], ctxd, sdd, ocfg, gen_len=20)
+            assert torch.equal(ids, T_(g['greedy_ids'])[:, :21])
+            assert (lps - T_(g['greedy_lp'])[:, :20]).abs().max() < 1e-4
+
+
+def test_tail_local_index_one_quirk():
+    """ignore_index=1 is applied to cluster-local targets (adaptive_loss.py:57-60)."""
+    torch.manual_seed(0)
+    E = 8
+    sd = {'adaptive_softmax.head.word_proj.weight': torch.randn(10, E),
+          'adaptive_softmax.head.class_proj.weight': torch.randn(2, E),
+          'adaptive_softmax.tail.0.0.weight': torch.randn(E, E),
+          'adaptive_softmax.tail.0.2.weight': torch.randn(10, E),
+          'adaptive_softmax.tail.1.0.weight': torch.randn(E, E),
+          'adaptive_softmax.tail.1.2.weight': torch.randn(10, E)}
+    X = torch.randn(1, 4, E)
+    full = -restate.adaptive_log_prob(X, sd, [10, 20, 30])[0]
+    t_ok = torch.tensor([[5, 12, 22, 1]])
+    t_quirk = torch.tensor([[5, 11, 21, 1]])
+    l_ok, n, _ = restate.adaptive_loss(X, t_ok, sd, [10, 20, 30])
+    true_ok = sum(full[i, t_ok[0, i]] for i in range(3))
+    assert n == 3 and abs(l_ok.item() - true_ok.item()) < 1e-4
+    l_q, _, _ = restate.adaptive_loss(X, t_quirk, sd, [10, 20, 30])
+    true_q = sum(full[i, t_quirk[0, i]] for i in range(3))
+    assert l_q.item() < true_q.item() - 1e-3      # tail terms of local index 1 are dropped

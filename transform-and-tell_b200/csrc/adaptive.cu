@@ -1,0 +1,348 @@
+// Adaptive softmax / adaptive loss pieces (tell/modules/softmax.py:144-222,
+// tell/modules/criteria/adaptive_loss.py:27-73) and row gather/scatter helpers.
+// The logit GEMMs run in gemm.cu; this file holds the data-dependent parts the reference does
+// with boolean masks and nonzero() host syncs: cluster target remap + ordered compaction on the
+// device, row-wise log-sum-exp cross entropy with ignore_index, its backward, and the
+// full-vocabulary log-prob / argmax used by greedy decoding.
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int AD_MAX_CLUSTERS = 8;
+
+struct AdaptiveCut {
+  int n_clusters;                  // head + tails
+  int cutoff[AD_MAX_CLUSTERS];     // cutoff[0] = head words, ..., cutoff[n_clusters-1] = vocab
+};
+
+// softmax.py:144-167 adapt_target.  Single CTA, ordered (deterministic) compaction.
+//   head_target[n] = id                       if id < cutoff[0]
+//                  = cutoff[0] + i            if cutoff[i] <= id < cutoff[i+1]
+//   tail i: idx[i][slot] = n, local[i][slot] = id - cutoff[i]  for rows in band i, in row order.
+__global__ void adaptive_prepare_kernel(const long long* __restrict__ target, int N,
+                                        AdaptiveCut cut, int pad_idx,
+                                        int* __restrict__ head_target, int* __restrict__ tail_idx,
+                                        int* __restrict__ tail_local, int* __restrict__ tail_count,
+                                        int* __restrict__ ntokens) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // head targets + non-pad count
+  int cnt = 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const long long id = target[n];
+    int ht = static_cast<int>(id);
+    for (int i = 0; i + 1 < cut.n_clusters; ++i)
+      if (id >= cut.cutoff[i] && id < cut.cutoff[i + 1]) ht = cut.cutoff[0] + i;
+    head_target[n] = ht;
+    cnt += (id != pad_idx) ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) warp_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < nw; ++w) s += warp_cnt[w];
+    if (ntokens) *ntokens = s;
+  }
+  // ordered compaction per tail
+  for (int i = 0; i + 1 < cut.n_clusters; ++i) {
+    __syncthreads();
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int n0 = 0; n0 < N; n0 += blockDim.x) {
+      const int n = n0 + threadIdx.x;
+      long long id = -1;
+      if (n < N) id = target[n];
+      const bool in = (id >= cut.cutoff[i] && id < cut.cutoff[i + 1]);
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) warp_cnt[warp] = __popc(bal);
+      __syncthreads();
+      int off = base;
+      for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+      if (in) {
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        tail_idx[static_cast<long long>(i) * N + slot] = n;
+        tail_local[static_cast<long long>(i) * N + slot] = static_cast<int>(id - cut.cutoff[i]);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int s = base;
+        for (int w = 0; w < nw; ++w) s += warp_cnt[w];
+        base = s;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) tail_count[i] = base;
+  }
+}
+
+// dst[i,:] = src[idx[i],:] for i < count, else 0.   (X.index_select(0, target_idxs[i]), softmax.py:185)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                   const int* __restrict__ count_ptr, float* __restrict__ dst,
+                                   int cap, int E4) {
+  const int count = count_ptr ? min(*count_ptr, cap) : cap;
+  const long long total = static_cast<long long>(cap) * E4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / E4), c = static_cast<int>(i - static_cast<long long>(r) * E4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < count) v = __ldg(reinterpret_cast<const float4*>(src) + static_cast<long long>(idx[r]) * E4 + c);
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+}
+// dst[idx[i],:] += src[i,:] for i < count (atomic: idx may repeat for embedding grads).
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                        const int* __restrict__ count_ptr, float* __restrict__ dst,
+                                        int cap, int E) {
+  const int count = count_ptr ? min(*count_ptr, cap) : cap;
+  const long long total = static_cast<long long>(count) * E;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / E), c = static_cast<int>(i - static_cast<long long>(r) * E);
+    const int d = idx[r];
+    if (d >= 0) atomicAdd(dst + static_cast<long long>(d) * E + c, src[i]);
+  }
+}
+
+// F.cross_entropy(logits, target, ignore_index, reduction='sum') per row + saved lse.
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ logits, long long ld, const int* __restrict__ target,
+              const int* __restrict__ count_ptr, int M, int V, int ignore_index,
+              float* __restrict__ lse, float* __restrict__ row_loss) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int count = count_ptr ? min(*count_ptr, M) : M;
+  if (r >= count) {
+    if (threadIdx.x == 0) { row_loss[r] = 0.f; lse[r] = 0.f; }
+    return;
+  }
+  const float* x = logits + r * ld;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) m = fmaxf(m, x[j]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(x[j] - m);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float l = m + logf(s);
+    lse[r] = l;
+    const int t = target[r];
+    row_loss[r] = (t == ignore_index) ? 0.f : (l - x[t]);
+  }
+}
+
+// In place: logits <- (softmax - onehot(target)) * scale ; ignored / out-of-range rows <- 0.
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(float* __restrict__ logits, long long ld, const int* __restrict__ target,
+              const int* __restrict__ count_ptr, int M, int V, int ignore_index,
+              const float* __restrict__ lse, const float* __restrict__ scale_ptr) {
+  const int r = blockIdx.x;
+  const int count = count_ptr ? min(*count_ptr, M) : M;
+  float* x = logits + r * ld;
+  const int t = r < count ? target[r] : ignore_index;
+  if (r >= count || t == ignore_index) {
+    for (int j = threadIdx.x; j < V; j += blockDim.x) x[j] = 0.f;
+    return;
+  }
+  const float l = lse[r];
+  const float sc = scale_ptr ? *scale_ptr : 1.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float g = expf(x[j] - l);
+    if (j == t) g -= 1.f;
+    x[j] = g * sc;
+  }
+}
+
+// loss = sum(row_loss[0..n)) / ln2 / ntokens ; scale = upstream / (ln2 * ntokens)
+// transformer_faces_objects.py:85-90.  Single CTA, fixed summation order (deterministic).
+__global__ void loss_finalize_kernel(const float* __restrict__ row_loss, long long n,
+                                     const int* __restrict__ ntokens, float* __restrict__ loss,
+                                     float* __restrict__ scale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += row_loss[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float denom = 0.69314718055994530942f * static_cast<float>(*ntokens);
+    if (loss) *loss = s / denom;
+    if (scale) *scale = 1.f / denom;
+  }
+}
+
+// softmax.py:193-222 get_log_prob (+ topk(1) of transformer_faces_objects.py:443-464).
+// One CTA per row.  head [M, c0 + n_tails], tails[i] [M, V_i].
+struct LogProbArgs {
+  const float* head; long long ld_head;
+  const float* tail[AD_MAX_CLUSTERS - 1]; long long ld_tail[AD_MAX_CLUSTERS - 1];
+  AdaptiveCut cut;
+  float* log_probs;      // [M, vocab] or null
+  long long* argmax_id;  // [M] or null
+  float* argmax_lp;      // [M] or null
+  int M;
+};
+__global__ void __launch_bounds__(256)
+adaptive_logprob_kernel(const LogProbArgs a) {
+  __shared__ float red[32];
+  __shared__ float best_v[256];
+  __shared__ int best_i[256];
+  const int r = blockIdx.x;
+  const int c0 = a.cut.cutoff[0];
+  const int n_tails = a.cut.n_clusters - 1;
+  const int vocab = a.cut.cutoff[a.cut.n_clusters - 1];
+  const int head_n = c0 + n_tails;
+  const float* h = a.head + r * a.ld_head;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < head_n; j += blockDim.x) m = fmaxf(m, h[j]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < head_n; j += blockDim.x) s += expf(h[j] - m);
+  s = block_sum(s, red);
+  const float head_lse = m + logf(s);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < c0; j += blockDim.x) {
+    const float lp = h[j] - head_lse;
+    if (a.log_probs) a.log_probs[static_cast<long long>(r) * vocab + j] = lp;
+    if (lp > bv) { bv = lp; bi = j; }
+  }
+  for (int i = 0; i < n_tails; ++i) {
+    const int Vi = a.cut.cutoff[i + 1] - a.cut.cutoff[i];
+    const float* t = a.tail[i] + r * a.ld_tail[i];
+    float tm = -INFINITY;
+    for (int j = threadIdx.x; j < Vi; j += blockDim.x) tm = fmaxf(tm, t[j]);
+    tm = block_max(tm, red);
+    float ts = 0.f;
+    for (int j = threadIdx.x; j < Vi; j += blockDim.x) ts += expf(t[j] - tm);
+    ts = block_sum(ts, red);
+    const float prior = h[c0 + i] - head_lse;
+    const float off = prior - (tm + logf(ts));
+    for (int j = threadIdx.x; j < Vi; j += blockDim.x) {
+      const float lp = t[j] + off;
+      const int id = a.cut.cutoff[i] + j;
+      if (a.log_probs) a.log_probs[static_cast<long long>(r) * vocab + id] = lp;
+      if (lp > bv) { bv = lp; bi = id; }
+    }
+  }
+  if (a.argmax_id || a.argmax_lp) {
+    best_v[threadIdx.x] = bv;
+    best_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const float v2 = best_v[threadIdx.x + o];
+        const int i2 = best_i[threadIdx.x + o];
+        // ties -> lowest index (torch.topk on CPU returns the first maximal element)
+        if (v2 > best_v[threadIdx.x] || (v2 == best_v[threadIdx.x] && i2 < best_i[threadIdx.x])) {
+          best_v[threadIdx.x] = v2;
+          best_i[threadIdx.x] = i2;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (a.argmax_id) a.argmax_id[r] = best_i[0];
+      if (a.argmax_lp) a.argmax_lp[r] = best_v[0];
+    }
+  }
+}
+
+static inline int flat_grid2(long long n) {
+  long long g = ceil_div_ll(n, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+static int make_cut(const int* cutoffs, int n_clusters, AdaptiveCut* cut) {
+  TT_REQUIRE(cutoffs && n_clusters >= 1 && n_clusters <= AD_MAX_CLUSTERS,
+             "adaptive: n_clusters must be in [1,%d]", AD_MAX_CLUSTERS);
+  cut->n_clusters = n_clusters;
+  for (int i = 0; i < n_clusters; ++i) cut->cutoff[i] = cutoffs[i];
+  return TT_OK;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_adaptive_prepare(const long long* target, int N, const int* cutoffs,
+                                   int n_clusters, int pad_idx, int* head_target, int* tail_idx,
+                                   int* tail_local, int* tail_count, int* ntokens, void* stream) {
+  TT_REQUIRE(target && head_target, "tt_adaptive_prepare: null pointer");
+  AdaptiveCut cut;
+  int rc = make_cut(cutoffs, n_clusters, &cut);
+  if (rc != TT_OK) return rc;
+  TT_REQUIRE(n_clusters == 1 || (tail_idx && tail_local && tail_count),
+             "tt_adaptive_prepare: null tail buffers");
+  if (N <= 0) return TT_OK;
+  adaptive_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      target, N, cut, pad_idx, head_target, tail_idx, tail_local, tail_count, ntokens);
+  return check_launch("adaptive_prepare_kernel");
+}
+
+extern "C" int tt_gather_rows(const float* src, const int* idx, const int* count_ptr, float* dst,
+                              int cap, int E, void* stream) {
+  TT_REQUIRE(src && idx && dst, "tt_gather_rows: null pointer");
+  TT_REQUIRE(E % 4 == 0, "tt_gather_rows: E must be a multiple of 4");
+  if (cap <= 0) return TT_OK;
+  gather_rows_kernel<<<flat_grid2(static_cast<long long>(cap) * (E / 4)), 256, 0,
+                       (cudaStream_t)stream>>>(src, idx, count_ptr, dst, cap, E / 4);
+  return check_launch("gather_rows_kernel");
+}
+
+extern "C" int tt_scatter_add_rows(const float* src, const int* idx, const int* count_ptr,
+                                   float* dst, int cap, int E, void* stream) {
+  TT_REQUIRE(src && idx && dst, "tt_scatter_add_rows: null pointer");
+  if (cap <= 0) return TT_OK;
+  scatter_add_rows_kernel<<<flat_grid2(static_cast<long long>(cap) * E), 256, 0,
+                            (cudaStream_t)stream>>>(src, idx, count_ptr, dst, cap, E);
+  return check_launch("scatter_add_rows_kernel");
+}
+
+extern "C" int tt_ce_fwd(const float* logits, long long ld, const int* target,
+                         const int* count_ptr, int M, int V, int ignore_index, float* lse,
+                         float* row_loss, void* stream) {
+  TT_REQUIRE(logits && target && lse && row_loss, "tt_ce_fwd: null pointer");
+  if (M <= 0) return TT_OK;
+  ce_fwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, count_ptr, M, V,
+                                                     ignore_index, lse, row_loss);
+  return check_launch("ce_fwd_kernel");
+}
+
+extern "C" int tt_ce_bwd(float* logits, long long ld, const int* target, const int* count_ptr,
+                         int M, int V, int ignore_index, const float* lse, const float* scale_ptr,
+                         void* stream) {
+  TT_REQUIRE(logits && target && lse, "tt_ce_bwd: null pointer");
+  if (M <= 0) return TT_OK;
+  ce_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, count_ptr, M, V,
+                                                     ignore_index, lse, scale_ptr);
+  return check_launch("ce_bwd_kernel");
+}
+
+extern "C" int tt_loss_finalize(const float* row_loss, long long n, const int* ntokens,
+                                float* loss, float* scale, void* stream) {
+  TT_REQUIRE(row_loss && ntokens, "tt_loss_finalize: null pointer");
+  loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, n, ntokens, loss, scale);
+  return check_launch("loss_finalize_kernel");
+}
+
+extern "C" int tt_adaptive_logprob(const float* head, long long ld_head, const float* const* tails,
+                                   const long long* ld_tails, const int* cutoffs, int n_clusters,
+                                   int M, float* log_probs, long long* argmax_id, float* argmax_lp,
+                                   void* stream) {
+  TT_REQUIRE(head, "tt_adaptive_logprob: null pointer");
+  LogProbArgs a{};
+  int rc = make_cut(cutoffs, n_clusters, &a.cut);
+  if (rc != TT_OK) return rc;
+  a.head = head; a.ld_head = ld_head;
+  for (int i = 0; i + 1 < n_clusters; ++i) {
+    TT_REQUIRE(tails && tails[i] && ld_tails, "tt_adaptive_logprob: null tail %d", i);
+    a.tail[i] = tails[i];
+    a.ld_tail[i] = ld_tails[i];
+  }
+  a.log_probs = log_probs; a.argmax_id = argmax_id; a.argmax_lp = argmax_lp; a.M = M;
+  if (M <= 0) return TT_OK;
+  adaptive_logprob_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("adaptive_logprob_kernel");
+}

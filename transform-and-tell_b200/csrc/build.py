@@ -16,7 +16,7 @@ BUILD = os.path.join(HERE, 'build')
 LIB = os.path.join(os.path.dirname(HERE), 'tell_b200', 'libtt_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--use_fast_math', '-Xptxas', '-v',
+         '-Xcompiler', '-fPIC', '-Xptxas', '-v',
          '-I', os.path.join(ROOT, 'include')]
 
 

@@ -22,7 +22,7 @@ __device__ __forceinline__ void seg_values(float x, __nv_bfloat16 (&o)[3]) {
 template <int SPLIT>
 __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src,
                                  __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
-                                 int cols) {
+                                 int cols, long long seg) {
   // one thread per 4 consecutive columns
   const int c4 = cols >> 2;
   const long long total = static_cast<long long>(rows) * c4;
@@ -50,7 +50,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&p0);
         u.y = *reinterpret_cast<uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(dst + r * ld_dst + static_cast<long long>(s) * cols + c) = u;
+        *reinterpret_cast<uint2*>(dst + r * ld_dst + s * seg + c) = u;
       }
     }
   }
@@ -59,7 +59,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src
 template <int SPLIT>
 __global__ void cast_rows_scalar_kernel(const float* __restrict__ src, long long ld_src,
                                         __nv_bfloat16* __restrict__ dst, long long ld_dst,
-                                        int rows, int cols) {
+                                        int rows, int cols, long long seg) {
   const long long total = static_cast<long long>(rows) * cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -71,7 +71,7 @@ __global__ void cast_rows_scalar_kernel(const float* __restrict__ src, long long
     } else {
       __nv_bfloat16 o[3];
       seg_values<SPLIT>(x, o);
-      for (int s = 0; s < 3; ++s) dst[r * ld_dst + static_cast<long long>(s) * cols + c] = o[s];
+      for (int s = 0; s < 3; ++s) dst[r * ld_dst + s * seg + c] = o[s];
     }
   }
 }
@@ -80,7 +80,7 @@ __global__ void cast_rows_scalar_kernel(const float* __restrict__ src, long long
 template <int SPLIT>
 __global__ void cast_transpose_kernel(const float* __restrict__ src, long long ld_src,
                                       __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
-                                      int cols) {
+                                      int cols, long long seg) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -98,7 +98,7 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, long long l
         __nv_bfloat16 o[3];
         seg_values<SPLIT>(x, o);
 #pragma unroll
-        for (int s = 0; s < 3; ++s) dst[c * ld_dst + static_cast<long long>(s) * rows + r] = o[s];
+        for (int s = 0; s < 3; ++s) dst[c * ld_dst + s * seg + r] = o[s];
       }
     }
   }
@@ -106,13 +106,14 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, long long l
 
 template <int SPLIT>
 static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst,
-                         int rows, int cols, int transpose, cudaStream_t s) {
+                         int rows, int cols, int transpose, long long seg, cudaStream_t s) {
+  if (seg <= 0) seg = transpose ? rows : cols;
   if (transpose) {
     dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
-    cast_transpose_kernel<SPLIT><<<grid, block, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    cast_transpose_kernel<SPLIT><<<grid, block, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, seg);
     return check_launch("cast_transpose_kernel");
   }
-  const bool vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
+  const bool vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && (seg % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
   const long long work = vec ? static_cast<long long>(rows) * (cols / 4)
@@ -121,16 +122,18 @@ static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst,
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   if (vec)
-    cast_rows_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    cast_rows_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, seg);
   else
-    cast_rows_scalar_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    cast_rows_scalar_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols,
+                                                               seg);
   return check_launch("cast_rows_kernel");
 }
 
 }  // namespace tt
 
 extern "C" int tt_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst,
-                            int rows, int cols, int transpose, int split, void* stream) {
+                            int rows, int cols, int transpose, int split, long long seg_stride,
+                            void* stream) {
   using namespace tt;
   TT_REQUIRE(src && dst, "tt_cast_bf16: null pointer");
   TT_REQUIRE(rows >= 0 && cols >= 0, "tt_cast_bf16: bad shape");
@@ -139,8 +142,8 @@ extern "C" int tt_cast_bf16(const float* src, long long ld_src, void* dst, long 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
   switch (split) {
-    case 0: return cast_dispatch<0>(src, ld_src, d, ld_dst, rows, cols, transpose, s);
-    case 1: return cast_dispatch<1>(src, ld_src, d, ld_dst, rows, cols, transpose, s);
-    default: return cast_dispatch<2>(src, ld_src, d, ld_dst, rows, cols, transpose, s);
+    case 0: return cast_dispatch<0>(src, ld_src, d, ld_dst, rows, cols, transpose, seg_stride, s);
+    case 1: return cast_dispatch<1>(src, ld_src, d, ld_dst, rows, cols, transpose, seg_stride, s);
+    default: return cast_dispatch<2>(src, ld_src, d, ld_dst, rows, cols, transpose, seg_stride, s);
   }
 }

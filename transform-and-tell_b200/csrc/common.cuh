@@ -221,6 +221,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- counter-based dropout RNG
+// Stateless: the keep/drop decision is a pure function of (seed, element index), so the backward
+// pass regenerates the forward mask instead of storing it.  splitmix64 finaliser.
+__device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32);
+}
+// Effective seed = call seed mixed with an optional device-resident step counter, so a captured
+// CUDA graph draws fresh masks on every replay.
+__device__ __forceinline__ unsigned long long mix_seed(unsigned long long seed,
+                                                       const unsigned long long* step_ptr) {
+  return step_ptr ? seed + (*step_ptr) * 0xD6E8FEB86659FD93ull : seed;
+}
+// 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx,
+                                               float p, float inv_keep) {
+  if (p <= 0.f) return 1.f;
+  const float u = static_cast<float>(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));

@@ -1,0 +1,206 @@
+// DynamicConv1dTBC core (tell/modules/convolutions/dynamic.py:285-336, _forward_expanded):
+//   p[t,b,h,:]   = softmax_K(z[t,b,h,:])                 (all K taps, even those that hit t' < 0)
+//   w            = DropConnect(p)                         (dynamic.py:305-306)
+//   out[t,b,hR+r] = sum_k w[t,b,h,k] * x[t-(K-1)+k, b, hR+r]   (x = 0 for negative time)
+// The reference builds a [B*H, T, T+K-1] band matrix and bmm's it (O(T^2) memory); here one CTA owns
+// a (batch, head, 32-step) tile: the x window is staged once in shared memory (HBM-bound, ~2x reuse
+// factor (TT+K-1)/TT instead of K), one warp per time step, the K<=32 taps live one per lane and the
+// softmax is a warp-shuffle reduction.
+// LightweightConv1dTBC (lightweight.py:88-240) is the same kernel with z broadcast over (t,b).
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int DC_TT = 32;      // time steps per CTA
+constexpr int DC_MAXK = 32;    // taps (one per lane)
+constexpr int DC_MAXR = 64;    // channels per head
+constexpr int DC_ROWS = DC_TT + DC_MAXK - 1;
+constexpr int DC_LD = DC_MAXR + 1;  // padded row pitch (bank-conflict free column walks)
+
+struct DynConvArgs {
+  const float* x;     // [T,B,C]
+  const float* z;     // [T,B,H,K] logits (or [H,K] when z_tb_stride == 0)
+  long long z_tb_stride;  // elements between consecutive (t,b) rows of z (H*K, or 0 = broadcast)
+  float* out;         // [T,B,C]
+  float* probs;       // [T,B,H,K] softmax output saved for backward (may be null)
+  int T, B, C, H, K;
+  int softmax;
+  float p_drop;
+  unsigned long long seed;
+  const unsigned long long* step_ptr;
+};
+
+__global__ void __launch_bounds__(256)
+dynconv_fwd_kernel(DynConvArgs a) {
+  a.seed = mix_seed(a.seed, a.step_ptr);
+  __shared__ float xs[DC_ROWS][DC_LD];
+  const int R = a.C / a.H;
+  const int K = a.K;
+  const int bh = blockIdx.x;
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int t0 = blockIdx.y * DC_TT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = DC_TT + K - 1;
+  // stage x[t0-K+1 .. t0+TT-1, b, hR .. hR+R)
+  for (int i = threadIdx.x; i < nrows * R; i += blockDim.x) {
+    const int row = i / R, c = i - row * R;
+    const int t = t0 - (K - 1) + row;
+    float v = 0.f;
+    if (t >= 0 && t < a.T) v = __ldg(a.x + (static_cast<long long>(t) * a.B + b) * a.C + h * R + c);
+    xs[row][c] = v;
+  }
+  __syncthreads();
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  for (int tt = warp; tt < DC_TT; tt += (blockDim.x >> 5)) {
+    const int t = t0 + tt;
+    if (t >= a.T) break;  // warp-uniform
+    const long long tb = static_cast<long long>(t) * a.B + b;
+    float zk = -INFINITY;
+    if (lane < K) zk = __ldg(a.z + tb * a.z_tb_stride + h * K + lane);
+    float pk;
+    if (a.softmax) {
+      const float m = warp_max(zk);
+      const float e = lane < K ? expf(zk - m) : 0.f;
+      const float s = warp_sum(e);
+      pk = e / s;
+    } else {
+      pk = lane < K ? zk : 0.f;
+    }
+    const long long widx = (tb * a.H + h) * K + lane;
+    if (a.probs && lane < K) a.probs[widx] = pk;
+    float wk = pk;
+    if (a.p_drop > 0.f && lane < K)
+      wk *= dropout_scale(a.seed, static_cast<unsigned long long>(widx), a.p_drop, inv_keep);
+    for (int c0 = 0; c0 < R; c0 += 32) {  // warp-uniform trip count: the shuffles need all lanes
+      const int c = c0 + lane;
+      const int cc = c < R ? c : 0;
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += __shfl_sync(0xffffffffu, wk, k) * xs[tt + k][cc];
+      if (c < R) a.out[tb * a.C + h * R + c] = acc;
+    }
+  }
+}
+
+struct DynConvBwdArgs {
+  const float* dout;  // [T,B,C]
+  const float* x;     // [T,B,C]
+  const float* probs; // [T,B,H,K] (softmax output; or raw weights when softmax == 0)
+  float* dx;          // [T,B,C]
+  float* dz;          // [T,B,H,K]
+  int T, B, C, H, K;
+  int softmax;
+  float p_drop;
+  unsigned long long seed;
+  const unsigned long long* step_ptr;
+};
+
+// dp[t,h,k] = sum_c dout[t,c] x[t-K+1+k,c];  dz = softmax_bwd(dp * mask/(1-q));
+// dx[s,c]   = sum_k w[s+K-1-k,h,k] dout[s+K-1-k,c]     (SURVEY 3.4 backward formulas)
+__global__ void __launch_bounds__(256)
+dynconv_bwd_kernel(DynConvBwdArgs a) {
+  a.seed = mix_seed(a.seed, a.step_ptr);
+  __shared__ float xs[DC_ROWS][DC_LD];   // x rows   t0-K+1 .. t0+TT-1
+  __shared__ float ds[DC_ROWS][DC_LD];   // dout rows t0 .. t0+TT+K-2
+  __shared__ float ws[DC_ROWS][DC_MAXK]; // w rows    t0 .. t0+TT+K-2
+  const int R = a.C / a.H;
+  const int K = a.K;
+  const int bh = blockIdx.x;
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int t0 = blockIdx.y * DC_TT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = DC_TT + K - 1;
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  for (int i = threadIdx.x; i < nrows * R; i += blockDim.x) {
+    const int row = i / R, c = i - row * R;
+    const int tx = t0 - (K - 1) + row;
+    const int td = t0 + row;
+    float v = 0.f, d = 0.f;
+    if (tx >= 0 && tx < a.T)
+      v = __ldg(a.x + (static_cast<long long>(tx) * a.B + b) * a.C + h * R + c);
+    if (td < a.T) d = __ldg(a.dout + (static_cast<long long>(td) * a.B + b) * a.C + h * R + c);
+    xs[row][c] = v;
+    ds[row][c] = d;
+  }
+  for (int i = threadIdx.x; i < nrows * K; i += blockDim.x) {
+    const int row = i / K, k = i - row * K;
+    const int t = t0 + row;
+    float w = 0.f;
+    if (t < a.T) {
+      const long long widx = ((static_cast<long long>(t) * a.B + b) * a.H + h) * K + k;
+      w = __ldg(a.probs + widx);
+      if (a.p_drop > 0.f)
+        w *= dropout_scale(a.seed, static_cast<unsigned long long>(widx), a.p_drop, inv_keep);
+    }
+    ws[row][k] = w;
+  }
+  __syncthreads();
+  for (int tt = warp; tt < DC_TT; tt += (blockDim.x >> 5)) {
+    const int t = t0 + tt;
+    if (t >= a.T) break;
+    const long long tb = static_cast<long long>(t) * a.B + b;
+    // ---- dz: lane k owns tap k
+    float dp = 0.f;
+    if (lane < K) {
+      for (int c = 0; c < R; ++c) dp += ds[tt][c] * xs[tt + lane][c];
+    }
+    const long long widx = (tb * a.H + h) * K + lane;
+    float dw = dp;
+    if (a.p_drop > 0.f && lane < K)
+      dw *= dropout_scale(a.seed, static_cast<unsigned long long>(widx), a.p_drop, inv_keep);
+    float dzk = dw;
+    if (a.softmax) {
+      const float pk = lane < K ? __ldg(a.probs + widx) : 0.f;
+      const float dot = warp_sum(lane < K ? pk * dw : 0.f);
+      dzk = pk * (dw - dot);
+    }
+    if (lane < K) a.dz[widx] = dzk;
+    // ---- dx for time s = t
+    for (int c = lane; c < R; c += 32) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const int row = tt + (K - 1) - k;  // t' - t0, t' = s + K-1-k
+        acc += ws[row][k] * ds[row][c];
+      }
+      a.dx[tb * a.C + h * R + c] = acc;
+    }
+  }
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+static int dynconv_check(int T, int B, int C, int H, int K) {
+  TT_REQUIRE(T >= 0 && B > 0 && C > 0 && H > 0 && K > 0, "dynconv: bad shape");
+  TT_REQUIRE(C % H == 0 && C / H <= DC_MAXR, "dynconv: channels per head must be <= %d (got %d)",
+             DC_MAXR, C / H);
+  TT_REQUIRE(K <= DC_MAXK, "dynconv: kernel size must be <= %d (got %d)", DC_MAXK, K);
+  return TT_OK;
+}
+
+extern "C" int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_stride, float* out,
+                              float* probs, int T, int B, int C, int H, int K, int softmax,
+                              float p_drop, unsigned long long seed, void* stream) {
+  TT_REQUIRE(x && z && out, "tt_dynconv_fwd: null pointer");
+  int rc = dynconv_check(T, B, C, H, K);
+  if (rc != TT_OK) return rc;
+  if (T == 0) return TT_OK;
+  DynConvArgs a{x, z, z_tb_stride, out, probs, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
+  dim3 grid(B * H, ceil_div(T, DC_TT));
+  dynconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("dynconv_fwd_kernel");
+}
+
+extern "C" int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float* dx,
+                              float* dz, int T, int B, int C, int H, int K, int softmax,
+                              float p_drop, unsigned long long seed, void* stream) {
+  TT_REQUIRE(dout && x && probs && dx && dz, "tt_dynconv_bwd: null pointer");
+  int rc = dynconv_check(T, B, C, H, K);
+  if (rc != TT_OK) return rc;
+  if (T == 0) return TT_OK;
+  DynConvBwdArgs a{dout, x, probs, dx, dz, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
+  dim3 grid(B * H, ceil_div(T, DC_TT));
+  dynconv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("dynconv_bwd_kernel");
+}

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias) + residual
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = act(alpha * (A[M,K] . B[N,K]^T + bias) + residual)
 //
 // Persistent, warp-specialised (one CTA per SM):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 tiles, 128B swizzle
@@ -26,6 +26,8 @@ struct GemmArgs {
   const float* bias;
   const float* residual;
   long long ldr;
+  const __nv_bfloat16* residual16;
+  long long ldr16;
   float alpha;
   int act;
   int accumulate;
@@ -176,15 +178,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (col0 >= g.N) continue;  // warp-uniform
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (g.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
         }
-        if (g.act != TT_ACT_NONE) {
+        if (g.alpha != 1.f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+          for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
         }
         if (!row_ok) continue;
         const bool full = (col0 + 32 <= g.N) && g.vec_ok;
@@ -196,6 +198,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const float4 t = __ldg(rp + j);
               v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
+          }
+          if (g.residual16 != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(g.residual16 + row * g.ldr16 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = __ldg(rp + j);
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                v[8 * j + 2 * e] += __low2float(h2);
+                v[8 * j + 2 * e + 1] += __high2float(h2);
+              }
+            }
+          }
+          if (g.act != TT_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
           }
           if (g.C != nullptr) {
             float4* cp = reinterpret_cast<float4*>(g.C + row * g.ldc + col0);
@@ -233,6 +253,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (col < g.N) {
               float o = v[j];
               if (g.residual != nullptr) o += __ldg(g.residual + row * g.ldr + col);
+              if (g.residual16 != nullptr) o += __bfloat162float(g.residual16[row * g.ldr16 + col]);
+              o = apply_act(o, g.act);
               if (g.C != nullptr) {
                 float* cp = g.C + row * g.ldc + col;
                 if (g.accumulate) o += *cp;
@@ -328,6 +350,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.C16 = reinterpret_cast<__nv_bfloat16*>(p->C16); g.ldc16 = p->ldc16;
   g.bias = p->bias;
   g.residual = p->residual; g.ldr = p->ldr;
+  g.residual16 = reinterpret_cast<const __nv_bfloat16*>(p->residual16); g.ldr16 = p->ldr16;
   g.alpha = p->alpha; g.act = p->act; g.accumulate = p->accumulate;
   g.m_limit = p->m_limit;
   bool vec = true;
@@ -335,6 +358,8 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   if (p->C16) vec = vec && (reinterpret_cast<uintptr_t>(p->C16) & 15) == 0 && (p->ldc16 % 8 == 0);
   if (p->residual)
     vec = vec && (reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && (p->ldr % 4 == 0);
+  if (p->residual16)
+    vec = vec && (reinterpret_cast<uintptr_t>(p->residual16) & 15) == 0 && (p->ldr16 % 8 == 0);
   g.vec_ok = vec ? 1 : 0;
 
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);

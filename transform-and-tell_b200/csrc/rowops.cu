@@ -1,0 +1,516 @@
+// Row-wise HBM-bound kernels of the decoder layer: residual + dropout + LayerNorm (fwd/bwd), GLU
+// (fwd/bwd), dropout, weight-norm (fwd/bwd), NaN-row masking, vector helpers.
+// One warp per row, float4 accesses, warp-shuffle reductions, no shared memory.
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
+
+static inline int row_grid(long long rows) {
+  long long g = ceil_div_ll(rows, ROW_WARPS);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// x = res + dropout(h) (written back into h), y = LN(x) * gamma + beta.
+// decoder_faces_objects.py:263-266, :283-287, :361-364 (dropout, residual add, post-LayerNorm).
+__global__ void ln_fwd_kernel(float* __restrict__ h, const float* __restrict__ res,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ y, long long ldy, float* __restrict__ mean,
+                              float* __restrict__ rstd, int N, int E, float eps, float p,
+                              unsigned long long seed, const unsigned long long* step_ptr) {
+  seed = mix_seed(seed, step_ptr);
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int E4 = E >> 2;
+  for (int r = warp_global; r < N; r += nwarps) {
+    float4* hr = reinterpret_cast<float4*>(h + static_cast<long long>(r) * E);
+    const float4* rr = res ? reinterpret_cast<const float4*>(res + static_cast<long long>(r) * E)
+                           : nullptr;
+    float s = 0.f;
+    for (int c = lane; c < E4; c += 32) {
+      float4 v = hr[c];
+      if (p > 0.f) {
+        const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
+        v.x *= dropout_scale(seed, base, p, inv_keep);
+        v.y *= dropout_scale(seed, base + 1, p, inv_keep);
+        v.z *= dropout_scale(seed, base + 2, p, inv_keep);
+        v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+      }
+      if (rr) {
+        const float4 q = __ldg(rr + c);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      hr[c] = v;
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    s = warp_sum(s);
+    const float mu = s / E;
+    float ss = 0.f;
+    for (int c = lane; c < E4; c += 32) {
+      const float4 v = hr[c];
+      const float a = v.x - mu, b = v.y - mu, d = v.z - mu, e = v.w - mu;
+      ss += (a * a + b * b) + (d * d + e * e);
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / E + eps);
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+    float4* yr = reinterpret_cast<float4*>(y + static_cast<long long>(r) * ldy);
+    for (int c = lane; c < E4; c += 32) {
+      const float4 v = hr[c];
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = (v.x - mu) * rs * gm.x + bt.x;
+      o.y = (v.y - mu) * rs * gm.y + bt.y;
+      o.z = (v.z - mu) * rs * gm.z + bt.z;
+      o.w = (v.w - mu) * rs * gm.w + bt.w;
+      yr[c] = o;
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; dh = dx * dropmask/(1-p).
+// dgamma/dbeta are accumulated with one atomicAdd per (CTA-warp, column) at the end.
+template <int MAXC>  // float4 chunks per lane: E <= 128 * MAXC
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy,
+                              const float* __restrict__ x, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                              float* __restrict__ dx, float* __restrict__ dh,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int E,
+                              float p, unsigned long long seed,
+                              const unsigned long long* step_ptr) {
+  seed = mix_seed(seed, step_ptr);
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int E4 = E >> 2;
+  float4 acc_g[MAXC], acc_b[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int r = warp_global; r < N; r += nwarps) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + static_cast<long long>(r) * lddy);
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E);
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+    float4 g4[MAXC], xh4[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < E4) {
+        const float4 d = __ldg(dyr + c);
+        const float4 xv = __ldg(xr + c);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        float4 xh, g;
+        xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs;
+        xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
+        g.x = d.x * gm.x; g.y = d.y * gm.y; g.z = d.z * gm.z; g.w = d.w * gm.w;
+        s1 += (g.x + g.y) + (g.z + g.w);
+        s2 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+        acc_g[i].x += d.x * xh.x; acc_g[i].y += d.y * xh.y;
+        acc_g[i].z += d.z * xh.z; acc_g[i].w += d.w * xh.w;
+        acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
+        g4[i] = g; xh4[i] = xh;
+      }
+    }
+    s1 = warp_sum(s1) / E;
+    s2 = warp_sum(s2) / E;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < E4) {
+        float4 o;
+        o.x = rs * (g4[i].x - s1 - xh4[i].x * s2);
+        o.y = rs * (g4[i].y - s1 - xh4[i].y * s2);
+        o.z = rs * (g4[i].z - s1 - xh4[i].z * s2);
+        o.w = rs * (g4[i].w - s1 - xh4[i].w * s2);
+        if (dx) reinterpret_cast<float4*>(dx + static_cast<long long>(r) * E)[c] = o;
+        if (dh) {
+          if (p > 0.f) {
+            const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
+            o.x *= dropout_scale(seed, base, p, inv_keep);
+            o.y *= dropout_scale(seed, base + 1, p, inv_keep);
+            o.z *= dropout_scale(seed, base + 2, p, inv_keep);
+            o.w *= dropout_scale(seed, base + 3, p, inv_keep);
+          }
+          reinterpret_cast<float4*>(dh + static_cast<long long>(r) * E)[c] = o;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < E4) {
+      if (dgamma) {
+        atomicAdd(dgamma + 4 * c, acc_g[i].x); atomicAdd(dgamma + 4 * c + 1, acc_g[i].y);
+        atomicAdd(dgamma + 4 * c + 2, acc_g[i].z); atomicAdd(dgamma + 4 * c + 3, acc_g[i].w);
+      }
+      if (dbeta) {
+        atomicAdd(dbeta + 4 * c, acc_b[i].x); atomicAdd(dbeta + 4 * c + 1, acc_b[i].y);
+        atomicAdd(dbeta + 4 * c + 2, acc_b[i].z); atomicAdd(dbeta + 4 * c + 3, acc_b[i].w);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GLU over the last dim: out[n,c] = h[n,c] * sigmoid(h[n,C+c])   (nn.GLU, decoder_faces_objects.py:193-195,259-260)
+__global__ void glu_fwd_kernel(const float* __restrict__ h, float* __restrict__ out, long long n4,
+                               int C4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c = static_cast<int>(i - r * C4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(h) + r * 2 * C4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(h) + r * 2 * C4 + C4 + c);
+    float4 o;
+    o.x = a.x * sigmoidf_(b.x); o.y = a.y * sigmoidf_(b.y);
+    o.z = a.z * sigmoidf_(b.z); o.w = a.w * sigmoidf_(b.w);
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+__global__ void glu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ h,
+                               float* __restrict__ dh, long long n4, int C4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c = static_cast<int>(i - r * C4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(h) + r * 2 * C4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(h) + r * 2 * C4 + C4 + c);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dout) + i);
+    float4 da, db;
+    float s;
+    s = sigmoidf_(b.x); da.x = d.x * s; db.x = d.x * a.x * s * (1.f - s);
+    s = sigmoidf_(b.y); da.y = d.y * s; db.y = d.y * a.y * s * (1.f - s);
+    s = sigmoidf_(b.z); da.z = d.z * s; db.z = d.z * a.z * s * (1.f - s);
+    s = sigmoidf_(b.w); da.w = d.w * s; db.w = d.w * a.w * s * (1.f - s);
+    reinterpret_cast<float4*>(dh)[r * 2 * C4 + c] = da;
+    reinterpret_cast<float4*>(dh)[r * 2 * C4 + C4 + c] = db;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = x * dropmask/(1-p)  (F.dropout; same call regenerates the mask for the backward).
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                               float p, unsigned long long seed,
+                               const unsigned long long* step_ptr) {
+  seed = mix_seed(seed, step_ptr);
+  const float inv_keep = 1.f / (1.f - p);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = x[i] * dropout_scale(seed, static_cast<unsigned long long>(i), p, inv_keep);
+}
+
+// y = a*x + b*y (vector), used for the RoBERTa layer mix and gradient accumulation.
+__global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                             float a, float b) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight norm (nn.utils.weight_norm, dim=0):  w[o,:] = g[o] * v[o,:] / ||v[o,:]||   linear.py:30-34
+__global__ void wnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                 float* __restrict__ w, float* __restrict__ norm, int O, int I) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int o = warp_global; o < O; o += nwarps) {
+    const float* vr = v + static_cast<long long>(o) * I;
+    float s = 0.f;
+    for (int i = lane; i < I; i += 32) s += vr[i] * vr[i];
+    s = warp_sum(s);
+    const float nrm = sqrtf(s);
+    const float sc = g[o] / nrm;
+    if (lane == 0 && norm) norm[o] = nrm;
+    float* wr = w + static_cast<long long>(o) * I;
+    for (int i = lane; i < I; i += 32) wr[i] = vr[i] * sc;
+  }
+}
+// dg[o] = <dw,v>/||v|| ; dv = g/||v|| * (dw - v <dw,v>/||v||^2)
+__global__ void wnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                 const float* __restrict__ g, const float* __restrict__ norm,
+                                 float* __restrict__ dv, float* __restrict__ dg, int O, int I) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int o = warp_global; o < O; o += nwarps) {
+    const float* vr = v + static_cast<long long>(o) * I;
+    const float* dr = dw + static_cast<long long>(o) * I;
+    float s = 0.f;
+    for (int i = lane; i < I; i += 32) s += dr[i] * vr[i];
+    s = warp_sum(s);
+    const float nrm = norm[o];
+    const float gg = g[o];
+    if (lane == 0) dg[o] = s / nrm;
+    const float a = gg / nrm, b = s / (nrm * nrm);
+    float* o_ = dv + static_cast<long long>(o) * I;
+    for (int i = lane; i < I; i += 32) o_[i] = a * (dr[i] - vr[i] * b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask[r] = any(isnan(x[r,:])); NaN rows are zeroed in place.  transformer_faces_objects.py:374-379
+__global__ void nan_rows_kernel(float* __restrict__ x, uint8_t* __restrict__ mask, int R, int D) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int r = warp_global; r < R; r += nwarps) {
+    float* xr = x + static_cast<long long>(r) * D;
+    int bad = 0;
+    for (int i = lane; i < D; i += 32) bad |= (xr[i] != xr[i]) ? 1 : 0;
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad)
+      for (int i = lane; i < D; i += 32) xr[i] = 0.f;
+    if (lane == 0) mask[r] = bad ? 1 : 0;
+  }
+}
+
+static inline int flat_grid(long long n) {
+  long long g = ceil_div_ll(n, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_ln_fwd(float* h, const float* res, const float* gamma, const float* beta,
+                         float* y, long long ldy, float* mean, float* rstd, int N, int E, float eps,
+                         float p_drop, unsigned long long seed, void* stream) {
+  TT_REQUIRE(h && gamma && beta && y, "tt_ln_fwd: null pointer");
+  TT_REQUIRE(E > 0 && E % 4 == 0 && ldy % 4 == 0, "tt_ln_fwd: E and ldy must be multiples of 4");
+  TT_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "tt_ln_fwd: bad dropout p");
+  if (N <= 0) return TT_OK;
+  ln_fwd_kernel<<<row_grid(N), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      h, res, gamma, beta, y, ldy, mean, rstd, N, E, eps, p_drop, seed, rng_step_ptr());
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int tt_ln_bwd(const float* dy, long long lddy, const float* x, const float* mean,
+                         const float* rstd, const float* gamma, float* dx, float* dh,
+                         float* dgamma, float* dbeta, int N, int E, float p_drop,
+                         unsigned long long seed, void* stream) {
+  TT_REQUIRE(dy && x && mean && rstd && gamma, "tt_ln_bwd: null pointer");
+  TT_REQUIRE(E > 0 && E % 4 == 0 && E <= 1024 && lddy % 4 == 0,
+             "tt_ln_bwd: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  if (N <= 0) return TT_OK;
+  // fewer, fatter warps so the dgamma/dbeta atomics stay cheap
+  int grid = row_grid(N);
+  if (grid > num_sms()) grid = num_sms();
+  if (E <= 256)
+    ln_bwd_kernel<2><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
+  else
+    ln_bwd_kernel<8><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
+  return check_launch("ln_bwd_kernel");
+}
+
+extern "C" int tt_glu_fwd(const float* h, float* out, long long N, int C, void* stream) {
+  TT_REQUIRE(h && out, "tt_glu_fwd: null pointer");
+  TT_REQUIRE(C > 0 && C % 4 == 0, "tt_glu_fwd: C must be a multiple of 4");
+  if (N <= 0) return TT_OK;
+  const long long n4 = N * (C / 4);
+  glu_fwd_kernel<<<flat_grid(n4), 256, 0, (cudaStream_t)stream>>>(h, out, n4, C / 4);
+  return check_launch("glu_fwd_kernel");
+}
+
+extern "C" int tt_glu_bwd(const float* dout, const float* h, float* dh, long long N, int C,
+                          void* stream) {
+  TT_REQUIRE(dout && h && dh, "tt_glu_bwd: null pointer");
+  TT_REQUIRE(C > 0 && C % 4 == 0, "tt_glu_bwd: C must be a multiple of 4");
+  if (N <= 0) return TT_OK;
+  const long long n4 = N * (C / 4);
+  glu_bwd_kernel<<<flat_grid(n4), 256, 0, (cudaStream_t)stream>>>(dout, h, dh, n4, C / 4);
+  return check_launch("glu_bwd_kernel");
+}
+
+extern "C" int tt_dropout(const float* x, float* y, long long n, float p,
+                          unsigned long long seed, void* stream) {
+  TT_REQUIRE(x && y, "tt_dropout: null pointer");
+  TT_REQUIRE(p >= 0.f && p < 1.f, "tt_dropout: bad p");
+  if (n <= 0) return TT_OK;
+  dropout_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, rng_step_ptr());
+  return check_launch("dropout_kernel");
+}
+
+extern "C" int tt_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {
+  TT_REQUIRE(x && y, "tt_axpby: null pointer");
+  if (n <= 0) return TT_OK;
+  axpby_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, a, b);
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int tt_wnorm_fwd(const float* v, const float* g, float* w, float* norm, int O, int I,
+                            void* stream) {
+  TT_REQUIRE(v && g && w, "tt_wnorm_fwd: null pointer");
+  if (O <= 0 || I <= 0) return TT_OK;
+  wnorm_fwd_kernel<<<row_grid(O), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(v, g, w, norm, O, I);
+  return check_launch("wnorm_fwd_kernel");
+}
+
+extern "C" int tt_wnorm_bwd(const float* dw, const float* v, const float* g, const float* norm,
+                            float* dv, float* dg, int O, int I, void* stream) {
+  TT_REQUIRE(dw && v && g && norm && dv && dg, "tt_wnorm_bwd: null pointer");
+  if (O <= 0 || I <= 0) return TT_OK;
+  wnorm_bwd_kernel<<<row_grid(O), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(dw, v, g, norm, dv, dg,
+                                                                           O, I);
+  return check_launch("wnorm_bwd_kernel");
+}
+
+extern "C" int tt_nan_rows(float* x, uint8_t* mask, int R, int D, void* stream) {
+  TT_REQUIRE(x && mask, "tt_nan_rows: null pointer");
+  if (R <= 0) return TT_OK;
+  if (D <= 0) {
+    cudaMemsetAsync(mask, 0, R, (cudaStream_t)stream);
+    return TT_OK;
+  }
+  nan_rows_kernel<<<row_grid(R), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mask, R, D);
+  return check_launch("nan_rows_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace tt {
+// out[c] (+)= scale * sum_r x[r,c]   (bias gradients).  32 columns per CTA, 8 row-lanes.
+__global__ void colsum_kernel(const float* __restrict__ x, long long ld, int M, int N,
+                              float* __restrict__ out, float scale, int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < N)
+    for (int r = threadIdx.y; r < M; r += 8) s += x[r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    t *= scale;
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+// dx = dy * (y > 0)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                float* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+// transformer_faces_objects.py:355-364: out = sum_l softmax(w)[l] * hiddens[l]   (bf16 hiddens)
+__global__ void layer_mix_fwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
+                                     const float* __restrict__ w, int L, long long n,
+                                     float* __restrict__ out) {
+  __shared__ float sw[64];
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int l = 0; l < L; ++l) m = fmaxf(m, w[l]);
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) { sw[l] = expf(w[l] - m); s += sw[l]; }
+    for (int l = 0; l < L; ++l) sw[l] /= s;
+  }
+  __syncthreads();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) acc += sw[l] * __bfloat162float(hid[l * layer_stride + i]);
+    out[i] = acc;
+  }
+}
+// dots[l] += sum_i dout[i] * hiddens[l][i]   (then softmax backward on the host-free finisher)
+__global__ void layer_mix_bwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
+                                     const float* __restrict__ dout, int L, long long n,
+                                     float* __restrict__ dots) {
+  __shared__ float red[32];
+  for (int l = 0; l < L; ++l) {
+    float s = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      s += dout[i] * __bfloat162float(hid[l * layer_stride + i]);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(dots + l, s);
+  }
+}
+// dw[l] = p[l] * (dots[l] - sum_j p[j] dots[j]),  p = softmax(w)
+__global__ void softmax_bwd_small_kernel(const float* __restrict__ w, const float* __restrict__ dots,
+                                         int L, float* __restrict__ dw) {
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int l = 0; l < L; ++l) m = fmaxf(m, w[l]);
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += expf(w[l] - m);
+    float dot = 0.f;
+    for (int l = 0; l < L; ++l) dot += expf(w[l] - m) / s * dots[l];
+    for (int l = 0; l < L; ++l) dw[l] = expf(w[l] - m) / s * (dots[l] - dot);
+  }
+}
+}  // namespace tt
+
+extern "C" int tt_colsum(const float* x, long long ld, int M, int N, float* out, float scale,
+                         int accumulate, void* stream) {
+  TT_REQUIRE(x && out, "tt_colsum: null pointer");
+  if (N <= 0) return TT_OK;
+  dim3 block(32, 8);
+  colsum_kernel<<<ceil_div(N, 32), block, 0, (cudaStream_t)stream>>>(x, ld, M, N, out, scale,
+                                                                     accumulate);
+  return check_launch("colsum_kernel");
+}
+
+namespace tt {
+__global__ void scalar_mul_kernel(const float* a, const float* b, float* out) { *out = *a * *b; }
+}  // namespace tt
+extern "C" int tt_scalar_mul(const float* a, const float* b, float* out, void* stream) {
+  TT_REQUIRE(a && b && out, "tt_scalar_mul: null pointer");
+  scalar_mul_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a, b, out);
+  return check_launch("scalar_mul_kernel");
+}
+
+extern "C" int tt_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream) {
+  TT_REQUIRE(dy && y && dx, "tt_relu_bwd: null pointer");
+  if (n <= 0) return TT_OK;
+  relu_bwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+  return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int tt_layer_mix_fwd(const void* hiddens, long long layer_stride, const float* w, int L,
+                                long long n, float* out, void* stream) {
+  TT_REQUIRE(hiddens && w && out, "tt_layer_mix_fwd: null pointer");
+  TT_REQUIRE(L > 0 && L <= 64, "tt_layer_mix_fwd: L must be in [1,64]");
+  if (n <= 0) return TT_OK;
+  layer_mix_fwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, w, L, n, out);
+  return check_launch("layer_mix_fwd_kernel");
+}
+
+extern "C" int tt_layer_mix_bwd(const void* hiddens, long long layer_stride, const float* w,
+                                const float* dout, int L, long long n, float* dots, float* dw,
+                                void* stream) {
+  TT_REQUIRE(hiddens && w && dout && dots && dw, "tt_layer_mix_bwd: null pointer");
+  TT_REQUIRE(L > 0 && L <= 64, "tt_layer_mix_bwd: L must be in [1,64]");
+  cudaMemsetAsync(dots, 0, sizeof(float) * L, (cudaStream_t)stream);
+  if (n > 0) {
+    int grid = flat_grid(n);
+    if (grid > 2 * num_sms()) grid = 2 * num_sms();
+    layer_mix_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, dout, L, n, dots);
+    int rc = check_launch("layer_mix_bwd_kernel");
+    if (rc != TT_OK) return rc;
+  }
+  softmax_bwd_small_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(w, dots, L, dw);
+  return check_launch("softmax_bwd_small_kernel");
+}

@@ -18,6 +18,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static const unsigned long long* g_step_ptr = nullptr;
+const unsigned long long* rng_step_ptr() { return g_step_ptr; }
+
+__global__ void rng_step_advance_kernel(unsigned long long* p) { *p += 1ull; }
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
@@ -91,4 +96,10 @@ const char* tt_last_error(void) { return tt::g_err; }
 int tt_abi_version(void) { return 1; }
 long long tt_launch_count(void) { return tt::g_launches.load(); }
 void tt_reset_launch_count(void) { tt::g_launches.store(0); }
+void tt_set_rng_step_ptr(const unsigned long long* dev_ptr) { tt::g_step_ptr = dev_ptr; }
+int tt_rng_step_advance(unsigned long long* dev_ptr, void* stream) {
+  if (!dev_ptr) { tt::set_error("tt_rng_step_advance: null pointer"); return TT_ERR_INVALID; }
+  tt::rng_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_ptr);
+  return tt::check_launch("rng_step_advance_kernel");
+}
 }

@@ -4,6 +4,8 @@
 
 namespace tt {
 void count_launch(int n);
+// Device scalar mixed into every dropout seed (see tt_set_rng_step_ptr); may be null.
+const unsigned long long* rng_step_ptr();
 // 2-D bf16 tensor map, 128-byte swizzle, zero fill out of bounds.
 // inner = contiguous extent (elements), ld_elems = row stride (elements, multiple of 8).
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,

@@ -27,6 +27,7 @@ class TtGemmParams(ctypes.Structure):
                 ('C16', c_void_p), ('ldc16', c_ll),
                 ('bias', c_void_p),
                 ('residual', c_void_p), ('ldr', c_ll),
+                ('residual16', c_void_p), ('ldr16', c_ll),
                 ('alpha', c_float), ('act', c_int), ('accumulate', c_int),
                 ('m_limit', c_void_p)]
 

@@ -1,0 +1,54 @@
+"""Process-wide knobs of the B200 path.
+
+precision
+    'bf16'    bf16 tensor-core operands, fp32 accumulation (throughput mode; the reference
+              trained in apex-O2 fp16, tell/training/callback_apex_trainer.py:121-125).
+    'bf16x3'  every GEMM operand is split x = hi + lo (two bf16) and the product is evaluated as
+              hi.hi + lo.hi + hi.lo on the same tcgen05 kernel with K tripled: ~2^-16 relative
+              error, used for the "fp32 logits within 1e-3 / token-exact greedy" parity gate.
+"""
+import itertools
+
+import torch
+
+precision = 'bf16'
+
+_seed_base = 0x5EED
+_counter = itertools.count(1)
+_step = None  # device-resident step counter mixed into every dropout seed
+
+
+def set_precision(p):
+    global precision
+    assert p in ('bf16', 'bf16x3')
+    precision = p
+
+
+def manual_seed(seed):
+    """Re-seeds the dropout streams (the analogue of torch.manual_seed for our kernels)."""
+    global _seed_base, _counter
+    _seed_base = int(seed)
+    _counter = itertools.count(1)
+
+
+def next_seed():
+    """A fresh 64-bit stream id per dropout site per call."""
+    return (_seed_base * 0x9E3779B97F4A7C15 + next(_counter) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+
+
+def enable_device_step(device='cuda'):
+    """Registers a device-side step counter with the library so that CUDA-graph replays draw
+    fresh dropout masks (see tt_set_rng_step_ptr).  Returns the counter tensor."""
+    global _step
+    from . import _lib
+    if _step is None:
+        _step = torch.zeros(1, dtype=torch.int64, device=device)
+        _lib.lib().tt_set_rng_step_ptr(_lib.c_void_p(_step.data_ptr()))
+    return _step
+
+
+def advance_device_step():
+    from . import _lib
+    if _step is not None:
+        _lib.call('tt_rng_step_advance', _lib.c_void_p(_step.data_ptr()),
+                  _lib.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -1,0 +1,445 @@
+"""torch.autograd glue around the C-ABI kernels.
+
+Each Function's forward AND backward call only libtt_b200.so kernels (through tell_b200.ops);
+torch is used for tensor allocation, views and autograd bookkeeping.  The backward formulas are
+the ones the reference leaves to torch autograd.
+"""
+import torch
+from torch.autograd import Function
+
+from . import config, ops
+
+
+def operand(x, side, transpose=False):
+    """fp32 [R,C] -> bf16 tcgen05 GEMM operand (K-contiguous).  side: 'a' (activations/left) or
+    'b' (weights/right); in bf16x3 mode the two sides get complementary hi/lo patterns."""
+    if config.precision == 'bf16':
+        split = 0
+    else:
+        split = 1 if side == 'a' else 2
+    return ops.cast_bf16(x, transpose=transpose, split=split)
+
+
+def _c(x):
+    return x if x.is_contiguous() else x.contiguous()
+
+
+class LinearFn(Function):
+    """y = act(alpha * (x @ w^T + bias)); x [M,K], w [N,K] (F.linear / GehringLinear / in_proj)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha=1.0, act=ops.ACT_NONE):
+        a16 = operand(x, 'a')
+        b16 = operand(w, 'b')
+        y = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act)
+        ctx.alpha, ctx.act, ctx.has_bias = alpha, act, bias is not None
+        ctx.save_for_backward(x, w, y if act != ops.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.act == ops.ACT_RELU:
+            dy = ops.relu_bwd(dy, y)
+        elif ctx.act != ops.ACT_NONE:
+            raise NotImplementedError('backward of fused GELU is not needed on this path')
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_tn(operand(dy, 'a'), operand(w, 'b', transpose=True), alpha=ctx.alpha)
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_tn(operand(dy, 'a', transpose=True), operand(x, 'b', transpose=True),
+                             alpha=ctx.alpha)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy, scale=ctx.alpha)
+        return dx, dw, db, None, None
+
+
+class KVProjFn(Function):
+    """kv [R, 2E] = [x @ wk^T + bk | x @ wv^T + bv]: the key and value projections of one context
+    share the cast of x and land in one buffer the attention kernel reads with stride 2E
+    (multi_head.py:500-518 in_proj_k / in_proj_v)."""
+
+    @staticmethod
+    def forward(ctx, x, wk, wv, bias_kv):
+        E = wk.shape[0]
+        a16 = operand(x, 'a')
+        kv = torch.empty((x.shape[0], 2 * E), dtype=torch.float32, device=x.device)
+        ops.gemm_tn(a16, operand(wk, 'b'), out=kv[:, :E], bias=None if bias_kv is None else bias_kv[:E])
+        ops.gemm_tn(a16, operand(wv, 'b'), out=kv[:, E:], bias=None if bias_kv is None else bias_kv[E:])
+        ctx.has_bias = bias_kv is not None
+        ctx.save_for_backward(x, wk, wv)
+        return kv
+
+    @staticmethod
+    def backward(ctx, dkv):
+        x, wk, wv = ctx.saved_tensors
+        dkv = _c(dkv)
+        E = wk.shape[0]
+        dk, dv = dkv[:, :E], dkv[:, E:]
+        dx = dwk = dwv = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_tn(operand(dk, 'a'), operand(wk, 'b', transpose=True))
+            ops.gemm_tn(operand(dv, 'a'), operand(wv, 'b', transpose=True), out=dx, accumulate=True)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            xT = operand(x, 'b', transpose=True)
+            dwk = ops.gemm_tn(operand(dk, 'a', transpose=True), xT)
+            dwv = ops.gemm_tn(operand(dv, 'a', transpose=True), xT)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = ops.colsum(dkv)
+        return dx, dwk, dwv, db
+
+
+class WeightNormFn(Function):
+    """w = g * v / ||v||_row  (nn.utils.weight_norm dim=0; linear.py:30-34)."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        w, norm = ops.wnorm_fwd(v, g)
+        ctx.save_for_backward(v, g, norm)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g, norm = ctx.saved_tensors
+        dv, dg = ops.wnorm_bwd(_c(dw), v, g, norm)
+        return dv, dg
+
+
+class ResidualLayerNormFn(Function):
+    """y = LayerNorm(res + dropout(h)).  h (a GEMM output nobody else reads) is overwritten with
+    the pre-norm sum, which is what the backward needs."""
+
+    @staticmethod
+    def forward(ctx, h, res, gamma, beta, p, seed, eps=1e-5):
+        y, mean, rstd = ops.ln_fwd(h, res, gamma, beta, eps, p, seed)
+        ctx.p, ctx.seed, ctx.has_res = p, seed, res is not None
+        ctx.save_for_backward(h, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        if ctx.p > 0:
+            dx, dh = ops.ln_bwd(_c(dy), x, mean, rstd, gamma, ctx.p, ctx.seed,
+                                want_dx=ctx.has_res, dgamma=dgamma, dbeta=dbeta)
+        else:
+            dx, _ = ops.ln_bwd(_c(dy), x, mean, rstd, gamma, 0.0, 0, want_dh=False,
+                               dgamma=dgamma, dbeta=dbeta)
+            dh = dx
+        return dh, (dx if ctx.has_res else None), dgamma, dbeta, None, None, None
+
+
+class ContextLayerNormFn(Function):
+    """The four parallel branches of decoder_faces_objects.py:272-352 after their out_proj:
+    Y[:, c*E:(c+1)*E] = LN_c(X + dropout(h_c)), written straight into the concatenated buffer that
+    context_fc consumes (replaces torch.cat, :354)."""
+
+    @staticmethod
+    def forward(ctx, X, p, seeds, eps, n, *args):
+        hs, gammas, betas = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        N, E = X.shape
+        Y = torch.empty((N, n * E), dtype=torch.float32, device=X.device)
+        saved = [X]
+        for c in range(n):
+            _, mean, rstd = ops.ln_fwd(hs[c], X, gammas[c], betas[c], eps, p, seeds[c],
+                                       out=Y[:, c * E:(c + 1) * E])
+            saved += [hs[c], mean, rstd, gammas[c]]
+        ctx.n, ctx.p, ctx.seeds = n, p, seeds
+        ctx.save_for_backward(*saved)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        saved = ctx.saved_tensors
+        X = saved[0]
+        n = ctx.n
+        N, E = X.shape
+        dY = _c(dY)
+        dX = None
+        dhs, dgs, dbs = [], [], []
+        for c in range(n):
+            x, mean, rstd, gamma = saved[1 + 4 * c:5 + 4 * c]
+            dg, db = torch.zeros_like(gamma), torch.zeros_like(gamma)
+            dyc = dY[:, c * E:(c + 1) * E]
+            if ctx.p > 0:
+                dx, dh = ops.ln_bwd(dyc, x, mean, rstd, gamma, ctx.p, ctx.seeds[c], dgamma=dg,
+                                    dbeta=db)
+            else:
+                dx, _ = ops.ln_bwd(dyc, x, mean, rstd, gamma, 0.0, 0, want_dh=False, dgamma=dg,
+                                   dbeta=db)
+                dh = dx
+            if dX is None:
+                dX = dx if ctx.p > 0 else dx.clone()
+            else:
+                ops.axpby(dx, dX, 1.0, 1.0)
+            dhs.append(dh)
+            dgs.append(dg)
+            dbs.append(db)
+        return (dX, None, None, None, None) + tuple(dhs) + tuple(dgs) + tuple(dbs)
+
+
+class Transpose01Fn(Function):
+    """[A,B,C] -> [B,A,C] (the decoder's T x B x C <-> B x T x C flips)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.transpose01(_c(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.transpose01(_c(dy))
+
+
+class GLUFn(Function):
+    @staticmethod
+    def forward(ctx, h):
+        ctx.save_for_backward(h)
+        return ops.glu_fwd(h)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (h,) = ctx.saved_tensors
+        return ops.glu_bwd(_c(dout), h)
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(_c(x), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(_c(dy), ctx.p, ctx.seed), None, None
+
+
+class DynConvFn(Function):
+    """x [T,B,C], z [T,B,H*K] -> out [T,B,C]  (dynamic.py:302-335)."""
+
+    @staticmethod
+    def forward(ctx, x, z, H, K, softmax, p, seed):
+        out, probs = ops.dynconv_fwd(x, z, H, K, softmax, p, seed)
+        ctx.cfg = (H, K, softmax, p, seed)
+        ctx.save_for_backward(x, probs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, probs = ctx.saved_tensors
+        H, K, softmax, p, seed = ctx.cfg
+        dx, dz = ops.dynconv_bwd(_c(dout), x, probs, H, K, softmax, p, seed)
+        T, B, _ = x.shape
+        return dx, dz.view(T, B, H * K), None, None, None, None, None
+
+
+class LightConvFn(Function):
+    """LightweightConv1dTBC (lightweight.py:88-240): static taps w [H,K] shared over (t,b)."""
+
+    @staticmethod
+    def forward(ctx, x, w, H, K, softmax, p, seed):
+        out, probs = ops.dynconv_fwd(x, w, H, K, softmax, p, seed, broadcast=True)
+        ctx.cfg = (H, K, softmax, p, seed)
+        ctx.save_for_backward(x, probs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, probs = ctx.saved_tensors
+        H, K, softmax, p, seed = ctx.cfg
+        dx, dz = ops.dynconv_bwd(_c(dout), x, probs, H, K, softmax, p, seed)
+        T, B, _ = x.shape
+        dw = ops.colsum(dz.view(T * B, H * K)).view(H, K)
+        return dx, dw, None, None, None, None, None
+
+
+class AttentionFn(Function):
+    """q [T*B,E] (scaled), kv [S*B,2E] (or None when the context is empty) -> out [T*B,E]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, bias_k, bias_v, mask, T, B, S, H, zero_row, p, seed, need_weights):
+        E = q.shape[1]
+        D = E // H
+        k = kv[:, :E] if S > 0 else None
+        v = kv[:, E:] if S > 0 else None
+        bk = bias_k.view(-1) if bias_k is not None else None
+        bv = bias_v.view(-1) if bias_v is not None else None
+        out, lse = ops.attn_fwd(q, k, v, bk, bv, mask, T, B, S, H, D, zero_row, p, seed)
+        ctx.cfg = (T, B, S, H, D, zero_row, p, seed)
+        ctx.save_for_backward(q, kv, bias_k, bias_v, mask, out, lse)
+        weights = None
+        if need_weights:
+            weights = ops.attn_avg_weights(q, k, bk, mask, lse, T, B, S, H, D, zero_row)
+            ctx.mark_non_differentiable(weights)
+        return out, weights
+
+    @staticmethod
+    def backward(ctx, dout, _dweights):
+        q, kv, bias_k, bias_v, mask, out, lse = ctx.saved_tensors
+        T, B, S, H, D, zero_row, p, seed = ctx.cfg
+        E = H * D
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv) if S > 0 else None
+        dbk = torch.zeros_like(bias_k) if bias_k is not None else None
+        dbv = torch.zeros_like(bias_v) if bias_v is not None else None
+        ops.attn_bwd(_c(dout), q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None,
+                     bias_k.view(-1) if bias_k is not None else None,
+                     bias_v.view(-1) if bias_v is not None else None, mask, out, lse, dq,
+                     dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None,
+                     dbk, dbv, T, B, S, H, D, zero_row, p, seed)
+        return (dq, dkv, dbk, dbv) + (None,) * 9
+
+
+def _rep():
+    return 1 if config.precision == 'bf16' else 3
+
+
+def concat_k_operand(mats, side, device):
+    """One bf16 operand whose K axis is the concatenation of `mats` ([R, K_i] each)."""
+    R = mats[0].shape[0]
+    Ktot = sum(m.shape[1] for m in mats)
+    rep = _rep()
+    buf = ops.bf16_buffer(R, Ktot * rep, device)
+    split = 0 if rep == 1 else (1 if side == 'a' else 2)
+    off = 0
+    for m in mats:
+        ops.cast_bf16(m, split=split, out=buf[:, off:], seg_stride=Ktot)
+        off += m.shape[1]
+    return buf
+
+
+def concat_kT_operand(mats, side, device):
+    """Operand [C, sum_i R_i] = concatenation along K of the TRANSPOSES of `mats` ([R_i, C])."""
+    C = mats[0].shape[1]
+    Ktot = sum(m.shape[0] for m in mats)
+    rep = _rep()
+    buf = ops.bf16_buffer(C, Ktot * rep, device)
+    split = 0 if rep == 1 else (1 if side == 'a' else 2)
+    off = 0
+    for m in mats:
+        ops.cast_bf16(m, transpose=True, split=split, out=buf[:, off:], seg_stride=Ktot)
+        off += m.shape[0]
+    return buf
+
+
+class EmbedFn(Function):
+    """AdaptiveEmbedding + sinusoidal positions (adaptive.py:61-76, positional.py:167-211,
+    sum_text_field_embedder.py:117): out[t*B+b] = scale * sum_band proj_band(emb_band[id]) + pos.
+    The band projections are one GEMM over K = n_bands*E (bands are disjoint, so the gathered
+    operand is zero outside the token's band)."""
+
+    @staticmethod
+    def forward(ctx, ids, pos_table, start_pos, pad, scale, cutoffs, n, *args):
+        tables, projs = args[:n], args[n:2 * n]
+        B, T = ids.shape
+        E = projs[0].shape[0]
+        A = ops.embed_gather(ids, cutoffs, tables, E, tbc=True)          # [T*B, n*E]
+        pos = ops.make_positions(ids, pad, False, start_pos, tbc=True)   # [T,B] int32
+        posv = ops.gather_rows(pos_table, pos.view(-1))                  # [T*B, E]
+        w16 = concat_k_operand(list(projs), 'b', ids.device)             # [E, n*E(*3)]
+        out = ops.gemm_tn(operand(A, 'a'), w16, alpha=scale, residual=posv)
+        ctx.cfg = (n, scale, cutoffs, E)
+        ctx.save_for_backward(ids, A, *tables, *projs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, scale, cutoffs, E = ctx.cfg
+        saved = ctx.saved_tensors
+        ids, A = saved[0], saved[1]
+        tables, projs = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        dout = _c(dout)
+        d16 = operand(dout, 'a')
+        d16T = operand(dout, 'a', transpose=True)
+        dA = torch.empty_like(A)
+        dtables, dprojs = [], []
+        for i in range(n):
+            ops.gemm_tn(d16, operand(projs[i], 'b', transpose=True), out=dA[:, i * E:(i + 1) * E],
+                        alpha=scale)
+            dprojs.append(ops.gemm_tn(d16T, operand(A[:, i * E:(i + 1) * E], 'b', transpose=True),
+                                      alpha=scale))
+            dtables.append(torch.zeros_like(tables[i]))
+        ops.embed_scatter_grad(ids, cutoffs, dtables, E, dA, padding_idx=0, tbc=True)
+        return (None,) * 7 + tuple(dtables) + tuple(dprojs)
+
+
+class LayerMixFn(Function):
+    """X_article = sum_l softmax(bert_weight)[l] * h_l  (transformer_faces_objects.py:355-364).
+    hiddens: bf16 [L, R, E] from the frozen encoder (no grad); grad flows to bert_weight only."""
+
+    @staticmethod
+    def forward(ctx, hiddens, w):
+        ctx.save_for_backward(hiddens, w)
+        return ops.layer_mix_fwd(hiddens, w)
+
+    @staticmethod
+    def backward(ctx, dout):
+        hiddens, w = ctx.saved_tensors
+        return None, ops.layer_mix_bwd(hiddens, w, _c(dout))
+
+
+class AdaptiveLossFn(Function):
+    """AdaptiveSoftmax.forward + AdaptiveLoss + loss/ln2/ntokens in one node
+    (softmax.py:169-191, adaptive_loss.py:27-73, transformer_faces_objects.py:82-90).
+    Inputs: X [N,E]; target int64 [N]; word0 [c0,E], class_proj [n_tails,E],
+    then per tail: proj_i [E,E], words_i [V_i,E].  Returns (loss [1], ntokens int32 [1]).
+    Tail rows are compacted on the device (no nonzero() sync); every cluster's logits live in an
+    fp32 buffer of capacity N rows and GEMMs stop at the device-side row count."""
+
+    @staticmethod
+    def forward(ctx, X, target, cutoffs, pad_idx, word0, class_proj, *tails):
+        N, E = X.shape
+        nt = len(cutoffs) - 1
+        head_t, tail_idx, tail_local, tail_count, ntok = ops.adaptive_prepare(target, cutoffs,
+                                                                              pad_idx)
+        hw16 = ops.bf16_buffer(cutoffs[0] + nt, E * _rep(), X.device)
+        split_b = 0 if _rep() == 1 else 2
+        ops.cast_bf16(word0, split=split_b, out=hw16[:cutoffs[0]])
+        ops.cast_bf16(class_proj, split=split_b, out=hw16[cutoffs[0]:])
+        head_logits = ops.gemm_tn(operand(X, 'a'), hw16)
+        row_loss = torch.empty((nt + 1, N), dtype=torch.float32, device=X.device)
+        head_lse, _ = ops.ce_fwd(head_logits, head_t, None, pad_idx, row_loss[0])
+        saved_tail = []
+        for i in range(nt):
+            proj, words = tails[2 * i], tails[2 * i + 1]
+            cnt = tail_count[i:i + 1]
+            Xg = ops.gather_rows(X, tail_idx[i], cnt, cap=N)
+            P = ops.gemm_tn(operand(Xg, 'a'), operand(proj, 'b'), m_limit=cnt)
+            logits = ops.gemm_tn(operand(P, 'a'), operand(words, 'b'), m_limit=cnt)
+            lse, _ = ops.ce_fwd(logits, tail_local[i], cnt, pad_idx, row_loss[i + 1])
+            saved_tail += [Xg, P, logits, lse]
+        loss, scale = ops.loss_finalize(row_loss, ntok)
+        ctx.cfg = (cutoffs, pad_idx, nt)
+        ctx.save_for_backward(X, word0, class_proj, head_logits, head_lse, head_t, tail_idx,
+                              tail_local, tail_count, scale, *tails, *saved_tail)
+        ctx.mark_non_differentiable(ntok)
+        return loss, ntok
+
+    @staticmethod
+    def backward(ctx, dloss, _dntok):
+        cutoffs, pad_idx, nt = ctx.cfg
+        s = ctx.saved_tensors
+        (X, word0, class_proj, head_logits, head_lse, head_t, tail_idx, tail_local, tail_count,
+         scale) = s[:10]
+        tails = s[10:10 + 2 * nt]
+        saved_tail = s[10 + 2 * nt:]
+        c0 = cutoffs[0]
+        gscale = ops.scalar_mul(scale, _c(dloss).view(1))       # upstream grad stays on device
+        dlog = ops.ce_bwd_(head_logits, head_t, head_lse, gscale, None, pad_idx)   # in place
+        dX = ops.gemm_tn(operand(dlog, 'a'),
+                         concat_kT_operand([word0, class_proj], 'b', X.device))
+        dW_head = ops.gemm_tn(operand(dlog, 'a', transpose=True), operand(X, 'b', transpose=True))
+        dtails = []
+        for i in range(nt):
+            proj, words = tails[2 * i], tails[2 * i + 1]
+            Xg, P, logits, lse = saved_tail[4 * i:4 * i + 4]
+            cnt = tail_count[i:i + 1]
+            dl = ops.ce_bwd_(logits, tail_local[i], lse, gscale, cnt, pad_idx)   # rows >= cnt := 0
+            dP = ops.gemm_tn(operand(dl, 'a'), operand(words, 'b', transpose=True), m_limit=cnt)
+            dwords = ops.gemm_tn(operand(dl, 'a', transpose=True), operand(P, 'b', transpose=True))
+            dXg = ops.gemm_tn(operand(dP, 'a'), operand(proj, 'b', transpose=True), m_limit=cnt)
+            dproj = ops.gemm_tn(operand(dP, 'a', transpose=True), operand(Xg, 'b', transpose=True))
+            ops.scatter_add_rows(dXg, tail_idx[i], dX, cnt)
+            dtails += [dproj, dwords]
+        return (dX, None, None, None, dW_head[:c0], dW_head[c0:]) + tuple(dtails)

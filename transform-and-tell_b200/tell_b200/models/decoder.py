@@ -1,0 +1,262 @@
+"""The DynamicConv decoder family of tell/models/decoder_*.py on the B200 kernels.
+
+One N-context layer covers the four reference variants, which differ only in their context list:
+    dynamic_conv_decoder_faces_objects      image, article, faces, obj   (decoder_faces_objects.py)
+    dynamic_conv_decoder_faces_parallel     image, article, faces        (decoder_faces_parallel.py)
+    dynamic_conv_decoder_flattened          image, article               (decoder_flattened.py)
+    dynamic_conv_decoder_flattened_no_image article                      (decoder_flattened_no_image.py)
+State-dict keys and constructor kwargs are the reference's.
+"""
+import torch
+import torch.nn as nn
+
+from .. import config
+from .. import functional as Fn
+from .. import ops
+from ..modules import (AdaptiveEmbedding, AdaptiveSoftmax, DynamicConv1dTBC, GehringLinear,
+                       LayerNorm, LightweightConv1dTBC, MultiHeadAttention, TextFieldEmbedder)
+from ..registry import Registrable
+from ..utils import eval_str_list
+
+
+class Decoder(nn.Module, Registrable):
+    pass
+
+
+class DecoderLayer(nn.Module, Registrable):
+    pass
+
+
+_KV_KEY = 'tell_b200.kv_cache'   # our own incremental-state entry (projected contexts)
+
+
+class DynamicConvDecoderLayer(DecoderLayer):
+    """decoder_faces_objects.py:183-379 generalised over the context list.
+    context_dims: ordered {name: kdim}."""
+
+    def __init__(self, decoder_embed_dim, decoder_conv_dim, decoder_glu, decoder_conv_type,
+                 weight_softmax, decoder_attention_heads, weight_dropout, dropout, relu_dropout,
+                 input_dropout, decoder_normalize_before, attention_dropout, decoder_ffn_embed_dim,
+                 context_dims, kernel_size=0):
+        super().__init__()
+        if decoder_normalize_before:
+            raise NotImplementedError('decoder_normalize_before=True is not used by the shipped configs')
+        self.embed_dim = decoder_embed_dim
+        self.conv_dim = decoder_conv_dim
+        self.glu = bool(decoder_glu)
+        self.linear1 = GehringLinear(self.embed_dim, (2 if self.glu else 1) * self.conv_dim)
+        if decoder_conv_type == 'lightweight':
+            self.conv = LightweightConv1dTBC(self.conv_dim, kernel_size, padding_l=kernel_size - 1,
+                                             weight_softmax=weight_softmax,
+                                             num_heads=decoder_attention_heads,
+                                             weight_dropout=weight_dropout)
+        elif decoder_conv_type == 'dynamic':
+            self.conv = DynamicConv1dTBC(self.conv_dim, kernel_size, padding_l=kernel_size - 1,
+                                         weight_softmax=weight_softmax,
+                                         num_heads=decoder_attention_heads,
+                                         weight_dropout=weight_dropout)
+        else:
+            raise NotImplementedError
+        self.linear2 = GehringLinear(self.conv_dim, self.embed_dim)
+        self.dropout = dropout
+        self.relu_dropout = relu_dropout
+        self.input_dropout = input_dropout
+        self.normalize_before = decoder_normalize_before
+        self.conv_layer_norm = LayerNorm(self.embed_dim)
+        self.context_names = list(context_dims.keys())
+        self.context_attns = nn.ModuleDict()
+        self.context_attn_lns = nn.ModuleDict()
+        for name, kdim in context_dims.items():
+            self.context_attns[name] = MultiHeadAttention(
+                self.embed_dim, decoder_attention_heads, kdim=kdim, vdim=kdim,
+                dropout=attention_dropout)
+            self.context_attn_lns[name] = LayerNorm(self.embed_dim)
+        self.context_fc = GehringLinear(self.embed_dim * len(context_dims), self.embed_dim)
+        self.fc1 = GehringLinear(self.embed_dim, decoder_ffn_embed_dim)
+        self.fc2 = GehringLinear(decoder_ffn_embed_dim, self.embed_dim)
+        self.final_layer_norm = LayerNorm(self.embed_dim)
+        self.need_attn = True
+
+    def _p(self, p):
+        return p if self.training else 0.0
+
+    @staticmethod
+    def _seed(p):
+        return config.next_seed() if p > 0 else 0
+
+    def forward(self, X, contexts, incremental_state, kv_cache=None):
+        """X [T,B,E] -> ([T,B,E], {ctx: head-averaged attention [B,T,S+2]} in eval mode)."""
+        T, B, E = X.shape
+        N = T * B
+        X2 = X.reshape(N, E)
+        # ---- conv block (decoder_faces_objects.py:256-266)
+        p_in = self._p(self.input_dropout)
+        h = Fn.DropoutFn.apply(X2, p_in, self._seed(p_in)) if p_in > 0 else X2
+        h = self.linear1(h)
+        if self.glu:
+            h = Fn.GLUFn.apply(h)
+        h = self.conv(h.view(T, B, self.conv_dim), incremental_state=incremental_state)
+        h = self.linear2(h.reshape(N, self.conv_dim))
+        p = self._p(self.dropout)
+        X2 = Fn.ResidualLayerNormFn.apply(h, X2.contiguous(), self.conv_layer_norm.weight,
+                                          self.conv_layer_norm.bias, p, self._seed(p),
+                                          self.conv_layer_norm.eps)
+        # ---- parallel cross-attention branches (:272-352), all reading the same X2
+        need_w = (not self.training) and self.need_attn
+        attns, hs = {}, []
+        for name in self.context_names:
+            mha = self.context_attns[name]
+            if kv_cache is not None and name in kv_cache:
+                kv = kv_cache[name]
+            else:
+                kv = mha.project_kv(contexts[name])
+                if kv_cache is not None:
+                    kv_cache[name] = kv
+            a, w = mha.attend(X2.view(T, B, E), kv, contexts[name + '_mask'], need_w)
+            hs.append(Fn.LinearFn.apply(a, mha.out_proj.weight, mha.out_proj.bias))
+            if w is not None:
+                attns[name] = w
+        lns = [self.context_attn_lns[n] for n in self.context_names]
+        n = len(hs)
+        seeds = tuple(self._seed(p) for _ in range(n))
+        Xc = Fn.ContextLayerNormFn.apply(X2, p, seeds, lns[0].eps, n, *hs,
+                                         *[l.weight for l in lns], *[l.bias for l in lns])
+        # ---- context_fc + FFN (:354-364)
+        X2 = self.context_fc(Xc)
+        h = self.fc1(X2, act=ops.ACT_RELU)
+        p_relu = self._p(self.relu_dropout)
+        if p_relu > 0:
+            h = Fn.DropoutFn.apply(h, p_relu, self._seed(p_relu))
+        h = self.fc2(h)
+        X2 = Fn.ResidualLayerNormFn.apply(h, X2, self.final_layer_norm.weight,
+                                          self.final_layer_norm.bias, p, self._seed(p),
+                                          self.final_layer_norm.eps)
+        return X2.view(T, B, E), attns
+
+    def make_generation_fast_(self, need_attn=False, **kwargs):
+        self.need_attn = need_attn
+
+
+class _DynamicConvDecoderBase(Decoder):
+    CONTEXTS = None  # ordered {name: kdim}, set by subclasses
+
+    def __init__(self, vocab, embedder: TextFieldEmbedder, max_target_positions, dropout,
+                 share_decoder_input_output_embed, decoder_output_dim, decoder_conv_dim,
+                 decoder_glu, decoder_conv_type, weight_softmax, decoder_attention_heads,
+                 weight_dropout, relu_dropout, input_dropout, decoder_normalize_before,
+                 attention_dropout, decoder_ffn_embed_dim, decoder_kernel_size_list,
+                 adaptive_softmax_cutoff=None, tie_adaptive_weights=False,
+                 adaptive_softmax_dropout=0, tie_adaptive_proj=False, adaptive_softmax_factor=0,
+                 decoder_layers=6, final_norm=True, padding_idx=0, namespace='target_tokens',
+                 vocab_size=None, section_attn=False, swap=False, article_embed_size=1024):
+        super().__init__()
+        self.vocab = vocab
+        vocab_size = vocab_size or vocab.get_vocab_size(namespace)
+        self.dropout = dropout
+        self.share_input_output_embed = share_decoder_input_output_embed
+        embed_dim = embedder.get_output_dim()
+        self.embed_dim = embed_dim
+        self.max_target_positions = max_target_positions
+        self.embedder = embedder
+        context_dims = dict(self.CONTEXTS)
+        if 'article' in context_dims:
+            context_dims['article'] = article_embed_size
+        self.layers = nn.ModuleList([
+            DynamicConvDecoderLayer(embed_dim, decoder_conv_dim, decoder_glu, decoder_conv_type,
+                                    weight_softmax, decoder_attention_heads, weight_dropout,
+                                    dropout, relu_dropout, input_dropout, decoder_normalize_before,
+                                    attention_dropout, decoder_ffn_embed_dim, context_dims,
+                                    kernel_size=decoder_kernel_size_list[i])
+            for i in range(decoder_layers)])
+        self.adaptive_softmax = None
+        if adaptive_softmax_cutoff is None:
+            raise NotImplementedError('the shipped configs always use the adaptive softmax')
+        adaptive_inputs = None
+        if isinstance(embedder, AdaptiveEmbedding):
+            adaptive_inputs = embedder
+        elif hasattr(embedder, 'token_embedder_adaptive'):
+            adaptive_inputs = embedder.token_embedder_adaptive
+        elif tie_adaptive_weights:
+            raise ValueError('Cannot locate adaptive_inputs.')
+        self.adaptive_softmax = AdaptiveSoftmax(
+            vocab_size, embed_dim, eval_str_list(adaptive_softmax_cutoff, type=int),
+            dropout=adaptive_softmax_dropout, adaptive_inputs=adaptive_inputs,
+            factor=adaptive_softmax_factor, tie_proj=tie_adaptive_proj)
+        self.register_buffer('version', torch.Tensor([2]))
+        self.normalize = decoder_normalize_before and final_norm
+
+    @classmethod
+    def _from_params(cls, params, **extras):
+        params = dict(params)
+        embedder = TextFieldEmbedder.from_params(params.pop('embedder'))
+        import inspect
+        sig = inspect.signature(cls.__init__)
+        unknown = [k for k in params if k not in sig.parameters]
+        if unknown:
+            from ..registry import ConfigurationError
+            raise ConfigurationError('Extra parameters passed to %s: %s' % (cls.__name__, unknown))
+        return cls(vocab=extras.get('vocab'), embedder=embedder, **params)
+
+    def forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
+        """Hot-path entry: returns X in decoder layout [T,B,E] (no final transpose) + extras."""
+        X2, ids = self.embedder.embed_tbc(prev_target, incremental_state)
+        B, T = ids.shape
+        p = self.dropout if self.training else 0.0
+        if p > 0:
+            X2 = Fn.DropoutFn.apply(X2, p, config.next_seed())
+        X = X2.view(T, B, self.embed_dim)
+        attns, inner_states = [], [X]
+        caches = None
+        if incremental_state is not None:
+            caches = incremental_state.setdefault(_KV_KEY, [dict() for _ in self.layers])
+        for i, layer in enumerate(self.layers):
+            attn = None
+            if not use_layers or i in use_layers:
+                X, attn = layer(X, contexts, incremental_state,
+                                caches[i] if caches is not None else None)
+                inner_states.append(X)
+            attns.append(attn)
+        return X, {'attn': attns, 'inner_states': inner_states}
+
+    def forward(self, prev_target, contexts, incremental_state=None, use_layers=None, **kwargs):
+        """decoder_faces_objects.py:95-142: -> (X [B,T,E], {'attn', 'inner_states'})."""
+        X, extra = self.forward_tbc(prev_target, contexts, incremental_state, use_layers)
+        return Fn.Transpose01Fn.apply(X), extra
+
+    def max_positions(self):
+        return self.max_target_positions
+
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        out = self.adaptive_softmax.get_log_prob(net_output[0], None)
+        return out if log_probs else out.exp()
+
+    def filter_incremental_state(self, incremental_state, active_idx):
+        """decoder_faces_objects.py:175-180 (+ our projected-context cache, same batch axis)."""
+        if incremental_state is None:
+            return
+        for key in incremental_state:
+            if 'DynamicConv1dTBC' in key:
+                incremental_state[key] = incremental_state[key][:, active_idx]
+        if _KV_KEY in incremental_state:
+            raise NotImplementedError('row compaction with a projected-context cache: use '
+                                      'the masked (non-compacting) greedy loop of the model')
+
+
+@Decoder.register('dynamic_conv_decoder_faces_objects')
+class DynamicConvFacesObjectsDecoder(_DynamicConvDecoderBase):
+    CONTEXTS = (('image', 2048), ('article', 1024), ('faces', 512), ('obj', 2048))
+
+
+@Decoder.register('dynamic_conv_decoder_faces_parallel')
+class DynamicConvFacesParallelDecoder(_DynamicConvDecoderBase):
+    CONTEXTS = (('image', 2048), ('article', 1024), ('faces', 512))
+
+
+@Decoder.register('dynamic_conv_decoder_flattened')
+class DynamicConvFlattenedDecoder(_DynamicConvDecoderBase):
+    CONTEXTS = (('image', 2048), ('article', 1024))
+
+
+@Decoder.register('dynamic_conv_decoder_flattened_no_image')
+class DynamicConvDecoderNoImage(_DynamicConvDecoderBase):
+    CONTEXTS = (('article', 1024),)

@@ -28,7 +28,7 @@ def _check_cuda(*ts):
             raise _lib.TtError('tell_b200 ops need CUDA tensors (no CPU fallback); got %s' % t.device)
 
 
-def cast_bf16(x, transpose=False, split=0, out=None):
+def cast_bf16(x, transpose=False, split=0, out=None, seg_stride=0):
     """fp32 [R,C] -> bf16 GEMM operand ([R,C*rep] or [C,R*rep] when transposed); see tt_cast_bf16."""
     _check_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
@@ -43,13 +43,26 @@ def cast_bf16(x, transpose=False, split=0, out=None):
             buf.zero_()
         out = buf[:, :shape[1]]
     _lib.call('tt_cast_bf16', _ptr(x), c_ll(x.stride(0)), _ptr(out), c_ll(out.stride(0)),
-              c_int(rows), c_int(cols), c_int(1 if transpose else 0), c_int(split), _stream())
+              c_int(rows), c_int(cols), c_int(1 if transpose else 0), c_int(split),
+              c_ll(seg_stride), _stream())
+    return out
+
+
+def bf16_buffer(rows, cols, device):
+    """Zero-initialised bf16 operand buffer whose row pitch is a multiple of 8 elements (TMA)."""
+    ld = (cols + 7) // 8 * 8
+    return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)[:, :cols]
+
+
+def scalar_mul(a, b):
+    out = torch.empty_like(a)
+    _lib.call('tt_scalar_mul', _ptr(a), _ptr(b), _ptr(out), _stream())
     return out
 
 
 def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act=ACT_NONE,
-            accumulate=False, m_limit=None, want32=True, want16=False):
-    """C[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual, bf16 operands, fp32 accumulate."""
+            accumulate=False, m_limit=None, want32=True, want16=False, residual16=None):
+    """C[M,N] = act(alpha * (a[M,K] @ b[N,K]^T + bias) + residual), bf16 operands, fp32 accumulate."""
     _check_cuda(a, b, out, out16, bias, residual)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1], (a.shape, b.shape)
@@ -57,7 +70,9 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     M, K = a.shape
     N = b.shape[0]
     if out is None and want32:
-        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        # with a dynamic row limit the untouched rows must be defined (they feed later GEMMs)
+        alloc = torch.zeros if m_limit is not None else torch.empty
+        out = alloc((M, N), dtype=torch.float32, device=a.device)
     if out16 is None and want16:
         out16 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     p = TtGemmParams()
@@ -77,6 +92,9 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
         assert residual.dtype == torch.float32 and residual.shape == (M, N)
         assert residual.stride(1) == 1
         p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
+    if residual16 is not None:
+        assert residual16.dtype == torch.bfloat16 and residual16.shape == (M, N)
+        p.residual16, p.ldr16 = residual16.data_ptr(), residual16.stride(0)
     p.alpha = alpha
     p.act = act
     p.accumulate = 1 if accumulate else 0
@@ -87,3 +105,295 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     if out is not None and out16 is not None:
         return out, out16
     return out if out is not None else out16
+
+
+# --------------------------------------------------------------------------- row-wise kernels
+def _ull(x):
+    return ctypes.c_ulonglong(int(x) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _f32(*shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+def ln_fwd(h, res, gamma, beta, eps=1e-5, p=0.0, seed=0, out=None):
+    """h [N,E] is overwritten with x = res + dropout(h); returns (y, mean, rstd)."""
+    _check_cuda(h, res, gamma, beta)
+    N, E = h.shape
+    assert h.is_contiguous() and (res is None or res.is_contiguous())
+    y = out if out is not None else _f32(N, E, like=h)
+    mean, rstd = _f32(N, like=h), _f32(N, like=h)
+    _lib.call('tt_ln_fwd', _ptr(h), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(y),
+              c_ll(y.stride(0)), _ptr(mean), _ptr(rstd), c_int(N), c_int(E), c_float(eps),
+              c_float(p), _ull(seed), _stream())
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, p=0.0, seed=0, want_dx=True, want_dh=True, dgamma=None,
+           dbeta=None):
+    _check_cuda(dy, x)
+    N, E = x.shape
+    assert dy.stride(1) == 1
+    dx = _f32(N, E, like=x) if want_dx else None
+    dh = _f32(N, E, like=x) if want_dh else None
+    _lib.call('tt_ln_bwd', _ptr(dy), c_ll(dy.stride(0)), _ptr(x), _ptr(mean), _ptr(rstd),
+              _ptr(gamma), _ptr(dx), _ptr(dh), _ptr(dgamma), _ptr(dbeta), c_int(N), c_int(E),
+              c_float(p), _ull(seed), _stream())
+    return dx, dh
+
+
+def glu_fwd(h):
+    N, C2 = h.shape
+    out = _f32(N, C2 // 2, like=h)
+    _lib.call('tt_glu_fwd', _ptr(h), _ptr(out), c_ll(N), c_int(C2 // 2), _stream())
+    return out
+
+
+def glu_bwd(dout, h):
+    N, C2 = h.shape
+    dh = torch.empty_like(h)
+    _lib.call('tt_glu_bwd', _ptr(dout), _ptr(h), _ptr(dh), c_ll(N), c_int(C2 // 2), _stream())
+    return dh
+
+
+def dropout(x, p, seed):
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.call('tt_dropout', _ptr(x), _ptr(y), c_ll(x.numel()), c_float(p), _ull(seed), _stream())
+    return y
+
+
+def axpby(x, y, a, b):
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    _lib.call('tt_axpby', _ptr(x), _ptr(y), c_ll(x.numel()), c_float(a), c_float(b), _stream())
+    return y
+
+
+def wnorm_fwd(v, g):
+    O, I = v.shape
+    w, norm = torch.empty_like(v), _f32(O, like=v)
+    _lib.call('tt_wnorm_fwd', _ptr(v), _ptr(g), _ptr(w), _ptr(norm), c_int(O), c_int(I), _stream())
+    return w, norm
+
+
+def wnorm_bwd(dw, v, g, norm):
+    O, I = v.shape
+    dv, dg = torch.empty_like(v), torch.empty_like(g)
+    _lib.call('tt_wnorm_bwd', _ptr(dw), _ptr(v), _ptr(g), _ptr(norm), _ptr(dv), _ptr(dg),
+              c_int(O), c_int(I), _stream())
+    return dv, dg
+
+
+def nan_rows_(x):
+    """In place: zero NaN rows of x [..., D]; returns the bool row mask."""
+    D = x.shape[-1]
+    R = x.numel() // D if D > 0 else int(torch.Size(x.shape[:-1]).numel())
+    mask = torch.empty(x.shape[:-1], dtype=torch.uint8, device=x.device)
+    assert x.is_contiguous()
+    _lib.call('tt_nan_rows', _ptr(x), _ptr(mask), c_int(R), c_int(D), _stream())
+    return mask.bool()
+
+
+def colsum(x, scale=1.0, out=None, accumulate=False):
+    M, N = x.shape
+    if out is None:
+        out = _f32(N, like=x)
+    _lib.call('tt_colsum', _ptr(x), c_ll(x.stride(0)), c_int(M), c_int(N), _ptr(out),
+              c_float(scale), c_int(1 if accumulate else 0), _stream())
+    return out
+
+
+def relu_bwd(dy, y):
+    dx = torch.empty_like(y)
+    _lib.call('tt_relu_bwd', _ptr(dy), _ptr(y), _ptr(dx), c_ll(y.numel()), _stream())
+    return dx
+
+
+def layer_mix_fwd(hiddens, w):
+    """hiddens bf16 [L, R, E]; w fp32 [L] -> fp32 [R, E]."""
+    L = hiddens.shape[0]
+    n = hiddens[0].numel()
+    out = torch.empty(hiddens.shape[1:], dtype=torch.float32, device=hiddens.device)
+    _lib.call('tt_layer_mix_fwd', _ptr(hiddens), c_ll(hiddens.stride(0)), _ptr(w), c_int(L),
+              c_ll(n), _ptr(out), _stream())
+    return out
+
+
+def layer_mix_bwd(hiddens, w, dout):
+    L = hiddens.shape[0]
+    dots, dw = _f32(L, like=w), _f32(L, like=w)
+    _lib.call('tt_layer_mix_bwd', _ptr(hiddens), c_ll(hiddens.stride(0)), _ptr(w), _ptr(dout),
+              c_int(L), c_ll(hiddens[0].numel()), _ptr(dots), _ptr(dw), _stream())
+    return dw
+
+
+# --------------------------------------------------------------------------- dynamic conv
+def dynconv_fwd(x, z, H, K, softmax=True, p=0.0, seed=0, broadcast=False):
+    T, B, C = x.shape
+    out = torch.empty_like(x)
+    probs = _f32(T, B, H, K, like=x)
+    _lib.call('tt_dynconv_fwd', _ptr(x), _ptr(z), c_ll(0 if broadcast else H * K), _ptr(out),
+              _ptr(probs), c_int(T), c_int(B), c_int(C), c_int(H), c_int(K),
+              c_int(1 if softmax else 0), c_float(p), _ull(seed), _stream())
+    return out, probs
+
+
+def dynconv_bwd(dout, x, probs, H, K, softmax=True, p=0.0, seed=0):
+    T, B, C = x.shape
+    dx = torch.empty_like(x)
+    dz = _f32(T, B, H, K, like=x)
+    _lib.call('tt_dynconv_bwd', _ptr(dout), _ptr(x), _ptr(probs), _ptr(dx), _ptr(dz), c_int(T),
+              c_int(B), c_int(C), c_int(H), c_int(K), c_int(1 if softmax else 0), c_float(p),
+              _ull(seed), _stream())
+    return dx, dz
+
+
+# --------------------------------------------------------------------------- attention
+def attn_fwd(q, k, v, bias_k, bias_v, mask, T, B, S, H, D, zero_row=True, p=0.0, seed=0):
+    """q [T*B, >=E] view, k/v [S*B, >=E] views (row strides honoured); returns (out [T*B,E], lse)."""
+    E = H * D
+    out = _f32(T * B, E, like=q)
+    lse = _f32(B, H, T, like=q)
+    _lib.call('tt_attn_fwd', _ptr(q), _ptr(k if S > 0 else None), _ptr(v if S > 0 else None),
+              _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out), _ptr(lse), c_int(T), c_int(B),
+              c_int(S), c_int(H), c_int(D), c_ll(q.stride(0)),
+              c_ll(k.stride(0) if S > 0 else E), c_ll(E), c_int(1 if zero_row else 0),
+              c_float(p), _ull(seed), _stream())
+    return out, lse
+
+
+def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k, dbias_v, T, B, S,
+             H, D, zero_row=True, p=0.0, seed=0):
+    """dq/dk/dv are caller-allocated views with the same row strides as q/k/v."""
+    E = H * D
+    assert dout.stride(0) == E and out.stride(0) == E and dq.stride(0) == q.stride(0)
+    if S > 0:
+        assert dk.stride(0) == k.stride(0) and dv.stride(0) == k.stride(0)
+    _lib.call('tt_attn_bwd', _ptr(dout), _ptr(q), _ptr(k if S > 0 else None),
+              _ptr(v if S > 0 else None), _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out),
+              _ptr(lse), _ptr(dq), _ptr(dk if S > 0 else None), _ptr(dv if S > 0 else None),
+              _ptr(dbias_k), _ptr(dbias_v), c_int(T), c_int(B), c_int(S), c_int(H), c_int(D),
+              c_ll(q.stride(0)), c_ll(k.stride(0) if S > 0 else E), c_ll(E),
+              c_int(1 if zero_row else 0), c_float(p), _ull(seed), _stream())
+
+
+def attn_avg_weights(q, k, bias_k, mask, lse, T, B, S, H, D, zero_row=True):
+    L = S + (1 if bias_k is not None else 0) + (1 if zero_row else 0)
+    w = torch.zeros((B, T, L), dtype=torch.float32, device=q.device)
+    E = H * D
+    _lib.call('tt_attn_avg_weights', _ptr(q), _ptr(k if S > 0 else None), _ptr(bias_k), _ptr(mask),
+              _ptr(lse), _ptr(w), c_int(T), c_int(B), c_int(S), c_int(H), c_int(D),
+              c_ll(q.stride(0)), c_ll(k.stride(0) if S > 0 else E), c_int(1 if zero_row else 0),
+              _stream())
+    return w
+
+
+# --------------------------------------------------------------------------- adaptive softmax
+def _int_array(vals):
+    return (c_int * len(vals))(*vals)
+
+
+def adaptive_prepare(target, cutoffs, pad_idx=1):
+    """target int64 [N] -> head_target [N], tail_idx [n_tails,N], tail_local, tail_count, ntokens."""
+    N = target.numel()
+    nt = len(cutoffs) - 1
+    dev = target.device
+    head_t = torch.empty(N, dtype=torch.int32, device=dev)
+    tail_idx = torch.zeros((max(nt, 1), N), dtype=torch.int32, device=dev)
+    tail_local = torch.zeros((max(nt, 1), N), dtype=torch.int32, device=dev)
+    tail_count = torch.zeros(max(nt, 1), dtype=torch.int32, device=dev)
+    ntok = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call('tt_adaptive_prepare', _ptr(target), c_int(N), _int_array(cutoffs),
+              c_int(len(cutoffs)), c_int(pad_idx), _ptr(head_t), _ptr(tail_idx), _ptr(tail_local),
+              _ptr(tail_count), _ptr(ntok), _stream())
+    return head_t, tail_idx, tail_local, tail_count, ntok
+
+
+def gather_rows(src, idx, count=None, cap=None):
+    E = src.shape[1]
+    cap = cap if cap is not None else idx.numel()
+    dst = _f32(cap, E, like=src)
+    _lib.call('tt_gather_rows', _ptr(src), _ptr(idx), _ptr(count), _ptr(dst), c_int(cap), c_int(E),
+              _stream())
+    return dst
+
+
+def scatter_add_rows(src, idx, dst, count=None):
+    cap, E = src.shape
+    _lib.call('tt_scatter_add_rows', _ptr(src), _ptr(idx), _ptr(count), _ptr(dst), c_int(cap),
+              c_int(E), _stream())
+    return dst
+
+
+def ce_fwd(logits, target, count=None, ignore_index=1, row_loss=None):
+    M, V = logits.shape
+    lse = _f32(M, like=logits)
+    if row_loss is None:
+        row_loss = _f32(M, like=logits)
+    _lib.call('tt_ce_fwd', _ptr(logits), c_ll(logits.stride(0)), _ptr(target), _ptr(count),
+              c_int(M), c_int(V), c_int(ignore_index), _ptr(lse), _ptr(row_loss), _stream())
+    return lse, row_loss
+
+
+def ce_bwd_(logits, target, lse, scale, count=None, ignore_index=1):
+    M, V = logits.shape
+    _lib.call('tt_ce_bwd', _ptr(logits), c_ll(logits.stride(0)), _ptr(target), _ptr(count),
+              c_int(M), c_int(V), c_int(ignore_index), _ptr(lse), _ptr(scale), _stream())
+    return logits
+
+
+def loss_finalize(row_loss, ntokens):
+    loss, scale = _f32(1, like=row_loss), _f32(1, like=row_loss)
+    _lib.call('tt_loss_finalize', _ptr(row_loss), c_ll(row_loss.numel()), _ptr(ntokens),
+              _ptr(loss), _ptr(scale), _stream())
+    return loss, scale
+
+
+def adaptive_logprob(head, tails, cutoffs, want_logprobs=True, want_argmax=True):
+    M = head.shape[0]
+    nt = len(cutoffs) - 1
+    lp = _f32(M, cutoffs[-1], like=head) if want_logprobs else None
+    am = torch.empty(M, dtype=torch.int64, device=head.device) if want_argmax else None
+    amlp = _f32(M, like=head) if want_argmax else None
+    tp = (c_void_p * max(nt, 1))(*[t.data_ptr() for t in tails])
+    tl = (c_ll * max(nt, 1))(*[t.stride(0) for t in tails])
+    _lib.call('tt_adaptive_logprob', _ptr(head), c_ll(head.stride(0)), tp, tl,
+              _int_array(cutoffs), c_int(len(cutoffs)), c_int(M), _ptr(lp), _ptr(am), _ptr(amlp),
+              _stream())
+    return lp, am, amlp
+
+
+# --------------------------------------------------------------------------- embedding
+def embed_gather(ids, cutoffs, tables, E, tbc=True):
+    B, T = ids.shape
+    nb = len(cutoffs)
+    out = _f32(B * T, nb * E, like=tables[0])
+    tp = (c_void_p * nb)(*[t.data_ptr() for t in tables])
+    _lib.call('tt_embed_gather', _ptr(ids), c_int(B), c_int(T), c_int(1 if tbc else 0),
+              _int_array(cutoffs), c_int(nb), tp, c_int(E), _ptr(out), _stream())
+    return out
+
+
+def embed_scatter_grad(ids, cutoffs, grads, E, dA, padding_idx=0, tbc=True):
+    B, T = ids.shape
+    nb = len(cutoffs)
+    gp = (c_void_p * nb)(*[(g.data_ptr() if g is not None else 0) for g in grads])
+    _lib.call('tt_embed_scatter_grad', _ptr(ids), c_int(B), c_int(T), c_int(1 if tbc else 0),
+              _int_array(cutoffs), c_int(nb), gp, c_int(E), c_int(padding_idx), _ptr(dA), _stream())
+
+
+def make_positions(ids, pad=1, left_pad=False, start_pos=0, tbc=False):
+    B, T = ids.shape
+    pos = torch.empty((T, B) if tbc else (B, T), dtype=torch.int32, device=ids.device)
+    _lib.call('tt_make_positions', _ptr(ids), c_int(B), c_int(T), c_int(pad),
+              c_int(1 if left_pad else 0), c_int(start_pos), c_int(1 if tbc else 0), _ptr(pos),
+              _stream())
+    return pos
+
+
+def transpose01(x):
+    A, B, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B, A, C), dtype=torch.float32, device=x.device)
+    _lib.call('tt_transpose01', _ptr(x), _ptr(out), c_int(A), c_int(B), c_int(C), _stream())
+    return out
