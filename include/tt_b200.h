@@ -223,6 +223,33 @@ int tt_layer_mix_fwd(const void* hiddens, long long layer_stride, const float* w
 int tt_layer_mix_bwd(const void* hiddens, long long layer_stride, const float* w,
                      const float* dout, int L, long long n, float* dots, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Frozen encoders (inference only, bf16 activations).
+ * ResNet-152, tell/models/resnet.py:92-117 (torchvision Bottleneck, BatchNorm folded into the
+ * conv weights/bias at load time): each convolution = im2col (NHWC) + tt_gemm_bf16_tn whose
+ * epilogue adds the folded bias, the identity branch (residual16) and applies ReLU.
+ */
+/* out[(b,ho,wo), (kh,kw,c)] bf16, K zero-padded to Kp (multiple of 8); in: NHWC bf16. */
+int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int KH, int KW,
+                   int stride, int pad, int Kp, void* stream);
+/* same from the NCHW fp32 input image (first 7x7/2 convolution). */
+int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int W, int C, int KH, int KW,
+                       int stride, int pad, int Kp, void* stream);
+int tt_maxpool3x3s2_nhwc(const void* in, void* out, int B, int H, int W, int C, void* stream);
+int tt_bf16_to_f32(const void* in, float* out, long long n, void* stream);
+/* RoBERTa-large (fairseq hub `roberta.large`, extract_features(return_all_hiddens=True)); call
+ * site transformer_faces_objects.py:352-353.  x = tok[ids] + pos[pad + #non-pad so far];
+ * is_pad [B*S] flags padding rows. */
+int tt_roberta_embed(const long long* ids, const float* tok, const float* pos, float* x,
+                     uint8_t* is_pad, int B, int S, int E, int pad, void* stream);
+/* y16 (bf16) = LayerNorm(x fp32) * gamma + beta; rows with row_zero[r] != 0 are zeroed. */
+int tt_ln_fwd16(const float* x, const float* gamma, const float* beta, void* y16,
+                const uint8_t* row_zero, int N, int E, float eps, void* stream);
+/* Flash self-attention on bf16 tensor cores: qkv [B*S, 3*H*D] (q pre-scaled), mask [B,S] (1 = pad)
+ * -> out [B*S, H*D] bf16.  D must be 64. */
+int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_mask, void* out, int B, int S,
+                       int H, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

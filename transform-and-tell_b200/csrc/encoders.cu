@@ -1,0 +1,443 @@
+// Kernels of the two frozen encoders on the hot path (inference-only, bf16 activations):
+//   ResNet-152 image encoder (tell/models/resnet.py:92-117): NHWC im2col feeding the tcgen05 GEMM
+//     (bias = folded BatchNorm, residual + ReLU in the GEMM epilogue), 3x3/2 max-pool;
+//   RoBERTa-large article encoder (fairseq, called at transformer_faces_objects.py:352-353):
+//     embedding + LayerNorm, fp32->bf16 LayerNorm, flash self-attention on mma.sync bf16 tensor cores.
+#include <mma.h>
+
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+// ------------------------------------------------------------------------------------------ im2col
+// out[(b,ho,wo), (kh,kw,c)] = in[b, ho*s - p + kh, wo*s - p + kw, c]  (zero outside), K padded to Kp.
+// NHWC bf16 input, 8 channels (16 B) per thread.
+__global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                   int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
+                                   int stride, int pad, int Kp) {
+  const int C8 = C >> 3;
+  const int chunks_per_row = Kp >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * chunks_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % chunks_per_row);
+    const long long row = i / chunks_per_row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int tap = ch / C8;
+    if (tap < KH * KW) {
+      const int c8 = ch - tap * C8;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      const int wo = static_cast<int>(row % Wo);
+      const long long t = row / Wo;
+      const int ho = static_cast<int>(t % Ho);
+      const int b = static_cast<int>(t / Ho);
+      const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + hi) * W + wi) * C) + c8);
+    }
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+// First layer: NCHW fp32 image, scalar path (C = 3).  K index = (kh*KW + kw)*C + c.
+__global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                       int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
+                                       int stride, int pad, int Kp) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
+  const int K = KH * KW * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kp);
+    const long long row = i / Kp;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, tap = k / C;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      const int wo = static_cast<int>(row % Wo);
+      const long long t = row / Wo;
+      const int ho = static_cast<int>(t % Ho);
+      const int b = static_cast<int>(t / Ho);
+      const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+        v = __ldg(in + ((static_cast<long long>(b) * C + c) * H + hi) * W + wi);
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// 3x3 stride-2 pad-1 max pool, NHWC bf16, 8 channels per thread (resnet.py:98 maxpool).
+__global__ void maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in,
+                                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
+                                         int Ho, int Wo) {
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * 2 - 1 + kh;
+      if (hi < 0 || hi >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * 2 - 1 + kw;
+        if (wi < 0 || wi >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + hi) * W + wi) * C) + c8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m[2 * j] = fmaxf(m[2 * j], __low2float(h2[j]));
+          m[2 * j + 1] = fmaxf(m[2 * j + 1], __high2float(h2[j]));
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                   long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm -> bf16
+// y16 = LN(x) * gamma + beta, optionally zeroing rows flagged in row_zero (padding positions of the
+// RoBERTa embedding output).  One warp per row.
+__global__ void ln_fwd16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                const uint8_t* __restrict__ row_zero, int N, int E, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int E4 = E >> 2;
+  for (int r = warp_global; r < N; r += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E);
+    float s = 0.f;
+    for (int c = lane; c < E4; c += 32) {
+      const float4 v = __ldg(xr + c);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mu = warp_sum(s) / E;
+    float ss = 0.f;
+    for (int c = lane; c < E4; c += 32) {
+      const float4 v = __ldg(xr + c);
+      const float a = v.x - mu, b = v.y - mu, d = v.z - mu, e = v.w - mu;
+      ss += (a * a + b * b) + (d * d + e * e);
+    }
+    const float rs = rsqrtf(warp_sum(ss) / E + eps);
+    const float keep = (row_zero && row_zero[r]) ? 0.f : 1.f;
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(r) * E);
+    for (int c = lane; c < E4; c += 32) {
+      const float4 v = __ldg(xr + c);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(keep * ((v.x - mu) * rs * g.x + bt.x),
+                                                keep * ((v.y - mu) * rs * g.y + bt.y));
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(keep * ((v.z - mu) * rs * g.z + bt.z),
+                                                keep * ((v.w - mu) * rs * g.w + bt.w));
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      yr[c] = u;
+    }
+  }
+}
+
+// RoBERTa embedding sum: x[r,:] = tok[ids[r]] + pos[position(r)], positions = pad+1+index for non-pad
+// tokens (learned positional embedding, fairseq utils.make_positions), pad rows flagged for zeroing.
+__global__ void roberta_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                                     const float* __restrict__ pos, float* __restrict__ x,
+                                     uint8_t* __restrict__ is_pad, int B, int S, int E4, int pad) {
+  const int r = blockIdx.x;
+  const int b = r / S, t = r - b * S;
+  const long long id = ids[r];
+  // position = pad + (number of non-pad tokens in ids[b, 0..t]) for non-pad tokens (cumsum form)
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int j = threadIdx.x; j <= t; j += blockDim.x) c += ids[static_cast<long long>(b) * S + j] != pad;
+  atomicAdd(&cnt, c);
+  __syncthreads();
+  const bool real = id != pad;
+  const int p = real ? pad + cnt : pad;
+  if (threadIdx.x == 0) is_pad[r] = real ? 0 : 1;
+  const float4* tr = reinterpret_cast<const float4*>(tok) + id * E4;
+  const float4* pr = reinterpret_cast<const float4*>(pos) + static_cast<long long>(p) * E4;
+  float4* xr = reinterpret_cast<float4*>(x) + static_cast<long long>(r) * E4;
+  for (int j = threadIdx.x; j < E4; j += blockDim.x) {
+    const float4 a = __ldg(tr + j), q = __ldg(pr + j);
+    xr[j] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ flash self-attention
+// qkv [B*S, 3E] bf16 (q pre-scaled), key padding mask [B,S]; out [B*S, E] bf16.  D = 64.
+// CTA = 64 queries (4 warps x 16 rows) of one (b,h); loop over 64-key tiles; S = QK^T and O += PV on
+// mma.sync.m16n8k16 bf16 with fp32 accumulation, online softmax in registers.
+constexpr int FA_BM = 64, FA_BN = 64, FA_D = 64, FA_LD = FA_D + 8;  // +8 bf16 pad: conflict-free ldmatrix
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                            const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                                  const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(128)
+flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ mask,
+                       __nv_bfloat16* __restrict__ out, int B, int S, int H) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[FA_BM][FA_LD];
+  __shared__ __align__(16) __nv_bfloat16 sK[FA_BN][FA_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[FA_BN][FA_LD];
+  __shared__ float sMask[FA_BN];
+  const int E = H * FA_D;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int q0 = blockIdx.x * FA_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const long long ld = 3LL * E;
+  const __nv_bfloat16* qbase = qkv + static_cast<long long>(b) * S * ld + h * FA_D;
+  const __nv_bfloat16* kbase = qbase + E;
+  const __nv_bfloat16* vbase = qbase + 2 * E;
+
+  // Q tile -> smem (rows beyond S are zero)
+  for (int i = threadIdx.x; i < FA_BM * (FA_D / 8); i += blockDim.x) {
+    const int r = i / (FA_D / 8), c8 = i % (FA_D / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < S) v = __ldg(reinterpret_cast<const uint4*>(qbase + (q0 + r) * ld) + c8);
+    *reinterpret_cast<uint4*>(&sQ[r][c8 * 8]) = v;
+  }
+  __syncthreads();
+  // Q fragments for this warp's 16 rows: 4 k-steps of 16
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int row = warp * 16 + (lane & 15);
+    const int col = ks * 16 + (lane >> 4) * 8;
+    ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], &sQ[row][col]);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int j0 = 0; j0 < S; j0 += FA_BN) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < FA_BN * (FA_D / 8); i += blockDim.x) {
+      const int r = i / (FA_D / 8), c8 = i % (FA_D / 8);
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (j0 + r < S) {
+        kv = __ldg(reinterpret_cast<const uint4*>(kbase + (j0 + r) * ld) + c8);
+        vv = __ldg(reinterpret_cast<const uint4*>(vbase + (j0 + r) * ld) + c8);
+      }
+      *reinterpret_cast<uint4*>(&sK[r][c8 * 8]) = kv;
+      *reinterpret_cast<uint4*>(&sV[r][c8 * 8]) = vv;
+    }
+    for (int i = threadIdx.x; i < FA_BN; i += blockDim.x) {
+      const int j = j0 + i;
+      sMask[i] = (j < S && !(mask && mask[static_cast<long long>(b) * S + j])) ? 0.f : -INFINITY;
+    }
+    __syncthreads();
+    // S = Q K^T : 8 n-tiles of 8 keys
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // pairs of n-tiles
+        uint32_t b0, b1, b2, b3;
+        const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(b0, b1, b2, b3, &sK[row][col]);
+        mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+      }
+    }
+    // mask + online softmax (rows g and g+8 of the warp's 16)
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float mk0 = sMask[n * 8 + 2 * tg], mk1 = sMask[n * 8 + 2 * tg + 1];
+      s[n][0] += mk0; s[n][1] += mk1; s[n][2] += mk0; s[n][3] += mk1;
+      tm0 = fmaxf(tm0, fmaxf(s[n][0], s[n][1]));
+      tm1 = fmaxf(tm1, fmaxf(s[n][2], s[n][3]));
+    }
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+    const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
+    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mn0);
+    const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mn1);
+    const float base0 = (mn0 == -INFINITY) ? 0.f : mn0, base1 = (mn1 == -INFINITY) ? 0.f : mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];  // P as A fragments: k-step kk covers keys kk*16..kk*16+15 = n-tiles 2kk, 2kk+1
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = __expf(s[n][0] - base0), p1 = __expf(s[n][1] - base0);
+      const float p2 = __expf(s[n][2] - base1), p3 = __expf(s[n][3] - base1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      const int kk = n >> 1, hi = n & 1;
+      pf[kk][hi * 2 + 0] = pack_bf16(p0, p1);
+      pf[kk][hi * 2 + 1] = pack_bf16(p2, p3);
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
+    }
+    // O += P V : k = keys (4 k-steps), n = dims (8 n-tiles), V row-major -> transposed ldmatrix
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(b0, b1, b2, b3, &sV[row][col]);
+        mma_bf16_16816(o[2 * np], pf[kk], b0, b1);
+        mma_bf16_16816(o[2 * np + 1], pf[kk], b2, b3);
+      }
+    }
+  }
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = h * FA_D + n * 8 + 2 * tg;
+    if (r0 < S)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * S + r0) * E + col) =
+          pack_bf16(o[n][0] * i0, o[n][1] * i0);
+    if (r1 < S)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * S + r1) * E + col) =
+          pack_bf16(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
+static inline int flat_grid3(long long n) {
+  long long g = ceil_div_ll(n, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, int C, int KH, int KW,
+                              int stride, int pad, int Kp, void* stream) {
+  TT_REQUIRE(in && out, "tt_im2col_nhwc: null pointer");
+  TT_REQUIRE(C % 8 == 0 && Kp % 8 == 0 && Kp >= KH * KW * C, "tt_im2col_nhwc: C, Kp must be multiples of 8");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
+  if (total <= 0) return TT_OK;
+  im2col_nhwc_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+      Ho, Wo, KH, KW, stride, pad, Kp);
+  return check_launch("im2col_nhwc_kernel");
+}
+
+extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int W, int C, int KH,
+                                  int KW, int stride, int pad, int Kp, void* stream) {
+  TT_REQUIRE(in && out, "tt_im2col_nchw_f32: null pointer");
+  TT_REQUIRE(Kp >= KH * KW * C, "tt_im2col_nchw_f32: Kp too small");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
+  if (total <= 0) return TT_OK;
+  im2col_nchw_f32_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
+  return check_launch("im2col_nchw_f32_kernel");
+}
+
+extern "C" int tt_maxpool3x3s2_nhwc(const void* in, void* out, int B, int H, int W, int C,
+                                    void* stream) {
+  TT_REQUIRE(in && out, "tt_maxpool3x3s2_nhwc: null pointer");
+  TT_REQUIRE(C % 8 == 0, "tt_maxpool3x3s2_nhwc: C must be a multiple of 8");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  if (total <= 0) return TT_OK;
+  maxpool3x3s2_nhwc_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+      Ho, Wo);
+  return check_launch("maxpool3x3s2_nhwc_kernel");
+}
+
+extern "C" int tt_bf16_to_f32(const void* in, float* out, long long n, void* stream) {
+  TT_REQUIRE(in && out, "tt_bf16_to_f32: null pointer");
+  if (n <= 0) return TT_OK;
+  bf16_to_f32_kernel<<<flat_grid3(n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), out, n);
+  return check_launch("bf16_to_f32_kernel");
+}
+
+extern "C" int tt_ln_fwd16(const float* x, const float* gamma, const float* beta, void* y16,
+                           const uint8_t* row_zero, int N, int E, float eps, void* stream) {
+  TT_REQUIRE(x && gamma && beta && y16, "tt_ln_fwd16: null pointer");
+  TT_REQUIRE(E % 4 == 0, "tt_ln_fwd16: E must be a multiple of 4");
+  if (N <= 0) return TT_OK;
+  long long g = ceil_div_ll(N, 8);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (g > cap) g = cap;
+  ln_fwd16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(
+      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y16), row_zero, N, E, eps);
+  return check_launch("ln_fwd16_kernel");
+}
+
+extern "C" int tt_roberta_embed(const long long* ids, const float* tok, const float* pos, float* x,
+                                uint8_t* is_pad, int B, int S, int E, int pad, void* stream) {
+  TT_REQUIRE(ids && tok && pos && x && is_pad, "tt_roberta_embed: null pointer");
+  TT_REQUIRE(E % 4 == 0, "tt_roberta_embed: E must be a multiple of 4");
+  if (B * S <= 0) return TT_OK;
+  roberta_embed_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>(ids, tok, pos, x, is_pad, B, S, E / 4,
+                                                               pad);
+  return check_launch("roberta_embed_kernel");
+}
+
+extern "C" int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_mask, void* out, int B,
+                                  int S, int H, int D, void* stream) {
+  TT_REQUIRE(qkv && out, "tt_flash_self_attn: null pointer");
+  TT_REQUIRE(D == FA_D, "tt_flash_self_attn: head_dim must be %d (got %d)", FA_D, D);
+  if (B <= 0 || S <= 0) return TT_OK;
+  dim3 grid(ceil_div(S, FA_BM), B * H);
+  flash_self_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), key_padding_mask,
+      reinterpret_cast<__nv_bfloat16*>(out), B, S, H);
+  return check_launch("flash_self_attn_kernel");
+}

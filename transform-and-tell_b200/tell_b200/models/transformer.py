@@ -1,0 +1,213 @@
+"""Top-level caption models of tell/models/transformer_faces_objects.py and
+tell/models/transformer_flattened.py on the B200 kernels.
+
+Same registry names, constructor kwargs, forward()/generate() signatures and output dict keys as
+the reference.  The two frozen encoders cannot be downloaded here (no network), so they are
+constructed randomly initialised (or injected through the extra `resnet=` / `roberta=` kwargs);
+their state dicts use torchvision's / fairseq's key names so real checkpoints load unchanged."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .. import ops
+from ..modules import Criterion
+from ..registry import Registrable
+from .decoder import Decoder
+from .resnet import resnet152
+from .roberta import RobertaEncoder
+
+
+class Model(nn.Module, Registrable):
+    pass
+
+
+class _CaptionModelBase(Model):
+    USES_FACES = True
+    USES_OBJECTS = True
+    USES_IMAGE = True
+
+    def __init__(self, vocab, decoder, criterion, evaluate_mode=False, attention_dim=1024,
+                 hidden_size=1024, dropout=0.1, vocab_size=50264, model_name='roberta-base',
+                 namespace='bpe', index='roberta', padding_value=1, use_context=True,
+                 sampling_topk=1, sampling_temp=1.0, weigh_bert=False, initializer=None,
+                 resnet=None, roberta=None):
+        super().__init__()
+        self.decoder = decoder
+        self.criterion = criterion
+        self.index = index
+        self.namespace = namespace
+        self.resnet = resnet if resnet is not None else resnet152()
+        self.roberta = roberta if roberta is not None else RobertaEncoder()
+        self.use_context = use_context
+        self.padding_idx = padding_value
+        self.evaluate_mode = evaluate_mode
+        self.sampling_topk = sampling_topk
+        self.sampling_temp = sampling_temp
+        self.weigh_bert = weigh_bert
+        n_hidden = self.roberta.n_layers + 1
+        if weigh_bert:
+            self.bert_weight = nn.Parameter(torch.empty(n_hidden).uniform_())
+        for p in self.resnet.parameters():           # `no_grad: ^resnet|^roberta` (config.yaml:150)
+            p.requires_grad_(False)
+        for p in self.roberta.parameters():
+            p.requires_grad_(False)
+        self.n_batches = 0
+        self.n_samples = 0
+        self.gen_len = 100
+
+    @classmethod
+    def _from_params(cls, params, **extras):
+        params = dict(params)
+        decoder = Decoder.from_params(params.pop('decoder'))
+        criterion = Criterion.from_params(params.pop('criterion'))
+        params.pop('initializer', None)
+        return cls(vocab=None, decoder=decoder, criterion=criterion, **params, **extras)
+
+    # ------------------------------------------------------------------ _forward (:311-397)
+    def _forward(self, context, image, caption, face_embeds=None, obj_embeds=None):
+        caption_ids = caption[self.index]
+        target_ids = caption_ids[:, 1:].contiguous()
+        caption_ids = caption_ids[:, :-1].contiguous()
+        caption[self.index] = caption_ids            # the reference mutates the dict (:329)
+        article_ids = context[self.index]
+        B, S = article_ids.shape
+        contexts = {}
+        if self.USES_IMAGE:
+            feats = self.resnet.features_nhwc(image)                 # [B,7,7,2048] bf16 == [B,49,2048]
+            P = feats.shape[1] * feats.shape[2]
+            X_image = ops.bf16_to_f32(feats).view(B, P, feats.shape[3])
+            contexts['image'] = Fn.Transpose01Fn.apply(X_image)      # [49,B,2048]
+            contexts['image_mask'] = torch.zeros((B, P), dtype=torch.bool, device=image.device)
+        hid, is_pad = self.roberta.all_hiddens(article_ids)          # bf16 [25, B*S, E]
+        if self.weigh_bert:
+            X_article = Fn.LayerMixFn.apply(hid, self.bert_weight)
+        else:
+            X_article = ops.bf16_to_f32(hid[-1])
+        E = X_article.shape[-1]
+        contexts['article'] = Fn.Transpose01Fn.apply(X_article.view(B, S, E))
+        contexts['article_mask'] = article_ids == self.padding_idx
+        contexts['sections'] = None
+        contexts['sections_mask'] = None
+        if self.USES_FACES:
+            face_masks = ops.nan_rows_(face_embeds)                  # in place, like the reference
+            contexts['faces'] = Fn.Transpose01Fn.apply(face_embeds) if face_embeds.shape[2] > 0 \
+                else face_embeds.transpose(0, 1)
+            contexts['faces_mask'] = face_masks
+        if self.USES_OBJECTS:
+            obj_masks = ops.nan_rows_(obj_embeds)
+            contexts['obj'] = Fn.Transpose01Fn.apply(obj_embeds) if obj_embeds.shape[2] > 0 \
+                else obj_embeds.transpose(0, 1)
+            contexts['obj_mask'] = obj_masks
+        return caption_ids, target_ids, contexts
+
+    # ------------------------------------------------------------------ forward (:67-140)
+    def forward(self, context, image, caption, face_embeds=None, obj_embeds=None, metadata=None,
+                names=None, attn_idx=None):
+        caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
+                                                          obj_embeds)
+        X, _ = self.decoder.forward_tbc(caption, contexts)           # [T,B,E], no transpose needed
+        T, B, E = X.shape
+        # the loss is a sum over tokens, so (t,b) order with the target transposed alike is exact
+        tgt_tb = target_ids.t().contiguous()
+        loss, ntokens = self.criterion.fused(self.decoder.adaptive_softmax, (X.view(T * B, E), None),
+                                             tgt_tb)
+        output_dict = {'loss': loss.view(()), 'sample_size': ntokens}
+        if not self.training and self.evaluate_mode:
+            _, gen_ids, attns = self._generate(caption_ids, contexts, attn_idx)
+            output_dict['captions'] = [m['caption'] for m in metadata] if metadata else None
+            output_dict['metadata'] = metadata
+            output_dict['attns'] = attns
+            output_dict['gen_ids'] = gen_ids.cpu().numpy()
+        self.n_samples += caption_ids.shape[0]
+        self.n_batches += 1
+        return output_dict
+
+    # ------------------------------------------------------------------ _generate (:399-494)
+    @torch.no_grad()
+    def _generate(self, caption_ids, contexts, attn_idx=None, early_exit=True, sync_every=8):
+        """Greedy decode (sampling_topk=1: multinomial over one candidate == argmax).  Device
+        resident: all rows stay in the batch, finished rows are masked (emit pad / log-prob 0),
+        projected contexts are cached, and the host is consulted only every `sync_every` steps.
+        Emits the same token_ids [B, 1+n] / log_probs [B, n] matrices as the reference's
+        compacting loop."""
+        if self.sampling_topk != 1:
+            raise NotImplementedError('only greedy decoding (sampling_topk=1) is implemented')
+        was_training = self.decoder.training
+        self.decoder.eval()
+        need_attn = [l.need_attn for l in self.decoder.layers]
+        for l in self.decoder.layers:
+            l.need_attn = False
+        eos, pad = 2, self.padding_idx
+        B = caption_ids.shape[0]
+        dev = caption_ids.device
+        state = {}
+        prev = caption_ids[:, 0:1].contiguous()
+        active = prev[:, 0] != eos
+        ids_cols, lp_cols, any_active = [prev], [], []
+        n_steps = 0
+        for i in range(self.gen_len):
+            X, _ = self.decoder.forward_tbc({self.index: prev}, contexts, incremental_state=state)
+            tok, lp = self.decoder.adaptive_softmax.greedy(X.view(B, -1))
+            lp = lp / self.sampling_temp
+            tok = torch.where(active, tok, torch.full_like(tok, pad))
+            lp = torch.where(active, lp, torch.zeros_like(lp))
+            ids_cols.append(tok.view(B, 1))
+            lp_cols.append(lp.view(B, 1))
+            active = active & (tok != eos)
+            any_active.append(active.any())
+            prev = tok.view(B, 1)
+            n_steps += 1
+            if early_exit and (i + 1) % sync_every == 0 and not bool(any_active[-1]):
+                break
+        if early_exit:
+            flags = torch.stack(any_active).cpu()
+            dead = (~flags).nonzero()
+            if dead.numel() > 0:
+                n_steps = int(dead[0]) + 1       # the reference stops after the first all-done step
+        token_ids = torch.cat(ids_cols[:1 + n_steps], dim=1)
+        log_probs = torch.cat(lp_cols[:n_steps], dim=1)
+        for l, n in zip(self.decoder.layers, need_attn):
+            l.need_attn = n
+        self.decoder.train(was_training)
+        return log_probs, token_ids, []
+
+    # ------------------------------------------------------------------ generate (:142-309)
+    @torch.no_grad()
+    def generate(self, context, image, face_embeds=None, obj_embeds=None, metadata=None,
+                 names=None, attn_idx=None):
+        """Demo entry point: same inputs as the reference; returns generated ids and log-probs
+        (the word-level attention post-processing of :159-304 is host-side string work, out of
+        scope)."""
+        B = image.shape[0]
+        caption = {self.index: context[self.index].new_zeros(B, 2)}
+        caption_ids, _, contexts = self._forward(context, image, caption, face_embeds, obj_embeds)
+        log_probs, gen_ids, _ = self._generate(caption_ids, contexts, attn_idx)
+        return {'generated_indices': gen_ids, 'log_probs': log_probs, 'metadata': metadata}
+
+    def get_metrics(self, reset=False):
+        metrics = {'_n_batches': self.n_batches, '_n_samples': self.n_samples}
+        if reset:
+            self.n_batches = 0
+            self.n_samples = 0
+        return metrics
+
+
+@Model.register('transformer_faces_objects')
+class TransformerFacesObjectModel(_CaptionModelBase):
+    pass
+
+
+@Model.register('transformer_faces')
+class TransformerFacesModel(_CaptionModelBase):
+    USES_OBJECTS = False
+
+
+@Model.register('transformer_flattened')
+class TransformerFlattenedModel(_CaptionModelBase):
+    """transformer_flattened.py:23-238 (used by 4_no_image .. 7_*): no faces / objects.  As in the
+    reference, the ResNet still runs even when the decoder ignores the image
+    (transformer_flattened.py:49,185)."""
+    USES_FACES = False
+    USES_OBJECTS = False

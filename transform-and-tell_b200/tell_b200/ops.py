@@ -397,3 +397,63 @@ def transpose01(x):
     out = torch.empty((B, A, C), dtype=torch.float32, device=x.device)
     _lib.call('tt_transpose01', _ptr(x), _ptr(out), c_int(A), c_int(B), c_int(C), _stream())
     return out
+
+
+# --------------------------------------------------------------------------- frozen encoders
+def im2col_nhwc(x, KH, KW, stride, pad):
+    """x [B,H,W,C] bf16 -> ([B*Ho*Wo, Kp] bf16, Ho, Wo)."""
+    B, H, W, C = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    Kp = (KH * KW * C + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_im2col_nhwc', _ptr(x), _ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
+              c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(Kp), _stream())
+    return out, Ho, Wo
+
+
+def im2col_nchw_f32(x, KH, KW, stride, pad, Kp):
+    B, C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    out = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_im2col_nchw_f32', _ptr(x), _ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
+              c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(Kp), _stream())
+    return out, Ho, Wo
+
+
+def maxpool3x3s2_nhwc(x):
+    B, H, W, C = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_maxpool3x3s2_nhwc', _ptr(x), _ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
+              _stream())
+    return out
+
+
+def bf16_to_f32(x):
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _lib.call('tt_bf16_to_f32', _ptr(x), _ptr(out), c_ll(x.numel()), _stream())
+    return out
+
+
+def roberta_embed(ids, tok, pos, pad=1):
+    B, S = ids.shape
+    E = tok.shape[1]
+    x = _f32(B * S, E, like=tok)
+    is_pad = torch.empty(B * S, dtype=torch.uint8, device=ids.device)
+    _lib.call('tt_roberta_embed', _ptr(ids), _ptr(tok), _ptr(pos), _ptr(x), _ptr(is_pad), c_int(B),
+              c_int(S), c_int(E), c_int(pad), _stream())
+    return x, is_pad
+
+
+def ln_fwd16(x, gamma, beta, out16, row_zero=None, eps=1e-5):
+    N, E = x.shape
+    _lib.call('tt_ln_fwd16', _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out16), _ptr(row_zero),
+              c_int(N), c_int(E), c_float(eps), _stream())
+    return out16
+
+
+def flash_self_attn(qkv, mask, B, S, H, D):
+    out = torch.empty((B * S, H * D), dtype=torch.bfloat16, device=qkv.device)
+    _lib.call('tt_flash_self_attn', _ptr(qkv), _ptr(mask), _ptr(out), c_int(B), c_int(S), c_int(H),
+              c_int(D), _stream())
+    return out

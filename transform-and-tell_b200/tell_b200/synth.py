@@ -177,3 +177,71 @@ def decoder_inputs(cfg, B, T, S, F=4, O=16, P=49, seed=1234):
         contexts['obj'] = o.transpose(0, 1).contiguous()
         contexts['obj_mask'] = m
     return cap, contexts
+
+
+def resnet_state_dict(layers=(3, 8, 36, 3), seed=0):
+    """torchvision-keyed ResNet weights with non-trivial BatchNorm statistics."""
+    rs = np.random.RandomState(seed)
+
+    def n(*shape, std=1.0):
+        return torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + '.weight'] = n(cout, cin, k, k, std=math.sqrt(2.0 / (cin * k * k)))
+
+    def bn(name, c, gain=1.0):
+        sd[name + '.weight'] = gain * (1 + 0.1 * n(c))
+        sd[name + '.bias'] = 0.05 * n(c)
+        sd[name + '.running_mean'] = 0.1 * n(c)
+        sd[name + '.running_var'] = torch.from_numpy((0.5 + rs.random_sample(c)).astype(np.float32))
+        sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    conv('conv1', 64, 3, 7)
+    bn('bn1', 64)
+    inplanes = 64
+    for li, (planes, nb) in enumerate(zip((64, 128, 256, 512), layers)):
+        for bi in range(nb):
+            p = 'layer%d.%d.' % (li + 1, bi)
+            stride = 2 if (li > 0 and bi == 0) else 1
+            conv(p + 'conv1', planes, inplanes, 1); bn(p + 'bn1', planes)
+            conv(p + 'conv2', planes, planes, 3); bn(p + 'bn2', planes)
+            conv(p + 'conv3', planes * 4, planes, 1); bn(p + 'bn3', planes * 4, gain=0.5)
+            if bi == 0 and (stride != 1 or inplanes != planes * 4):
+                conv(p + 'downsample.0', planes * 4, inplanes, 1); bn(p + 'downsample.1', planes * 4)
+            inplanes = planes * 4
+    sd['fc.weight'] = n(1000, 2048, std=0.01)
+    sd['fc.bias'] = torch.zeros(1000)
+    return sd
+
+
+def roberta_state_dict(n_layers, embed_dim, ffn, vocab, max_pos, seed=0):
+    """fairseq-keyed (decoder.sentence_encoder.*) RoBERTa encoder weights."""
+    rs = np.random.RandomState(seed)
+
+    def n(*shape, std=1.0):
+        return torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+
+    E = embed_dim
+    p = 'decoder.sentence_encoder.'
+    sd = {p + 'embed_tokens.weight': n(vocab, E, std=0.5),
+          p + 'embed_positions.weight': n(max_pos, E, std=0.5),
+          p + 'emb_layer_norm.weight': 1 + 0.1 * n(E), p + 'emb_layer_norm.bias': 0.05 * n(E)}
+    sd[p + 'embed_tokens.weight'][1] = 0
+    sd[p + 'embed_positions.weight'][1] = 0
+    for i in range(n_layers):
+        lp = p + 'layers.%d.' % i
+        sd[lp + 'self_attn.in_proj_weight'] = n(3 * E, E, std=1.0 / math.sqrt(E))
+        sd[lp + 'self_attn.in_proj_bias'] = n(3 * E, std=0.02)
+        sd[lp + 'self_attn.out_proj.weight'] = n(E, E, std=1.0 / math.sqrt(E))
+        sd[lp + 'self_attn.out_proj.bias'] = n(E, std=0.02)
+        sd[lp + 'self_attn_layer_norm.weight'] = 1 + 0.1 * n(E)
+        sd[lp + 'self_attn_layer_norm.bias'] = 0.05 * n(E)
+        sd[lp + 'fc1.weight'] = n(ffn, E, std=1.0 / math.sqrt(E))
+        sd[lp + 'fc1.bias'] = n(ffn, std=0.02)
+        sd[lp + 'fc2.weight'] = n(E, ffn, std=1.0 / math.sqrt(ffn))
+        sd[lp + 'fc2.bias'] = n(E, std=0.02)
+        sd[lp + 'final_layer_norm.weight'] = 1 + 0.1 * n(E)
+        sd[lp + 'final_layer_norm.bias'] = 0.05 * n(E)
+    return sd
