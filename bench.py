@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- caption samples/sec, train forward+backward, NYTimes-shaped synthetic batches.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's sm_100a path)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference algorithm on host cores)
+
+Workload (BASELINE.json configs[1]): full Transform-and-Tell model -- ResNet-152 + RoBERTa-large
+(frozen) + 4-layer DynamicConv decoder with image/article/faces/objects cross-attention + adaptive
+softmax loss -- batch 16 per GPU, caption 50 tokens, article 512 tokens, 4 faces, 16 objects,
+dropout ON, random-init weights of the real architecture, synthetic data.
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'transform-and-tell_b200'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'caption samples/sec (train fwd+bwd)'
+UNIT = 'samples/s'
+# algorithmic work per sample of cfg 2 (decoder fwd+bwd 66.2 + RoBERTa 335 + ResNet 23.1)
+GFLOP_PER_SAMPLE = 424.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['bf16_tflops_sustained']), float(p['hbm_gbs']), 'measured'
+    except Exception:
+        return 1400.0, 6650.0, 'fallback'
+
+
+# ------------------------------------------------------------------------------------ synthetic batch
+def make_batch(B, T=50, S=512, F=4, O=16, vocab=50265, seed=1234):
+    from tell_b200 import synth
+    rs = np.random.RandomState(seed)
+    cap = synth.caption_batch(B, T + 1, vocab, rs, min_len=20)
+    art = synth.article_batch(B, S, vocab, rs, min_len=S // 2)
+    image = torch.from_numpy(rs.standard_normal((B, 3, 224, 224)).astype(np.float32))
+    faces = synth.nan_padded(B, F, 512, rs, 'faces')
+    objs = synth.nan_padded(B, O, 2048, rs, 'obj')
+    return dict(caption=cap, article=art, image=image, faces=faces, objs=objs)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def build_model(device):
+    from tell_b200.models import (DynamicConvFacesObjectsDecoder, RobertaEncoder,
+                                  TransformerFacesObjectModel, resnet152)
+    from tell_b200.modules import AdaptiveLoss
+    from tell_b200 import synth
+    from tell_b200.testing import build_decoder
+    torch.manual_seed(1234)
+    with torch.device(device):
+        dec = build_decoder(synth.CFG_FULL, DynamicConvFacesObjectsDecoder)
+        model = TransformerFacesObjectModel(None, dec, AdaptiveLoss(1), weigh_bert=True,
+                                            resnet=resnet152(), roberta=RobertaEncoder(),
+                                            vocab_size=50265)
+    # non-degenerate BatchNorm statistics for the random-init ResNet
+    for m in model.resnet.modules():
+        if hasattr(m, 'running_var'):
+            m.running_var.uniform_(0.5, 1.5)
+            m.running_mean.normal_(0, 0.1)
+    return model.to(device).train()
+
+
+def run_b200(args):
+    from tell_b200 import _lib, config
+    from tell_b200.parallel import FlatGradients
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.lib()
+    config.set_precision('bf16')
+    config.manual_seed(1234 + rank)
+    config.enable_device_step(dev)
+    B = args.batch
+    model = build_model(dev)
+    # the flat gradient buffer only exists where there is a collective to feed
+    fg = FlatGradients(model.parameters(), attach=False) if world > 1 else None
+    params = [p for p in model.parameters() if p.requires_grad]
+    host = make_batch(B, seed=1234 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    static = {k: v.to(dev) for k, v in host.items()}        # buffers the step reads (and mutates)
+    pristine = {k: v.clone() for k, v in static.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.zeros(1).pin_memory()
+    out_loss = torch.zeros(1, device=dev)
+
+    def fwd_bwd():
+        for p in params:          # backward then WRITES each gradient (no accumulate kernels)
+            p.grad = None
+        config.advance_device_step()
+        out = model(context={'roberta': static['article']}, image=static['image'],
+                    caption={'roberta': static['caption']}, face_embeds=static['faces'],
+                    obj_embeds=static['objs'], metadata=None)
+        out['loss'].backward()
+        out_loss.copy_(out['loss'].detach().view(1))
+        if fg is not None:
+            fg.pack()             # one batched copy into the all-reduce buffer
+
+    def restore():
+        for k in ('faces', 'objs'):       # forward() zeroes NaN rows in place, like the reference
+            static[k].copy_(pristine[k])
+
+    # ---- warm-up (eager): lazy weight folding, cudaFuncSetAttribute, allocator pools
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup) if args.no_graph else 3):
+            restore()
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(stream)
+    torch.cuda.synchronize()
+    # ---- count launches of OUR kernels in one step, then capture the step in a CUDA graph
+    _lib.reset_launch_count()
+    restore()
+    fwd_bwd()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count()
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        restore()
+        with torch.cuda.graph(graph):
+            fwd_bwd()
+        torch.cuda.synchronize()
+
+    def step(e2e):
+        if e2e:
+            for k in static:
+                static[k].copy_(pinned[k], non_blocking=True)
+        else:
+            restore()
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
+        if world > 1:
+            fg.allreduce_mean()
+        if e2e:
+            loss_host.copy_(out_loss, non_blocking=True)
+
+    def timed(e2e, steps, warmup):
+        for _ in range(warmup):
+            step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step(e2e)
+        e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_value = timed(False, args.steps, max(3, args.warmup))
+    ms_e2e = timed(True, args.steps, 3)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    loss_val = float(loss_host.item())
+
+    # ---- live per-kernel timing (CUDA events around every C-ABI call, eager, rank 0)
+    roof, breakdown = None, None
+    if rank == 0:
+        _lib.PROFILE, _lib.GEMM_FLOPS[:] = [], []
+        n_prof = 2
+        for _ in range(n_prof):
+            restore()
+            fwd_bwd()
+        torch.cuda.synchronize()
+        agg, total = {}, 0.0
+        for name, s, e in _lib.PROFILE:
+            t = s.elapsed_time(e)
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += t
+            a[1] += 1
+            total += t
+        flops = sum(_lib.GEMM_FLOPS) / n_prof
+        _lib.PROFILE = None
+        gemm_ms = agg['tt_gemm_bf16_tn'][0] / n_prof
+        gemm_calls = agg['tt_gemm_bf16_tn'][1] // n_prof
+        peak_tf, peak_bw, src = peaks()
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_kernel (tcgen05)', 'achieved': round(achieved, 1),
+                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(achieved / peak_tf, 4),
+                'peak_source': src + ' bf16_tflops_sustained', 'traffic': None,
+                'launches_per_step': gemm_calls, 'flop_per_step': flops,
+                'avg_launch_us': round(gemm_ms * 1e3 / max(1, gemm_calls), 2),
+                'share_of_step_kernel_time': round(agg['tt_gemm_bf16_tn'][0] / total, 4)}
+        breakdown = {k: {'ms_per_step': round(v[0] / n_prof, 4), 'launches': v[1] // n_prof}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_tf, _, src = peaks()
+    value = world * B / (ms_value * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+    line = {
+        'metric': METRIC, 'value': round(value, 2), 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': round(ms_value, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic', 'impl': 'b200',
+        'config': {'workload': 'cfg2: full transform-and-tell (ResNet-152 + RoBERTa-large + 4-layer '
+                               'DynamicConv decoder, image+article+faces+objects), batch 16/GPU, '
+                               'T=50, S=512, F=4, O=16, dropout on, fwd+bwd (no optimizer step)',
+                   'global_batch': world * B, 'parallelism': 'dp%d' % world,
+                   'cuda_graph': graph is not None,
+                   'l2': 'working set per step (weights + activations, >2 GB) exceeds the 126 MB L2'},
+        'e2e': {'value': round(e2e, 2), 'unit': UNIT, 'ms_per_step': round(ms_e2e, 4),
+                'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches_per_step * args.steps),
+        'gpu_launches_per_step': int(launches_per_step),
+        'loss': loss_val,
+        'step_roofline': {'gflop_per_sample': GFLOP_PER_SAMPLE,
+                          'achieved_tflops': round(value / world * GFLOP_PER_SAMPLE / 1e3, 1),
+                          'frac_of_peak': round(value / world * GFLOP_PER_SAMPLE / 1e3 / peak_tf, 4),
+                          'peak_source': src},
+        'roofline': roof, 'kernel_breakdown': breakdown,
+        'clocks': sampler.summary() if sampler else None,
+    }
+    if not args.skip_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_baseline(budget_s=25.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def _oracle_state(seed=0):
+    """Random-init full-size weights for the oracle (reference-shaped state dicts)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from tell_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    dec = synth.decoder_state_dict(synth.CFG_FULL, seed=seed)
+    rob = {}
+    E, F, p = 1024, 4096, 'decoder.sentence_encoder.'
+    rob[p + 'embed_tokens.weight'] = torch.randn(50265, E, generator=g) * 0.02
+    rob[p + 'embed_positions.weight'] = torch.randn(514, E, generator=g) * 0.02
+    rob[p + 'emb_layer_norm.weight'] = torch.ones(E)
+    rob[p + 'emb_layer_norm.bias'] = torch.zeros(E)
+    for i in range(24):
+        lp = p + 'layers.%d.' % i
+        for name, shape in (('self_attn.in_proj_weight', (3 * E, E)), ('self_attn.out_proj.weight', (E, E)),
+                            ('fc1.weight', (F, E)), ('fc2.weight', (E, F))):
+            rob[lp + name] = torch.randn(*shape, generator=g) * 0.02
+        for name, n in (('self_attn.in_proj_bias', 3 * E), ('self_attn.out_proj.bias', E),
+                        ('fc1.bias', F), ('fc2.bias', E)):
+            rob[lp + name] = torch.zeros(n)
+        for ln in ('self_attn_layer_norm', 'final_layer_norm'):
+            rob[lp + ln + '.weight'] = torch.ones(E)
+            rob[lp + ln + '.bias'] = torch.zeros(E)
+    res = synth.resnet_state_dict((3, 8, 36, 3), seed=seed)
+    return dec, rob, res
+
+
+def _oracle_step(batch, dec, rob, res, bert_weight, ocfg):
+    """One reference train step (forward + loss.backward(), no optimizer) on the CPU oracle:
+    transformer_faces_objects.py:67-90 with frozen encoders under no_grad."""
+    import restate
+    with torch.no_grad():
+        feats = restate.resnet152_forward(batch['image'], res, prefix='')
+        hid = restate.roberta_forward(batch['article'], rob, 24, 16, prefix='')
+    ctx = restate.build_contexts(feats, hid, bert_weight, batch['article'], batch['faces'].clone(),
+                                 batch['objs'].clone())
+    inp, tgt = restate.shift_caption(batch['caption'])
+    out, _ = restate.decoder_forward(inp, ctx, dec, ocfg)
+    _, _, loss = restate.adaptive_loss(out, tgt, dec, ocfg['cutoffs'])
+    loss.backward()
+    return float(loss.detach())
+
+
+def _prepare_oracle(B):
+    from tell_b200 import synth
+    dec, rob, res = _oracle_state()
+    pre = 'embedder.token_embedder_adaptive.embeddings.'
+    for k, v in dec.items():
+        if v.is_floating_point() and 'weights' not in k and 'version' not in k and '_float' not in k:
+            dec[k] = v.requires_grad_(True)
+    dec['adaptive_softmax.head.word_proj.weight'] = dec[pre + '0.0.weight']
+    for i in range(2):
+        dec['adaptive_softmax.tail.%d.2.weight' % i] = dec[pre + '%d.0.weight' % (i + 1)]
+    bw = torch.rand(25, requires_grad=True)
+    return dec, rob, res, bw, synth.oracle_cfg(synth.CFG_FULL), make_batch(B)
+
+
+def cpu_baseline(budget_s=25.0, B=2):
+    """The oracle (kind 'port': the reference modules are Python and cannot travel to the GPU box;
+    oracle/restate.py is pinned to them by golden vectors) timed on the host cores on a bounded
+    sample of the same workload."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dec, rob, res, bw, ocfg, batch = _prepare_oracle(B)
+    t0 = time.time()
+    _oracle_step(batch, dec, rob, res, bw, ocfg)          # warm-up
+    warm = time.time() - t0
+    n = max(1, min(5, int((budget_s - warm) / max(warm, 1e-3))))
+    t0 = time.time()
+    for _ in range(n):
+        _oracle_step(batch, dec, rob, res, bw, ocfg)
+    dt = (time.time() - t0) / n
+    return {'value': round(B / dt, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d timed step(s) of batch %d (same shapes: T=50, S=512, F=4, O=16; fp32; '
+                      'eval-free dropout-off oracle; %.1f s/step)' % (n, B, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 2
+    dec, rob, res, bw, ocfg, batch = _prepare_oracle(B)
+    budget = 150.0
+    t0 = time.time()
+    _oracle_step(batch, dec, rob, res, bw, ocfg)
+    first = time.time() - t0
+    warm = max(0, min(args.warmup, int(0.2 * budget / max(first, 1e-3))) - 1)
+    for _ in range(warm):
+        _oracle_step(batch, dec, rob, res, bw, ocfg)
+    steps = max(1, min(args.steps, int(0.7 * budget / max(first, 1e-3))))
+    t0 = time.time()
+    for _ in range(steps):
+        _oracle_step(batch, dec, rob, res, bw, ocfg)
+    dt = (time.time() - t0) / steps
+    value = B / dt
+    sample = ('%d timed step(s) of batch %d per step (of %d requested), T=50, S=512, F=4, O=16, '
+              'fp32, all %d host threads' % (steps, B, args.steps, cores))
+    line = {'metric': METRIC, 'value': round(value, 4), 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warm + 1, 'ms_per_step': round(dt * 1e3, 2),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'cfg2: full transform-and-tell (ResNet-152 + RoBERTa-large + 4-layer '
+                                   'DynamicConv decoder), reference algorithm (oracle port) on host CPU, '
+                                   'batch %d per step, fwd+bwd' % B},
+            'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': round(value, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -9,6 +9,7 @@
 // dK/dV: grid over key tiles) that recompute P from q, k and lse -- no atomics except for the
 // shared bias_k / bias_v rows.
 // Layout: q/out [T,B,E], k/v [S,B,E], head h = columns [h*D, (h+1)*D), D = 64 (or 16/32 in tests).
+#include "attention_args.cuh"
 #include "common.cuh"
 #include "runtime.h"
 
@@ -18,32 +19,6 @@ constexpr int AT_KT = 64;     // keys per tile
 constexpr int AT_QT = 16;     // queries per CTA in fwd / dq kernels (4 per warp)
 constexpr int AT_THREADS = 128;
 constexpr int AT_QW = 4;      // queries per warp
-
-struct AttnArgs {
-  const float* q;
-  const float* k;
-  const float* v;
-  const float* bias_k;  // [E] or null
-  const float* bias_v;
-  const uint8_t* mask;  // [B,S] 1 = padding, or null
-  float* out;           // [T,B,E]
-  float* lse;           // [B,H,T]
-  int T, B, S, H;
-  long long ldq, ldkv, ldo;  // row strides (elements) of q/dq, k/v/dk/dv, out/dout
-  int zero_row;         // add_zero_attn
-  float p_drop;
-  unsigned long long seed;
-  const unsigned long long* step_ptr;
-  // backward
-  const float* dout;
-  float* dq;
-  float* dk;
-  float* dv;
-  float* dbias_k;
-  float* dbias_v;
-  // head-averaged weights (eval): [B,T,L]
-  float* avg_w;
-};
 
 // Key tile loader: rows j0..j0+63 of the extended key sequence into smem (pitch D+1).
 template <int D>

@@ -1,0 +1,34 @@
+// Argument block shared by the fp32 SIMT (attention.cu) and bf16 tensor-core (attention_tc.cu)
+// cross-attention kernels.
+#pragma once
+#include <stdint.h>
+
+namespace tt {
+
+struct AttnArgs {
+  const float* q;
+  const float* k;
+  const float* v;
+  const float* bias_k;  // [E] or null
+  const float* bias_v;
+  const uint8_t* mask;  // [B,S] 1 = padding, or null
+  float* out;           // [T,B,E]
+  float* lse;           // [B,H,T]
+  int T, B, S, H;
+  long long ldq, ldkv, ldo;  // row strides (elements) of q/dq, k/v/dk/dv, out/dout
+  int zero_row;         // add_zero_attn
+  float p_drop;
+  unsigned long long seed;
+  const unsigned long long* step_ptr;
+  // backward
+  const float* dout;
+  float* dq;
+  float* dk;
+  float* dv;
+  float* dbias_k;
+  float* dbias_v;
+  // head-averaged weights (eval): [B,T,L]
+  float* avg_w;
+};
+
+}  // namespace tt

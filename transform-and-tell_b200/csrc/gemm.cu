@@ -7,6 +7,8 @@
 //   warps 4-7   epilogue       : tcgen05.ld accumulator -> registers -> alpha/bias/act/residual -> HBM
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, the
 // accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -302,19 +304,29 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return check_launch("gemm_bf16_tn_kernel");
 }
 
-// Tile-width heuristic: the widest BN that still yields at least one tile per SM; otherwise the
-// width giving the most tiles (small-M decoder GEMMs), never below 32.
+// Tile-width heuristic.  Operand re-reads from L2 scale with 1/BN (A is re-read N/BN times), so the
+// widest tile that still gives every SM a tile wins; when even BN=64 cannot fill the machine
+// (small-M decoder GEMMs) the per-SM L2 bandwidth is the limit and BN=64 keeps the most SMs busy
+// without the 2x A-traffic of BN=32.  TT_GEMM_BN overrides (experiments).
 static int pick_bn(int M, int N, int sms) {
-  const int num_m = ceil_div(M, BM);
-  const int cands[4] = {256, 128, 64, 32};
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (bn > 32 && N < bn) continue;
-    if (num_m * ceil_div(N, bn) >= sms) return bn;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TT_GEMM_BN");
+    forced = e ? atoi(e) : 0;
   }
-  // not enough tiles anywhere: prefer 64 unless 32 is needed to get past half the machine
-  if (num_m * ceil_div(N, 64) >= sms / 2 || N <= 32) return N >= 64 ? 64 : 32;
-  return 32;
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+  const int num_m = ceil_div(M, BM);
+  if (N <= 32) return 32;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (N < bn && i < 2) continue;
+    const int tiles = num_m * ceil_div(N, bn);
+    if (tiles >= sms - sms / 8) return bn;   // >= ~87% of the SMs get a tile
+  }
+  // under-filled machine: BN=128 if it already yields >= half the SMs' worth of tiles, else 64
+  if (N >= 128 && num_m * ceil_div(N, 128) >= sms / 2) return 128;
+  return 64;
 }
 
 }  // namespace tt

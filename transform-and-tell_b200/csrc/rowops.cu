@@ -150,19 +150,24 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy,
       }
     }
   }
+  // CTA-level reduction in shared memory, then ONE global atomic per column per CTA
+  extern __shared__ float ln_red[];   // [2][E]
+  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) ln_red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     const int c = lane + 32 * i;
     if (c < E4) {
-      if (dgamma) {
-        atomicAdd(dgamma + 4 * c, acc_g[i].x); atomicAdd(dgamma + 4 * c + 1, acc_g[i].y);
-        atomicAdd(dgamma + 4 * c + 2, acc_g[i].z); atomicAdd(dgamma + 4 * c + 3, acc_g[i].w);
-      }
-      if (dbeta) {
-        atomicAdd(dbeta + 4 * c, acc_b[i].x); atomicAdd(dbeta + 4 * c + 1, acc_b[i].y);
-        atomicAdd(dbeta + 4 * c + 2, acc_b[i].z); atomicAdd(dbeta + 4 * c + 3, acc_b[i].w);
-      }
+      atomicAdd(&ln_red[4 * c], acc_g[i].x); atomicAdd(&ln_red[4 * c + 1], acc_g[i].y);
+      atomicAdd(&ln_red[4 * c + 2], acc_g[i].z); atomicAdd(&ln_red[4 * c + 3], acc_g[i].w);
+      atomicAdd(&ln_red[E + 4 * c], acc_b[i].x); atomicAdd(&ln_red[E + 4 * c + 1], acc_b[i].y);
+      atomicAdd(&ln_red[E + 4 * c + 2], acc_b[i].z); atomicAdd(&ln_red[E + 4 * c + 3], acc_b[i].w);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, ln_red[i]);
+    if (dbeta) atomicAdd(dbeta + i, ln_red[E + i]);
   }
 }
 
@@ -313,11 +318,12 @@ extern "C" int tt_ln_bwd(const float* dy, long long lddy, const float* x, const 
   // fewer, fatter warps so the dgamma/dbeta atomics stay cheap
   int grid = row_grid(N);
   if (grid > num_sms()) grid = num_sms();
+  const size_t smem = 2 * static_cast<size_t>(E) * sizeof(float);
   if (E <= 256)
-    ln_bwd_kernel<2><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    ln_bwd_kernel<2><<<grid, ROW_WARPS * 32, smem, (cudaStream_t)stream>>>(
         dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
   else
-    ln_bwd_kernel<8><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    ln_bwd_kernel<8><<<grid, ROW_WARPS * 32, smem, (cudaStream_t)stream>>>(
         dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
   return check_launch("ln_bwd_kernel");
 }
@@ -387,22 +393,25 @@ extern "C" int tt_nan_rows(float* x, uint8_t* mask, int R, int D, void* stream) 
 
 // ------------------------------------------------------------------------------------------------
 namespace tt {
-// out[c] (+)= scale * sum_r x[r,c]   (bias gradients).  32 columns per CTA, 8 row-lanes.
+// out[c] += scale * sum_r x[r,c]   (bias gradients).  2-D grid: 32 columns x COLSUM_ROWS rows per
+// CTA, one atomicAdd per column per CTA (out is zeroed first unless accumulating).
+constexpr int COLSUM_ROWS = 256;
 __global__ void colsum_kernel(const float* __restrict__ x, long long ld, int M, int N,
-                              float* __restrict__ out, float scale, int accumulate) {
+                              float* __restrict__ out, float scale) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * COLSUM_ROWS;
+  const int r1 = min(M, r0 + COLSUM_ROWS);
   float s = 0.f;
   if (c < N)
-    for (int r = threadIdx.y; r < M; r += 8) s += x[r * ld + c];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + c];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    t *= scale;
-    out[c] = accumulate ? out[c] + t : t;
+    atomicAdd(out + c, t * scale);
   }
 }
 // dx = dy * (y > 0)
@@ -412,9 +421,10 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dx[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
-// transformer_faces_objects.py:355-364: out = sum_l softmax(w)[l] * hiddens[l]   (bf16 hiddens)
+// transformer_faces_objects.py:355-364: out = sum_l softmax(w)[l] * hiddens[l]   (bf16 hiddens).
+// 8 elements (16 B of bf16) per thread per layer; n must be a multiple of 8.
 __global__ void layer_mix_fwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
-                                     const float* __restrict__ w, int L, long long n,
+                                     const float* __restrict__ w, int L, long long n8,
                                      float* __restrict__ out) {
   __shared__ float sw[64];
   if (threadIdx.x == 0) {
@@ -425,25 +435,58 @@ __global__ void layer_mix_fwd_kernel(const __nv_bfloat16* __restrict__ hid, long
     for (int l = 0; l < L; ++l) sw[l] /= s;
   }
   __syncthreads();
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc += sw[l] * __bfloat162float(hid[l * layer_stride + i]);
-    out[i] = acc;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(hid + l * layer_stride) + i);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const float wl = sw[l];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += wl * __low2float(h2[j]);
+        acc[2 * j + 1] += wl * __high2float(h2[j]);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
-// dots[l] += sum_i dout[i] * hiddens[l][i]   (then softmax backward on the host-free finisher)
+// dots[l] += sum_i dout[i] * hiddens[l][i]: dout is read ONCE, the L partial sums live in registers.
+template <int MAXL>
 __global__ void layer_mix_bwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
-                                     const float* __restrict__ dout, int L, long long n,
+                                     const float* __restrict__ dout, int L, long long n8,
                                      float* __restrict__ dots) {
   __shared__ float red[32];
-  for (int l = 0; l < L; ++l) {
-    float s = 0.f;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-      s += dout[i] * __bfloat162float(hid[l * layer_stride + i]);
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(dots + l, s);
+  float acc[MAXL];
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) acc[l] = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dout) + 2 * i);
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(dout) + 2 * i + 1);
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l) {
+      if (l < L) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(hid + l * layer_stride) + i);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+        acc[l] += d0.x * __low2float(h2[0]) + d0.y * __high2float(h2[0]) +
+                  d0.z * __low2float(h2[1]) + d0.w * __high2float(h2[1]) +
+                  d1.x * __low2float(h2[2]) + d1.y * __high2float(h2[2]) +
+                  d1.z * __low2float(h2[3]) + d1.w * __high2float(h2[3]);
+      }
+    }
+  }
+  for (int l = 0; l < L && l < MAXL; ++l) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j)
+      if (j == l) v = acc[j];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) atomicAdd(dots + l, v);
   }
 }
 // dw[l] = p[l] * (dots[l] - sum_j p[j] dots[j]),  p = softmax(w)
@@ -465,9 +508,10 @@ extern "C" int tt_colsum(const float* x, long long ld, int M, int N, float* out,
                          int accumulate, void* stream) {
   TT_REQUIRE(x && out, "tt_colsum: null pointer");
   if (N <= 0) return TT_OK;
-  dim3 block(32, 8);
-  colsum_kernel<<<ceil_div(N, 32), block, 0, (cudaStream_t)stream>>>(x, ld, M, N, out, scale,
-                                                                     accumulate);
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream);
+  if (M <= 0) return TT_OK;
+  dim3 block(32, 8), grid(ceil_div(N, 32), ceil_div(M, COLSUM_ROWS));
+  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ld, M, N, out, scale);
   return check_launch("colsum_kernel");
 }
 
@@ -491,9 +535,10 @@ extern "C" int tt_layer_mix_fwd(const void* hiddens, long long layer_stride, con
                                 long long n, float* out, void* stream) {
   TT_REQUIRE(hiddens && w && out, "tt_layer_mix_fwd: null pointer");
   TT_REQUIRE(L > 0 && L <= 64, "tt_layer_mix_fwd: L must be in [1,64]");
+  TT_REQUIRE(n % 8 == 0 && layer_stride % 8 == 0, "tt_layer_mix_fwd: n and layer_stride must be multiples of 8");
   if (n <= 0) return TT_OK;
-  layer_mix_fwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, w, L, n, out);
+  layer_mix_fwd_kernel<<<flat_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, w, L, n / 8, out);
   return check_launch("layer_mix_fwd_kernel");
 }
 
@@ -501,13 +546,14 @@ extern "C" int tt_layer_mix_bwd(const void* hiddens, long long layer_stride, con
                                 const float* dout, int L, long long n, float* dots, float* dw,
                                 void* stream) {
   TT_REQUIRE(hiddens && w && dout && dots && dw, "tt_layer_mix_bwd: null pointer");
-  TT_REQUIRE(L > 0 && L <= 64, "tt_layer_mix_bwd: L must be in [1,64]");
+  TT_REQUIRE(L > 0 && L <= 32, "tt_layer_mix_bwd: L must be in [1,32]");
   cudaMemsetAsync(dots, 0, sizeof(float) * L, (cudaStream_t)stream);
+  TT_REQUIRE(n % 8 == 0 && layer_stride % 8 == 0, "tt_layer_mix_bwd: n and layer_stride must be multiples of 8");
   if (n > 0) {
-    int grid = flat_grid(n);
-    if (grid > 2 * num_sms()) grid = 2 * num_sms();
-    layer_mix_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, dout, L, n, dots);
+    int grid = flat_grid(n / 8);
+    if (grid > 4 * num_sms()) grid = 4 * num_sms();
+    layer_mix_bwd_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, dout, L, n / 8, dots);
     int rc = check_launch("layer_mix_bwd_kernel");
     if (rc != TT_OK) return rc;
   }

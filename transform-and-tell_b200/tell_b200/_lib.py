@@ -55,9 +55,23 @@ def check(rc, what):
         raise TtError('%s failed (%d): %s' % (what, rc, msg))
 
 
+# When PROFILE is a list, every C-ABI call is bracketed by CUDA events on the launching stream
+# (bench.py's live per-kernel timing); GEMM_FLOPS collects the algorithmic FLOPs of GEMM calls.
+PROFILE = None
+GEMM_FLOPS = []
+
+
 def call(name, *args):
     fn = getattr(lib(), name)
+    if PROFILE is None:
+        check(fn(*args), name)
+        return
+    import torch
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     check(fn(*args), name)
+    e.record()
+    PROFILE.append((name, s, e))
 
 
 def launch_count():

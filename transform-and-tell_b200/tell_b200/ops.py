@@ -101,6 +101,8 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     if m_limit is not None:
         assert m_limit.dtype == torch.int32
         p.m_limit = m_limit.data_ptr()
+    if _lib.PROFILE is not None:
+        _lib.GEMM_FLOPS.append(0.0 if m_limit is not None else 2.0 * M * N * K)
     _lib.call('tt_gemm_bf16_tn', ctypes.byref(p), _stream())
     if out is not None and out16 is not None:
         return out, out16
