@@ -160,6 +160,19 @@ int tt_attn_avg_weights(const float* q, const float* k, const float* bias_k,
                         int B, int S, int H, int D, long long ldq, long long ldkv, int zero_row,
                         void* stream);
 
+/* Tensor-core (bf16 mma.sync, fp32 accumulate/softmax) variants of tt_attn_fwd / tt_attn_bwd with
+ * identical arguments; head_dim must be 64.  Used in the bf16 throughput mode. */
+int tt_attn_fwd_tc(const float* q, const float* k, const float* v, const float* bias_k,
+                   const float* bias_v, const uint8_t* key_padding_mask, float* out, float* lse,
+                   int T, int B, int S, int H, int D, long long ldq, long long ldkv, long long ldo,
+                   int zero_row, float p_drop, unsigned long long seed, void* stream);
+int tt_attn_bwd_tc(const float* dout, const float* q, const float* k, const float* v,
+                   const float* bias_k, const float* bias_v, const uint8_t* key_padding_mask,
+                   const float* out, const float* lse, float* dq, float* dk, float* dv,
+                   float* dbias_k, float* dbias_v, int T, int B, int S, int H, int D, long long ldq,
+                   long long ldkv, long long ldo, int zero_row, float p_drop,
+                   unsigned long long seed, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Adaptive softmax / loss, tell/modules/softmax.py:144-222, criteria/adaptive_loss.py:27-73.
  * cutoffs = {c0, c1, ..., vocab} (n_clusters entries: head + tails).

@@ -224,6 +224,62 @@ def test_attention_fwd_bwd(T, B, S, H, D):
     assert (w.cpu() - p.detach().mean(1)).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize('T,B,S', [(50, 2, 130), (50, 2, 512), (70, 1, 4), (9, 2, 0), (1, 3, 70)])
+def test_attention_tensor_core_path(T, B, S):
+    """bf16 tensor-core kernels vs the fp32 definition: relative error budget 2e-2 (bf16 operands);
+    also agrees with its own forward under dropout (fwd/bwd regenerate the same mask)."""
+    from tell_b200 import ops
+    torch.manual_seed(S + T)
+    H, D = 4, 64
+    E = H * D
+    q = (torch.randn(T, B, E) * D ** -0.5).requires_grad_(True)
+    k = torch.randn(S, B, E, requires_grad=True)
+    v = torch.randn(S, B, E, requires_grad=True)
+    bk = (torch.randn(E) * 0.5).requires_grad_(True)
+    bv = (torch.randn(E) * 0.5).requires_grad_(True)
+    mask = torch.zeros(B, S, dtype=torch.bool)
+    if S > 3:
+        mask[0, S // 2:] = True
+        mask[-1, :] = True
+    o, p = _attn_ref(q, k, v, bk, bv, mask, H)
+    do = torch.randn(T, B, E)
+    o.backward(do)
+    qc, kc, vc = cuda(q.detach()).view(T * B, E), cuda(k.detach()).view(S * B, E), \
+        cuda(v.detach()).view(S * B, E)
+    mc = cuda(mask.to(torch.uint8)) if S > 0 else None
+    bkc, bvc = cuda(bk.detach()), cuda(bv.detach())
+    oc, lse = ops.attn_fwd(qc, kc, vc, bkc, bvc, mc, T, B, S, H, D, tc=True)
+
+    def close(a, b, tol=2e-2):
+        return (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    assert close(oc.cpu().view(T, B, E), o.detach())
+    dq = torch.empty_like(qc)
+    dk, dv = torch.empty_like(kc), torch.empty_like(vc)
+    dbk, dbv = torch.zeros(E, device='cuda'), torch.zeros(E, device='cuda')
+    ops.attn_bwd(cuda(do).view(T * B, E), qc, kc, vc, bkc, bvc, mc, oc, lse, dq, dk, dv, dbk, dbv,
+                 T, B, S, H, D, tc=True)
+    assert close(dq.cpu().view(T, B, E), q.grad)
+    if S > 0:
+        assert close(dk.cpu().view(S, B, E), k.grad)
+        assert close(dv.cpu().view(S, B, E), v.grad)
+    assert close(dbk.cpu(), bk.grad, 3e-2) and close(dbv.cpu(), bv.grad, 3e-2)
+    # dropout: the SIMT and tensor-core kernels draw the same mask for the same seed
+    o1, l1 = ops.attn_fwd(qc, kc, vc, bkc, bvc, mc, T, B, S, H, D, p=0.25, seed=7, tc=True)
+    o2, l2 = ops.attn_fwd(qc, kc, vc, bkc, bvc, mc, T, B, S, H, D, p=0.25, seed=7, tc=False)
+    assert close(o1, o2)
+    d1 = [torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc),
+          torch.zeros(E, device='cuda'), torch.zeros(E, device='cuda')]
+    d2 = [torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc),
+          torch.zeros(E, device='cuda'), torch.zeros(E, device='cuda')]
+    ops.attn_bwd(cuda(do).view(T * B, E), qc, kc, vc, bkc, bvc, mc, o2, l2, *d1, T, B, S, H, D,
+                 p=0.25, seed=7, tc=True)
+    ops.attn_bwd(cuda(do).view(T * B, E), qc, kc, vc, bkc, bvc, mc, o2, l2, *d2, T, B, S, H, D,
+                 p=0.25, seed=7, tc=False)
+    for x, y in zip(d1, d2):
+        if x.numel():
+            assert close(x, y, 3e-2)
+
+
 def test_attention_strided_and_dropout():
     from tell_b200 import ops
     torch.manual_seed(5)

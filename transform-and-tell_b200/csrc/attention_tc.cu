@@ -1,0 +1,440 @@
+// Tensor-core version of the decoder cross-attention (same math and argument block as
+// attention.cu; multi_head.py:355-466): bf16 operands on mma.sync.m16n8k16 with fp32 accumulation,
+// fp32 softmax statistics.  Used in the 'bf16' throughput mode; the fp32 SIMT kernels of
+// attention.cu remain the parity-mode ('bf16x3') path.  D = 64.
+//   forward : CTA = (b, h, 64 queries), 4 warps x 16 query rows, loop over 64-key tiles
+//   dQ      : same tiling; S = QK^T, dP = dO V^T, dS = P*(dP*drop - D), dQ += dS K
+//   dK/dV   : CTA = (b, h, 64 keys), 4 warps x 16 key rows, loop over 64-query tiles using the
+//             transposed products S^T = K Q^T, dP^T = V dO^T so that P^T / dS^T are A operands:
+//             dV += P^T dO, dK += dS^T Q
+// q/k/v/dO arrive as fp32 (row strides honoured) and are converted to bf16 while being staged in
+// shared memory; outputs are fp32.
+#include "attention_args.cuh"
+#include "common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int TC_BM = 64, TC_BN = 64, TC_D = 64, TC_LD = TC_D + 8;
+
+// rows [r0, r0+64) x 64 dims of an fp32 matrix -> bf16 smem tile (rows >= nrows are zero).
+// src row r lives at base + (r * B + b) * ld + h*64.
+__device__ __forceinline__ void stage_tile(const float* __restrict__ base, long long ld, int B, int b,
+                                           int h, int r0, int nrows,
+                                           __nv_bfloat16 (*dst)[TC_LD]) {
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+    const int r = i >> 4, c4 = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < nrows)
+      v = __ldg(reinterpret_cast<const float4*>(base + (static_cast<long long>(r0 + r) * B + b) * ld +
+                                                h * TC_D) + c4);
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y);
+    u.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(&dst[r][c4 * 4]) = u;
+  }
+}
+
+// Key/value tile j0..j0+63 of the extended key set [ctx rows ; bias row ; zero row] + additive mask.
+__device__ __forceinline__ void stage_kv(const AttnArgs& a, int b, int h, int j0, int L,
+                                         __nv_bfloat16 (*sK)[TC_LD], __nv_bfloat16 (*sV)[TC_LD],
+                                         float* sMask) {
+  const bool has_bias = a.bias_k != nullptr;
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+    const int r = i >> 4, c4 = i & 15;
+    const int j = j0 + r;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (j < a.S) {
+      const long long off = (static_cast<long long>(j) * a.B + b) * a.ldkv + h * TC_D;
+      kv = __ldg(reinterpret_cast<const float4*>(a.k + off) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(a.v + off) + c4);
+    } else if (has_bias && j == a.S) {
+      kv = __ldg(reinterpret_cast<const float4*>(a.bias_k + h * TC_D) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(a.bias_v + h * TC_D) + c4);
+    }
+    uint2 u;
+    u.x = pack_bf16(kv.x, kv.y); u.y = pack_bf16(kv.z, kv.w);
+    *reinterpret_cast<uint2*>(&sK[r][c4 * 4]) = u;
+    u.x = pack_bf16(vv.x, vv.y); u.y = pack_bf16(vv.z, vv.w);
+    *reinterpret_cast<uint2*>(&sV[r][c4 * 4]) = u;
+  }
+  for (int r = threadIdx.x; r < 64; r += blockDim.x) {
+    const int j = j0 + r;
+    bool ok;
+    if (j < a.S) ok = !(a.mask && a.mask[static_cast<long long>(b) * a.S + j]);
+    else ok = j < L;
+    sMask[r] = ok ? 0.f : -INFINITY;
+  }
+}
+
+// A fragments (16 rows x 64 k) of the warp's row block from a [64][TC_LD] tile.
+__device__ __forceinline__ void load_a_frags(const __nv_bfloat16 (*tile)[TC_LD], int warp, int lane,
+                                             uint32_t (&f)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldmatrix_x4(f[ks][0], f[ks][1], f[ks][2], f[ks][3],
+                &tile[warp * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+}
+// C[16 x 64] += A(frags, 16 x 64) . Bt^T where Bt is a [64 n][64 k] row-major tile (B[k][n] = Bt[n][k]).
+__device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const uint32_t (&af)[4][4],
+                                         const __nv_bfloat16 (*bt)[TC_LD], int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4(b0, b1, b2, b3,
+                  &bt[np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + ((lane >> 3) & 1) * 8]);
+      mma_bf16_16816(c[2 * np], af[ks], b0, b1);
+      mma_bf16_16816(c[2 * np + 1], af[ks], b2, b3);
+    }
+  }
+}
+// C[16 x 64] += P(frags, 16 x 64 k) . Bm where Bm is a [64 k][64 n] row-major tile.
+__device__ __forceinline__ void mma_p_b(float (&c)[8][4], const uint32_t (&pf)[4][4],
+                                        const __nv_bfloat16 (*bm)[TC_LD], int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(b0, b1, b2, b3,
+                        &bm[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+      mma_bf16_16816(c[2 * np], pf[kk], b0, b1);
+      mma_bf16_16816(c[2 * np + 1], pf[kk], b2, b3);
+    }
+  }
+}
+__device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n) c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128)
+attn_fwd_tc_kernel(AttnArgs a) {
+  a.seed = mix_seed(a.seed, a.step_ptr);
+  __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sK[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[64][TC_LD];
+  __shared__ float sMask[64];
+  const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
+  const int q0 = blockIdx.y * TC_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+  __syncthreads();
+  uint32_t qf[4][4];
+  load_a_frags(sQ, warp, lane, qf);
+  float o[8][4];
+  zero_acc(o);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int t0 = q0 + warp * 16 + g, t1 = t0 + 8;
+  const unsigned long long base0 = (static_cast<unsigned long long>(bh) * a.T + t0) * L;
+  const unsigned long long base1 = (static_cast<unsigned long long>(bh) * a.T + t1) * L;
+  for (int j0 = 0; j0 < L; j0 += TC_BN) {
+    __syncthreads();
+    stage_kv(a, b, h, j0, L, sK, sV, sMask);
+    __syncthreads();
+    float s[8][4];
+    zero_acc(s);
+    mma_a_bt(s, qf, sK, lane);
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float k0 = sMask[n * 8 + 2 * tg], k1 = sMask[n * 8 + 2 * tg + 1];
+      s[n][0] += k0; s[n][1] += k1; s[n][2] += k0; s[n][3] += k1;
+      tm0 = fmaxf(tm0, fmaxf(s[n][0], s[n][1]));
+      tm1 = fmaxf(tm1, fmaxf(s[n][2], s[n][3]));
+    }
+    tm0 = quad_max(tm0);
+    tm1 = quad_max(tm1);
+    const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
+    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mn0);
+    const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mn1);
+    const float b0 = (mn0 == -INFINITY) ? 0.f : mn0, b1 = (mn1 == -INFINITY) ? 0.f : mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      float p0 = __expf(s[n][0] - b0), p1 = __expf(s[n][1] - b0);
+      float p2 = __expf(s[n][2] - b1), p3 = __expf(s[n][3] - b1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      if (a.p_drop > 0.f) {
+        const int j = j0 + n * 8 + 2 * tg;
+        p0 *= dropout_scale(a.seed, base0 + j, a.p_drop, inv_keep);
+        p1 *= dropout_scale(a.seed, base0 + j + 1, a.p_drop, inv_keep);
+        p2 *= dropout_scale(a.seed, base1 + j, a.p_drop, inv_keep);
+        p3 *= dropout_scale(a.seed, base1 + j + 1, a.p_drop, inv_keep);
+      }
+      pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    l0 = l0 * c0 + quad_sum(rs0);
+    l1 = l1 * c1 + quad_sum(rs1);
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
+    }
+    mma_p_b(o, pf, sV, lane);
+  }
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = h * TC_D + n * 8 + 2 * tg;
+    if (t0 < a.T)
+      *reinterpret_cast<float2*>(a.out + (static_cast<long long>(t0) * a.B + b) * a.ldo + col) =
+          make_float2(o[n][0] * i0, o[n][1] * i0);
+    if (t1 < a.T)
+      *reinterpret_cast<float2*>(a.out + (static_cast<long long>(t1) * a.B + b) * a.ldo + col) =
+          make_float2(o[n][2] * i1, o[n][3] * i1);
+  }
+  if (tg == 0 && a.lse) {
+    if (t0 < a.T) a.lse[static_cast<long long>(bh) * a.T + t0] = m0 + logf(l0);
+    if (t1 < a.T) a.lse[static_cast<long long>(bh) * a.T + t1] = m1 + logf(l1);
+  }
+}
+
+// D[t] = sum_c dO[t,c] * O[t,c] and lse[t] for the 64 queries q0.. into shared memory.
+__device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h, int bh, int q0,
+                                                float* sD, float* sLse) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < 64; r += (blockDim.x >> 5)) {
+    const int t = q0 + r;
+    float d = 0.f;
+    if (t < a.T) {
+      const long long off = (static_cast<long long>(t) * a.B + b) * a.ldo + h * TC_D;
+      d = __ldg(a.dout + off + lane) * __ldg(a.out + off + lane) +
+          __ldg(a.dout + off + lane + 32) * __ldg(a.out + off + lane + 32);
+    }
+    d = warp_sum(d);
+    if (lane == 0) {
+      sD[r] = d;
+      sLse[r] = t < a.T ? a.lse[static_cast<long long>(bh) * a.T + t] : INFINITY;  // p := 0 beyond T
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dQ
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_tc_kernel(AttnArgs a) {
+  a.seed = mix_seed(a.seed, a.step_ptr);
+  __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sK[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[64][TC_LD];
+  __shared__ float sMask[64], sD[64], sLse[64];
+  const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
+  const int q0 = blockIdx.y * TC_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+  stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
+  stage_row_stats(a, b, h, bh, q0, sD, sLse);
+  __syncthreads();
+  uint32_t qf[4][4], dof[4][4];
+  load_a_frags(sQ, warp, lane, qf);
+  load_a_frags(sdO, warp, lane, dof);
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const float lse0 = sLse[r0], lse1 = sLse[r1], D0 = sD[r0], D1 = sD[r1];
+  const unsigned long long base0 = (static_cast<unsigned long long>(bh) * a.T + q0 + r0) * L;
+  const unsigned long long base1 = (static_cast<unsigned long long>(bh) * a.T + q0 + r1) * L;
+  float dq[8][4];
+  zero_acc(dq);
+  for (int j0 = 0; j0 < L; j0 += TC_BN) {
+    __syncthreads();
+    stage_kv(a, b, h, j0, L, sK, sV, sMask);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    zero_acc(s);
+    zero_acc(dp);
+    mma_a_bt(s, qf, sK, lane);
+    mma_a_bt(dp, dof, sV, lane);
+    uint32_t dsf[4][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int jj = n * 8 + 2 * tg;
+      const float k0 = sMask[jj], k1 = sMask[jj + 1];
+      float sc0 = 1.f, sc1 = 1.f, sc2 = 1.f, sc3 = 1.f;
+      if (a.p_drop > 0.f) {
+        sc0 = dropout_scale(a.seed, base0 + j0 + jj, a.p_drop, inv_keep);
+        sc1 = dropout_scale(a.seed, base0 + j0 + jj + 1, a.p_drop, inv_keep);
+        sc2 = dropout_scale(a.seed, base1 + j0 + jj, a.p_drop, inv_keep);
+        sc3 = dropout_scale(a.seed, base1 + j0 + jj + 1, a.p_drop, inv_keep);
+      }
+      const float p0 = __expf(s[n][0] + k0 - lse0), p1 = __expf(s[n][1] + k1 - lse0);
+      const float p2 = __expf(s[n][2] + k0 - lse1), p3 = __expf(s[n][3] + k1 - lse1);
+      dsf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * (dp[n][0] * sc0 - D0), p1 * (dp[n][1] * sc1 - D0));
+      dsf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * (dp[n][2] * sc2 - D1), p3 * (dp[n][3] * sc3 - D1));
+    }
+    mma_p_b(dq, dsf, sK, lane);
+  }
+  const int t0 = q0 + r0, t1 = q0 + r1;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = h * TC_D + n * 8 + 2 * tg;
+    if (t0 < a.T)
+      *reinterpret_cast<float2*>(a.dq + (static_cast<long long>(t0) * a.B + b) * a.ldq + col) =
+          make_float2(dq[n][0], dq[n][1]);
+    if (t1 < a.T)
+      *reinterpret_cast<float2*>(a.dq + (static_cast<long long>(t1) * a.B + b) * a.ldq + col) =
+          make_float2(dq[n][2], dq[n][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dK, dV
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_tc_kernel(AttnArgs a) {
+  a.seed = mix_seed(a.seed, a.step_ptr);
+  __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sK[64][TC_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[64][TC_LD];
+  __shared__ float sMask[64], sD[64], sLse[64];
+  const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
+  const int j0 = blockIdx.y * TC_BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const bool has_bias = a.bias_k != nullptr;
+  const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
+  const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  stage_kv(a, b, h, j0, L, sK, sV, sMask);
+  __syncthreads();
+  uint32_t kf[4][4], vf[4][4];
+  load_a_frags(sK, warp, lane, kf);
+  load_a_frags(sV, warp, lane, vf);
+  const int r0 = warp * 16 + g, r1 = r0 + 8;       // key rows of this thread
+  const float km0 = sMask[r0], km1 = sMask[r1];
+  float dk[8][4], dv[8][4];
+  zero_acc(dk);
+  zero_acc(dv);
+  for (int q0 = 0; q0 < a.T; q0 += TC_BM) {
+    __syncthreads();
+    stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+    stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
+    stage_row_stats(a, b, h, bh, q0, sD, sLse);
+    __syncthreads();
+    float st[8][4], dpt[8][4];      // S^T and dP^T: rows = keys, cols = queries
+    zero_acc(st);
+    zero_acc(dpt);
+    mma_a_bt(st, kf, sQ, lane);
+    mma_a_bt(dpt, vf, sdO, lane);
+    uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int tt = n * 8 + 2 * tg;             // query column (and tt+1)
+      const float lse_a = sLse[tt], lse_b = sLse[tt + 1], Da = sD[tt], Db = sD[tt + 1];
+      float sc0 = 1.f, sc1 = 1.f, sc2 = 1.f, sc3 = 1.f;
+      if (a.p_drop > 0.f) {
+        const unsigned long long ba = (static_cast<unsigned long long>(bh) * a.T + q0 + tt) * L;
+        const unsigned long long bb = ba + L;
+        sc0 = dropout_scale(a.seed, ba + j0 + r0, a.p_drop, inv_keep);
+        sc1 = dropout_scale(a.seed, bb + j0 + r0, a.p_drop, inv_keep);
+        sc2 = dropout_scale(a.seed, ba + j0 + r1, a.p_drop, inv_keep);
+        sc3 = dropout_scale(a.seed, bb + j0 + r1, a.p_drop, inv_keep);
+      }
+      const float p0 = __expf(st[n][0] + km0 - lse_a), p1 = __expf(st[n][1] + km0 - lse_b);
+      const float p2 = __expf(st[n][2] + km1 - lse_a), p3 = __expf(st[n][3] + km1 - lse_b);
+      pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * sc0, p1 * sc1);
+      pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * sc2, p3 * sc3);
+      dsf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * (dpt[n][0] * sc0 - Da), p1 * (dpt[n][1] * sc1 - Db));
+      dsf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * (dpt[n][2] * sc2 - Da), p3 * (dpt[n][3] * sc3 - Db));
+    }
+    mma_p_b(dv, pf, sdO, lane);
+    mma_p_b(dk, dsf, sQ, lane);
+  }
+  const int ja = j0 + r0, jb = j0 + r1;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int c = n * 8 + 2 * tg;
+    if (ja < a.S) {
+      const long long off = (static_cast<long long>(ja) * a.B + b) * a.ldkv + h * TC_D + c;
+      *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][0], dk[n][1]);
+      *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][0], dv[n][1]);
+    } else if (has_bias && ja == a.S) {
+      if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][0]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][1]); }
+      if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][0]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][1]); }
+    }
+    if (jb < a.S) {
+      const long long off = (static_cast<long long>(jb) * a.B + b) * a.ldkv + h * TC_D + c;
+      *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][2], dk[n][3]);
+      *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][2], dv[n][3]);
+    } else if (has_bias && jb == a.S) {
+      if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][2]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][3]); }
+      if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][2]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][3]); }
+    }
+  }
+}
+
+static int tc_check(const AttnArgs& a, int D) {
+  TT_REQUIRE(D == TC_D, "attention (tensor-core path): head_dim must be %d (got %d)", TC_D, D);
+  TT_REQUIRE(a.ldq % 4 == 0 && a.ldkv % 4 == 0 && a.ldo % 4 == 0,
+             "attention (tensor-core path): row strides must be multiples of 4");
+  return TT_OK;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_attn_fwd_tc(const float* q, const float* k, const float* v, const float* bias_k,
+                              const float* bias_v, const uint8_t* key_padding_mask, float* out,
+                              float* lse, int T, int B, int S, int H, int D, long long ldq,
+                              long long ldkv, long long ldo, int zero_row, float p_drop,
+                              unsigned long long seed, void* stream) {
+  TT_REQUIRE(q && out && lse, "tt_attn_fwd_tc: null pointer");
+  TT_REQUIRE(S == 0 || (k && v), "tt_attn_fwd_tc: null k/v with S > 0");
+  TT_REQUIRE((bias_k == nullptr) == (bias_v == nullptr), "tt_attn_fwd_tc: bias_k/bias_v mismatch");
+  TT_REQUIRE(S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0) > 0, "tt_attn_fwd_tc: empty key set");
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgs a{};
+  a.q = q; a.k = k; a.v = v; a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
+  a.out = out; a.lse = lse; a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row;
+  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo;
+  a.p_drop = p_drop; a.seed = seed; a.step_ptr = rng_step_ptr();
+  int rc = tc_check(a, D);
+  if (rc != TT_OK) return rc;
+  dim3 grid(B * H, ceil_div(T, TC_BM));
+  attn_fwd_tc_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+extern "C" int tt_attn_bwd_tc(const float* dout, const float* q, const float* k, const float* v,
+                              const float* bias_k, const float* bias_v,
+                              const uint8_t* key_padding_mask, const float* out, const float* lse,
+                              float* dq, float* dk, float* dv, float* dbias_k, float* dbias_v,
+                              int T, int B, int S, int H, int D, long long ldq, long long ldkv,
+                              long long ldo, int zero_row, float p_drop, unsigned long long seed,
+                              void* stream) {
+  TT_REQUIRE(dout && q && out && lse && dq, "tt_attn_bwd_tc: null pointer");
+  TT_REQUIRE(S == 0 || (k && v && dk && dv), "tt_attn_bwd_tc: null k/v/dk/dv with S > 0");
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgs a{};
+  a.q = q; a.k = k; a.v = v; a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
+  a.out = const_cast<float*>(out); a.lse = const_cast<float*>(lse);
+  a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row; a.p_drop = p_drop; a.seed = seed;
+  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo; a.step_ptr = rng_step_ptr();
+  a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv; a.dbias_k = dbias_k; a.dbias_v = dbias_v;
+  int rc = tc_check(a, D);
+  if (rc != TT_OK) return rc;
+  const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+  dim3 grid(B * H, ceil_div(T, TC_BM));
+  attn_bwd_dq_tc_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  rc = check_launch("attn_bwd_dq_tc_kernel");
+  if (rc != TT_OK) return rc;
+  dim3 grid2(B * H, ceil_div(L, TC_BN));
+  attn_bwd_dkv_tc_kernel<<<grid2, 128, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("attn_bwd_dkv_tc_kernel");
+}

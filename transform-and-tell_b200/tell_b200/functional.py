@@ -265,8 +265,9 @@ class AttentionFn(Function):
         v = kv[:, E:] if S > 0 else None
         bk = bias_k.view(-1) if bias_k is not None else None
         bv = bias_v.view(-1) if bias_v is not None else None
-        out, lse = ops.attn_fwd(q, k, v, bk, bv, mask, T, B, S, H, D, zero_row, p, seed)
-        ctx.cfg = (T, B, S, H, D, zero_row, p, seed)
+        tc = config.precision == 'bf16' and D == 64      # tensor-core kernels in throughput mode
+        out, lse = ops.attn_fwd(q, k, v, bk, bv, mask, T, B, S, H, D, zero_row, p, seed, tc=tc)
+        ctx.cfg = (T, B, S, H, D, zero_row, p, seed, tc)
         ctx.save_for_backward(q, kv, bias_k, bias_v, mask, out, lse)
         weights = None
         if need_weights:
@@ -277,7 +278,7 @@ class AttentionFn(Function):
     @staticmethod
     def backward(ctx, dout, _dweights):
         q, kv, bias_k, bias_v, mask, out, lse = ctx.saved_tensors
-        T, B, S, H, D, zero_row, p, seed = ctx.cfg
+        T, B, S, H, D, zero_row, p, seed, tc = ctx.cfg
         E = H * D
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv) if S > 0 else None
@@ -287,7 +288,7 @@ class AttentionFn(Function):
                      bias_k.view(-1) if bias_k is not None else None,
                      bias_v.view(-1) if bias_v is not None else None, mask, out, lse, dq,
                      dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None,
-                     dbk, dbv, T, B, S, H, D, zero_row, p, seed)
+                     dbk, dbv, T, B, S, H, D, zero_row, p, seed, tc=tc)
         return (dq, dkv, dbk, dbv) + (None,) * 9
 
 
