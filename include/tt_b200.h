@@ -53,6 +53,7 @@ int tt_rng_step_advance(unsigned long long* dev_ptr, void* stream);
  *   tell/modules/token_embedders/adaptive.py:61-76 (band projections),
  *   tell/modules/convolutions/dynamic.py:300 (filter logits).
  * lda/ldb/ldc/... are row strides in ELEMENTS; lda, ldb multiples of 8; A, B 16-byte aligned.
+ * With trans_a/trans_b the same kernel reads MN-major operands (UMMA descriptor major bits).
  * C (fp32) and/or C16 (bf16) receive the result; accumulate!=0 adds into C (fp32 only).
  * m_limit (device int, optional): only the first min(M, *m_limit) rows are computed.
  */
@@ -75,6 +76,12 @@ typedef struct {
   int act;
   int accumulate;
   const int* m_limit;
+  /* Operand storage.  0: [M,K] / [N,K] row-major (K contiguous, "K-major").
+   * 1: stored transposed, [K,M] / [K,N] row-major (M or N contiguous, "MN-major"); lda/ldb are
+   * then the row strides of that storage.  Lets the backward GEMMs (dX = dY.W, dW = dY^T.X)
+   * consume the forward's operands in place instead of materialising transposes. */
+  int trans_a;
+  int trans_b;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
 

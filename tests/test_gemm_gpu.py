@@ -109,3 +109,26 @@ def test_gemm_split_precision():
     assert err < 2e-4, err
     c1 = ops.gemm_tn(ops.cast_bf16(x), ops.cast_bf16(w))
     assert (c1 - ref).abs().max().item() > err
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (800, 1024, 1024), (1024, 4096, 800),
+                                   (300, 200, 136), (64, 64, 8192), (2048, 30265, 800), (50, 40, 24)])
+@pytest.mark.parametrize('ta,tb', [(True, False), (False, True), (True, True)])
+def test_gemm_mn_major_operands(M, N, K, ta, tb):
+    """trans_a / trans_b: the kernel reads [K,M] / [K,N] storage through MN-major UMMA descriptors."""
+    from tell_b200 import ops
+    torch.manual_seed(M + N + K)
+
+    def pad8(t):
+        r, c = t.shape
+        buf = torch.zeros(r, (c + 7) // 8 * 8, device='cuda', dtype=torch.bfloat16)
+        buf[:, :c] = t
+        return buf[:, :c]
+    a = torch.randn(M, K, device='cuda').bfloat16()
+    b = torch.randn(N, K, device='cuda').bfloat16()
+    a_st = pad8(a.t().contiguous()) if ta else pad8(a)
+    b_st = pad8(b.t().contiguous()) if tb else pad8(b)
+    c = ops.gemm_tn(a_st, b_st, trans_a=ta, trans_b=tb)
+    ref = a.float() @ b.float().t()
+    err = (c - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K, ta, tb, err)

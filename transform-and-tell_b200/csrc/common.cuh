@@ -213,11 +213,26 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+// UMMA descriptor for an MN-major operand (the M or N index is contiguous in memory), 128-byte
+// swizzle.  The stage holds one TMA box per 64-element MN chunk, each box = 64 k-rows x 128 B:
+//   inside a box, 8-row k-groups are 1024 B apart (SBO); consecutive MN chunks are one box =
+//   8192 B apart (LBO).  One MMA (K = 16) consumes two k-groups.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;                    // LBO: next 64-element MN chunk
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // SBO: next 8 k-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.  a_mn / b_mn: operand is MN-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn = false,
+                                                       bool b_mn = false) {
   return (1u << 4)                       // D format = F32
          | (1u << 7)                     // A format = BF16
          | (1u << 10)                    // B format = BF16
+         | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u)
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 

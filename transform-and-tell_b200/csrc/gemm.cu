@@ -53,7 +53,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN>
+template <int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs g) {
@@ -114,8 +114,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (!TA) {
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {  // MN-major: one 64(m) x 64(k) box per 64-row chunk of the tile
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sA + stage * Cfg::A_BYTES + c * 8192, &tmA, &full_bar[stage],
+                          m_blk * BM + c * 64, kb * BK);
+          }
+          if (!TB) {
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sB + stage * Cfg::B_BYTES + c * 8192, &tmB, &full_bar[stage],
+                          n_blk * BN + c * 64, kb * BK);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -125,7 +139,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, TA, TB);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -140,8 +154,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
+            // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows = 2048 B
+            const uint64_t da = TA ? umma_desc_mnmajor_sw128(a_addr + k * UMMA_K * 128)
+                                   : umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t db = TB ? umma_desc_mnmajor_sw128(b_addr + k * UMMA_K * 128)
+                                   : umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -284,13 +301,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
-                       cudaStream_t stream) {
+template <int BN, bool TA, bool TB>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
+                         cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, TA, TB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -300,8 +317,28 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     attr_set = true;
   }
-  gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  gemm_bf16_tn_kernel<BN, TA, TB><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
   return check_launch("gemm_bf16_tn_kernel");
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
+                       bool ta, bool tb, cudaStream_t stream) {
+  if (ta) {
+    if (tb) {
+      if constexpr (BN >= 64) return launch_gemm_t<BN, true, true>(tmA, tmB, g, grid, stream);
+    } else {
+      return launch_gemm_t<BN, true, false>(tmA, tmB, g, grid, stream);
+    }
+  } else {
+    if (tb) {
+      if constexpr (BN >= 64) return launch_gemm_t<BN, false, true>(tmA, tmB, g, grid, stream);
+    } else {
+      return launch_gemm_t<BN, false, false>(tmA, tmB, g, grid, stream);
+    }
+  }
+  set_error("tt_gemm_bf16_tn: transposed B needs a tile width >= 64");
+  return TT_ERR_INVALID;
 }
 
 // Tile-width heuristic.  Operand re-reads from L2 scale with 1/BN (A is re-read N/BN times), so the
@@ -339,21 +376,29 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   if (p->M == 0) return TT_OK;
   TT_REQUIRE(p->A && p->B, "tt_gemm_bf16_tn: null operand");
   TT_REQUIRE(p->C || p->C16, "tt_gemm_bf16_tn: no output buffer");
-  TT_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->lda >= p->K && p->ldb >= p->K,
-             "tt_gemm_bf16_tn: lda/ldb must be multiples of 8 and >= K (lda=%lld ldb=%lld K=%d)",
-             p->lda, p->ldb, p->K);
+  const bool ta = p->trans_a != 0, tb = p->trans_b != 0;
+  TT_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->lda >= (ta ? p->M : p->K) &&
+                 p->ldb >= (tb ? p->N : p->K),
+             "tt_gemm_bf16_tn: lda/ldb must be multiples of 8 and cover a stored row "
+             "(lda=%lld ldb=%lld M=%d N=%d K=%d ta=%d tb=%d)",
+             p->lda, p->ldb, p->M, p->N, p->K, (int)ta, (int)tb);
   TT_REQUIRE((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
              "tt_gemm_bf16_tn: operands must be 16-byte aligned");
   TT_REQUIRE(!(p->accumulate && !p->C), "tt_gemm_bf16_tn: accumulate needs the fp32 output");
 
   const int sms = num_sms();
-  const int bn = pick_bn(p->M, p->N, sms);
+  int bn = pick_bn(p->M, p->N, sms);
+  if (tb && bn < 64) bn = 64;   // an MN-major B tile is built from 64-column TMA boxes
 
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
+  // K-major operand: rows = M (or N), inner = K, box 64(k) x rows.  MN-major operand (stored
+  // [K, M] or [K, N]): rows = K, inner = M (or N), box 64(mn) x 64(k).
+  int rc = ta ? make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->M, (uint64_t)p->K, (uint64_t)p->lda, 64, BK)
+              : make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
   if (rc != TT_OK) return rc;
-  rc = make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->ldb, BK, bn);
+  rc = tb ? make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->N, (uint64_t)p->K, (uint64_t)p->ldb, 64, BK)
+          : make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->ldb, BK, bn);
   if (rc != TT_OK) return rc;
 
   GemmArgs g;
@@ -378,9 +423,9 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   const int grid = tiles < sms ? tiles : sms;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return launch_gemm<256>(tmA, tmB, g, grid, s);
-    case 128: return launch_gemm<128>(tmA, tmB, g, grid, s);
-    case 64: return launch_gemm<64>(tmA, tmB, g, grid, s);
-    default: return launch_gemm<32>(tmA, tmB, g, grid, s);
+    case 256: return launch_gemm<256>(tmA, tmB, g, grid, ta, tb, s);
+    case 128: return launch_gemm<128>(tmA, tmB, g, grid, ta, tb, s);
+    case 64: return launch_gemm<64>(tmA, tmB, g, grid, ta, tb, s);
+    default: return launch_gemm<32>(tmA, tmB, g, grid, ta, tb, s);
   }
 }

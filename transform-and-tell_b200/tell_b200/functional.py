@@ -24,6 +24,14 @@ def _c(x):
     return x if x.is_contiguous() else x.contiguous()
 
 
+def _fast():
+    """bf16 throughput mode: backward GEMMs read the forward's bf16 operands in place through
+    MN-major UMMA descriptors (trans_a / trans_b) -- no transposed copies, no weight re-casts.
+    In bf16x3 mode the hi/lo segments run along the contraction axis, which differs between
+    forward and backward, so that mode re-casts (explicit transposes)."""
+    return config.precision == 'bf16'
+
+
 class LinearFn(Function):
     """y = act(alpha * (x @ w^T + bias)); x [M,K], w [N,K] (F.linear / GehringLinear / in_proj)."""
 
@@ -32,8 +40,12 @@ class LinearFn(Function):
         a16 = operand(x, 'a')
         b16 = operand(w, 'b')
         y = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act)
-        ctx.alpha, ctx.act, ctx.has_bias = alpha, act, bias is not None
-        ctx.save_for_backward(x, w, y if act != ops.ACT_NONE else None)
+        ctx.alpha, ctx.act, ctx.has_bias, ctx.fast = alpha, act, bias is not None, _fast()
+        keep_y = y if act != ops.ACT_NONE else None
+        if ctx.fast:
+            ctx.save_for_backward(a16, b16, keep_y)
+        else:
+            ctx.save_for_backward(x, w, keep_y)
         return y
 
     @staticmethod
@@ -45,11 +57,18 @@ class LinearFn(Function):
         elif ctx.act != ops.ACT_NONE:
             raise NotImplementedError('backward of fused GELU is not needed on this path')
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = ops.gemm_tn(operand(dy, 'a'), operand(w, 'b', transpose=True), alpha=ctx.alpha)
-        if ctx.needs_input_grad[1]:
-            dw = ops.gemm_tn(operand(dy, 'a', transpose=True), operand(x, 'b', transpose=True),
-                             alpha=ctx.alpha)
+        if ctx.fast:
+            dy16 = operand(dy, 'a')                      # [M, N]: K-major for dx, MN-major for dw
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(dy16, w, alpha=ctx.alpha, trans_b=True)          # dy . W
+            if ctx.needs_input_grad[1]:
+                dw = ops.gemm_tn(dy16, x, alpha=ctx.alpha, trans_a=True, trans_b=True)  # dy^T . x
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(operand(dy, 'a'), operand(w, 'b', transpose=True), alpha=ctx.alpha)
+            if ctx.needs_input_grad[1]:
+                dw = ops.gemm_tn(operand(dy, 'a', transpose=True), operand(x, 'b', transpose=True),
+                                 alpha=ctx.alpha)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy, scale=ctx.alpha)
         return dx, dw, db, None, None
@@ -64,11 +83,15 @@ class KVProjFn(Function):
     def forward(ctx, x, wk, wv, bias_kv):
         E = wk.shape[0]
         a16 = operand(x, 'a')
+        wk16, wv16 = operand(wk, 'b'), operand(wv, 'b')
         kv = torch.empty((x.shape[0], 2 * E), dtype=torch.float32, device=x.device)
-        ops.gemm_tn(a16, operand(wk, 'b'), out=kv[:, :E], bias=None if bias_kv is None else bias_kv[:E])
-        ops.gemm_tn(a16, operand(wv, 'b'), out=kv[:, E:], bias=None if bias_kv is None else bias_kv[E:])
-        ctx.has_bias = bias_kv is not None
-        ctx.save_for_backward(x, wk, wv)
+        ops.gemm_tn(a16, wk16, out=kv[:, :E], bias=None if bias_kv is None else bias_kv[:E])
+        ops.gemm_tn(a16, wv16, out=kv[:, E:], bias=None if bias_kv is None else bias_kv[E:])
+        ctx.has_bias, ctx.fast = bias_kv is not None, _fast()
+        if ctx.fast:
+            ctx.save_for_backward(a16, wk16, wv16)
+        else:
+            ctx.save_for_backward(x, wk, wv)
         return kv
 
     @staticmethod
@@ -78,13 +101,25 @@ class KVProjFn(Function):
         E = wk.shape[0]
         dk, dv = dkv[:, :E], dkv[:, E:]
         dx = dwk = dwv = db = None
-        if ctx.needs_input_grad[0]:
-            dx = ops.gemm_tn(operand(dk, 'a'), operand(wk, 'b', transpose=True))
-            ops.gemm_tn(operand(dv, 'a'), operand(wv, 'b', transpose=True), out=dx, accumulate=True)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            xT = operand(x, 'b', transpose=True)
-            dwk = ops.gemm_tn(operand(dk, 'a', transpose=True), xT)
-            dwv = ops.gemm_tn(operand(dv, 'a', transpose=True), xT)
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if ctx.fast:
+            d16 = operand(dkv, 'a')                                  # [R, 2E] in one cast
+            dk16, dv16 = d16[:, :E], d16[:, E:]
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(dk16, wk, trans_b=True)
+                ops.gemm_tn(dv16, wv, out=dx, accumulate=True, trans_b=True)
+            if need_w:
+                dwk = ops.gemm_tn(dk16, x, trans_a=True, trans_b=True)
+                dwv = ops.gemm_tn(dv16, x, trans_a=True, trans_b=True)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(operand(dk, 'a'), operand(wk, 'b', transpose=True))
+                ops.gemm_tn(operand(dv, 'a'), operand(wv, 'b', transpose=True), out=dx,
+                            accumulate=True)
+            if need_w:
+                xT = operand(x, 'b', transpose=True)
+                dwk = ops.gemm_tn(operand(dk, 'a', transpose=True), xT)
+                dwv = ops.gemm_tn(operand(dv, 'a', transpose=True), xT)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = ops.colsum(dkv)
         return dx, dwk, dwv, db
@@ -339,28 +374,41 @@ class EmbedFn(Function):
         pos = ops.make_positions(ids, pad, False, start_pos, tbc=True)   # [T,B] int32
         posv = ops.gather_rows(pos_table, pos.view(-1))                  # [T*B, E]
         w16 = concat_k_operand(list(projs), 'b', ids.device)             # [E, n*E(*3)]
-        out = ops.gemm_tn(operand(A, 'a'), w16, alpha=scale, residual=posv)
-        ctx.cfg = (n, scale, cutoffs, E)
-        ctx.save_for_backward(ids, A, *tables, *projs)
+        a16 = operand(A, 'a')
+        out = ops.gemm_tn(a16, w16, alpha=scale, residual=posv)
+        ctx.cfg = (n, scale, cutoffs, E, _fast())
+        if ctx.cfg[4]:
+            ctx.save_for_backward(ids, a16, w16, *tables)
+        else:
+            ctx.save_for_backward(ids, A, *tables, *projs)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        n, scale, cutoffs, E = ctx.cfg
+        n, scale, cutoffs, E, fast = ctx.cfg
         saved = ctx.saved_tensors
-        ids, A = saved[0], saved[1]
-        tables, projs = saved[2:2 + n], saved[2 + n:2 + 2 * n]
         dout = _c(dout)
-        d16 = operand(dout, 'a')
-        d16T = operand(dout, 'a', transpose=True)
-        dA = torch.empty_like(A)
-        dtables, dprojs = [], []
-        for i in range(n):
-            ops.gemm_tn(d16, operand(projs[i], 'b', transpose=True), out=dA[:, i * E:(i + 1) * E],
-                        alpha=scale)
-            dprojs.append(ops.gemm_tn(d16T, operand(A[:, i * E:(i + 1) * E], 'b', transpose=True),
-                                      alpha=scale))
-            dtables.append(torch.zeros_like(tables[i]))
+        ids = saved[0]
+        if fast:
+            a16, w16 = saved[1], saved[2]
+            tables = saved[3:3 + n]
+            d16 = operand(dout, 'a')
+            dA = ops.gemm_tn(d16, w16, alpha=scale, trans_b=True)                     # [N, n*E]
+            dW = ops.gemm_tn(d16, a16, alpha=scale, trans_a=True, trans_b=True)       # [E, n*E]
+            dprojs = [dW[:, i * E:(i + 1) * E] for i in range(n)]
+        else:
+            A = saved[1]
+            tables, projs = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+            d16 = operand(dout, 'a')
+            d16T = operand(dout, 'a', transpose=True)
+            dA = torch.empty_like(A)
+            dprojs = []
+            for i in range(n):
+                ops.gemm_tn(d16, operand(projs[i], 'b', transpose=True),
+                            out=dA[:, i * E:(i + 1) * E], alpha=scale)
+                dprojs.append(ops.gemm_tn(d16T, operand(A[:, i * E:(i + 1) * E], 'b', transpose=True),
+                                          alpha=scale))
+        dtables = [torch.zeros_like(t) for t in tables]
         ops.embed_scatter_grad(ids, cutoffs, dtables, E, dA, padding_idx=0, tbc=True)
         return (None,) * 7 + tuple(dtables) + tuple(dprojs)
 
@@ -392,13 +440,15 @@ class AdaptiveLossFn(Function):
     def forward(ctx, X, target, cutoffs, pad_idx, word0, class_proj, *tails):
         N, E = X.shape
         nt = len(cutoffs) - 1
+        fast = _fast()
         head_t, tail_idx, tail_local, tail_count, ntok = ops.adaptive_prepare(target, cutoffs,
                                                                               pad_idx)
         hw16 = ops.bf16_buffer(cutoffs[0] + nt, E * _rep(), X.device)
         split_b = 0 if _rep() == 1 else 2
         ops.cast_bf16(word0, split=split_b, out=hw16[:cutoffs[0]])
         ops.cast_bf16(class_proj, split=split_b, out=hw16[cutoffs[0]:])
-        head_logits = ops.gemm_tn(operand(X, 'a'), hw16)
+        x16 = operand(X, 'a')
+        head_logits = ops.gemm_tn(x16, hw16)
         row_loss = torch.empty((nt + 1, N), dtype=torch.float32, device=X.device)
         head_lse, _ = ops.ce_fwd(head_logits, head_t, None, pad_idx, row_loss[0])
         saved_tail = []
@@ -406,41 +456,60 @@ class AdaptiveLossFn(Function):
             proj, words = tails[2 * i], tails[2 * i + 1]
             cnt = tail_count[i:i + 1]
             Xg = ops.gather_rows(X, tail_idx[i], cnt, cap=N)
-            P = ops.gemm_tn(operand(Xg, 'a'), operand(proj, 'b'), m_limit=cnt)
-            logits = ops.gemm_tn(operand(P, 'a'), operand(words, 'b'), m_limit=cnt)
+            xg16, proj16 = operand(Xg, 'a'), operand(proj, 'b')
+            P = ops.gemm_tn(xg16, proj16, m_limit=cnt)
+            p16, words16 = operand(P, 'a'), operand(words, 'b')
+            logits = ops.gemm_tn(p16, words16, m_limit=cnt)
             lse, _ = ops.ce_fwd(logits, tail_local[i], cnt, pad_idx, row_loss[i + 1])
-            saved_tail += [Xg, P, logits, lse]
+            saved_tail += ([xg16, p16, proj16, words16, logits, lse] if fast
+                           else [Xg, P, proj, words, logits, lse])
         loss, scale = ops.loss_finalize(row_loss, ntok)
-        ctx.cfg = (cutoffs, pad_idx, nt)
-        ctx.save_for_backward(X, word0, class_proj, head_logits, head_lse, head_t, tail_idx,
-                              tail_local, tail_count, scale, *tails, *saved_tail)
+        ctx.cfg = (cutoffs, pad_idx, nt, fast)
+        head_saved = (x16, hw16) if fast else (X, word0, class_proj)
+        ctx.n_head = len(head_saved)
+        ctx.save_for_backward(*head_saved, head_logits, head_lse, head_t, tail_idx, tail_local,
+                              tail_count, scale, *saved_tail)
         ctx.mark_non_differentiable(ntok)
         return loss, ntok
 
     @staticmethod
     def backward(ctx, dloss, _dntok):
-        cutoffs, pad_idx, nt = ctx.cfg
+        cutoffs, pad_idx, nt, fast = ctx.cfg
         s = ctx.saved_tensors
-        (X, word0, class_proj, head_logits, head_lse, head_t, tail_idx, tail_local, tail_count,
-         scale) = s[:10]
-        tails = s[10:10 + 2 * nt]
-        saved_tail = s[10 + 2 * nt:]
+        head_saved, s = s[:ctx.n_head], s[ctx.n_head:]
+        head_logits, head_lse, head_t, tail_idx, tail_local, tail_count, scale = s[:7]
+        saved_tail = s[7:]
         c0 = cutoffs[0]
         gscale = ops.scalar_mul(scale, _c(dloss).view(1))       # upstream grad stays on device
         dlog = ops.ce_bwd_(head_logits, head_t, head_lse, gscale, None, pad_idx)   # in place
-        dX = ops.gemm_tn(operand(dlog, 'a'),
-                         concat_kT_operand([word0, class_proj], 'b', X.device))
-        dW_head = ops.gemm_tn(operand(dlog, 'a', transpose=True), operand(X, 'b', transpose=True))
+        dlog16 = operand(dlog, 'a')
+        if fast:
+            x16, hw16 = head_saved
+            dX = ops.gemm_tn(dlog16, hw16, trans_b=True)
+            dW_head = ops.gemm_tn(dlog16, x16, trans_a=True, trans_b=True)
+        else:
+            X, word0, class_proj = head_saved
+            dX = ops.gemm_tn(dlog16, concat_kT_operand([word0, class_proj], 'b', dlog.device))
+            dW_head = ops.gemm_tn(operand(dlog, 'a', transpose=True), operand(X, 'b', transpose=True))
         dtails = []
         for i in range(nt):
-            proj, words = tails[2 * i], tails[2 * i + 1]
-            Xg, P, logits, lse = saved_tail[4 * i:4 * i + 4]
+            a0, a1, a2, a3, logits, lse = saved_tail[6 * i:6 * i + 6]
             cnt = tail_count[i:i + 1]
             dl = ops.ce_bwd_(logits, tail_local[i], lse, gscale, cnt, pad_idx)   # rows >= cnt := 0
-            dP = ops.gemm_tn(operand(dl, 'a'), operand(words, 'b', transpose=True), m_limit=cnt)
-            dwords = ops.gemm_tn(operand(dl, 'a', transpose=True), operand(P, 'b', transpose=True))
-            dXg = ops.gemm_tn(operand(dP, 'a'), operand(proj, 'b', transpose=True), m_limit=cnt)
-            dproj = ops.gemm_tn(operand(dP, 'a', transpose=True), operand(Xg, 'b', transpose=True))
+            dl16 = operand(dl, 'a')
+            if fast:
+                xg16, p16, proj16, words16 = a0, a1, a2, a3
+                dP = ops.gemm_tn(dl16, words16, m_limit=cnt, trans_b=True)
+                dwords = ops.gemm_tn(dl16, p16, trans_a=True, trans_b=True)
+                dP16 = operand(dP, 'a')
+                dXg = ops.gemm_tn(dP16, proj16, m_limit=cnt, trans_b=True)
+                dproj = ops.gemm_tn(dP16, xg16, trans_a=True, trans_b=True)
+            else:
+                Xg, P, proj, words = a0, a1, a2, a3
+                dP = ops.gemm_tn(dl16, operand(words, 'b', transpose=True), m_limit=cnt)
+                dwords = ops.gemm_tn(operand(dl, 'a', transpose=True), operand(P, 'b', transpose=True))
+                dXg = ops.gemm_tn(operand(dP, 'a'), operand(proj, 'b', transpose=True), m_limit=cnt)
+                dproj = ops.gemm_tn(operand(dP, 'a', transpose=True), operand(Xg, 'b', transpose=True))
             ops.scatter_add_rows(dXg, tail_idx[i], dX, cnt)
             dtails += [dproj, dwords]
         return (dX, None, None, None, dW_head[:c0], dW_head[c0:]) + tuple(dtails)

@@ -61,14 +61,16 @@ def scalar_mul(a, b):
 
 
 def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act=ACT_NONE,
-            accumulate=False, m_limit=None, want32=True, want16=False, residual16=None):
+            accumulate=False, m_limit=None, want32=True, want16=False, residual16=None,
+            trans_a=False, trans_b=False):
     """C[M,N] = act(alpha * (a[M,K] @ b[N,K]^T + bias) + residual), bf16 operands, fp32 accumulate."""
     _check_cuda(a, b, out, out16, bias, residual)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1], (a.shape, b.shape)
-    assert a.stride(1) == 1 and b.stride(1) == 1
-    M, K = a.shape
-    N = b.shape[0]
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    # trans_a: a is stored [K, M]; trans_b: b is stored [K, N]
+    K, M = (a.shape[0], a.shape[1]) if trans_a else (a.shape[1], a.shape[0])
+    Kb, N = (b.shape[0], b.shape[1]) if trans_b else (b.shape[1], b.shape[0])
+    assert K == Kb, (a.shape, b.shape, trans_a, trans_b)
     if out is None and want32:
         # with a dynamic row limit the untouched rows must be defined (they feed later GEMMs)
         alloc = torch.zeros if m_limit is not None else torch.empty
@@ -98,6 +100,7 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     p.alpha = alpha
     p.act = act
     p.accumulate = 1 if accumulate else 0
+    p.trans_a, p.trans_b = (1 if trans_a else 0), (1 if trans_b else 0)
     if m_limit is not None:
         assert m_limit.dtype == torch.int32
         p.m_limit = m_limit.data_ptr()
