@@ -4,7 +4,7 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (B) bf16 tiles, 128B swizzle
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma 128xBNx16 (kind::f16, fp32 accum in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue       : tcgen05.ld accumulator -> registers -> alpha/bias/act/residual -> HBM
+//   warps 4-11  epilogue       : tcgen05.ld accumulator -> registers -> alpha/bias/act/residual -> HBM
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, the
 // accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
 #include <cstdlib>
@@ -17,7 +17,7 @@ namespace tt {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 
 struct GemmArgs {
   int M, N, K;
@@ -91,7 +91,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], GEMM_THREADS - 128);
     }
     fence_barrier_init();
   }
@@ -176,54 +176,75 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // A warp may only touch TMEM lanes [32*(warp%4), +32): two warps share each lane quarter and
+    // split the tile's 32-column chunks between them (even / odd).  Every thread owns one row of
+    // the chunk; bias and residual are fetched with 16-byte loads issued BEFORE waiting on the
+    // TMEM load so their latency overlaps it.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const long long row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
+        const int col0 = n_blk * BN + c * 32;
+        const bool in_n = col0 < g.N;                       // warp-uniform
+        const bool full = in_n && (col0 + 32 <= g.N) && g.vec_ok;
+        float4 bv[8];
+        float4 rv[8];
+        uint4 rh[4];
+        if (full) {
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);
+          }
+          if (row_ok && g.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              rv[j] = __ldg(reinterpret_cast<const float4*>(g.residual + row * g.ldr + col0) + j);
+          }
+          if (row_ok && g.residual16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              rh[j] = __ldg(reinterpret_cast<const uint4*>(g.residual16 + row * g.ldr16 + col0) + j);
+          }
+        }
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32);
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= g.N) continue;  // warp-uniform
+        if (!in_n || !row_ok) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (g.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
-        }
-        if (g.alpha != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
-        }
-        if (!row_ok) continue;
-        const bool full = (col0 + 32 <= g.N) && g.vec_ok;
         if (full) {
-          if (g.residual != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(g.residual + row * g.ldr + col0);
+          if (g.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(rp + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+            }
+          }
+          if (g.alpha != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+          }
+          if (g.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
             }
           }
           if (g.residual16 != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(g.residual16 + row * g.ldr16 + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 t = __ldg(rp + j);
-              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+              const uint32_t w[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
@@ -253,24 +274,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint4* hp = reinterpret_cast<uint4*>(g.C16 + row * g.ldc16 + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
               uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&p0);
-              u.y = *reinterpret_cast<uint32_t*>(&p1);
-              u.z = *reinterpret_cast<uint32_t*>(&p2);
-              u.w = *reinterpret_cast<uint32_t*>(&p3);
+              u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
               hp[j] = u;
             }
           }
         } else {
+          // ragged N or unaligned pointers: scalar path
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
             if (col < g.N) {
               float o = v[j];
+              if (g.bias != nullptr) o += __ldg(g.bias + col);
+              o *= g.alpha;
               if (g.residual != nullptr) o += __ldg(g.residual + row * g.ldr + col);
               if (g.residual16 != nullptr) o += __bfloat162float(g.residual16[row * g.ldr16 + col]);
               o = apply_act(o, g.act);
@@ -417,6 +437,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     vec = vec && (reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && (p->ldr % 4 == 0);
   if (p->residual16)
     vec = vec && (reinterpret_cast<uintptr_t>(p->residual16) & 15) == 0 && (p->ldr16 % 8 == 0);
+  if (p->bias) vec = vec && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
   g.vec_ok = vec ? 1 : 0;
 
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
