@@ -25,6 +25,7 @@ __global__ void adaptive_prepare_kernel(const long long* __restrict__ target, in
                                         int* __restrict__ head_target, int* __restrict__ tail_idx,
                                         int* __restrict__ tail_local, int* __restrict__ tail_count,
                                         int* __restrict__ ntokens) {
+  pdl_prologue();
   __shared__ int warp_cnt[32];
   __shared__ int base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -82,6 +83,7 @@ __global__ void adaptive_prepare_kernel(const long long* __restrict__ target, in
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
                                    const int* __restrict__ count_ptr, float* __restrict__ dst,
                                    int cap, int E4) {
+  pdl_prologue();
   const int count = count_ptr ? min(*count_ptr, cap) : cap;
   const long long total = static_cast<long long>(cap) * E4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -96,6 +98,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
                                         const int* __restrict__ count_ptr, float* __restrict__ dst,
                                         int cap, int E) {
+  pdl_prologue();
   const int count = count_ptr ? min(*count_ptr, cap) : cap;
   const long long total = static_cast<long long>(count) * E;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const float* __restrict__ logits, long long ld, const int* __restrict__ target,
               const int* __restrict__ count_ptr, int M, int V, int ignore_index,
               float* __restrict__ lse, float* __restrict__ row_loss) {
+  pdl_prologue();
   __shared__ float red[32];
   const int r = blockIdx.x;
   const int count = count_ptr ? min(*count_ptr, M) : M;
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(256)
 ce_bwd_kernel(float* __restrict__ logits, long long ld, const int* __restrict__ target,
               const int* __restrict__ count_ptr, int M, int V, int ignore_index,
               const float* __restrict__ lse, const float* __restrict__ scale_ptr) {
+  pdl_prologue();
   const int r = blockIdx.x;
   const int count = count_ptr ? min(*count_ptr, M) : M;
   float* x = logits + r * ld;
@@ -160,6 +165,7 @@ ce_bwd_kernel(float* __restrict__ logits, long long ld, const int* __restrict__ 
 __global__ void loss_finalize_kernel(const float* __restrict__ row_loss, long long n,
                                      const int* __restrict__ ntokens, float* __restrict__ loss,
                                      float* __restrict__ scale) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) s += row_loss[i];
@@ -184,6 +190,7 @@ struct LogProbArgs {
 };
 __global__ void __launch_bounds__(256)
 adaptive_logprob_kernel(const LogProbArgs a) {
+  pdl_prologue();
   __shared__ float red[32];
   __shared__ float best_v[256];
   __shared__ int best_i[256];
@@ -276,7 +283,7 @@ extern "C" int tt_adaptive_prepare(const long long* target, int N, const int* cu
   TT_REQUIRE(n_clusters == 1 || (tail_idx && tail_local && tail_count),
              "tt_adaptive_prepare: null tail buffers");
   if (N <= 0) return TT_OK;
-  adaptive_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+  launch_k(adaptive_prepare_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 
       target, N, cut, pad_idx, head_target, tail_idx, tail_local, tail_count, ntokens);
   return check_launch("adaptive_prepare_kernel");
 }
@@ -286,8 +293,7 @@ extern "C" int tt_gather_rows(const float* src, const int* idx, const int* count
   TT_REQUIRE(src && idx && dst, "tt_gather_rows: null pointer");
   TT_REQUIRE(E % 4 == 0, "tt_gather_rows: E must be a multiple of 4");
   if (cap <= 0) return TT_OK;
-  gather_rows_kernel<<<flat_grid2(static_cast<long long>(cap) * (E / 4)), 256, 0,
-                       (cudaStream_t)stream>>>(src, idx, count_ptr, dst, cap, E / 4);
+  launch_k(gather_rows_kernel, dim3(flat_grid2(static_cast<long long>(cap) * (E / 4))), dim3(256), 0, (cudaStream_t)stream, src, idx, count_ptr, dst, cap, E / 4);
   return check_launch("gather_rows_kernel");
 }
 
@@ -295,8 +301,7 @@ extern "C" int tt_scatter_add_rows(const float* src, const int* idx, const int* 
                                    float* dst, int cap, int E, void* stream) {
   TT_REQUIRE(src && idx && dst, "tt_scatter_add_rows: null pointer");
   if (cap <= 0) return TT_OK;
-  scatter_add_rows_kernel<<<flat_grid2(static_cast<long long>(cap) * E), 256, 0,
-                            (cudaStream_t)stream>>>(src, idx, count_ptr, dst, cap, E);
+  launch_k(scatter_add_rows_kernel, dim3(flat_grid2(static_cast<long long>(cap) * E)), dim3(256), 0, (cudaStream_t)stream, src, idx, count_ptr, dst, cap, E);
   return check_launch("scatter_add_rows_kernel");
 }
 
@@ -305,7 +310,7 @@ extern "C" int tt_ce_fwd(const float* logits, long long ld, const int* target,
                          float* row_loss, void* stream) {
   TT_REQUIRE(logits && target && lse && row_loss, "tt_ce_fwd: null pointer");
   if (M <= 0) return TT_OK;
-  ce_fwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, count_ptr, M, V,
+  launch_k(ce_fwd_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target, count_ptr, M, V,
                                                      ignore_index, lse, row_loss);
   return check_launch("ce_fwd_kernel");
 }
@@ -315,7 +320,7 @@ extern "C" int tt_ce_bwd(float* logits, long long ld, const int* target, const i
                          void* stream) {
   TT_REQUIRE(logits && target && lse, "tt_ce_bwd: null pointer");
   if (M <= 0) return TT_OK;
-  ce_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, count_ptr, M, V,
+  launch_k(ce_bwd_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target, count_ptr, M, V,
                                                      ignore_index, lse, scale_ptr);
   return check_launch("ce_bwd_kernel");
 }
@@ -323,7 +328,7 @@ extern "C" int tt_ce_bwd(float* logits, long long ld, const int* target, const i
 extern "C" int tt_loss_finalize(const float* row_loss, long long n, const int* ntokens,
                                 float* loss, float* scale, void* stream) {
   TT_REQUIRE(row_loss && ntokens, "tt_loss_finalize: null pointer");
-  loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, n, ntokens, loss, scale);
+  launch_k(loss_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, row_loss, n, ntokens, loss, scale);
   return check_launch("loss_finalize_kernel");
 }
 
@@ -343,6 +348,6 @@ extern "C" int tt_adaptive_logprob(const float* head, long long ld_head, const f
   }
   a.log_probs = log_probs; a.argmax_id = argmax_id; a.argmax_lp = argmax_lp; a.M = M;
   if (M <= 0) return TT_OK;
-  adaptive_logprob_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(adaptive_logprob_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("adaptive_logprob_kernel");
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ void load_kv_tile(const AttnArgs& a, int b, int h, in
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ float qs[AT_QT][D];
   __shared__ float ks[AT_KT][D + 1];
@@ -157,6 +158,7 @@ attn_fwd_kernel(AttnArgs a) {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_weights_kernel(const AttnArgs a) {
+  pdl_prologue();
   __shared__ float qs[AT_QT][D];
   __shared__ float ks[AT_KT][D + 1];
   __shared__ float kvalid[AT_KT];
@@ -209,6 +211,7 @@ attn_weights_kernel(const AttnArgs a) {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_dq_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ float qs[AT_QT][D];
   __shared__ float dos[AT_QT][D];
@@ -317,6 +320,7 @@ attn_bwd_dq_kernel(AttnArgs a) {
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_dkv_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   extern __shared__ float dkv_smem[];
   float (*qs)[D] = reinterpret_cast<float (*)[D]>(dkv_smem);
@@ -436,11 +440,11 @@ static int attn_launch(const AttnArgs& a, int mode, cudaStream_t s) {
   const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
   if (mode == 0) {
     dim3 grid(a.B * a.H, ceil_div(a.T, AT_QT));
-    attn_fwd_kernel<D><<<grid, AT_THREADS, 0, s>>>(a);
+    launch_k(attn_fwd_kernel<D>, dim3(grid), dim3(AT_THREADS), 0, s, a);
     return check_launch("attn_fwd_kernel");
   } else if (mode == 1) {
     dim3 grid(a.B * a.H, ceil_div(a.T, AT_QT));
-    attn_bwd_dq_kernel<D><<<grid, AT_THREADS, 0, s>>>(a);
+    launch_k(attn_bwd_dq_kernel<D>, dim3(grid), dim3(AT_THREADS), 0, s, a);
     int rc = check_launch("attn_bwd_dq_kernel");
     if (rc != TT_OK) return rc;
     dim3 grid2(a.B * a.H, ceil_div(L, AT_KT));
@@ -453,11 +457,11 @@ static int attn_launch(const AttnArgs& a, int mode, cudaStream_t s) {
                            kDkvSmem);
       attr_set = true;
     }
-    attn_bwd_dkv_kernel<D><<<grid2, AT_THREADS, kDkvSmem, s>>>(a);
+    launch_k(attn_bwd_dkv_kernel<D>, dim3(grid2), dim3(AT_THREADS), kDkvSmem, s, a);
     return check_launch("attn_bwd_dkv_kernel");
   } else {
     dim3 grid(a.B * a.H, ceil_div(a.T, AT_QT));
-    attn_weights_kernel<D><<<grid, AT_THREADS, 0, s>>>(a);
+    launch_k(attn_weights_kernel<D>, dim3(grid), dim3(AT_THREADS), 0, s, a);
     return check_launch("attn_weights_kernel");
   }
 }

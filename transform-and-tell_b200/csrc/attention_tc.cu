@@ -121,6 +121,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128)
 attn_fwd_tc_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[64][TC_LD];
@@ -230,6 +231,7 @@ __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h,
 // ------------------------------------------------------------------------------------------ dQ
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_tc_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
@@ -298,6 +300,7 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
 // ------------------------------------------------------------------------------------------ dK, dV
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_tc_kernel(AttnArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
@@ -407,7 +410,7 @@ extern "C" int tt_attn_fwd_tc(const float* q, const float* k, const float* v, co
   int rc = tc_check(a, D);
   if (rc != TT_OK) return rc;
   dim3 grid(B * H, ceil_div(T, TC_BM));
-  attn_fwd_tc_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
   return check_launch("attn_fwd_tc_kernel");
 }
 
@@ -431,10 +434,10 @@ extern "C" int tt_attn_bwd_tc(const float* dout, const float* q, const float* k,
   if (rc != TT_OK) return rc;
   const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
   dim3 grid(B * H, ceil_div(T, TC_BM));
-  attn_bwd_dq_tc_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  launch_k(attn_bwd_dq_tc_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
   rc = check_launch("attn_bwd_dq_tc_kernel");
   if (rc != TT_OK) return rc;
   dim3 grid2(B * H, ceil_div(L, TC_BN));
-  attn_bwd_dkv_tc_kernel<<<grid2, 128, 0, (cudaStream_t)stream>>>(a);
+  launch_k(attn_bwd_dkv_tc_kernel, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
   return check_launch("attn_bwd_dkv_tc_kernel");
 }

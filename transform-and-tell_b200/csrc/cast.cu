@@ -23,6 +23,7 @@ template <int SPLIT>
 __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src,
                                  __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
                                  int cols, long long seg) {
+  pdl_prologue();
   // one thread per 4 consecutive columns
   const int c4 = cols >> 2;
   const long long total = static_cast<long long>(rows) * c4;
@@ -60,6 +61,7 @@ template <int SPLIT>
 __global__ void cast_rows_scalar_kernel(const float* __restrict__ src, long long ld_src,
                                         __nv_bfloat16* __restrict__ dst, long long ld_dst,
                                         int rows, int cols, long long seg) {
+  pdl_prologue();
   const long long total = static_cast<long long>(rows) * cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -81,6 +83,7 @@ template <int SPLIT>
 __global__ void cast_transpose_kernel(const float* __restrict__ src, long long ld_src,
                                       __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
                                       int cols, long long seg) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -110,7 +113,7 @@ static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst,
   if (seg <= 0) seg = transpose ? rows : cols;
   if (transpose) {
     dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
-    cast_transpose_kernel<SPLIT><<<grid, block, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, seg);
+    launch_k(cast_transpose_kernel<SPLIT>, dim3(grid), dim3(block), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
     return check_launch("cast_transpose_kernel");
   }
   const bool vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && (seg % 4 == 0) &&
@@ -122,9 +125,9 @@ static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst,
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   if (vec)
-    cast_rows_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, seg);
+    launch_k(cast_rows_kernel<SPLIT>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
   else
-    cast_rows_scalar_kernel<SPLIT><<<(int)blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols,
+    launch_k(cast_rows_scalar_kernel<SPLIT>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols,
                                                                seg);
   return check_launch("cast_rows_kernel");
 }

@@ -26,6 +26,21 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 int num_sms();
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// With TT_PDL=1 every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (launch_k in runtime.h): the NEXT kernel in the stream may be scheduled while this one is still
+// running.  Correctness rule:
+// pdl_wait() (griddepcontrol.wait: all prerequisite grids complete, their writes visible) is executed
+// before the first access to global memory.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

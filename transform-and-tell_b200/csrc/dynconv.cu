@@ -33,6 +33,7 @@ struct DynConvArgs {
 
 __global__ void __launch_bounds__(256)
 dynconv_fwd_kernel(DynConvArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ float xs[DC_ROWS][DC_LD];
   const int R = a.C / a.H;
@@ -99,6 +100,7 @@ struct DynConvBwdArgs {
 // dx[s,c]   = sum_k w[s+K-1-k,h,k] dout[s+K-1-k,c]     (SURVEY 3.4 backward formulas)
 __global__ void __launch_bounds__(256)
 dynconv_bwd_kernel(DynConvBwdArgs a) {
+  pdl_prologue();
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ float xs[DC_ROWS][DC_LD];   // x rows   t0-K+1 .. t0+TT-1
   __shared__ float ds[DC_ROWS][DC_LD];   // dout rows t0 .. t0+TT+K-2
@@ -188,7 +190,7 @@ extern "C" int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_str
   if (T == 0) return TT_OK;
   DynConvArgs a{x, z, z_tb_stride, out, probs, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
   dim3 grid(B * H, ceil_div(T, DC_TT));
-  dynconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(dynconv_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("dynconv_fwd_kernel");
 }
 
@@ -201,6 +203,6 @@ extern "C" int tt_dynconv_bwd(const float* dout, const float* x, const float* pr
   if (T == 0) return TT_OK;
   DynConvBwdArgs a{dout, x, probs, dx, dz, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
   dim3 grid(B * H, ceil_div(T, DC_TT));
-  dynconv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(dynconv_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("dynconv_bwd_kernel");
 }

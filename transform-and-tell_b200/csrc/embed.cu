@@ -21,6 +21,7 @@ struct EmbedBands {
 // ids [B,T] (row-major).  Output row n = t*B + b when tbc != 0, else b*T + t.
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, int B, int T, int tbc,
                                     EmbedBands bands, int E4, float* __restrict__ out) {
+  pdl_prologue();
   const int n = blockIdx.x;
   const int b = tbc ? n % B : n / T, t = tbc ? n / B : n % T;
   const long long id = ids[static_cast<long long>(b) * T + t];
@@ -43,6 +44,7 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, int B, in
 __global__ void embed_scatter_kernel(const long long* __restrict__ ids, int B, int T, int tbc,
                                      EmbedBands bands, int E, int padding_idx,
                                      const float* __restrict__ dA) {
+  pdl_prologue();
   const int n = blockIdx.x;
   const int b = tbc ? n % B : n / T, t = tbc ? n / B : n % T;
   const long long id = ids[static_cast<long long>(b) * T + t];
@@ -62,6 +64,7 @@ __global__ void embed_scatter_kernel(const long long* __restrict__ ids, int B, i
 __global__ void make_positions_kernel(const long long* __restrict__ ids, int B, int T, int pad,
                                       int left_pad, int start_pos, int tbc,
                                       int* __restrict__ pos) {
+  pdl_prologue();
   const int b = blockIdx.x;
   __shared__ int nonpad;
   if (threadIdx.x == 0) nonpad = 0;
@@ -81,6 +84,7 @@ __global__ void make_positions_kernel(const long long* __restrict__ ids, int B, 
 // out[b,a,:] = in[a,b,:]   ([A,B,C] -> [B,A,C]); decoder_faces_objects.py:109,129 transposes.
 __global__ void transpose01_kernel(const float* __restrict__ in, float* __restrict__ out, int A,
                                    int B, int C4) {
+  pdl_prologue();
   const long long total = static_cast<long long>(A) * B * C4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -118,7 +122,7 @@ extern "C" int tt_embed_gather(const long long* ids, int B, int T, int tbc, cons
   int rc = make_bands(cutoffs, n_bands, tables, nullptr, &bd);
   if (rc != TT_OK) return rc;
   if (B * T <= 0) return TT_OK;
-  embed_gather_kernel<<<B * T, 128, 0, (cudaStream_t)stream>>>(ids, B, T, tbc, bd, E / 4, out);
+  launch_k(embed_gather_kernel, dim3(B * T), dim3(128), 0, (cudaStream_t)stream, ids, B, T, tbc, bd, E / 4, out);
   return check_launch("embed_gather_kernel");
 }
 
@@ -130,7 +134,7 @@ extern "C" int tt_embed_scatter_grad(const long long* ids, int B, int T, int tbc
   int rc = make_bands(cutoffs, n_bands, nullptr, grads, &bd);
   if (rc != TT_OK) return rc;
   if (B * T <= 0) return TT_OK;
-  embed_scatter_kernel<<<B * T, 128, 0, (cudaStream_t)stream>>>(ids, B, T, tbc, bd, E, padding_idx,
+  launch_k(embed_scatter_kernel, dim3(B * T), dim3(128), 0, (cudaStream_t)stream, ids, B, T, tbc, bd, E, padding_idx,
                                                                dA);
   return check_launch("embed_scatter_kernel");
 }
@@ -139,7 +143,7 @@ extern "C" int tt_make_positions(const long long* ids, int B, int T, int pad, in
                                  int start_pos, int tbc, int* pos, void* stream) {
   TT_REQUIRE(ids && pos, "tt_make_positions: null pointer");
   if (B * T <= 0) return TT_OK;
-  make_positions_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(ids, B, T, pad, left_pad, start_pos,
+  launch_k(make_positions_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, ids, B, T, pad, left_pad, start_pos,
                                                             tbc, pos);
   return check_launch("make_positions_kernel");
 }
@@ -152,6 +156,6 @@ extern "C" int tt_transpose01(const float* in, float* out, int A, int B, int C, 
   long long g = ceil_div_ll(total, 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (g > cap) g = cap;
-  transpose01_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(in, out, A, B, C / 4);
+  launch_k(transpose01_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, in, out, A, B, C / 4);
   return check_launch("transpose01_kernel");
 }

@@ -16,6 +16,7 @@ namespace tt {
 __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                    int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
                                    int stride, int pad, int Kp) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int chunks_per_row = Kp >> 3;
   const long long total = static_cast<long long>(B) * Ho * Wo * chunks_per_row;
@@ -43,6 +44,7 @@ __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                        int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
                                        int stride, int pad, int Kp) {
+  pdl_prologue();
   const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
   const int K = KH * KW * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -69,6 +71,7 @@ __global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat
 __global__ void maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in,
                                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                                          int Ho, int Wo) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(B) * Ho * Wo * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -106,6 +109,7 @@ __global__ void maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in,
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
                                    long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = __bfloat162float(in[i]);
@@ -117,6 +121,7 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 __global__ void ln_fwd16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                 const uint8_t* __restrict__ row_zero, int N, int E, float eps) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -159,6 +164,7 @@ __global__ void ln_fwd16_kernel(const float* __restrict__ x, const float* __rest
 __global__ void roberta_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
                                      const float* __restrict__ pos, float* __restrict__ x,
                                      uint8_t* __restrict__ is_pad, int B, int S, int E4, int pad) {
+  pdl_prologue();
   const int r = blockIdx.x;
   const int b = r / S, t = r - b * S;
   const long long id = ids[r];
@@ -191,6 +197,7 @@ constexpr int FA_BM = 64, FA_BN = 64, FA_D = 64, FA_LD = FA_D + 8;  // +8 bf16 p
 __global__ void __launch_bounds__(128)
 flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ mask,
                        __nv_bfloat16* __restrict__ out, int B, int S, int H) {
+  pdl_prologue();
   __shared__ __align__(16) __nv_bfloat16 sQ[FA_BM][FA_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[FA_BN][FA_LD];
   __shared__ __align__(16) __nv_bfloat16 sV[FA_BN][FA_LD];
@@ -345,7 +352,7 @@ extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, in
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
   if (total <= 0) return TT_OK;
-  im2col_nhwc_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(im2col_nhwc_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
       Ho, Wo, KH, KW, stride, pad, Kp);
   return check_launch("im2col_nhwc_kernel");
@@ -358,7 +365,7 @@ extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int 
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
   if (total <= 0) return TT_OK;
-  im2col_nchw_f32_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(im2col_nchw_f32_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
       in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
   return check_launch("im2col_nchw_f32_kernel");
 }
@@ -370,7 +377,7 @@ extern "C" int tt_maxpool3x3s2_nhwc(const void* in, void* out, int B, int H, int
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
   if (total <= 0) return TT_OK;
-  maxpool3x3s2_nhwc_kernel<<<flat_grid3(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(maxpool3x3s2_nhwc_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
       Ho, Wo);
   return check_launch("maxpool3x3s2_nhwc_kernel");
@@ -379,7 +386,7 @@ extern "C" int tt_maxpool3x3s2_nhwc(const void* in, void* out, int B, int H, int
 extern "C" int tt_bf16_to_f32(const void* in, float* out, long long n, void* stream) {
   TT_REQUIRE(in && out, "tt_bf16_to_f32: null pointer");
   if (n <= 0) return TT_OK;
-  bf16_to_f32_kernel<<<flat_grid3(n), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(bf16_to_f32_kernel, dim3(flat_grid3(n)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(in), out, n);
   return check_launch("bf16_to_f32_kernel");
 }
@@ -392,7 +399,7 @@ extern "C" int tt_ln_fwd16(const float* x, const float* gamma, const float* beta
   long long g = ceil_div_ll(N, 8);
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (g > cap) g = cap;
-  ln_fwd16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(
+  launch_k(ln_fwd16_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, 
       x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y16), row_zero, N, E, eps);
   return check_launch("ln_fwd16_kernel");
 }
@@ -402,7 +409,7 @@ extern "C" int tt_roberta_embed(const long long* ids, const float* tok, const fl
   TT_REQUIRE(ids && tok && pos && x && is_pad, "tt_roberta_embed: null pointer");
   TT_REQUIRE(E % 4 == 0, "tt_roberta_embed: E must be a multiple of 4");
   if (B * S <= 0) return TT_OK;
-  roberta_embed_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>(ids, tok, pos, x, is_pad, B, S, E / 4,
+  launch_k(roberta_embed_kernel, dim3(B * S), dim3(128), 0, (cudaStream_t)stream, ids, tok, pos, x, is_pad, B, S, E / 4,
                                                                pad);
   return check_launch("roberta_embed_kernel");
 }
@@ -413,7 +420,7 @@ extern "C" int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_ma
   TT_REQUIRE(D == FA_D, "tt_flash_self_attn: head_dim must be %d (got %d)", FA_D, D);
   if (B <= 0 || S <= 0) return TT_OK;
   dim3 grid(ceil_div(S, FA_BM), B * H);
-  flash_self_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+  launch_k(flash_self_attn_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), key_padding_mask,
       reinterpret_cast<__nv_bfloat16*>(out), B, S, H);
   return check_launch("flash_self_attn_kernel");

@@ -73,12 +73,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  int M = g.M;
-  if (g.m_limit != nullptr) M = min(M, __ldg(g.m_limit));
-  const int num_m = (M + BM - 1) / BM;
-  const int num_n = (g.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_k = (g.K + BK - 1) / BK;
+  pdl_launch_dependents();   // the next kernel may start its own prologue
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -103,6 +98,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
+  // the previous kernel; from here on we touch its outputs.
+  pdl_wait();
+  int M = g.M;
+  if (g.m_limit != nullptr) M = min(M, __ldg(g.m_limit));
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (g.K + BK - 1) / BK;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -337,7 +341,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
     }
     attr_set = true;
   }
-  gemm_bf16_tn_kernel<BN, TA, TB><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  launch_k(gemm_bf16_tn_kernel<BN, TA, TB>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, g);
   return check_launch("gemm_bf16_tn_kernel");
 }
 

@@ -22,6 +22,7 @@ __global__ void ln_fwd_kernel(float* __restrict__ h, const float* __restrict__ r
                               float* __restrict__ y, long long ldy, float* __restrict__ mean,
                               float* __restrict__ rstd, int N, int E, float eps, float p,
                               unsigned long long seed, const unsigned long long* step_ptr) {
+  pdl_prologue();
   seed = mix_seed(seed, step_ptr);
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -88,6 +89,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int E,
                               float p, unsigned long long seed,
                               const unsigned long long* step_ptr) {
+  pdl_prologue();
   seed = mix_seed(seed, step_ptr);
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -175,6 +177,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy,
 // GLU over the last dim: out[n,c] = h[n,c] * sigmoid(h[n,C+c])   (nn.GLU, decoder_faces_objects.py:193-195,259-260)
 __global__ void glu_fwd_kernel(const float* __restrict__ h, float* __restrict__ out, long long n4,
                                int C4) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C4;
@@ -189,6 +192,7 @@ __global__ void glu_fwd_kernel(const float* __restrict__ h, float* __restrict__ 
 }
 __global__ void glu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ h,
                                float* __restrict__ dh, long long n4, int C4) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C4;
@@ -212,6 +216,7 @@ __global__ void glu_bwd_kernel(const float* __restrict__ dout, const float* __re
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                float p, unsigned long long seed,
                                const unsigned long long* step_ptr) {
+  pdl_prologue();
   seed = mix_seed(seed, step_ptr);
   const float inv_keep = 1.f / (1.f - p);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -222,6 +227,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 // y = a*x + b*y (vector), used for the RoBERTa layer mix and gradient accumulation.
 __global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                              float a, float b) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
@@ -231,6 +237,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y,
 // Weight norm (nn.utils.weight_norm, dim=0):  w[o,:] = g[o] * v[o,:] / ||v[o,:]||   linear.py:30-34
 __global__ void wnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                  float* __restrict__ w, float* __restrict__ norm, int O, int I) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -250,6 +257,7 @@ __global__ void wnorm_fwd_kernel(const float* __restrict__ v, const float* __res
 __global__ void wnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                  const float* __restrict__ g, const float* __restrict__ norm,
                                  float* __restrict__ dv, float* __restrict__ dg, int O, int I) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -271,6 +279,7 @@ __global__ void wnorm_bwd_kernel(const float* __restrict__ dw, const float* __re
 // ------------------------------------------------------------------------------------------------
 // mask[r] = any(isnan(x[r,:])); NaN rows are zeroed in place.  transformer_faces_objects.py:374-379
 __global__ void nan_rows_kernel(float* __restrict__ x, uint8_t* __restrict__ mask, int R, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -302,7 +311,7 @@ extern "C" int tt_ln_fwd(float* h, const float* res, const float* gamma, const f
   TT_REQUIRE(E > 0 && E % 4 == 0 && ldy % 4 == 0, "tt_ln_fwd: E and ldy must be multiples of 4");
   TT_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "tt_ln_fwd: bad dropout p");
   if (N <= 0) return TT_OK;
-  ln_fwd_kernel<<<row_grid(N), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  launch_k(ln_fwd_kernel, dim3(row_grid(N)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, 
       h, res, gamma, beta, y, ldy, mean, rstd, N, E, eps, p_drop, seed, rng_step_ptr());
   return check_launch("ln_fwd_kernel");
 }
@@ -320,10 +329,10 @@ extern "C" int tt_ln_bwd(const float* dy, long long lddy, const float* x, const 
   if (grid > num_sms()) grid = num_sms();
   const size_t smem = 2 * static_cast<size_t>(E) * sizeof(float);
   if (E <= 256)
-    ln_bwd_kernel<2><<<grid, ROW_WARPS * 32, smem, (cudaStream_t)stream>>>(
+    launch_k(ln_bwd_kernel<2>, dim3(grid), dim3(ROW_WARPS * 32), smem, (cudaStream_t)stream, 
         dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
   else
-    ln_bwd_kernel<8><<<grid, ROW_WARPS * 32, smem, (cudaStream_t)stream>>>(
+    launch_k(ln_bwd_kernel<8>, dim3(grid), dim3(ROW_WARPS * 32), smem, (cudaStream_t)stream, 
         dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());
   return check_launch("ln_bwd_kernel");
 }
@@ -333,7 +342,7 @@ extern "C" int tt_glu_fwd(const float* h, float* out, long long N, int C, void* 
   TT_REQUIRE(C > 0 && C % 4 == 0, "tt_glu_fwd: C must be a multiple of 4");
   if (N <= 0) return TT_OK;
   const long long n4 = N * (C / 4);
-  glu_fwd_kernel<<<flat_grid(n4), 256, 0, (cudaStream_t)stream>>>(h, out, n4, C / 4);
+  launch_k(glu_fwd_kernel, dim3(flat_grid(n4)), dim3(256), 0, (cudaStream_t)stream, h, out, n4, C / 4);
   return check_launch("glu_fwd_kernel");
 }
 
@@ -343,7 +352,7 @@ extern "C" int tt_glu_bwd(const float* dout, const float* h, float* dh, long lon
   TT_REQUIRE(C > 0 && C % 4 == 0, "tt_glu_bwd: C must be a multiple of 4");
   if (N <= 0) return TT_OK;
   const long long n4 = N * (C / 4);
-  glu_bwd_kernel<<<flat_grid(n4), 256, 0, (cudaStream_t)stream>>>(dout, h, dh, n4, C / 4);
+  launch_k(glu_bwd_kernel, dim3(flat_grid(n4)), dim3(256), 0, (cudaStream_t)stream, dout, h, dh, n4, C / 4);
   return check_launch("glu_bwd_kernel");
 }
 
@@ -352,14 +361,14 @@ extern "C" int tt_dropout(const float* x, float* y, long long n, float p,
   TT_REQUIRE(x && y, "tt_dropout: null pointer");
   TT_REQUIRE(p >= 0.f && p < 1.f, "tt_dropout: bad p");
   if (n <= 0) return TT_OK;
-  dropout_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, rng_step_ptr());
+  launch_k(dropout_kernel, dim3(flat_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, y, n, p, seed, rng_step_ptr());
   return check_launch("dropout_kernel");
 }
 
 extern "C" int tt_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {
   TT_REQUIRE(x && y, "tt_axpby: null pointer");
   if (n <= 0) return TT_OK;
-  axpby_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, a, b);
+  launch_k(axpby_kernel, dim3(flat_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, y, n, a, b);
   return check_launch("axpby_kernel");
 }
 
@@ -367,7 +376,7 @@ extern "C" int tt_wnorm_fwd(const float* v, const float* g, float* w, float* nor
                             void* stream) {
   TT_REQUIRE(v && g && w, "tt_wnorm_fwd: null pointer");
   if (O <= 0 || I <= 0) return TT_OK;
-  wnorm_fwd_kernel<<<row_grid(O), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(v, g, w, norm, O, I);
+  launch_k(wnorm_fwd_kernel, dim3(row_grid(O)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, v, g, w, norm, O, I);
   return check_launch("wnorm_fwd_kernel");
 }
 
@@ -375,7 +384,7 @@ extern "C" int tt_wnorm_bwd(const float* dw, const float* v, const float* g, con
                             float* dv, float* dg, int O, int I, void* stream) {
   TT_REQUIRE(dw && v && g && norm && dv && dg, "tt_wnorm_bwd: null pointer");
   if (O <= 0 || I <= 0) return TT_OK;
-  wnorm_bwd_kernel<<<row_grid(O), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(dw, v, g, norm, dv, dg,
+  launch_k(wnorm_bwd_kernel, dim3(row_grid(O)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, dw, v, g, norm, dv, dg,
                                                                            O, I);
   return check_launch("wnorm_bwd_kernel");
 }
@@ -387,7 +396,7 @@ extern "C" int tt_nan_rows(float* x, uint8_t* mask, int R, int D, void* stream) 
     cudaMemsetAsync(mask, 0, R, (cudaStream_t)stream);
     return TT_OK;
   }
-  nan_rows_kernel<<<row_grid(R), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mask, R, D);
+  launch_k(nan_rows_kernel, dim3(row_grid(R)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, x, mask, R, D);
   return check_launch("nan_rows_kernel");
 }
 
@@ -398,6 +407,7 @@ namespace tt {
 constexpr int COLSUM_ROWS = 256;
 __global__ void colsum_kernel(const float* __restrict__ x, long long ld, int M, int N,
                               float* __restrict__ out, float scale) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * COLSUM_ROWS;
@@ -417,6 +427,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, int M, 
 // dx = dy * (y > 0)
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                 float* __restrict__ dx, long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dx[i] = y[i] > 0.f ? dy[i] : 0.f;
@@ -426,6 +437,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
 __global__ void layer_mix_fwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
                                      const float* __restrict__ w, int L, long long n8,
                                      float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float sw[64];
   if (threadIdx.x == 0) {
     float m = -INFINITY;
@@ -460,6 +472,7 @@ template <int MAXL>
 __global__ void layer_mix_bwd_kernel(const __nv_bfloat16* __restrict__ hid, long long layer_stride,
                                      const float* __restrict__ dout, int L, long long n8,
                                      float* __restrict__ dots) {
+  pdl_prologue();
   __shared__ float red[32];
   float acc[MAXL];
 #pragma unroll
@@ -492,6 +505,7 @@ __global__ void layer_mix_bwd_kernel(const __nv_bfloat16* __restrict__ hid, long
 // dw[l] = p[l] * (dots[l] - sum_j p[j] dots[j]),  p = softmax(w)
 __global__ void softmax_bwd_small_kernel(const float* __restrict__ w, const float* __restrict__ dots,
                                          int L, float* __restrict__ dw) {
+  pdl_prologue();
   if (threadIdx.x == 0) {
     float m = -INFINITY;
     for (int l = 0; l < L; ++l) m = fmaxf(m, w[l]);
@@ -511,23 +525,24 @@ extern "C" int tt_colsum(const float* x, long long ld, int M, int N, float* out,
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream);
   if (M <= 0) return TT_OK;
   dim3 block(32, 8), grid(ceil_div(N, 32), ceil_div(M, COLSUM_ROWS));
-  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ld, M, N, out, scale);
+  launch_k(colsum_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, x, ld, M, N, out, scale);
   return check_launch("colsum_kernel");
 }
 
 namespace tt {
-__global__ void scalar_mul_kernel(const float* a, const float* b, float* out) { *out = *a * *b; }
+__global__ void scalar_mul_kernel(const float* a, const float* b, float* out) {
+  pdl_prologue(); *out = *a * *b; }
 }  // namespace tt
 extern "C" int tt_scalar_mul(const float* a, const float* b, float* out, void* stream) {
   TT_REQUIRE(a && b && out, "tt_scalar_mul: null pointer");
-  scalar_mul_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a, b, out);
+  launch_k(scalar_mul_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, a, b, out);
   return check_launch("scalar_mul_kernel");
 }
 
 extern "C" int tt_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream) {
   TT_REQUIRE(dy && y && dx, "tt_relu_bwd: null pointer");
   if (n <= 0) return TT_OK;
-  relu_bwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+  launch_k(relu_bwd_kernel, dim3(flat_grid(n)), dim3(256), 0, (cudaStream_t)stream, dy, y, dx, n);
   return check_launch("relu_bwd_kernel");
 }
 
@@ -537,7 +552,7 @@ extern "C" int tt_layer_mix_fwd(const void* hiddens, long long layer_stride, con
   TT_REQUIRE(L > 0 && L <= 64, "tt_layer_mix_fwd: L must be in [1,64]");
   TT_REQUIRE(n % 8 == 0 && layer_stride % 8 == 0, "tt_layer_mix_fwd: n and layer_stride must be multiples of 8");
   if (n <= 0) return TT_OK;
-  layer_mix_fwd_kernel<<<flat_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(layer_mix_fwd_kernel, dim3(flat_grid(n / 8)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, w, L, n / 8, out);
   return check_launch("layer_mix_fwd_kernel");
 }
@@ -552,11 +567,11 @@ extern "C" int tt_layer_mix_bwd(const void* hiddens, long long layer_stride, con
   if (n > 0) {
     int grid = flat_grid(n / 8);
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
-    layer_mix_bwd_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_k(layer_mix_bwd_kernel<32>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(hiddens), layer_stride, dout, L, n / 8, dots);
     int rc = check_launch("layer_mix_bwd_kernel");
     if (rc != TT_OK) return rc;
   }
-  softmax_bwd_small_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(w, dots, L, dw);
+  launch_k(softmax_bwd_small_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, w, dots, L, dw);
   return check_launch("softmax_bwd_small_kernel");
 }

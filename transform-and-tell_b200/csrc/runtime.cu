@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "runtime.h"
@@ -21,7 +22,17 @@ void set_error(const char* fmt, ...) {
 static const unsigned long long* g_step_ptr = nullptr;
 const unsigned long long* rng_step_ptr() { return g_step_ptr; }
 
-__global__ void rng_step_advance_kernel(unsigned long long* p) { *p += 1ull; }
+__global__ void rng_step_advance_kernel(unsigned long long* p) {
+  pdl_prologue(); *p += 1ull; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TT_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured neutral under CUDA-graph replay
+  }
+  return v == 1;
+}
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -99,7 +110,7 @@ void tt_reset_launch_count(void) { tt::g_launches.store(0); }
 void tt_set_rng_step_ptr(const unsigned long long* dev_ptr) { tt::g_step_ptr = dev_ptr; }
 int tt_rng_step_advance(unsigned long long* dev_ptr, void* stream) {
   if (!dev_ptr) { tt::set_error("tt_rng_step_advance: null pointer"); return TT_ERR_INVALID; }
-  tt::rng_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_ptr);
+  tt::launch_k(tt::rng_step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, dev_ptr);
   return tt::check_launch("rng_step_advance_kernel");
 }
 }
