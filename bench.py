@@ -51,6 +51,62 @@ def make_batch(B, T=50, S=512, F=4, O=16, vocab=50265, seed=1234):
     return dict(caption=cap, article=art, image=image, faces=faces, objs=objs)
 
 
+# dram__bytes_read+write of one ncu --set full capture of the largest GEMM of the step (RoBERTa fc1,
+# M=8192 N=4096 K=1024, bf16 out): see profiles/r1_gemm_8192x4096x1024_full.txt.  Algorithmic bytes
+# of that launch: (8192*1024 + 4096*1024 + 8192*4096) * 2 B = 92.3 MB.
+GEMM_TRAFFIC_NOTE = 41630720   # bytes per launch of that GEMM (25.36 MB read + 16.27 MB written)
+
+
+def replay_gemm_signatures(sigs, n_prof, dev):
+    """Device time of every GEMM of one step: replay each unique signature from a CUDA graph."""
+    from tell_b200 import ops
+    tot_us, tot_flop, calls = 0.0, 0.0, 0
+    for key, cnt in sigs.items():
+        M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha = key
+        cnt = cnt // n_prof
+        if cnt == 0 or M == 0:
+            continue
+
+        def mk(rows, cols):
+            ld = (cols + 7) // 8 * 8
+            return [torch.randn(rows, ld, device=dev).bfloat16()[:, :cols] for _ in range(2)]
+        A = mk(K, M) if ta else mk(M, K)
+        Bm = mk(K, N) if tb else mk(N, K)
+        kw = dict(trans_a=ta, trans_b=tb, act=act, accumulate=accum, want32=False)
+        if o32:
+            kw['out'] = torch.zeros(M, N, device=dev)
+        if o16:
+            kw['out16'] = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        if bias:
+            kw['bias'] = torch.zeros(N, device=dev)
+        if res:
+            kw['residual'] = torch.zeros(M, N, device=dev)
+        if res16:
+            kw['residual16'] = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        if lim:
+            kw['m_limit'] = torch.tensor([max(1, M // 8)], dtype=torch.int32, device=dev)
+        for i in range(2):
+            ops.gemm_tn(A[i], Bm[i], **kw)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(16):
+                ops.gemm_tn(A[i % 2], Bm[i % 2], **kw)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        us = s.elapsed_time(e) * 1e3 / 48
+        tot_us += us * cnt
+        tot_flop += 0.0 if lim else 2.0 * M * N * K * cnt
+        calls += cnt
+        del g, A, Bm, kw
+    return tot_us, tot_flop, calls
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -220,15 +276,37 @@ def run_b200(args):
         sampler.join(timeout=2)
     loss_val = float(loss_host.item())
 
-    # ---- live per-kernel timing (CUDA events around every C-ABI call, eager, rank 0)
+    # ---- live per-kernel timing (rank 0)
+    # (1) kernel_breakdown: CUDA events around every C-ABI call of two eager steps.  Eager launches
+    #     are CPU-bound, so these include launch gaps: use them for SHARES of the step.
+    # (2) roofline of the dominant kernel (the tcgen05 GEMM): every GEMM signature of the step is
+    #     recorded and each unique one is replayed from a CUDA graph (16 launches, rotating between
+    #     two operand sets) between CUDA events -- device time per launch without host gaps.
     roof, breakdown = None, None
     if rank == 0:
+        from tell_b200 import ops
+        sigs = {}
+        orig_gemm = ops.gemm_tn
+
+        def rec_gemm(a, b, out=None, out16=None, **kw):
+            M = a.shape[1] if kw.get('trans_a') else a.shape[0]
+            K = a.shape[0] if kw.get('trans_a') else a.shape[1]
+            N = b.shape[1] if kw.get('trans_b') else b.shape[0]
+            key = (M, N, K, bool(kw.get('trans_a')), bool(kw.get('trans_b')),
+                   out16 is not None or bool(kw.get('want16')), out is not None or kw.get('want32', True),
+                   kw.get('bias') is not None, kw.get('act', 0), kw.get('residual') is not None,
+                   kw.get('residual16') is not None, bool(kw.get('accumulate')),
+                   kw.get('m_limit') is not None, float(kw.get('alpha', 1.0)) != 1.0)
+            sigs[key] = sigs.get(key, 0) + 1
+            return orig_gemm(a, b, out=out, out16=out16, **kw)
+        ops.gemm_tn = rec_gemm
         _lib.PROFILE, _lib.GEMM_FLOPS[:] = [], []
         n_prof = 2
         for _ in range(n_prof):
             restore()
             fwd_bwd()
         torch.cuda.synchronize()
+        ops.gemm_tn = orig_gemm
         agg, total = {}, 0.0
         for name, s, e in _lib.PROFILE:
             t = s.elapsed_time(e)
@@ -236,20 +314,26 @@ def run_b200(args):
             a[0] += t
             a[1] += 1
             total += t
-        flops = sum(_lib.GEMM_FLOPS) / n_prof
         _lib.PROFILE = None
-        gemm_ms = agg['tt_gemm_bf16_tn'][0] / n_prof
-        gemm_calls = agg['tt_gemm_bf16_tn'][1] // n_prof
-        peak_tf, peak_bw, src = peaks()
-        achieved = flops / (gemm_ms * 1e-3) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_kernel (tcgen05)', 'achieved': round(achieved, 1),
-                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(achieved / peak_tf, 4),
-                'peak_source': src + ' bf16_tflops_sustained', 'traffic': None,
-                'launches_per_step': gemm_calls, 'flop_per_step': flops,
-                'avg_launch_us': round(gemm_ms * 1e3 / max(1, gemm_calls), 2),
-                'share_of_step_kernel_time': round(agg['tt_gemm_bf16_tn'][0] / total, 4)}
         breakdown = {k: {'ms_per_step': round(v[0] / n_prof, 4), 'launches': v[1] // n_prof}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+        share = agg['tt_gemm_bf16_tn'][0] / total
+        del pristine, static
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        gemm_us, gemm_flop, gemm_calls = replay_gemm_signatures(sigs, n_prof, dev)
+        peak_tf, peak_bw, src = peaks()
+        achieved = gemm_flop / (gemm_us * 1e-6) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_kernel (tcgen05.mma + TMA)',
+                'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': round(achieved / peak_tf, 4), 'peak_source': src + ' bf16_tflops_sustained',
+                'traffic': GEMM_TRAFFIC_NOTE, 'launches_per_step': gemm_calls,
+                'flop_per_step': gemm_flop, 'device_ms_per_step': round(gemm_us / 1e3, 3),
+                'avg_launch_us': round(gemm_us / max(1, gemm_calls), 2),
+                'share_of_step_kernel_time': round(share, 4),
+                'method': 'each unique GEMM signature of the step replayed from a CUDA graph between '
+                          'CUDA events; algorithmic FLOP = sum 2*M*N*K (row-limited tail GEMMs counted '
+                          'as 0 FLOP but full time)'}
 
     if rank != 0:
         if world > 1:

@@ -115,3 +115,42 @@ def test_training_mode_dropout_runs_and_is_seeded():
         losses.append(loss.item())
         assert all(torch.isfinite(p.grad).all() for p in dec.parameters() if p.grad is not None)
     assert losses[0] == losses[1] and losses[0] != losses[2]
+
+
+def test_full_size_decoder_matches_oracle():
+    """BASELINE-size architecture (E=1024, 16 heads, 4 layers K=3/7/15/31, vocab 50265, cutoffs
+    5000/20000) on a small batch: decoder output, loss and 8 greedy steps vs the CPU oracle in
+    bf16x3 precision (fp32 logits within 1e-3, tokens exact)."""
+    import restate
+    from tell_b200 import config, synth
+    from tell_b200.models import DynamicConvFacesObjectsDecoder
+    from tell_b200.testing import build_decoder
+    config.set_precision('bf16x3')
+    cfg = synth.CFG_FULL
+    sd = synth.decoder_state_dict(cfg, seed=1, logit_gain=2.0)
+    dec = build_decoder(cfg, DynamicConvFacesObjectsDecoder, sd).cuda().eval()
+    cap, ctx = synth.decoder_inputs(cfg, B=2, T=12, S=40, F=4, O=6, P=9, seed=77)
+    inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    cctx = {k: v.cuda() for k, v in ctx.items()}
+    ocfg = synth.oracle_cfg(cfg)
+    with torch.no_grad():
+        out, _ = dec({'roberta': inp.cuda()}, cctx)
+        loss, ntok = dec.adaptive_softmax.fused_loss(out, tgt.cuda())
+        ref, _ = restate.decoder_forward(inp, ctx, sd, ocfg)
+        _, n, ref_loss = restate.adaptive_loss(ref, tgt, sd, ocfg['cutoffs'])
+        assert (out.cpu() - ref).abs().max() < 1e-3
+        assert int(ntok) == n and abs(loss.item() - ref_loss.item()) < 1e-3
+        lp = dec.get_normalized_probs((out[:, -1:], None), True).cpu()
+        ref_lp = restate.adaptive_log_prob(ref[:, -1:], sd, ocfg['cutoffs'])
+        assert (lp - ref_lp).abs().max() < 1e-3
+        # greedy: 8 steps, token-exact
+        rids, rlp = restate.greedy_generate(cap[:, 0:1], ctx, sd, ocfg, gen_len=8, early_exit=False)
+        state, prev, toks = {}, cap[:, 0:1].cuda(), []
+        for _ in range(8):
+            X, _ = dec.forward_tbc({'roberta': prev}, cctx, incremental_state=state)
+            tok, _ = dec.adaptive_softmax.greedy(X.view(2, -1))
+            toks.append(tok.view(2, 1))
+            prev = tok.view(2, 1)
+        assert torch.equal(torch.cat(toks, 1).cpu(), rids[:, 1:])
+    del dec
+    torch.cuda.empty_cache()

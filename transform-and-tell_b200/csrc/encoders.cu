@@ -194,84 +194,108 @@ __global__ void roberta_embed_kernel(const long long* __restrict__ ids, const fl
 // mma.sync.m16n8k16 bf16 with fp32 accumulation, online softmax in registers.
 constexpr int FA_BM = 64, FA_BN = 64, FA_D = 64, FA_LD = FA_D + 8;  // +8 bf16 pad: conflict-free ldmatrix
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// CTA = 128 queries (8 warps x 16 rows) of one (b,h); K/V tiles of 64 keys are double-buffered with
+// cp.async so the loads of tile j+1 overlap the MMAs/softmax of tile j.
+constexpr int FA_THREADS = 256;
+constexpr int FA_QROWS = 128;
+
+__global__ void __launch_bounds__(FA_THREADS)
 flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ mask,
                        __nv_bfloat16* __restrict__ out, int B, int S, int H) {
   pdl_prologue();
-  __shared__ __align__(16) __nv_bfloat16 sQ[FA_BM][FA_LD];
-  __shared__ __align__(16) __nv_bfloat16 sK[FA_BN][FA_LD];
-  __shared__ __align__(16) __nv_bfloat16 sV[FA_BN][FA_LD];
-  __shared__ float sMask[FA_BN];
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  typedef __nv_bfloat16 (*Tile)[FA_LD];
+  Tile sQ = reinterpret_cast<Tile>(fa_smem);                                   // [128][72]
+  Tile sK0 = reinterpret_cast<Tile>(fa_smem + FA_QROWS * FA_LD * 2);           // 2 x [64][72]
+  Tile sV0 = reinterpret_cast<Tile>(fa_smem + (FA_QROWS + 2 * FA_BN) * FA_LD * 2);
+  float* sMask = reinterpret_cast<float*>(fa_smem + (FA_QROWS + 4 * FA_BN) * FA_LD * 2);  // [2][64]
   const int E = H * FA_D;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-  const int q0 = blockIdx.x * FA_BM;
+  const int q0 = blockIdx.x * FA_QROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
   const long long ld = 3LL * E;
   const __nv_bfloat16* qbase = qkv + static_cast<long long>(b) * S * ld + h * FA_D;
   const __nv_bfloat16* kbase = qbase + E;
   const __nv_bfloat16* vbase = qbase + 2 * E;
+  constexpr float LOG2E = 1.4426950408889634f;
 
-  // Q tile -> smem (rows beyond S are zero)
-  for (int i = threadIdx.x; i < FA_BM * (FA_D / 8); i += blockDim.x) {
-    const int r = i / (FA_D / 8), c8 = i % (FA_D / 8);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q0 + r < S) v = __ldg(reinterpret_cast<const uint4*>(qbase + (q0 + r) * ld) + c8);
-    *reinterpret_cast<uint4*>(&sQ[r][c8 * 8]) = v;
+  auto load_kv = [&](int buf, int j0) {
+    Tile sK = sK0 + buf * FA_BN;
+    Tile sV = sV0 + buf * FA_BN;
+    for (int i = threadIdx.x; i < FA_BN * (FA_D / 8); i += FA_THREADS) {
+      const int r = i >> 3, c8 = i & 7;
+      const bool ok = j0 + r < S;
+      const long long row = ok ? (j0 + r) : 0;
+      cp_async16(&sK[r][c8 * 8], kbase + row * ld + c8 * 8, ok);
+      cp_async16(&sV[r][c8 * 8], vbase + row * ld + c8 * 8, ok);
+    }
+    if (threadIdx.x < FA_BN) {
+      const int j = j0 + threadIdx.x;
+      sMask[buf * FA_BN + threadIdx.x] =
+          (j < S && !(mask && mask[static_cast<long long>(b) * S + j])) ? 0.f : -INFINITY;
+    }
+  };
+
+  for (int i = threadIdx.x; i < FA_QROWS * (FA_D / 8); i += FA_THREADS) {
+    const int r = i >> 3, c8 = i & 7;
+    const bool ok = q0 + r < S;
+    cp_async16(&sQ[r][c8 * 8], qbase + (ok ? (q0 + r) : 0) * ld + c8 * 8, ok);
   }
+  load_kv(0, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
-  // Q fragments for this warp's 16 rows: 4 k-steps of 16
   uint32_t qf[4][4];
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const int row = warp * 16 + (lane & 15);
-    const int col = ks * 16 + (lane >> 4) * 8;
-    ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], &sQ[row][col]);
-  }
+  for (int ks = 0; ks < 4; ++ks)
+    ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3],
+                &sQ[warp * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
   float o[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max in log2 units
 
-  for (int j0 = 0; j0 < S; j0 += FA_BN) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < FA_BN * (FA_D / 8); i += blockDim.x) {
-      const int r = i / (FA_D / 8), c8 = i % (FA_D / 8);
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (j0 + r < S) {
-        kv = __ldg(reinterpret_cast<const uint4*>(kbase + (j0 + r) * ld) + c8);
-        vv = __ldg(reinterpret_cast<const uint4*>(vbase + (j0 + r) * ld) + c8);
-      }
-      *reinterpret_cast<uint4*>(&sK[r][c8 * 8]) = kv;
-      *reinterpret_cast<uint4*>(&sV[r][c8 * 8]) = vv;
-    }
-    for (int i = threadIdx.x; i < FA_BN; i += blockDim.x) {
-      const int j = j0 + i;
-      sMask[i] = (j < S && !(mask && mask[static_cast<long long>(b) * S + j])) ? 0.f : -INFINITY;
-    }
-    __syncthreads();
-    // S = Q K^T : 8 n-tiles of 8 keys
+  const int ntiles = (S + FA_BN - 1) / FA_BN;
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) load_kv(buf ^ 1, (t + 1) * FA_BN);   // prefetch next tile
+    cp_async_commit();
+    Tile sK = sK0 + buf * FA_BN;
+    Tile sV = sV0 + buf * FA_BN;
+    const float* mk = sMask + buf * FA_BN;
     float s[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {  // pairs of n-tiles
+      for (int np = 0; np < 4; ++np) {
         uint32_t b0, b1, b2, b3;
-        const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4(b0, b1, b2, b3, &sK[row][col]);
+        ldmatrix_x4(b0, b1, b2, b3,
+                    &sK[np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + ((lane >> 3) & 1) * 8]);
         mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
         mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
       }
     }
-    // mask + online softmax (rows g and g+8 of the warp's 16)
     float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float mk0 = sMask[n * 8 + 2 * tg], mk1 = sMask[n * 8 + 2 * tg + 1];
-      s[n][0] += mk0; s[n][1] += mk1; s[n][2] += mk0; s[n][3] += mk1;
+      const float k0 = mk[n * 8 + 2 * tg], k1 = mk[n * 8 + 2 * tg + 1];
+      s[n][0] = s[n][0] * LOG2E + k0; s[n][1] = s[n][1] * LOG2E + k1;
+      s[n][2] = s[n][2] * LOG2E + k0; s[n][3] = s[n][3] * LOG2E + k1;
       tm0 = fmaxf(tm0, fmaxf(s[n][0], s[n][1]));
       tm1 = fmaxf(tm1, fmaxf(s[n][2], s[n][3]));
     }
@@ -280,20 +304,19 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
     tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
     tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
     const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
-    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mn0);
-    const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mn1);
+    const float c0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - mn0);
+    const float c1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - mn1);
     const float base0 = (mn0 == -INFINITY) ? 0.f : mn0, base1 = (mn1 == -INFINITY) ? 0.f : mn1;
     float rs0 = 0.f, rs1 = 0.f;
-    uint32_t pf[4][4];  // P as A fragments: k-step kk covers keys kk*16..kk*16+15 = n-tiles 2kk, 2kk+1
+    uint32_t pf[4][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float p0 = __expf(s[n][0] - base0), p1 = __expf(s[n][1] - base0);
-      const float p2 = __expf(s[n][2] - base1), p3 = __expf(s[n][3] - base1);
+      const float p0 = exp2f(s[n][0] - base0), p1 = exp2f(s[n][1] - base0);
+      const float p2 = exp2f(s[n][2] - base1), p3 = exp2f(s[n][3] - base1);
       rs0 += p0 + p1;
       rs1 += p2 + p3;
-      const int kk = n >> 1, hi = n & 1;
-      pf[kk][hi * 2 + 0] = pack_bf16(p0, p1);
-      pf[kk][hi * 2 + 1] = pack_bf16(p2, p3);
+      pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
     rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
     rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
@@ -307,19 +330,19 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
     for (int n = 0; n < 8; ++n) {
       o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
     }
-    // O += P V : k = keys (4 k-steps), n = dims (8 n-tiles), V row-major -> transposed ldmatrix
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         uint32_t b0, b1, b2, b3;
-        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int col = np * 16 + (lane >> 4) * 8;
-        ldmatrix_x4_trans(b0, b1, b2, b3, &sV[row][col]);
+        ldmatrix_x4_trans(b0, b1, b2, b3,
+                          &sV[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
         mma_bf16_16816(o[2 * np], pf[kk], b0, b1);
         mma_bf16_16816(o[2 * np + 1], pf[kk], b2, b3);
       }
     }
+    cp_async_wait<0>();   // next tile landed
+    __syncthreads();      // everyone done with this tile's buffers before they are overwritten
   }
   const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
@@ -334,6 +357,7 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
           pack_bf16(o[n][2] * i1, o[n][3] * i1);
   }
 }
+constexpr int FA_SMEM = (FA_QROWS + 4 * FA_BN) * FA_LD * 2 + 2 * FA_BN * 4;
 
 static inline int flat_grid3(long long n) {
   long long g = ceil_div_ll(n, 256);
@@ -419,8 +443,13 @@ extern "C" int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_ma
   TT_REQUIRE(qkv && out, "tt_flash_self_attn: null pointer");
   TT_REQUIRE(D == FA_D, "tt_flash_self_attn: head_dim must be %d (got %d)", FA_D, D);
   if (B <= 0 || S <= 0) return TT_OK;
-  dim3 grid(ceil_div(S, FA_BM), B * H);
-  launch_k(flash_self_attn_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
+  dim3 grid(ceil_div(S, FA_QROWS), B * H);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(flash_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    attr_set = true;
+  }
+  launch_k(flash_self_attn_kernel, dim3(grid), dim3(FA_THREADS), FA_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), key_padding_mask,
       reinterpret_cast<__nv_bfloat16*>(out), B, S, H);
   return check_launch("flash_self_attn_kernel");
