@@ -75,54 +75,43 @@ class LinearFn(Function):
 
 
 class KVProjFn(Function):
-    """kv [R, 2E] = [x @ wk^T + bk | x @ wv^T + bv]: the key and value projections of one context
-    share the cast of x and land in one buffer the attention kernel reads with stride 2E
-    (multi_head.py:500-518 in_proj_k / in_proj_v)."""
+    """kv [R, 2E] = x @ [Wk; Wv]^T + [bk | bv]: the key and value projections of one context as ONE
+    GEMM whose output the attention kernels read with stride 2E (multi_head.py:500-518)."""
 
     @staticmethod
     def forward(ctx, x, wk, wv, bias_kv):
-        E = wk.shape[0]
         a16 = operand(x, 'a')
-        wk16, wv16 = operand(wk, 'b'), operand(wv, 'b')
-        kv = torch.empty((x.shape[0], 2 * E), dtype=torch.float32, device=x.device)
-        ops.gemm_tn(a16, wk16, out=kv[:, :E], bias=None if bias_kv is None else bias_kv[:E])
-        ops.gemm_tn(a16, wv16, out=kv[:, E:], bias=None if bias_kv is None else bias_kv[E:])
-        ctx.has_bias, ctx.fast = bias_kv is not None, _fast()
+        w16 = concat_rows_operand([wk, wv], 'b', x.device)          # [2E, kdim]
+        kv = ops.gemm_tn(a16, w16, bias=bias_kv)
+        ctx.has_bias, ctx.fast, ctx.E = bias_kv is not None, _fast(), wk.shape[0]
         if ctx.fast:
-            ctx.save_for_backward(a16, wk16, wv16)
+            ctx.save_for_backward(a16, w16)
         else:
             ctx.save_for_backward(x, wk, wv)
         return kv
 
     @staticmethod
     def backward(ctx, dkv):
-        x, wk, wv = ctx.saved_tensors
         dkv = _c(dkv)
-        E = wk.shape[0]
-        dk, dv = dkv[:, :E], dkv[:, E:]
-        dx = dwk = dwv = db = None
+        E = ctx.E
+        dx = dW = db = None
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         if ctx.fast:
-            d16 = operand(dkv, 'a')                                  # [R, 2E] in one cast
-            dk16, dv16 = d16[:, :E], d16[:, E:]
+            x, w = ctx.saved_tensors
+            d16 = operand(dkv, 'a')
             if ctx.needs_input_grad[0]:
-                dx = ops.gemm_tn(dk16, wk, trans_b=True)
-                ops.gemm_tn(dv16, wv, out=dx, accumulate=True, trans_b=True)
+                dx = ops.gemm_tn(d16, w, trans_b=True)
             if need_w:
-                dwk = ops.gemm_tn(dk16, x, trans_a=True, trans_b=True)
-                dwv = ops.gemm_tn(dv16, x, trans_a=True, trans_b=True)
+                dW = ops.gemm_tn(d16, x, trans_a=True, trans_b=True)
         else:
+            x, wk, wv = ctx.saved_tensors
             if ctx.needs_input_grad[0]:
-                dx = ops.gemm_tn(operand(dk, 'a'), operand(wk, 'b', transpose=True))
-                ops.gemm_tn(operand(dv, 'a'), operand(wv, 'b', transpose=True), out=dx,
-                            accumulate=True)
+                dx = ops.gemm_tn(operand(dkv, 'a'), concat_kT_operand([wk, wv], 'b', dkv.device))
             if need_w:
-                xT = operand(x, 'b', transpose=True)
-                dwk = ops.gemm_tn(operand(dk, 'a', transpose=True), xT)
-                dwv = ops.gemm_tn(operand(dv, 'a', transpose=True), xT)
+                dW = ops.gemm_tn(operand(dkv, 'a', transpose=True), operand(x, 'b', transpose=True))
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = ops.colsum(dkv)
-        return dx, dwk, dwv, db
+        return dx, (dW[:E] if dW is not None else None), (dW[E:] if dW is not None else None), db
 
 
 class WeightNormFn(Function):
@@ -325,6 +314,171 @@ class AttentionFn(Function):
                      dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None,
                      dbk, dbv, T, B, S, H, D, zero_row, p, seed, tc=tc)
         return (dq, dkv, dbk, dbv) + (None,) * 9
+
+
+def concat_rows_operand(mats, side, device):
+    """One bf16 operand [sum_i R_i, K(*rep)]: the row-wise concatenation of `mats` ([R_i, K])."""
+    K = mats[0].shape[1]
+    rep = 1 if config.precision == 'bf16' else 3
+    split = 0 if rep == 1 else (1 if side == 'a' else 2)
+    buf = ops.bf16_buffer(sum(m.shape[0] for m in mats), K * rep, device)
+    r0 = 0
+    for m in mats:
+        ops.cast_bf16(m, split=split, out=buf[r0:r0 + m.shape[0]])
+        r0 += m.shape[0]
+    return buf
+
+
+class FusedQProjFn(Function):
+    """The query projections of all n contexts of a layer share their input (decoder_faces_objects.py
+    :272-352 feeds the same X to every attention): Q_all [N, n*E] = alpha * (x @ [Wq_1;..;Wq_n]^T + b)
+    as ONE GEMM (multi_head.py:491-498 in_proj_q, :353 q *= scaling)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, n, *args):
+        ws, bs = args[:n], args[n:2 * n]
+        a16 = operand(x, 'a')
+        w16 = concat_rows_operand(list(ws), 'b', x.device)
+        bias = torch.cat([b.reshape(-1) for b in bs]) if bs[0] is not None else None
+        y = ops.gemm_tn(a16, w16, bias=bias, alpha=alpha)
+        ctx.cfg = (alpha, n, ws[0].shape[0], bias is not None, _fast())
+        if ctx.cfg[4]:
+            ctx.save_for_backward(a16, w16)
+        else:
+            ctx.save_for_backward(x, *ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        alpha, n, E, has_bias, fast = ctx.cfg
+        dy = _c(dy)
+        if fast:
+            a16, w16 = ctx.saved_tensors
+            d16 = operand(dy, 'a')
+            dx = ops.gemm_tn(d16, w16, alpha=alpha, trans_b=True)
+            dW = ops.gemm_tn(d16, a16, alpha=alpha, trans_a=True, trans_b=True)
+        else:
+            x, ws = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+            dx = ops.gemm_tn(operand(dy, 'a'), concat_kT_operand(list(ws), 'b', dy.device), alpha=alpha)
+            dW = ops.gemm_tn(operand(dy, 'a', transpose=True), operand(x, 'b', transpose=True),
+                             alpha=alpha)
+        dws = tuple(dW[c * E:(c + 1) * E] for c in range(n))
+        dbs = (None,) * n
+        if has_bias:
+            db = ops.colsum(dy, scale=alpha)
+            dbs = tuple(db[c * E:(c + 1) * E] for c in range(n))
+        return (dx, None, None) + dws + dbs
+
+
+class MultiCtxAttentionFn(Function):
+    """All n cross-attentions of a layer on one fused query buffer: q_c = Q_all[:, cE:(c+1)E],
+    out_c written into out_all[:, cE:(c+1)E] (row strides do the slicing, no copies)."""
+
+    @staticmethod
+    def forward(ctx, q_all, T, B, H, zero_row, p, seeds, need_weights, n, *args):
+        kvs, bks, bvs, masks = args[:n], args[n:2 * n], args[2 * n:3 * n], args[3 * n:4 * n]
+        E = q_all.shape[1] // n
+        D = E // H
+        tc = config.precision == 'bf16' and D == 64
+        out_all = torch.empty_like(q_all)
+        lses, weights, Ss = [], [], []
+        for c in range(n):
+            kv = kvs[c]
+            S = kv.shape[0] // B if kv is not None else 0
+            Ss.append(S)
+            q = q_all[:, c * E:(c + 1) * E]
+            bk = bks[c].view(-1) if bks[c] is not None else None
+            bv = bvs[c].view(-1) if bvs[c] is not None else None
+            _, lse = ops.attn_fwd(q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None, bk, bv,
+                                  masks[c] if S > 0 else None, T, B, S, H, D, zero_row, p, seeds[c],
+                                  tc=tc, out=out_all[:, c * E:(c + 1) * E])
+            lses.append(lse)
+            if need_weights:
+                weights.append(ops.attn_avg_weights(q, kv[:, :E] if S > 0 else None, bk,
+                                                    masks[c] if S > 0 else None, lse, T, B, S, H, D,
+                                                    zero_row))
+        ctx.cfg = (T, B, H, D, zero_row, p, seeds, n, tuple(Ss), tc)
+        ctx.save_for_backward(q_all, out_all, *kvs, *bks, *bvs, *masks, *lses)
+        ctx.mark_non_differentiable(*weights)
+        return (out_all,) + tuple(weights)
+
+    @staticmethod
+    def backward(ctx, dout_all, *_dw):
+        T, B, H, D, zero_row, p, seeds, n, Ss, tc = ctx.cfg
+        sv = ctx.saved_tensors
+        q_all, out_all = sv[0], sv[1]
+        kvs, bks, bvs = sv[2:2 + n], sv[2 + n:2 + 2 * n], sv[2 + 2 * n:2 + 3 * n]
+        masks, lses = sv[2 + 3 * n:2 + 4 * n], sv[2 + 4 * n:2 + 5 * n]
+        E = H * D
+        dout_all = _c(dout_all)
+        dq_all = torch.empty_like(q_all)
+        dkvs, dbks, dbvs = [], [], []
+        for c in range(n):
+            S, kv = Ss[c], kvs[c]
+            dkv = torch.empty_like(kv) if S > 0 else None
+            dbk = torch.zeros_like(bks[c]) if bks[c] is not None else None
+            dbv = torch.zeros_like(bvs[c]) if bvs[c] is not None else None
+            sl = slice(c * E, (c + 1) * E)
+            ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
+                         kv[:, E:] if S > 0 else None,
+                         bks[c].view(-1) if bks[c] is not None else None,
+                         bvs[c].view(-1) if bvs[c] is not None else None,
+                         masks[c] if S > 0 else None, out_all[:, sl], lses[c], dq_all[:, sl],
+                         dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None, dbk, dbv,
+                         T, B, S, H, D, zero_row, p, seeds[c], tc=tc)
+            dkvs.append(dkv)
+            dbks.append(dbk)
+            dbvs.append(dbv)
+        return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n
+
+
+class FusedOutProjFn(Function):
+    """h_c = a_c @ Wo_c^T + bo_c for the n attention outputs living side by side in a_all [N, n*E]
+    (multi_head.py:476 out_proj): one operand cast, n GEMMs reading column blocks by stride."""
+
+    @staticmethod
+    def forward(ctx, a_all, n, *args):
+        ws, bs = args[:n], args[n:2 * n]
+        E = a_all.shape[1] // n
+        a16 = operand(a_all, 'a')
+        rep = _rep()
+        w16s, hs = [], []
+        for c in range(n):
+            w16 = operand(ws[c], 'b')
+            w16s.append(w16)
+            if rep == 1:
+                a_c = a16[:, c * E:(c + 1) * E]
+            else:   # split layout is per full row: cast the block on its own
+                a_c = operand(a_all[:, c * E:(c + 1) * E], 'a')
+            hs.append(ops.gemm_tn(a_c, w16, bias=bs[c]))
+        ctx.cfg = (n, E, _fast(), bs[0] is not None)
+        if ctx.cfg[2]:
+            ctx.save_for_backward(a16, *w16s)
+        else:
+            ctx.save_for_backward(a_all, *ws)
+        return tuple(hs)
+
+    @staticmethod
+    def backward(ctx, *dhs):
+        n, E, fast, has_bias = ctx.cfg
+        sv = ctx.saved_tensors
+        a, ws = sv[0], sv[1:]
+        N = a.shape[0]
+        da_all = torch.empty((N, n * E), dtype=torch.float32, device=a.device)
+        dws, dbs = [], []
+        for c in range(n):
+            dh = _c(dhs[c])
+            sl = slice(c * E, (c + 1) * E)
+            if fast:
+                d16 = operand(dh, 'a')
+                ops.gemm_tn(d16, ws[c], out=da_all[:, sl], trans_b=True)
+                dws.append(ops.gemm_tn(d16, a[:, sl], trans_a=True, trans_b=True))
+            else:
+                ops.gemm_tn(operand(dh, 'a'), operand(ws[c], 'b', transpose=True), out=da_all[:, sl])
+                dws.append(ops.gemm_tn(operand(dh, 'a', transpose=True),
+                                       operand(a[:, sl], 'b', transpose=True)))
+            dbs.append(ops.colsum(dh) if has_bias else None)
+        return (da_all, None) + tuple(dws) + tuple(dbs)
 
 
 def _rep():

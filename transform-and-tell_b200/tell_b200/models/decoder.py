@@ -101,23 +101,37 @@ class DynamicConvDecoderLayer(DecoderLayer):
         X2 = Fn.ResidualLayerNormFn.apply(h, X2.contiguous(), self.conv_layer_norm.weight,
                                           self.conv_layer_norm.bias, p, self._seed(p),
                                           self.conv_layer_norm.eps)
-        # ---- parallel cross-attention branches (:272-352), all reading the same X2
+        # ---- parallel cross-attention branches (:272-352), all reading the same X2:
+        #      one fused Q GEMM, n attention launches on column blocks, n out_proj GEMMs
         need_w = (not self.training) and self.need_attn
-        attns, hs = {}, []
-        for name in self.context_names:
-            mha = self.context_attns[name]
-            if kv_cache is not None and name in kv_cache:
-                kv = kv_cache[name]
+        names = self.context_names
+        n = len(names)
+        mhas = [self.context_attns[nm] for nm in names]
+        kvs, masks = [], []
+        for nm, mha in zip(names, mhas):
+            if kv_cache is not None and nm in kv_cache:
+                kv = kv_cache[nm]
             else:
-                kv = mha.project_kv(contexts[name])
+                kv = mha.project_kv(contexts[nm])
                 if kv_cache is not None:
-                    kv_cache[name] = kv
-            a, w = mha.attend(X2.view(T, B, E), kv, contexts[name + '_mask'], need_w)
-            hs.append(Fn.LinearFn.apply(a, mha.out_proj.weight, mha.out_proj.bias))
-            if w is not None:
-                attns[name] = w
-        lns = [self.context_attn_lns[n] for n in self.context_names]
-        n = len(hs)
+                    kv_cache[nm] = kv
+            kvs.append(kv)
+            m = contexts[nm + '_mask']
+            masks.append(m.to(torch.uint8).contiguous() if (m is not None and kv is not None) else None)
+        E_ = self.embed_dim
+        q_ws = [mha._weights()[0] for mha in mhas]
+        q_bs = [mha.in_proj_bias[:E_] if mha.in_proj_bias is not None else None for mha in mhas]
+        Q_all = Fn.FusedQProjFn.apply(X2, mhas[0].scaling, n, *q_ws, *q_bs)
+        p_att = self._p(mhas[0].dropout)
+        seeds_a = tuple(self._seed(p_att) for _ in range(n))
+        res = Fn.MultiCtxAttentionFn.apply(Q_all, T, B, mhas[0].num_heads, mhas[0].add_zero_attn, p_att,
+                                           seeds_a, need_w, n, *kvs, *[m.bias_k for m in mhas],
+                                           *[m.bias_v for m in mhas], *masks)
+        A_all = res[0]
+        attns = {nm: w for nm, w in zip(names, res[1:])} if need_w else {}
+        hs = Fn.FusedOutProjFn.apply(A_all, n, *[m.out_proj.weight for m in mhas],
+                                     *[m.out_proj.bias for m in mhas])
+        lns = [self.context_attn_lns[nm] for nm in names]
         seeds = tuple(self._seed(p) for _ in range(n))
         Xc = Fn.ContextLayerNormFn.apply(X2, p, seeds, lns[0].eps, n, *hs,
                                          *[l.weight for l in lns], *[l.bias for l in lns])

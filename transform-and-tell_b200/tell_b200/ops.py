@@ -254,16 +254,19 @@ def dynconv_bwd(dout, x, probs, H, K, softmax=True, p=0.0, seed=0):
 
 
 # --------------------------------------------------------------------------- attention
-def attn_fwd(q, k, v, bias_k, bias_v, mask, T, B, S, H, D, zero_row=True, p=0.0, seed=0, tc=False):
-    """q [T*B, >=E] view, k/v [S*B, >=E] views (row strides honoured); returns (out [T*B,E], lse)."""
+def attn_fwd(q, k, v, bias_k, bias_v, mask, T, B, S, H, D, zero_row=True, p=0.0, seed=0, tc=False,
+             out=None):
+    """q [T*B, >=E] view, k/v [S*B, >=E] views (row strides honoured); returns (out [T*B,E], lse).
+    `out` may be a strided view (e.g. a column block of a [T*B, n*E] buffer)."""
     E = H * D
-    out = _f32(T * B, E, like=q)
+    if out is None:
+        out = _f32(T * B, E, like=q)
     lse = _f32(B, H, T, like=q)
     _lib.call('tt_attn_fwd_tc' if tc else 'tt_attn_fwd', _ptr(q), _ptr(k if S > 0 else None),
               _ptr(v if S > 0 else None),
               _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out), _ptr(lse), c_int(T), c_int(B),
               c_int(S), c_int(H), c_int(D), c_ll(q.stride(0)),
-              c_ll(k.stride(0) if S > 0 else E), c_ll(E), c_int(1 if zero_row else 0),
+              c_ll(k.stride(0) if S > 0 else E), c_ll(out.stride(0)), c_int(1 if zero_row else 0),
               c_float(p), _ull(seed), _stream())
     return out, lse
 
@@ -272,7 +275,7 @@ def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k,
              H, D, zero_row=True, p=0.0, seed=0, tc=False):
     """dq/dk/dv are caller-allocated views with the same row strides as q/k/v."""
     E = H * D
-    assert dout.stride(0) == E and out.stride(0) == E and dq.stride(0) == q.stride(0)
+    assert dout.stride(0) == out.stride(0) and dq.stride(0) == q.stride(0)
     if S > 0:
         assert dk.stride(0) == k.stride(0) and dv.stride(0) == k.stride(0)
     _lib.call('tt_attn_bwd_tc' if tc else 'tt_attn_bwd', _ptr(dout), _ptr(q),
@@ -280,7 +283,7 @@ def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k,
               _ptr(v if S > 0 else None), _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out),
               _ptr(lse), _ptr(dq), _ptr(dk if S > 0 else None), _ptr(dv if S > 0 else None),
               _ptr(dbias_k), _ptr(dbias_v), c_int(T), c_int(B), c_int(S), c_int(H), c_int(D),
-              c_ll(q.stride(0)), c_ll(k.stride(0) if S > 0 else E), c_ll(E),
+              c_ll(q.stride(0)), c_ll(k.stride(0) if S > 0 else E), c_ll(out.stride(0)),
               c_int(1 if zero_row else 0), c_float(p), _ull(seed), _stream())
 
 
