@@ -10,32 +10,12 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "runtime.h"
 
 namespace tt {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
-
-struct GemmArgs {
-  int M, N, K;
-  float* C;
-  long long ldc;
-  __nv_bfloat16* C16;
-  long long ldc16;
-  const float* bias;
-  const float* residual;
-  long long ldr;
-  const __nv_bfloat16* residual16;
-  long long ldr16;
-  float alpha;
-  int act;
-  int accumulate;
-  const int* m_limit;
-  int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
-};
 
 template <int BN>
 struct GemmCfg {
@@ -46,12 +26,6 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
 };
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == TT_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == TT_ACT_GELU) return gelu_erf(v);
-  return v;
-}
 
 template <int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -195,119 +169,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tcgen05_fence_after();
       const long long row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int col0 = n_blk * BN + c * 32;
-        const bool in_n = col0 < g.N;                       // warp-uniform
-        const bool full = in_n && (col0 + 32 <= g.N) && g.vec_ok;
-        float4 bv[8];
-        float4 rv[8];
-        uint4 rh[4];
-        if (full) {
-          if (g.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);
-          }
-          if (row_ok && g.residual != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              rv[j] = __ldg(reinterpret_cast<const float4*>(g.residual + row * g.ldr + col0) + j);
-          }
-          if (row_ok && g.residual16 != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              rh[j] = __ldg(reinterpret_cast<const uint4*>(g.residual16 + row * g.ldr16 + col0) + j);
-          }
-        }
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(acc * BN + c * 32);
-        tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
-        if (!in_n || !row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (full) {
-          if (g.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
-            }
-          }
-          if (g.alpha != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
-          }
-          if (g.residual != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
-            }
-          }
-          if (g.residual16 != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                v[8 * j + 2 * e] += __low2float(h2);
-                v[8 * j + 2 * e + 1] += __high2float(h2);
-              }
-            }
-          }
-          if (g.act != TT_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
-          }
-          if (g.C != nullptr) {
-            float4* cp = reinterpret_cast<float4*>(g.C + row * g.ldc + col0);
-            if (g.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = cp[j];
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (g.C16 != nullptr) {
-            uint4* hp = reinterpret_cast<uint4*>(g.C16 + row * g.ldc16 + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-              u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-              u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-              u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-              hp[j] = u;
-            }
-          }
-        } else {
-          // ragged N or unaligned pointers: scalar path
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < g.N) {
-              float o = v[j];
-              if (g.bias != nullptr) o += __ldg(g.bias + col);
-              o *= g.alpha;
-              if (g.residual != nullptr) o += __ldg(g.residual + row * g.ldr + col);
-              if (g.residual16 != nullptr) o += __bfloat162float(g.residual16[row * g.ldr16 + col]);
-              o = apply_act(o, g.act);
-              if (g.C != nullptr) {
-                float* cp = g.C + row * g.ldc + col;
-                if (g.accumulate) o += *cp;
-                *cp = o;
-              }
-              if (g.C16 != nullptr) g.C16[row * g.ldc16 + col] = __float2bfloat16_rn(o);
-            }
-          }
-        }
-      }
+      epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN),
+                          half, row, row_ok, n_blk * BN);
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
@@ -390,6 +254,8 @@ static int pick_bn(int M, int N, int sms) {
   return 64;
 }
 
+int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream);  // gemm2.cu
+
 }  // namespace tt
 
 extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
@@ -443,6 +309,11 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     vec = vec && (reinterpret_cast<uintptr_t>(p->residual16) & 15) == 0 && (p->ldr16 % 8 == 0);
   if (p->bias) vec = vec && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
   g.vec_ok = vec ? 1 : 0;
+
+  {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
+    const int r2 = gemm2_try(p, g, reinterpret_cast<cudaStream_t>(stream));
+    if (r2 != 0) return r2 > 0 ? TT_OK : r2;
+  }
 
   const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
   const int grid = tiles < sms ? tiles : sms;

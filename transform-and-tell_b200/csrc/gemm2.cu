@@ -1,0 +1,290 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM for the large K-major GEMMs of the frozen
+// encoders:  C[M,N] = act(alpha * (A[M,K] . B[N,K]^T + bias) + residual).
+//
+// Why: with one CTA per MMA, every SM must stream a full B tile (BN x 64) per k-block through its
+// own shared memory; the 128 B/clk shared-memory port (TMA fill + UMMA operand reads) then caps
+// the tensor pipe near 60-65 %.  A CTA pair (two SMs of one TPC, cluster 2x1) computes a 256 x BN
+// tile with ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 rows of A but only
+// HALF of B (BN/2 rows); the tensor cores of both SMs read both halves.  Per SM and k-block the
+// shared-memory traffic drops from 48 KB to 32 KB for the same 128 x 256 outputs.
+//
+// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs; the loads signal the LEADER's full
+// barrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs' barriers),
+// warp 2 TMEM allocator (cta_group::2, both CTAs), warps 4-11 epilogue (each CTA drains its own
+// 128 TMEM lanes = its 128 rows of the tile and reports to the leader's tmem_empty barrier).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "runtime.h"
+
+namespace tt {
+
+constexpr int G2_THREADS = 384;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN;               // double-buffered 128 x BN accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
+               : "memory");
+}
+// TMA tile load issued by either CTA of the pair; completes on the LEADER CTA's mbarrier
+// (peer bit of the shared::cluster barrier address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                 int c0, int c1) {
+  const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives (once all MMAs issued so far by this thread retire) on the barrier at this smem offset in
+// BOTH CTAs of the pair.
+__device__ __forceinline__ void umma2_commit_mcast(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// mbarrier arrive on the barrier at the same smem offset in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmArgs g) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader: one arrive.expect_tx + bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);   // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);              // one multicast commit per tile
+      mbar_init(&tmem_empty[s], 2 * 8);         // leader: 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // peer barriers initialised and peer TMEM allocated before any remote signal
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  int M = g.M;
+  if (g.m_limit != nullptr) M = min(M, __ldg(g.m_limit));
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);   // 256-row tiles
+  const int num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
+              const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
+              umma2_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma2_commit_mcast(&empty_bar[stage]);
+            if (kb == num_k - 1) umma2_commit_mcast(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps, both CTAs) =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const long long row = static_cast<long long>(m_blk) * 2 * BM + rank * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN),
+                          half, row, row_ok, n_blk * BN);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // report to the leader's barrier
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading our shared memory / TMEM through the pair MMA
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int pairs,
+                        cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm2 BN=%d): %s", BN, cudaGetErrorString(e));
+      return TT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  launch_k(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, g);
+  return check_launch("gemm2_bf16_kernel");
+}
+
+// Called by tt_gemm_bf16_tn for large K-major problems.  Returns 1 if it took the problem, 0 if
+// the caller should use the 1-CTA kernel, <0 on error.
+int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TT_GEMM_2CTA");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || p->trans_a || p->trans_b) return 0;
+  const int sms = num_sms();
+  const int pairs_max = sms / 2;
+  int bn = 0;
+  if (p->N >= 256 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 256) >= pairs_max) bn = 256;
+  else if (p->N >= 128 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 128) >= pairs_max) bn = 128;
+  if (bn == 0) return 0;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
+  if (rc != TT_OK) return rc;
+  rc = make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->ldb, BK, bn / 2);
+  if (rc != TT_OK) return rc;
+  const int tiles = ceil_div(p->M, 2 * BM) * ceil_div(p->N, bn);
+  const int pairs = tiles < pairs_max ? tiles : pairs_max;
+  rc = (bn == 256) ? launch_gemm2<256>(tmA, tmB, g, pairs, stream)
+                   : launch_gemm2<128>(tmA, tmB, g, pairs, stream);
+  return rc == TT_OK ? 1 : rc;
+}
+
+}  // namespace tt

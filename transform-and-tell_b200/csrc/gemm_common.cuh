@@ -1,0 +1,159 @@
+// Pieces shared by the 1-CTA (gemm.cu) and 2-CTA (gemm2.cu) tcgen05 GEMM kernels: argument block
+// and the register-level epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace tt {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+
+struct GemmArgs {
+  int M, N, K;
+  float* C;
+  long long ldc;
+  __nv_bfloat16* C16;
+  long long ldc16;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  const __nv_bfloat16* residual16;
+  long long ldr16;
+  float alpha;
+  int act;
+  int accumulate;
+  const int* m_limit;
+  int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == TT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == TT_ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+// Epilogue of one 128 x BN accumulator (one thread = one row, 32 columns per tcgen05.ld).
+// tmem_acc: TMEM address of column 0 of the accumulator, already offset to this warp's lane quarter.
+// Two warps share a lane quarter: `half` selects the even / odd 32-column chunks.
+// Result = act(alpha * (acc + bias) + residual) -> fp32 and/or bf16, optional += into C.
+template <int BN>
+__device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem_acc, int half,
+                                                long long row, bool row_ok, int n0) {
+  const int lane = threadIdx.x & 31;
+  (void)lane;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        const bool in_n = col0 < g.N;                       // warp-uniform
+        const bool full = in_n && (col0 + 32 <= g.N) && g.vec_ok;
+        float4 bv[8];
+        float4 rv[8];
+        uint4 rh[4];
+        if (full) {
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);
+          }
+          if (row_ok && g.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              rv[j] = __ldg(reinterpret_cast<const float4*>(g.residual + row * g.ldr + col0) + j);
+          }
+          if (row_ok && g.residual16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              rh[j] = __ldg(reinterpret_cast<const uint4*>(g.residual16 + row * g.ldr16 + col0) + j);
+          }
+        }
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + static_cast<uint32_t>(c * 32);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        if (!in_n || !row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (full) {
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+            }
+          }
+          if (g.alpha != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+          }
+          if (g.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
+            }
+          }
+          if (g.residual16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                v[8 * j + 2 * e] += __low2float(h2);
+                v[8 * j + 2 * e + 1] += __high2float(h2);
+              }
+            }
+          }
+          if (g.act != TT_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+          }
+          if (g.C != nullptr) {
+            float4* cp = reinterpret_cast<float4*>(g.C + row * g.ldc + col0);
+            if (g.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = cp[j];
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (g.C16 != nullptr) {
+            uint4* hp = reinterpret_cast<uint4*>(g.C16 + row * g.ldc16 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              hp[j] = u;
+            }
+          }
+        } else {
+          // ragged N or unaligned pointers: scalar path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < g.N) {
+              float o = v[j];
+              if (g.bias != nullptr) o += __ldg(g.bias + col);
+              o *= g.alpha;
+              if (g.residual != nullptr) o += __ldg(g.residual + row * g.ldr + col);
+              if (g.residual16 != nullptr) o += __bfloat162float(g.residual16[row * g.ldr16 + col]);
+              o = apply_act(o, g.act);
+              if (g.C != nullptr) {
+                float* cp = g.C + row * g.ldc + col;
+                if (g.accumulate) o += *cp;
+                *cp = o;
+              }
+              if (g.C16 != nullptr) g.C16[row * g.ldc16 + col] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+}
+
+}  // namespace tt
