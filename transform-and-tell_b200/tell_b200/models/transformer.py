@@ -65,8 +65,19 @@ class _CaptionModelBase(Model):
         params.pop('initializer', None)
         return cls(vocab=None, decoder=decoder, criterion=criterion, **params, **extras)
 
+    # ------------------------------------------------------------------ frozen encoders
+    @torch.no_grad()
+    def encode(self, context, image):
+        """The gradient-free part of _forward (:332, :352-353): ResNet features (NHWC bf16) and all
+        RoBERTa hidden states (bf16 [L+1, B*S, E]).  It depends on no trainable weight, so a
+        data-parallel trainer may run it for step i+1 while step i's gradient all-reduce is still
+        in flight; pass the result to forward(..., encoded=...)."""
+        feats = self.resnet.features_nhwc(image) if self.USES_IMAGE else None
+        hid, _ = self.roberta.all_hiddens(context[self.index])
+        return feats, hid
+
     # ------------------------------------------------------------------ _forward (:311-397)
-    def _forward(self, context, image, caption, face_embeds=None, obj_embeds=None):
+    def _forward(self, context, image, caption, face_embeds=None, obj_embeds=None, encoded=None):
         caption_ids = caption[self.index]
         target_ids = caption_ids[:, 1:].contiguous()
         caption_ids = caption_ids[:, :-1].contiguous()
@@ -74,14 +85,15 @@ class _CaptionModelBase(Model):
         article_ids = context[self.index]
         B, S = article_ids.shape
         contexts = {}
+        if encoded is None:
+            encoded = self.encode(context, image)
+        feats, hid = encoded
         if self.USES_IMAGE:
-            feats = self.resnet.features_nhwc(image)                 # [B,7,7,2048] bf16 == [B,49,2048]
-            P = feats.shape[1] * feats.shape[2]
+            P = feats.shape[1] * feats.shape[2]                      # [B,7,7,2048] bf16 == [B,49,2048]
             X_image = ops.bf16_to_f32(feats).view(B, P, feats.shape[3])
             contexts['image'] = Fn.Transpose01Fn.apply(X_image)      # [49,B,2048]
-            contexts['image_mask'] = torch.zeros((B, P), dtype=torch.bool, device=image.device)
-        hid, is_pad = self.roberta.all_hiddens(article_ids)          # bf16 [25, B*S, E]
-        if self.weigh_bert:
+            contexts['image_mask'] = torch.zeros((B, P), dtype=torch.bool, device=feats.device)
+        if self.weigh_bert:                                          # hid: bf16 [25, B*S, E]
             X_article = Fn.LayerMixFn.apply(hid, self.bert_weight)
         else:
             X_article = ops.bf16_to_f32(hid[-1])
@@ -104,9 +116,9 @@ class _CaptionModelBase(Model):
 
     # ------------------------------------------------------------------ forward (:67-140)
     def forward(self, context, image, caption, face_embeds=None, obj_embeds=None, metadata=None,
-                names=None, attn_idx=None):
+                names=None, attn_idx=None, encoded=None):
         caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
-                                                          obj_embeds)
+                                                          obj_embeds, encoded)
         X, _ = self.decoder.forward_tbc(caption, contexts)           # [T,B,E], no transpose needed
         T, B, E = X.shape
         # the loss is a sum over tokens, so (t,b) order with the target transposed alike is exact
