@@ -84,6 +84,10 @@ typedef struct {
   int trans_b;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
+/* Debug hook: when non-NULL, every CTA of the 1-CTA GEMM kernel writes 8 %globaltimer stamps (
+ * (entry, setup done, first TMA issued, first tile landed, last MMA issued, accumulator ready,
+ * epilogue done, exit) to dev_ptr[cta*8 ..]; NULL (default) disables it. */
+void tt_gemm_set_trace(long long* dev_ptr);
 
 /* fp32 [rows, cols] (row stride ld_src) -> bf16 operand for tt_gemm_bf16_tn.
  *   transpose==0: dst is [rows, cols*rep]   transpose!=0: dst is [cols, rows*rep]

@@ -62,9 +62,25 @@ for (M, N, K, o16, lim), cnt in shapes.items():
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) / 100 * 1e3
-    rows.append((us * cnt, cnt, M, N, K, o16, lim, us, 2.0 * M * N * K / us / 1e6))
+    # cuBLAS on the same shape (target, not product)
+    ob = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ac, wt = a.contiguous(), w.contiguous().t()
+    for _ in range(3):
+        torch.matmul(ac, wt, out=ob)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for _ in range(20):
+            torch.matmul(ac, wt, out=ob)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(5):
+        g2.replay()
+    e.record()
+    torch.cuda.synchronize()
+    us_cb = s.elapsed_time(e) / 100 * 1e3
+    rows.append((us * cnt, cnt, M, N, K, o16, lim, us, 2.0 * M * N * K / us / 1e6, us_cb))
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 print('unique shapes %d, launches %d, sum of isolated times %.2f ms' % (len(rows), sum(r[1] for r in rows), tot / 1e3))
 for r in rows[:60]:
-    print('tot %8.1f us  x%3d  M=%6d N=%6d K=%6d o16=%d lim=%d  %7.1f us  %7.1f TF' % r)
+    print('tot %8.1f us  x%3d  M=%6d N=%6d K=%6d o16=%d lim=%d  %7.1f us  %7.1f TF   cublas %7.1f us' % r)

@@ -44,10 +44,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // shuffled so the compiler knows the role index is warp-uniform (uniform-datapath code)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();   // the next kernel may start its own prologue
+  if (threadIdx.x == 0) trace_stamp(g, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -72,6 +74,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(g, 1);
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
   // the previous kernel; from here on we touch its outputs.
   pdl_wait();
@@ -84,40 +87,53 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+    // The whole warp runs the (warp-uniform) loop so that addresses / coordinates live in uniform
+    // registers; one elected lane issues.  A divergent `if (lane == 0)` region costs ~100 dependent
+    // SASS instructions (R2UR waterfall loops) per k-block = 0.2-0.3 us, which for narrow tiles is
+    // longer than the MMAs themselves.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), full_u = smem_u32(full_bar);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          const uint32_t bar = full_u + stage * 8;
+          mbar_arrive_expect_tx_u(bar, Cfg::STAGE_BYTES);
           if (!TA) {
-            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d_u(sA_u + stage * Cfg::A_BYTES, &tmA, bar, kb * BK, m_blk * BM);
           } else {  // MN-major: one 64(m) x 64(k) box per 64-row chunk of the tile
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d(sA + stage * Cfg::A_BYTES + c * 8192, &tmA, &full_bar[stage],
-                          m_blk * BM + c * 64, kb * BK);
+              tma_load_2d_u(sA_u + stage * Cfg::A_BYTES + c * 8192, &tmA, bar, m_blk * BM + c * 64, kb * BK);
           }
           if (!TB) {
-            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d_u(sB_u + stage * Cfg::B_BYTES, &tmB, bar, kb * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sB + stage * Cfg::B_BYTES + c * 8192, &tmB, &full_bar[stage],
-                          n_blk * BN + c * 64, kb * BK);
+              tma_load_2d_u(sB_u + stage * Cfg::B_BYTES + c * 8192, &tmB, bar, n_blk * BN + c * 64, kb * BK);
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == 0 && tile == blockIdx.x) trace_stamp(g, 2);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, TA, TB);
+    // descriptor templates: the start-address field (bits 0-13, 16-byte units) is advanced by adds
+    const uint64_t da0 = TA ? umma_desc_mnmajor_sw128(smem_u32(sA)) : umma_desc_kmajor_sw128(smem_u32(sA));
+    const uint64_t db0 = TB ? umma_desc_mnmajor_sw128(smem_u32(sB)) : umma_desc_kmajor_sw128(smem_u32(sB));
+    // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows = 2048 B
+    constexpr uint32_t KA = (TA ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+    constexpr uint32_t KB = (TB ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+    const uint32_t empty_u = smem_u32(empty_bar), tfull_u = smem_u32(tmem_full);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -127,20 +143,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+        const uint64_t da = da0 + static_cast<uint64_t>((stage * Cfg::A_BYTES) >> 4);
+        const uint64_t db = db0 + static_cast<uint64_t>((stage * Cfg::B_BYTES) >> 4);
+        if (elect_one()) {
+          if (kb == 0 && tile == blockIdx.x) trace_stamp(g, 3);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: 16 k = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows = 2048 B
-            const uint64_t da = TA ? umma_desc_mnmajor_sw128(a_addr + k * UMMA_K * 128)
-                                   : umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t db = TB ? umma_desc_mnmajor_sw128(b_addr + k * UMMA_K * 128)
-                                   : umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(d_tmem, da + k * KA, db + k * KB, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_u(empty_u + stage * 8);  // frees the smem slot when these MMAs retire
+          if (kb == num_k - 1) {
+            umma_commit_u(tfull_u + acc * 8);
+            if (tile == blockIdx.x) trace_stamp(g, 4);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -167,6 +181,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
+      if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 5);
       const long long row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < M;
       epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -174,6 +189,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                           half, row, row_ok, n_blk * BN);
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 6);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -186,6 +202,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (lane == 0) trace_stamp(g, 7);
   }
 }
 
@@ -256,7 +273,12 @@ static int pick_bn(int M, int N, int sms) {
 
 int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream);  // gemm2.cu
 
+static long long* g_trace = nullptr;
+long long* gemm_trace_ptr() { return g_trace; }
+
 }  // namespace tt
+
+extern "C" void tt_gemm_set_trace(long long* dev_ptr) { tt::g_trace = dev_ptr; }
 
 extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   using namespace tt;
@@ -309,6 +331,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     vec = vec && (reinterpret_cast<uintptr_t>(p->residual16) & 15) == 0 && (p->ldr16 % 8 == 0);
   if (p->bias) vec = vec && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
   g.vec_ok = vec ? 1 : 0;
+  g.trace = gemm_trace_ptr();
 
   {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
     const int r2 = gemm2_try(p, g, reinterpret_cast<cudaStream_t>(stream));

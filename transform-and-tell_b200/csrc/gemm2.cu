@@ -65,6 +65,21 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair_u(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
+                                                   int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mcast_u(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                            uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -109,7 +124,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -152,22 +167,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
-        const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
-        const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, row_a);
-          tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+    // Whole warp in the loop (uniform registers), one elected lane issues -- see gemm.cu.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const uint32_t full_u = smem_u32(full_bar);
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+      const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          const uint32_t bar = full_u + stage * 8;
+          if (leader) mbar_arrive_expect_tx_u(bar, 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_pair_u(sA_u + stage * Cfg::A_BYTES, &tmA, bar, kb * BK, row_a);
+          tma_load_2d_pair_u(sB_u + stage * Cfg::B_BYTES, &tmB, bar, kb * BK, row_b);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -175,6 +195,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const uint64_t da0 = umma_desc_kmajor_sw128(smem_u32(sA));
+      const uint64_t db0 = umma_desc_kmajor_sw128(smem_u32(sB));
+      constexpr uint32_t KS = (UMMA_K * 2) >> 4;   // 16 k = 32 B inside the swizzle row
+      const uint32_t empty_u = smem_u32(empty_bar), tfull_u = smem_u32(tmem_full);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -184,17 +208,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint64_t da = da0 + static_cast<uint64_t>((stage * Cfg::A_BYTES) >> 4);
+          const uint64_t db = db0 + static_cast<uint64_t>((stage * Cfg::B_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
-              const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
-              umma2_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma2_commit_mcast(&empty_bar[stage]);
-            if (kb == num_k - 1) umma2_commit_mcast(&tmem_full[acc]);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma2_bf16(d_tmem, da + k * KS, db + k * KS, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_commit_mcast_u(empty_u + stage * 8);
+            if (kb == num_k - 1) umma2_commit_mcast_u(tfull_u + acc * 8);
           }
           __syncwarp();
           if (++stage == STAGES) {

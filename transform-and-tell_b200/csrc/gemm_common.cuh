@@ -25,7 +25,17 @@ struct GemmArgs {
   int accumulate;
   const int* m_limit;
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
+  long long* trace;  // debug: [grid, 8] globaltimer stamps (tt_gemm_set_trace), normally null
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
+  if (g.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[blockIdx.x * 8 + slot] = static_cast<long long>(t);
+  }
+}
+long long* gemm_trace_ptr();
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == TT_ACT_RELU) return fmaxf(v, 0.f);
