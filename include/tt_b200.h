@@ -100,6 +100,38 @@ void tt_gemm_set_trace(long long* dev_ptr);
  * calls assemble ONE operand whose K axis is a concatenation (e.g. the band projections). */
 int tt_cast_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int rows,
                  int cols, int transpose, int split, long long seg_stride, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Weight bank: every weight operand of the decoder prepared by ONE launch per step, every
+ * weight-norm backward by ONE launch (bank.cu).  Replaces the per-module nn.utils.weight_norm
+ * recompute of GehringLinear (tell/modules/linear.py:30-34) and the per-call fp32->bf16 operand
+ * casts.  Tables live in DEVICE memory (built once per model; pointers are stable), rows of all
+ * segments are numbered consecutively: row0 = exclusive prefix sum of rows, ascending.
+ */
+typedef struct {
+  const float* src;  /* [rows, cols] fp32 (weight_v, or a plain weight), row stride ld_src */
+  const float* g;    /* weight_g [rows], or NULL: plain cast */
+  float* w32;        /* optional contiguous fp32 effective weight g*v/||v|| [rows, cols], or NULL */
+  float* norm;       /* optional ||v|| per row (kept for the backward), or NULL */
+  void* dst16;       /* bf16 operand [rows, cols], row stride ld_dst */
+  long long ld_src, ld_dst;
+  int rows, cols;
+  int row0;
+  int pad_;
+} TtPrepSeg;
+int tt_weight_prep(const TtPrepSeg* segs_dev, int nsegs, int total_rows, void* stream);
+typedef struct {
+  const float* dw;   /* dL/dw [rows, cols] contiguous */
+  const float* v;
+  const float* g;
+  const float* norm;
+  float* dv;         /* [rows, cols] */
+  float* dg;         /* [rows] */
+  int rows, cols;
+  int row0;
+  int pad_;
+} TtWnormBwdSeg;
+int tt_wnorm_bwd_multi(const TtWnormBwdSeg* segs_dev, int nsegs, int total_rows, void* stream);
+
 /* out[0] = a[0] * b[0] (device scalars; folds the upstream loss gradient without a host sync). */
 int tt_scalar_mul(const float* a, const float* b, float* out, void* stream);
 

@@ -7,7 +7,7 @@ the ones the reference leaves to torch autograd.
 import torch
 from torch.autograd import Function
 
-from . import config, ops
+from . import config, ops, weight_bank
 
 
 def operand(x, side, transpose=False):
@@ -15,6 +15,10 @@ def operand(x, side, transpose=False):
     'b' (weights/right); in bf16x3 mode the two sides get complementary hi/lo patterns."""
     if config.precision == 'bf16':
         split = 0
+        if side == 'b' and not transpose and weight_bank.ACTIVE is not None:
+            hit = weight_bank.ACTIVE.single(x)      # prepared by the step's one weight_prep launch
+            if hit is not None:
+                return hit
     else:
         split = 1 if side == 'a' else 2
     return ops.cast_bf16(x, transpose=transpose, split=split)
@@ -41,6 +45,7 @@ class LinearFn(Function):
         b16 = operand(w, 'b')
         y = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act)
         ctx.alpha, ctx.act, ctx.has_bias, ctx.fast = alpha, act, bias is not None, _fast()
+        ctx.bank, ctx.wkey = weight_bank.ACTIVE, w.data_ptr()
         keep_y = y if act != ops.ACT_NONE else None
         if ctx.fast:
             ctx.save_for_backward(a16, b16, keep_y)
@@ -62,7 +67,11 @@ class LinearFn(Function):
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(dy16, w, alpha=ctx.alpha, trans_b=True)          # dy . W
             if ctx.needs_input_grad[1]:
-                dw = ops.gemm_tn(dy16, x, alpha=ctx.alpha, trans_a=True, trans_b=True)  # dy^T . x
+                # weight-normalised matrices: dL/dw lands in the bank's flat buffer, where the
+                # single batched wnorm backward reads it
+                dest = ctx.bank.claim_dw(ctx.wkey) if ctx.bank is not None else None
+                dw = ops.gemm_tn(dy16, x, out=dest, alpha=ctx.alpha, trans_a=True,
+                                 trans_b=True)                                      # dy^T . x
         else:
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(operand(dy, 'a'), operand(w, 'b', transpose=True), alpha=ctx.alpha)
@@ -320,6 +329,10 @@ def concat_rows_operand(mats, side, device):
     """One bf16 operand [sum_i R_i, K(*rep)]: the row-wise concatenation of `mats` ([R_i, K])."""
     K = mats[0].shape[1]
     rep = 1 if config.precision == 'bf16' else 3
+    if rep == 1 and side == 'b' and weight_bank.ACTIVE is not None:
+        hit = weight_bank.ACTIVE.group('rows', mats)
+        if hit is not None:
+            return hit
     split = 0 if rep == 1 else (1 if side == 'a' else 2)
     buf = ops.bf16_buffer(sum(m.shape[0] for m in mats), K * rep, device)
     r0 = 0
@@ -490,6 +503,10 @@ def concat_k_operand(mats, side, device):
     R = mats[0].shape[0]
     Ktot = sum(m.shape[1] for m in mats)
     rep = _rep()
+    if rep == 1 and side == 'b' and weight_bank.ACTIVE is not None:
+        hit = weight_bank.ACTIVE.group('kcat', mats)
+        if hit is not None:
+            return hit
     buf = ops.bf16_buffer(R, Ktot * rep, device)
     split = 0 if rep == 1 else (1 if side == 'a' else 2)
     off = 0
@@ -597,10 +614,7 @@ class AdaptiveLossFn(Function):
         fast = _fast()
         head_t, tail_idx, tail_local, tail_count, ntok = ops.adaptive_prepare(target, cutoffs,
                                                                               pad_idx)
-        hw16 = ops.bf16_buffer(cutoffs[0] + nt, E * _rep(), X.device)
-        split_b = 0 if _rep() == 1 else 2
-        ops.cast_bf16(word0, split=split_b, out=hw16[:cutoffs[0]])
-        ops.cast_bf16(class_proj, split=split_b, out=hw16[cutoffs[0]:])
+        hw16 = concat_rows_operand([word0, class_proj], 'b', X.device)
         x16 = operand(X, 'a')
         head_logits = ops.gemm_tn(x16, hw16)
         row_loss = torch.empty((nt + 1, N), dtype=torch.float32, device=X.device)

@@ -13,6 +13,7 @@ import torch.nn as nn
 from .. import config
 from .. import functional as Fn
 from .. import ops
+from .. import weight_bank
 from ..modules import (AdaptiveEmbedding, AdaptiveSoftmax, DynamicConv1dTBC, GehringLinear,
                        LayerNorm, LightweightConv1dTBC, MultiHeadAttention, TextFieldEmbedder)
 from ..registry import Registrable
@@ -211,8 +212,40 @@ class _DynamicConvDecoderBase(Decoder):
             raise ConfigurationError('Extra parameters passed to %s: %s' % (cls.__name__, unknown))
         return cls(vocab=extras.get('vocab'), embedder=embedder, **params)
 
+    # ------------------------------------------------------------------ weight bank
+    use_weight_bank = True
+
+    def weight_scope(self, refresh=True):
+        """Context manager inside which every weight operand of this decoder comes from ONE
+        tt_weight_prep launch (weight_bank.py).  refresh=False reuses the operands prepared by an
+        earlier scope (incremental decoding: the weights do not change between steps).  Without a
+        usable bank (parity mode, CPU-less construction, disabled) it is a no-op scope."""
+        bank = None
+        if self.use_weight_bank and config.precision == 'bf16' \
+                and next(self.parameters()).is_cuda:
+            bank = getattr(self, '_bank', None)
+            if bank is None or bank._moved():
+                bank = weight_bank.WeightBank(self)
+                object.__setattr__(self, '_bank', bank)      # not a submodule / not in state_dict
+                refresh = True
+        scope = weight_bank.activate(bank)
+        if bank is not None:
+            if refresh or not bank.prepared_once or bank.log:
+                bank.current = bank.effective_weights()
+                bank.prepared_once = True
+            else:
+                bank.current = {id(e.v): e.w32 for e in bank.wn}
+        return scope
+
     def forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
         """Hot-path entry: returns X in decoder layout [T,B,E] (no final transpose) + extras."""
+        if weight_bank.ACTIVE is None or weight_bank.ACTIVE.module is not self:
+            first = incremental_state is None or _KV_KEY not in incremental_state
+            with self.weight_scope(refresh=first):
+                return self._forward_tbc(prev_target, contexts, incremental_state, use_layers)
+        return self._forward_tbc(prev_target, contexts, incremental_state, use_layers)
+
+    def _forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
         X2, ids = self.embedder.embed_tbc(prev_target, incremental_state)
         B, T = ids.shape
         p = self.dropout if self.training else 0.0

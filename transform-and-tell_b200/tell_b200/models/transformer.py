@@ -119,12 +119,13 @@ class _CaptionModelBase(Model):
                 names=None, attn_idx=None, encoded=None):
         caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
                                                           obj_embeds, encoded)
-        X, _ = self.decoder.forward_tbc(caption, contexts)           # [T,B,E], no transpose needed
-        T, B, E = X.shape
-        # the loss is a sum over tokens, so (t,b) order with the target transposed alike is exact
-        tgt_tb = target_ids.t().contiguous()
-        loss, ntokens = self.criterion.fused(self.decoder.adaptive_softmax, (X.view(T * B, E), None),
-                                             tgt_tb)
+        with self.decoder.weight_scope():      # one launch prepares every decoder weight operand
+            X, _ = self.decoder.forward_tbc(caption, contexts)       # [T,B,E], no transpose needed
+            T, B, E = X.shape
+            # the loss is a sum over tokens, so (t,b) order with the target transposed alike is exact
+            tgt_tb = target_ids.t().contiguous()
+            loss, ntokens = self.criterion.fused(self.decoder.adaptive_softmax,
+                                                 (X.view(T * B, E), None), tgt_tb)
         output_dict = {'loss': loss.view(()), 'sample_size': ntokens}
         if not self.training and self.evaluate_mode:
             _, gen_ids, attns = self._generate(caption_ids, contexts, attn_idx)
@@ -160,8 +161,11 @@ class _CaptionModelBase(Model):
         ids_cols, lp_cols, any_active = [prev], [], []
         n_steps = 0
         for i in range(self.gen_len):
-            X, _ = self.decoder.forward_tbc({self.index: prev}, contexts, incremental_state=state)
-            tok, lp = self.decoder.adaptive_softmax.greedy(X.view(B, -1))
+            # weights are constant during decoding: operands are prepared at step 0 only
+            with self.decoder.weight_scope(refresh=(i == 0)):
+                X, _ = self.decoder.forward_tbc({self.index: prev}, contexts,
+                                                incremental_state=state)
+                tok, lp = self.decoder.adaptive_softmax.greedy(X.view(B, -1))
             lp = lp / self.sampling_temp
             tok = torch.where(active, tok, torch.full_like(tok, pad))
             lp = torch.where(active, lp, torch.zeros_like(lp))

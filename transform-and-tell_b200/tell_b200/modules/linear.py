@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
-from .. import ops
+from .. import ops, weight_bank
 
 
 def linear(x, weight, bias=None, alpha=1.0, act=ops.ACT_NONE):
@@ -49,6 +49,11 @@ class GehringLinear(nn.Module):
 
     def effective_weight(self):
         if self.weight_norm:
+            bank = weight_bank.ACTIVE
+            if bank is not None and bank.current is not None:
+                w = bank.current.get(id(self.weight_v))     # from the step's one weight_prep launch
+                if w is not None:
+                    return w
             return Fn.WeightNormFn.apply(self.weight_v, self.weight_g)
         return self.weight
 

@@ -121,10 +121,8 @@ class AdaptiveSoftmax(nn.Module):
     def _cluster_logits(self, X2):
         a16 = Fn.operand(X2, 'a')
         c0, nt = self.cutoff[0], len(self.cutoff) - 1
-        hw16 = ops.bf16_buffer(c0 + nt, a16.shape[1], X2.device)
-        split_b = 0 if a16.shape[1] == X2.shape[1] else 2
-        ops.cast_bf16(self.head.word_proj.weight, split=split_b, out=hw16[:c0])
-        ops.cast_bf16(self.head.class_proj.weight, split=split_b, out=hw16[c0:])
+        hw16 = Fn.concat_rows_operand([self.head.word_proj.weight, self.head.class_proj.weight],
+                                      'b', X2.device)
         head = ops.gemm_tn(a16, hw16)
         tails = []
         tw = self._tail_weights()
