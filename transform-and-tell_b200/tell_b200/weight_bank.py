@@ -206,7 +206,7 @@ class WeightBank:
         hit = self.map.get(key)
         if hit is None and key not in self.log and self._backed(x) and x.dim() == 2 \
                 and x.stride(1) == 1:
-            self.log[key] = ('s', (x,))
+            self.log[key] = ('s', (x.detach(),))      # detached: must not pin an autograd graph
         return hit
 
     def group(self, kind, mats):
@@ -214,7 +214,7 @@ class WeightBank:
         hit = self.map.get(key)
         if hit is None and key not in self.log and all(
                 self._backed(m) and m.dim() == 2 and m.stride(1) == 1 for m in mats):
-            self.log[key] = (kind, tuple(mats))
+            self.log[key] = (kind, tuple(m.detach() for m in mats))
         return hit
 
     def claim_dw(self, wptr):
