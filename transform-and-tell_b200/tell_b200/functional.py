@@ -123,6 +123,87 @@ class KVProjFn(Function):
         return dx, (dW[:E] if dW is not None else None), (dW[E:] if dW is not None else None), db
 
 
+class GradSlab:
+    """Side channel between AllLayerKVProjFn and the attention backward: the L per-layer dL/dkv
+    blocks are written straight into column blocks of ONE [R, L*2E] buffer, so the projection's
+    backward is one operand cast + one dW GEMM (+ one dx GEMM) over all layers, with no
+    gather copies.  Allocated lazily by the first attention backward that needs it."""
+
+    def __init__(self, rows, width, n, device):
+        self.rows, self.width, self.n, self.device = rows, width, n, device
+        self.buf = None
+        self.written = set()
+
+    def block(self, l):
+        if self.buf is None:
+            self.buf = torch.empty((self.rows, self.n * self.width), dtype=torch.float32,
+                                   device=self.device)
+        self.written.add(l)
+        return self.buf[:, l * self.width:(l + 1) * self.width]
+
+
+class AllLayerKVProjFn(Function):
+    """The key|value projections of ONE context for ALL L decoder layers as one GEMM:
+    KV [R, L*2E] = x @ [Wk_0; Wv_0; ...; Wk_{L-1}; Wv_{L-1}]^T + bias  (multi_head.py:500-518, once
+    per layer in the reference).  The context does not depend on the layer, so x is cast once and
+    the N dimension is L times wider (8192 x 8192 x 1024 for the article instead of four
+    8192 x 2048 x 1024 GEMMs).  Returns L views [R, 2E] (row stride L*2E), read by stride."""
+
+    @staticmethod
+    def forward(ctx, x, L, slab, *args):
+        wks, wvs, biases = args[:L], args[L:2 * L], args[2 * L:3 * L]
+        E = wks[0].shape[0]
+        a16 = operand(x, 'a')
+        mats = []
+        for l in range(L):
+            mats += [wks[l], wvs[l]]
+        w16 = concat_rows_operand(mats, 'b', x.device)                  # [L*2E, kdim]
+        bias = torch.cat([b.reshape(-1) for b in biases]) if biases[0] is not None else None
+        KV = ops.gemm_tn(a16, w16, bias=bias)
+        ctx.cfg = (L, E, bias is not None, _fast())
+        ctx.slab = slab
+        if ctx.cfg[3]:
+            ctx.save_for_backward(a16, w16)
+        else:
+            ctx.save_for_backward(x, *mats)
+        return tuple(KV[:, l * 2 * E:(l + 1) * 2 * E] for l in range(L))
+
+    @staticmethod
+    def backward(ctx, *dkvs):
+        L, E, has_bias, fast = ctx.cfg
+        slab = ctx.slab
+        for l, d in enumerate(dkvs):
+            if d is None:
+                slab.block(l).zero_()
+            elif slab.buf is None or d.data_ptr() != slab.block(l).data_ptr():
+                slab.block(l).copy_(d)
+        D = slab.buf
+        slab.buf = None                       # the buffer belongs to this backward only
+        slab.written = set()
+        dx = dW = None
+        need_w = any(ctx.needs_input_grad[3:3 + 2 * L])
+        if fast:
+            a16, w16 = ctx.saved_tensors
+            d16 = operand(D, 'a')
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(d16, w16, trans_b=True)
+            if need_w:
+                dW = ops.gemm_tn(d16, a16, trans_a=True, trans_b=True)          # [L*2E, kdim]
+        else:
+            x, mats = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(operand(D, 'a'), concat_kT_operand(list(mats), 'b', D.device))
+            if need_w:
+                dW = ops.gemm_tn(operand(D, 'a', transpose=True), operand(x, 'b', transpose=True))
+        dwk = tuple(dW[(2 * l) * E:(2 * l + 1) * E] if dW is not None else None for l in range(L))
+        dwv = tuple(dW[(2 * l + 1) * E:(2 * l + 2) * E] if dW is not None else None for l in range(L))
+        dbs = (None,) * L
+        if has_bias:
+            db = ops.colsum(D)
+            dbs = tuple(db[l * 2 * E:(l + 1) * 2 * E] for l in range(L))
+        return (dx, None, None) + dwk + dwv + dbs
+
+
 class WeightNormFn(Function):
     """w = g * v / ||v||_row  (nn.utils.weight_norm dim=0; linear.py:30-34)."""
 
@@ -390,6 +471,8 @@ class MultiCtxAttentionFn(Function):
     @staticmethod
     def forward(ctx, q_all, T, B, H, zero_row, p, seeds, need_weights, n, *args):
         kvs, bks, bvs, masks = args[:n], args[n:2 * n], args[2 * n:3 * n], args[3 * n:4 * n]
+        # optional (GradSlab, layer) per context: where the backward writes dL/dkv
+        ctx.slabs = args[4 * n] if len(args) > 4 * n else (None,) * n
         E = q_all.shape[1] // n
         D = E // H
         tc = config.precision == 'bf16' and D == 64
@@ -428,7 +511,10 @@ class MultiCtxAttentionFn(Function):
         dkvs, dbks, dbvs = [], [], []
         for c in range(n):
             S, kv = Ss[c], kvs[c]
-            dkv = torch.empty_like(kv) if S > 0 else None
+            if S > 0 and ctx.slabs[c] is not None:
+                dkv = ctx.slabs[c][0].block(ctx.slabs[c][1])
+            else:
+                dkv = torch.empty_like(kv) if S > 0 else None
             dbk = torch.zeros_like(bks[c]) if bks[c] is not None else None
             dbv = torch.zeros_like(bvs[c]) if bvs[c] is not None else None
             sl = slice(c * E, (c + 1) * E)
@@ -442,7 +528,8 @@ class MultiCtxAttentionFn(Function):
             dkvs.append(dkv)
             dbks.append(dbk)
             dbvs.append(dbv)
-        return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n
+        return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n \
+            + (None,) * (1 if len(ctx.needs_input_grad) > 9 + 4 * n else 0)
 
 
 class FusedOutProjFn(Function):

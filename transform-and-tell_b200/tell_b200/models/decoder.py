@@ -125,9 +125,11 @@ class DynamicConvDecoderLayer(DecoderLayer):
         Q_all = Fn.FusedQProjFn.apply(X2, mhas[0].scaling, n, *q_ws, *q_bs)
         p_att = self._p(mhas[0].dropout)
         seeds_a = tuple(self._seed(p_att) for _ in range(n))
+        slabs = tuple(kv_cache.get(nm + '/slab') if kv_cache is not None else None for nm in names)
+        extra = (slabs,) if any(s_ is not None for s_ in slabs) else ()
         res = Fn.MultiCtxAttentionFn.apply(Q_all, T, B, mhas[0].num_heads, mhas[0].add_zero_attn, p_att,
                                            seeds_a, need_w, n, *kvs, *[m.bias_k for m in mhas],
-                                           *[m.bias_v for m in mhas], *masks)
+                                           *[m.bias_v for m in mhas], *masks, *extra)
         A_all = res[0]
         attns = {nm: w for nm, w in zip(names, res[1:])} if need_w else {}
         hs = Fn.FusedOutProjFn.apply(A_all, n, *[m.out_proj.weight for m in mhas],
@@ -245,6 +247,32 @@ class _DynamicConvDecoderBase(Decoder):
                 return self._forward_tbc(prev_target, contexts, incremental_state, use_layers)
         return self._forward_tbc(prev_target, contexts, incremental_state, use_layers)
 
+    batch_kv_layers = True
+
+    def _project_contexts_all_layers(self, contexts, caches):
+        """Key|value projections of every context for ALL layers up front: one GEMM per context
+        (N = L*2E) instead of one per (layer, context); see Fn.AllLayerKVProjFn.  Fills the
+        per-layer caches the layers read their projected contexts from."""
+        L = len(self.layers)
+        for nm in self.layers[0].context_names:
+            if nm in caches[0]:
+                continue
+            key = contexts[nm]
+            if key is None or key.shape[2] == 0 or key.shape[0] == 0:
+                continue                      # empty context: the per-layer path returns None
+            S, B, kd = key.shape
+            mhas = [layer.context_attns[nm] for layer in self.layers]
+            ws = [m._weights() for m in mhas]
+            E = mhas[0].embed_dim
+            biases = [m.in_proj_bias[E:] if m.in_proj_bias is not None else None for m in mhas]
+            slab = Fn.GradSlab(S * B, 2 * E, L, key.device) if torch.is_grad_enabled() else None
+            kvs = Fn.AllLayerKVProjFn.apply(key.reshape(S * B, kd), L, slab, *[w[1] for w in ws],
+                                            *[w[2] for w in ws], *biases)
+            for l in range(L):
+                caches[l][nm] = kvs[l]
+                if slab is not None:
+                    caches[l][nm + '/slab'] = (slab, l)
+
     def _forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
         X2, ids = self.embedder.embed_tbc(prev_target, incremental_state)
         B, T = ids.shape
@@ -253,9 +281,12 @@ class _DynamicConvDecoderBase(Decoder):
             X2 = Fn.DropoutFn.apply(X2, p, config.next_seed())
         X = X2.view(T, B, self.embed_dim)
         attns, inner_states = [], [X]
-        caches = None
         if incremental_state is not None:
             caches = incremental_state.setdefault(_KV_KEY, [dict() for _ in self.layers])
+        else:
+            caches = [dict() for _ in self.layers]
+        if self.batch_kv_layers and not use_layers:
+            self._project_contexts_all_layers(contexts, caches)
         for i, layer in enumerate(self.layers):
             attn = None
             if not use_layers or i in use_layers:
