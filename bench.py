@@ -179,6 +179,7 @@ def run_b200(args):
     config.set_precision('bf16')
     config.manual_seed(1234 + rank)
     config.enable_device_step(dev)
+    config.enable_zero_arena(dev)     # the step below consumes gradients before the next forward
     B = args.batch
     model = build_model(dev)
     # the flat gradient buffer only exists where there is a collective to feed

@@ -76,3 +76,27 @@ def test_bank_sees_weight_updates():
     X2r, _, _ = _step(ref, cap, ctx)
     assert not _close(X2, X1, 1e-3)
     assert _close(X2, X2r, 1e-5)
+
+
+def test_zero_arena_gradients_match():
+    """Small accumulate-into gradients served from the per-step zero arena (one memset per step)
+    equal the torch.zeros path; colsum through the vector kernel equals a torch column sum."""
+    from tell_b200 import config, ops
+    ref, cap, ctx = _build(True)
+    _, _, g0 = _step(ref, cap, ctx)
+    dec, cap, ctx = _build(True)
+    arena = config.enable_zero_arena('cuda')
+    try:
+        for step in range(2):
+            arena.reset()
+            _, _, g = _step(dec, cap, ctx)
+            assert arena.off > 0
+            for n in g0:
+                assert _close(g[n], g0[n], 1e-4), (step, n)
+    finally:
+        config.disable_zero_arena()
+    for (M, N) in [(800, 1024), (8192, 4096), (37, 20), (800, 30265), (5, 4)]:
+        x = torch.randn(M, N, device='cuda')
+        got = ops.colsum(x, scale=0.5)
+        want = x.double().sum(0).float() * 0.5
+        assert (got - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item()), (M, N)

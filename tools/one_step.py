@@ -16,6 +16,7 @@ from tell_b200.parallel import FlatGradients  # noqa: E402
 dev = torch.device('cuda', 0)
 config.set_precision(os.environ.get('TT_PRECISION', 'bf16'))
 config.manual_seed(1234)
+config.enable_zero_arena(dev)
 model = bench.build_model(dev)
 params = [p for p in model.parameters() if p.requires_grad]
 host = bench.make_batch(16)

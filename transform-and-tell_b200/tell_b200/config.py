@@ -52,3 +52,46 @@ def advance_device_step():
     if _step is not None:
         _lib.call('tt_rng_step_advance', _lib.c_void_p(_step.data_ptr()),
                   _lib.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+# --------------------------------------------------------------------------- zero arena (opt-in)
+class ZeroArena:
+    """Bump allocator over one pre-zeroed fp32 buffer for the many small accumulate-into gradients
+    of a backward pass (bias column sums, LayerNorm dgamma/dbeta, bias_k/bias_v): ONE memset per
+    step instead of one per tensor (~130 fill launches in the cfg-2 backward).
+
+    Contract (why it is opt-in): slices handed out during step i become parameter .grad tensors and
+    are zeroed again by reset() at the start of step i+1, so the trainer must consume (or copy)
+    gradients before the next forward and must not accumulate .grad across backward calls."""
+
+    def __init__(self, device, capacity=2 * 1024 * 1024):
+        self.buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self.capacity = capacity
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, n):
+        n_al = (n + 3) // 4 * 4           # keep every slice 16-byte aligned
+        if self.off + n_al > self.capacity:
+            return None
+        v = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return v
+
+
+zero_arena = None
+
+
+def enable_zero_arena(device='cuda', capacity=2 * 1024 * 1024):
+    global zero_arena
+    if zero_arena is None:
+        zero_arena = ZeroArena(device, capacity)
+    return zero_arena
+
+
+def disable_zero_arena():
+    global zero_arena
+    zero_arena = None

@@ -234,7 +234,7 @@ class ResidualLayerNormFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
-        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        dgamma, dbeta = ops.zeros_f32(gamma.shape, gamma), ops.zeros_f32(gamma.shape, gamma)
         if ctx.p > 0:
             dx, dh = ops.ln_bwd(_c(dy), x, mean, rstd, gamma, ctx.p, ctx.seed,
                                 want_dx=ctx.has_res, dgamma=dgamma, dbeta=dbeta)
@@ -275,7 +275,7 @@ class ContextLayerNormFn(Function):
         dhs, dgs, dbs = [], [], []
         for c in range(n):
             x, mean, rstd, gamma = saved[1 + 4 * c:5 + 4 * c]
-            dg, db = torch.zeros_like(gamma), torch.zeros_like(gamma)
+            dg, db = ops.zeros_f32(gamma.shape, gamma), ops.zeros_f32(gamma.shape, gamma)
             dyc = dY[:, c * E:(c + 1) * E]
             if ctx.p > 0:
                 dx, dh = ops.ln_bwd(dyc, x, mean, rstd, gamma, ctx.p, ctx.seeds[c], dgamma=dg,
@@ -396,8 +396,8 @@ class AttentionFn(Function):
         E = H * D
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv) if S > 0 else None
-        dbk = torch.zeros_like(bias_k) if bias_k is not None else None
-        dbv = torch.zeros_like(bias_v) if bias_v is not None else None
+        dbk = ops.zeros_f32(bias_k.shape, bias_k) if bias_k is not None else None
+        dbv = ops.zeros_f32(bias_v.shape, bias_v) if bias_v is not None else None
         ops.attn_bwd(_c(dout), q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None,
                      bias_k.view(-1) if bias_k is not None else None,
                      bias_v.view(-1) if bias_v is not None else None, mask, out, lse, dq,
@@ -515,8 +515,8 @@ class MultiCtxAttentionFn(Function):
                 dkv = ctx.slabs[c][0].block(ctx.slabs[c][1])
             else:
                 dkv = torch.empty_like(kv) if S > 0 else None
-            dbk = torch.zeros_like(bks[c]) if bks[c] is not None else None
-            dbv = torch.zeros_like(bvs[c]) if bvs[c] is not None else None
+            dbk = ops.zeros_f32(bks[c].shape, bks[c]) if bks[c] is not None else None
+            dbv = ops.zeros_f32(bvs[c].shape, bvs[c]) if bvs[c] is not None else None
             sl = slice(c * E, (c + 1) * E)
             ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
                          kv[:, E:] if S > 0 else None,

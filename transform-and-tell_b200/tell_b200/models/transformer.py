@@ -10,6 +10,7 @@ import math
 import torch
 import torch.nn as nn
 
+from .. import config
 from .. import functional as Fn
 from .. import ops
 from ..modules import Criterion
@@ -117,6 +118,8 @@ class _CaptionModelBase(Model):
     # ------------------------------------------------------------------ forward (:67-140)
     def forward(self, context, image, caption, face_embeds=None, obj_embeds=None, metadata=None,
                 names=None, attn_idx=None, encoded=None):
+        if config.zero_arena is not None and torch.is_grad_enabled():
+            config.zero_arena.reset()          # one memset for every small gradient of this step
         caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
                                                           obj_embeds, encoded)
         with self.decoder.weight_scope():      # one launch prepares every decoder weight operand

@@ -199,10 +199,29 @@ def nan_rows_(x):
     return mask.bool()
 
 
+def zeros_f32(shape, like):
+    """Zero-filled fp32 tensor for accumulate-into gradients; served from the per-step zero arena
+    (config.ZeroArena, one memset per step) when the trainer enabled it."""
+    from . import config
+    arena = config.zero_arena
+    if arena is not None and arena.buf.device == like.device:
+        n = 1
+        for d in shape:
+            n *= d
+        v = arena.take(n)
+        if v is not None:
+            return v.view(shape)
+    return torch.zeros(shape, dtype=torch.float32, device=like.device)
+
+
 def colsum(x, scale=1.0, out=None, accumulate=False):
     M, N = x.shape
     if out is None:
-        out = _f32(N, like=x)
+        from . import config
+        if config.zero_arena is not None:
+            out, accumulate = zeros_f32((N,), x), True      # pre-zeroed: skip the memset node
+        else:
+            out = _f32(N, like=x)
     _lib.call('tt_colsum', _ptr(x), c_ll(x.stride(0)), c_int(M), c_int(N), _ptr(out),
               c_float(scale), c_int(1 if accumulate else 0), _stream())
     return out
