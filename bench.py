@@ -180,6 +180,7 @@ def run_b200(args):
     config.manual_seed(1234 + rank)
     config.enable_device_step(dev)
     config.enable_zero_arena(dev)     # the step below consumes gradients before the next forward
+    config.enable_wgrad_stream(args.wgrad)   # weight-gradient GEMMs as a parallel graph branch
     B = args.batch
     model = build_model(dev)
     # the flat gradient buffer only exists where there is a collective to feed
@@ -398,7 +399,7 @@ def run_b200(args):
                                'DynamicConv decoder, image+article+faces+objects), batch 16/GPU, '
                                'T=50, S=512, F=4, O=16, dropout on, fwd+bwd (no optimizer step)',
                    'global_batch': world * B, 'parallelism': 'dp%d' % world,
-                   'cuda_graph': graph is not None,
+                   'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
                    'grad_allreduce': (None if world == 1 else args.grad_dtype + ', one flat buffer, '
                                       'overlapped with the next step\'s frozen-encoder forward'),
                    'l2': 'working set per step (weights + activations, >2 GB) exceeds the 126 MB L2'},
@@ -546,6 +547,9 @@ def main():
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--wgrad', type=int, default=0, choices=[0, 1, 2],
+                    help='weight-gradient stream: 0 off (fastest measured: graph branch fork/join edges cost '
+                         'more than the overlap wins), 1 weight-bank dW only, 2 + per-function forks')
     ap.add_argument('--grad-dtype', default='fp32', choices=['bf16', 'fp32'],
                     help='dtype of the gradient all-reduce payload (N > 1)')
     args = ap.parse_args()

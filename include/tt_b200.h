@@ -306,6 +306,42 @@ int tt_ln_fwd16(const float* x, const float* gamma, const float* beta, void* y16
 int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_mask, void* out, int B, int S,
                        int H, int D, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step: BertAdam as configured by
+ * expt/nytimes/9_transformer_objects/config.yaml:126-136 (allennlp 0.9 "bert_adam" ->
+ * pytorch-pretrained-bert 0.6.2 BertAdam.step, called at
+ * tell/training/callback_apex_trainer.py:238): per-TENSOR gradient clip to max_grad_norm, Adam
+ * moments without bias correction, decoupled-style weight decay added to the update, lr scaled by
+ * schedule(step / t_total).  All tensors of a parameter group in three launches.
+ * Segment table (device memory): one entry per tensor; chunk0 = exclusive prefix sum of
+ * ceil(n / tt_bertadam_chunk()) over the entries, ascending.
+ * step_dev: device int64 step counter (BertAdam's state['step'], shared by all tensors), read for
+ * the schedule and then incremented -- CUDA-graph replays advance it.
+ * loss_dev (optional): device scalar; if it is NaN the step is skipped entirely (parameters,
+ * moments and step untouched), the NaN-batch skip of callback_apex_trainer.py:225-227.
+ * partial: float[total_chunks]; scratch: float[2 + nsegs] (out: [0] = lr used, [1] = skipped flag,
+ * [2+i] = clip coefficient of tensor i).
+ */
+typedef struct {
+  float* p;        /* parameter (fp32 master copy), updated in place */
+  const float* g;  /* gradient */
+  float* m;        /* next_m */
+  float* v;        /* next_v */
+  long long n;     /* elements */
+  int chunk0;
+  int pad_;
+} TtAdamSeg;
+typedef enum { TT_SCHED_NONE = 0, TT_SCHED_WARMUP_LINEAR = 1, TT_SCHED_WARMUP_CONSTANT = 2 } TtSchedule;
+typedef struct {
+  float lr, b1, b2, e, weight_decay, max_grad_norm, warmup;
+  int schedule;        /* TtSchedule */
+  long long t_total;   /* <= 0: constant lr */
+} TtAdamHyper;
+int tt_bertadam_chunk(void);
+int tt_bertadam_step(const TtAdamSeg* segs_dev, int nsegs, int total_chunks,
+                     const TtAdamHyper* hyper, long long* step_dev, const float* loss_dev,
+                     float* partial, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,50 @@ def test_zero_arena_gradients_match():
         got = ops.colsum(x, scale=0.5)
         want = x.double().sum(0).float() * 0.5
         assert (got - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item()), (M, N)
+
+
+@pytest.mark.parametrize('level', [1, 2])
+def test_wgrad_stream_gradients_match(level):
+    """Weight gradients forked onto the second stream (functional.wgrad) equal the single-stream
+    backward -- eagerly and when the step is captured in a CUDA graph (the fork becomes a parallel
+    branch that must rejoin before the capture ends)."""
+    from tell_b200 import config
+    ref, cap, ctx = _build(True)
+    _step(ref, cap, ctx)
+    _, l0, g0 = _step(ref, cap, ctx)
+    dec, cap, ctx = _build(True)
+    config.enable_wgrad_stream(level)
+    try:
+        for step in range(3):
+            _, l, g = _step(dec, cap, ctx)
+            torch.cuda.synchronize()
+            assert set(g) == set(g0)
+            for n in g0:
+                assert _close(g[n], g0[n], 1e-4), (step, n)
+        # captured: replay twice, gradients land in the tensors produced during capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            _step(dec, cap, ctx)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        held = {}
+        with torch.cuda.graph(graph):
+            for p in dec.parameters():
+                p.grad = None
+            inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+            with dec.weight_scope():
+                X, _ = dec.forward_tbc({'roberta': inp}, ctx)
+                T, B, E = X.shape
+                loss, _ = dec.adaptive_softmax.fused_loss(X.view(T * B, E), tgt.t().contiguous())
+            loss.backward()
+            held = {n: p.grad for n, p in dec.named_parameters() if p.grad is not None}
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - l0.item()) < 1e-5 * max(1.0, abs(l0.item()))
+        for n in g0:
+            assert _close(held[n], g0[n], 1e-4), ('graph', n)
+    finally:
+        config.enable_wgrad_stream(0)

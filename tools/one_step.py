@@ -17,6 +17,7 @@ dev = torch.device('cuda', 0)
 config.set_precision(os.environ.get('TT_PRECISION', 'bf16'))
 config.manual_seed(1234)
 config.enable_zero_arena(dev)
+config.enable_wgrad_stream(int(os.environ.get('TT_WGRAD', '0')))
 model = bench.build_model(dev)
 params = [p for p in model.parameters() if p.requires_grad]
 host = bench.make_batch(16)

@@ -17,54 +17,88 @@ namespace tt {
 
 constexpr int TC_BM = 64, TC_BN = 64, TC_D = 64, TC_LD = TC_D + 8;
 
-// rows [r0, r0+64) x 64 dims of an fp32 matrix -> bf16 smem tile (rows >= nrows are zero).
-// src row r lives at base + (r * B + b) * ld + h*64.
-__device__ __forceinline__ void stage_tile(const float* __restrict__ base, long long ld, int B, int b,
-                                           int h, int r0, int nrows,
-                                           __nv_bfloat16 (*dst)[TC_LD]) {
-  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+constexpr int TC_THREADS = 128;   // every kernel here runs 4 warps
+constexpr int TC_ST = 64 * 16 / TC_THREADS;   // float4 loads per thread per 64x64 tile
+
+// rows [r0, r0+64) x 64 dims of an fp32 matrix -> registers (rows >= nrows are zero).
+// src row r lives at base + (r * B + b) * ld + h*64.  All TC_ST loads are issued back to back.
+__device__ __forceinline__ void load_tile(const float* __restrict__ base, long long ld, int B, int b,
+                                          int h, int r0, int nrows, float4 (&reg)[TC_ST]) {
+#pragma unroll
+  for (int it = 0; it < TC_ST; ++it) {
+    const int i = threadIdx.x + it * TC_THREADS;
     const int r = i >> 4, c4 = i & 15;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    reg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < nrows)
-      v = __ldg(reinterpret_cast<const float4*>(base + (static_cast<long long>(r0 + r) * B + b) * ld +
-                                                h * TC_D) + c4);
+      reg[it] = __ldg(reinterpret_cast<const float4*>(base + (static_cast<long long>(r0 + r) * B + b) * ld +
+                                                      h * TC_D) + c4);
+  }
+}
+__device__ __forceinline__ void store_tile(const float4 (&reg)[TC_ST], __nv_bfloat16 (*dst)[TC_LD]) {
+#pragma unroll
+  for (int it = 0; it < TC_ST; ++it) {
+    const int i = threadIdx.x + it * TC_THREADS;
+    const int r = i >> 4, c4 = i & 15;
     uint2 u;
-    u.x = pack_bf16(v.x, v.y);
-    u.y = pack_bf16(v.z, v.w);
+    u.x = pack_bf16(reg[it].x, reg[it].y);
+    u.y = pack_bf16(reg[it].z, reg[it].w);
     *reinterpret_cast<uint2*>(&dst[r][c4 * 4]) = u;
   }
 }
+__device__ __forceinline__ void stage_tile(const float* __restrict__ base, long long ld, int B, int b,
+                                           int h, int r0, int nrows,
+                                           __nv_bfloat16 (*dst)[TC_LD]) {
+  float4 reg[TC_ST];
+  load_tile(base, ld, B, b, h, r0, nrows, reg);
+  store_tile(reg, dst);
+}
 
-// Key/value tile j0..j0+63 of the extended key set [ctx rows ; bias row ; zero row] + additive mask.
-__device__ __forceinline__ void stage_kv(const AttnArgs& a, int b, int h, int j0, int L,
-                                         __nv_bfloat16 (*sK)[TC_LD], __nv_bfloat16 (*sV)[TC_LD],
-                                         float* sMask) {
+// Key/value tile j0..j0+63 of the extended key set [ctx rows ; bias row ; zero row] + additive mask,
+// split into a load phase (global -> registers; lets the caller prefetch the next tile while the
+// tensor cores work on the current one) and a store phase (registers -> bf16 smem).
+struct KvRegs {
+  float4 k[TC_ST], v[TC_ST];
+  float mask;     // threads 0..63: additive mask of key j0 + threadIdx.x
+};
+__device__ __forceinline__ void load_kv(const AttnArgs& a, int b, int h, int j0, int L, KvRegs& R) {
   const bool has_bias = a.bias_k != nullptr;
-  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+#pragma unroll
+  for (int it = 0; it < TC_ST; ++it) {
+    const int i = threadIdx.x + it * TC_THREADS;
     const int r = i >> 4, c4 = i & 15;
     const int j = j0 + r;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    R.k[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    R.v[it] = R.k[it];
     if (j < a.S) {
       const long long off = (static_cast<long long>(j) * a.B + b) * a.ldkv + h * TC_D;
-      kv = __ldg(reinterpret_cast<const float4*>(a.k + off) + c4);
-      vv = __ldg(reinterpret_cast<const float4*>(a.v + off) + c4);
+      R.k[it] = __ldg(reinterpret_cast<const float4*>(a.k + off) + c4);
+      R.v[it] = __ldg(reinterpret_cast<const float4*>(a.v + off) + c4);
     } else if (has_bias && j == a.S) {
-      kv = __ldg(reinterpret_cast<const float4*>(a.bias_k + h * TC_D) + c4);
-      vv = __ldg(reinterpret_cast<const float4*>(a.bias_v + h * TC_D) + c4);
+      R.k[it] = __ldg(reinterpret_cast<const float4*>(a.bias_k + h * TC_D) + c4);
+      R.v[it] = __ldg(reinterpret_cast<const float4*>(a.bias_v + h * TC_D) + c4);
     }
-    uint2 u;
-    u.x = pack_bf16(kv.x, kv.y); u.y = pack_bf16(kv.z, kv.w);
-    *reinterpret_cast<uint2*>(&sK[r][c4 * 4]) = u;
-    u.x = pack_bf16(vv.x, vv.y); u.y = pack_bf16(vv.z, vv.w);
-    *reinterpret_cast<uint2*>(&sV[r][c4 * 4]) = u;
   }
-  for (int r = threadIdx.x; r < 64; r += blockDim.x) {
-    const int j = j0 + r;
+  R.mask = 0.f;
+  if (threadIdx.x < 64) {
+    const int j = j0 + threadIdx.x;
     bool ok;
     if (j < a.S) ok = !(a.mask && a.mask[static_cast<long long>(b) * a.S + j]);
     else ok = j < L;
-    sMask[r] = ok ? 0.f : -INFINITY;
+    R.mask = ok ? 0.f : -INFINITY;
   }
+}
+__device__ __forceinline__ void store_kv(const KvRegs& R, __nv_bfloat16 (*sK)[TC_LD],
+                                         __nv_bfloat16 (*sV)[TC_LD], float* sMask) {
+  store_tile(R.k, sK);
+  store_tile(R.v, sV);
+  if (threadIdx.x < 64) sMask[threadIdx.x] = R.mask;
+}
+__device__ __forceinline__ void stage_kv(const AttnArgs& a, int b, int h, int j0, int L,
+                                         __nv_bfloat16 (*sK)[TC_LD], __nv_bfloat16 (*sV)[TC_LD],
+                                         float* sMask) {
+  KvRegs R;
+  load_kv(a, b, h, j0, L, R);
+  store_kv(R, sK, sV, sMask);
 }
 
 // A fragments (16 rows x 64 k) of the warp's row block from a [64][TC_LD] tile.
@@ -132,7 +166,14 @@ attn_fwd_tc_kernel(AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+  KvRegs nxt;
+  {
+    float4 qreg[TC_ST];
+    load_tile(a.q, a.ldq, a.B, b, h, q0, a.T, qreg);
+    load_kv(a, b, h, 0, L, nxt);              // first K/V tile in flight together with Q
+    store_tile(qreg, sQ);
+  }
+  store_kv(nxt, sK, sV, sMask);
   __syncthreads();
   uint32_t qf[4][4];
   load_a_frags(sQ, warp, lane, qf);
@@ -143,9 +184,12 @@ attn_fwd_tc_kernel(AttnArgs a) {
   const unsigned long long base0 = (static_cast<unsigned long long>(bh) * a.T + t0) * L;
   const unsigned long long base1 = (static_cast<unsigned long long>(bh) * a.T + t1) * L;
   for (int j0 = 0; j0 < L; j0 += TC_BN) {
-    __syncthreads();
-    stage_kv(a, b, h, j0, L, sK, sV, sMask);
-    __syncthreads();
+    if (j0 > 0) {
+      __syncthreads();                        // everyone is done with the previous tile
+      store_kv(nxt, sK, sV, sMask);
+      __syncthreads();
+    }
+    if (j0 + TC_BN < L) load_kv(a, b, h, j0 + TC_BN, L, nxt);   // prefetch under the MMAs below
     float s[8][4];
     zero_acc(s);
     mma_a_bt(s, qf, sK, lane);
@@ -209,22 +253,28 @@ attn_fwd_tc_kernel(AttnArgs a) {
 }
 
 // D[t] = sum_c dO[t,c] * O[t,c] and lse[t] for the 64 queries q0.. into shared memory.
+// Thread pair (2r, 2r+1) owns row r, 32 columns each: 16 independent float4 loads per thread, one
+// round of memory latency (the previous warp-per-row loop paid 16 dependent rounds per warp).
 __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h, int bh, int q0,
                                                 float* sD, float* sLse) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < 64; r += (blockDim.x >> 5)) {
-    const int t = q0 + r;
-    float d = 0.f;
-    if (t < a.T) {
-      const long long off = (static_cast<long long>(t) * a.B + b) * a.ldo + h * TC_D;
-      d = __ldg(a.dout + off + lane) * __ldg(a.out + off + lane) +
-          __ldg(a.dout + off + lane + 32) * __ldg(a.out + off + lane + 32);
-    }
-    d = warp_sum(d);
-    if (lane == 0) {
-      sD[r] = d;
-      sLse[r] = t < a.T ? a.lse[static_cast<long long>(bh) * a.T + t] : INFINITY;  // p := 0 beyond T
-    }
+  const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int t = q0 + r;
+  float d = 0.f;
+  if (t < a.T) {
+    const long long off = (static_cast<long long>(t) * a.B + b) * a.ldo + h * TC_D + half * 32;
+    const float4* pd = reinterpret_cast<const float4*>(a.dout + off);
+    const float4* po = reinterpret_cast<const float4*>(a.out + off);
+    float4 x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = __ldg(pd + i); y[i] = __ldg(po + i); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      d += (x[i].x * y[i].x + x[i].y * y[i].y) + (x[i].z * y[i].z + x[i].w * y[i].w);
+  }
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  if (half == 0) {
+    sD[r] = d;
+    sLse[r] = t < a.T ? a.lse[static_cast<long long>(bh) * a.T + t] : INFINITY;  // p := 0 beyond T
   }
 }
 
@@ -243,9 +293,17 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
-  stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
+  KvRegs nxt;
+  {
+    float4 qreg[TC_ST], doreg[TC_ST];
+    load_tile(a.q, a.ldq, a.B, b, h, q0, a.T, qreg);
+    load_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, doreg);
+    load_kv(a, b, h, 0, L, nxt);              // first K/V tile in flight together with Q, dO
+    store_tile(qreg, sQ);
+    store_tile(doreg, sdO);
+  }
   stage_row_stats(a, b, h, bh, q0, sD, sLse);
+  store_kv(nxt, sK, sV, sMask);
   __syncthreads();
   uint32_t qf[4][4], dof[4][4];
   load_a_frags(sQ, warp, lane, qf);
@@ -257,9 +315,12 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
   float dq[8][4];
   zero_acc(dq);
   for (int j0 = 0; j0 < L; j0 += TC_BN) {
-    __syncthreads();
-    stage_kv(a, b, h, j0, L, sK, sV, sMask);
-    __syncthreads();
+    if (j0 > 0) {
+      __syncthreads();
+      store_kv(nxt, sK, sV, sMask);
+      __syncthreads();
+    }
+    if (j0 + TC_BN < L) load_kv(a, b, h, j0 + TC_BN, L, nxt);   // prefetch under the MMAs below
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
@@ -313,7 +374,17 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   const bool has_bias = a.bias_k != nullptr;
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  stage_kv(a, b, h, j0, L, sK, sV, sMask);
+  {
+    KvRegs kv;
+    float4 qreg[TC_ST], doreg[TC_ST];
+    load_kv(a, b, h, j0, L, kv);                      // all loads of the first round in flight
+    load_tile(a.q, a.ldq, a.B, b, h, 0, a.T, qreg);
+    load_tile(a.dout, a.ldo, a.B, b, h, 0, a.T, doreg);
+    store_kv(kv, sK, sV, sMask);
+    store_tile(qreg, sQ);
+    store_tile(doreg, sdO);
+  }
+  stage_row_stats(a, b, h, bh, 0, sD, sLse);
   __syncthreads();
   uint32_t kf[4][4], vf[4][4];
   load_a_frags(sK, warp, lane, kf);
@@ -324,11 +395,13 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   zero_acc(dk);
   zero_acc(dv);
   for (int q0 = 0; q0 < a.T; q0 += TC_BM) {
-    __syncthreads();
-    stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
-    stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
-    stage_row_stats(a, b, h, bh, q0, sD, sLse);
-    __syncthreads();
+    if (q0 > 0) {
+      __syncthreads();
+      stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+      stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
+      stage_row_stats(a, b, h, bh, q0, sD, sLse);
+      __syncthreads();
+    }
     float st[8][4], dpt[8][4];      // S^T and dP^T: rows = keys, cols = queries
     zero_acc(st);
     zero_acc(dpt);

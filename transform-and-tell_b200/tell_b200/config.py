@@ -12,6 +12,8 @@ import itertools
 import torch
 
 precision = 'bf16'
+# weight gradients on a second stream (functional.wgrad); opt-in, throughput mode only
+wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks
 
 _seed_base = 0x5EED
 _counter = itertools.count(1)
@@ -22,6 +24,11 @@ def set_precision(p):
     global precision
     assert p in ('bf16', 'bf16x3')
     precision = p
+
+
+def enable_wgrad_stream(level=2):
+    global wgrad_stream
+    wgrad_stream = int(level)
 
 
 def manual_seed(seed):

@@ -28,6 +28,75 @@ def _c(x):
     return x if x.is_contiguous() else x.contiguous()
 
 
+class _WGradState:
+    stream = None      # the weight-gradient stream of this process
+    main = None        # stream the running backward was forked from
+    pending = False    # work has been forked since the last join
+    keep = []          # inputs of forked kernels, kept alive until the join
+
+
+class wgrad:
+    """`with wgrad(*inputs):` -- kernels launched inside run on the weight-gradient stream.
+
+    In the backward of y = x.W^T only dL/dx is on the critical path; dL/dW and the bias column sums
+    feed nothing before the end of the backward pass.  They are forked onto a second stream (a
+    parallel branch when the step is captured in a CUDA graph) so that the small, latency-bound
+    decoder kernels of the two chains overlap.  The branch is joined (a) before the batched
+    weight-norm backward reads the bank's dL/dw buffer and (b) by an autograd final callback, i.e.
+    before loss.backward() returns -- callers see ordinary stream semantics.
+    `inputs` are the tensors the forked kernels read; they are kept alive until the join so that
+    the allocator cannot hand their memory to later main-stream kernels.
+    Opt-in (config.wgrad_stream) and throughput mode only.  Deferred joins (level 1) are only used
+    for the bank's dL/dw buffers, which autograd never touches; everything else that may be summed,
+    sliced or copied by autograd on the main stream uses local=True (level 2) and joins before the
+    backward function returns."""
+
+    def __init__(self, *inputs, local=False):
+        self.inputs = inputs
+        self.cm = None
+        self.level = 2 if local else 1
+
+    def __enter__(self):
+        if not (config.wgrad_stream >= self.level and config.precision == 'bf16'):
+            return self
+        st = _WGradState
+        main = torch.cuda.current_stream()
+        if st.stream is None or st.stream.device != main.device:
+            st.stream = torch.cuda.Stream(device=main.device)
+        if main == st.stream:          # nested use: already on the branch
+            return self
+        if not st.pending:
+            from torch.autograd import Variable
+            Variable._execution_engine.queue_callback(wgrad_join)   # only legal inside backward
+            st.pending, st.main = True, main
+        st.stream.wait_stream(main)
+        st.keep.extend(t for t in self.inputs if t is not None)
+        self.cm = torch.cuda.stream(st.stream)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
+
+
+def wgrad_join(local=False):
+    """Main stream waits for everything forked with `wgrad` so far.  local=True: the join that
+    closes a fork made with wgrad(local=True) inside one backward function (outputs that autograd
+    may touch on the main stream right after the function returns)."""
+    st = _WGradState
+    if local and config.wgrad_stream < 2:
+        return
+    if st.pending:
+        st.main.wait_stream(st.stream)
+        cur = torch.cuda.current_stream()
+        if cur != st.main and cur != st.stream:
+            cur.wait_stream(st.stream)
+        st.pending = False
+        st.keep = []
+
+
 def _fast():
     """bf16 throughput mode: backward GEMMs read the forward's bf16 operands in place through
     MN-major UMMA descriptors (trans_a / trans_b) -- no transposed copies, no weight re-casts.
@@ -70,8 +139,14 @@ class LinearFn(Function):
                 # weight-normalised matrices: dL/dw lands in the bank's flat buffer, where the
                 # single batched wnorm backward reads it
                 dest = ctx.bank.claim_dw(ctx.wkey) if ctx.bank is not None else None
-                dw = ops.gemm_tn(dy16, x, out=dest, alpha=ctx.alpha, trans_a=True,
-                                 trans_b=True)                                      # dy^T . x
+                if dest is not None:
+                    # nothing reads the bank's dL/dw buffer before the batched weight-norm
+                    # backward (which joins): off the critical path, on the wgrad stream
+                    with wgrad(dy16, x):
+                        dw = ops.gemm_tn(dy16, x, out=dest, alpha=ctx.alpha, trans_a=True,
+                                         trans_b=True)                              # dy^T . x
+                else:
+                    dw = ops.gemm_tn(dy16, x, alpha=ctx.alpha, trans_a=True, trans_b=True)
         else:
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(operand(dy, 'a'), operand(w, 'b', transpose=True), alpha=ctx.alpha)
@@ -449,17 +524,22 @@ class FusedQProjFn(Function):
         if fast:
             a16, w16 = ctx.saved_tensors
             d16 = operand(dy, 'a')
+            db = None
+            with wgrad(d16, a16, dy, local=True):      # dW, db alongside dx; joined before return
+                dW = ops.gemm_tn(d16, a16, alpha=alpha, trans_a=True, trans_b=True)
+                if has_bias:
+                    db = ops.colsum(dy, scale=alpha)
             dx = ops.gemm_tn(d16, w16, alpha=alpha, trans_b=True)
-            dW = ops.gemm_tn(d16, a16, alpha=alpha, trans_a=True, trans_b=True)
+            wgrad_join(local=True)
         else:
             x, ws = ctx.saved_tensors[0], ctx.saved_tensors[1:]
             dx = ops.gemm_tn(operand(dy, 'a'), concat_kT_operand(list(ws), 'b', dy.device), alpha=alpha)
             dW = ops.gemm_tn(operand(dy, 'a', transpose=True), operand(x, 'b', transpose=True),
                              alpha=alpha)
+            db = ops.colsum(dy, scale=alpha) if has_bias else None
         dws = tuple(dW[c * E:(c + 1) * E] for c in range(n))
         dbs = (None,) * n
         if has_bias:
-            db = ops.colsum(dy, scale=alpha)
             dbs = tuple(db[c * E:(c + 1) * E] for c in range(n))
         return (dx, None, None) + dws + dbs
 
@@ -571,13 +651,16 @@ class FusedOutProjFn(Function):
             sl = slice(c * E, (c + 1) * E)
             if fast:
                 d16 = operand(dh, 'a')
+                with wgrad(d16, a, dh, local=True):    # dW_c, db_c alongside the dx GEMMs
+                    dws.append(ops.gemm_tn(d16, a[:, sl], trans_a=True, trans_b=True))
+                    dbs.append(ops.colsum(dh) if has_bias else None)
                 ops.gemm_tn(d16, ws[c], out=da_all[:, sl], trans_b=True)
-                dws.append(ops.gemm_tn(d16, a[:, sl], trans_a=True, trans_b=True))
             else:
                 ops.gemm_tn(operand(dh, 'a'), operand(ws[c], 'b', transpose=True), out=da_all[:, sl])
                 dws.append(ops.gemm_tn(operand(dh, 'a', transpose=True),
                                        operand(a[:, sl], 'b', transpose=True)))
-            dbs.append(ops.colsum(dh) if has_bias else None)
+                dbs.append(ops.colsum(dh) if has_bias else None)
+        wgrad_join(local=True)
         return (da_all, None) + tuple(dws) + tuple(dbs)
 
 

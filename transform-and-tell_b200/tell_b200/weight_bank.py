@@ -239,6 +239,8 @@ class _BankWNormFn(Function):
     @staticmethod
     def backward(ctx, *dws):
         bank = ctx.bank
+        from . import functional
+        functional.wgrad_join()          # dL/dw GEMMs forked onto the weight-gradient stream
         for e, dw in zip(bank.wn, dws):
             if dw is None:
                 e.dw.zero_()
