@@ -372,3 +372,45 @@ def roberta_forward(ids, sd, n_layers, heads, prefix='roberta.', padding_idx=1, 
                          sd[lp + 'final_layer_norm.bias'], eps)
         hiddens.append(x)
     return hiddens
+
+
+# ------------------------------------------------------------------------------------- optimizer
+def bert_adam_schedule(step, t_total, warmup, schedule='warmup_linear'):
+    """pytorch-pretrained-bert 0.6.2 `_LRSchedule.get_lr` + `WarmupLinearSchedule.get_lr_` /
+    `WarmupConstantSchedule.get_lr_` (the dependency behind `type: bert_adam`,
+    expt/nytimes/9_transformer_objects/config.yaml:126-132; un-vendored, pulled in by allennlp 0.9).
+    Plain Python floats, as there.  Parity unpinned: the package is absent from /root/reference and
+    the reference has no test for it; this follows the published source."""
+    if t_total < 0 or schedule in (None, 'none'):
+        return 1.0
+    warmup = max(warmup, 0.0)
+    progress = float(step) / t_total
+    if progress < warmup:
+        return progress / warmup
+    if schedule == 'warmup_constant':
+        return 1.0
+    return max((progress - 1.0) / (warmup - 1.0), 0.0)
+
+
+def bert_adam_step(params, grads, state, lr, warmup=-1, t_total=-1, schedule='warmup_linear',
+                   b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, max_grad_norm=1.0):
+    """One `BertAdam.step()` (pytorch-pretrained-bert 0.6.2 optimization.py, the optimizer stepped at
+    tell/training/callback_apex_trainer.py:238) over lists of fp32 tensors, in place.
+    state: list of dicts {'step', 'next_m', 'next_v'} (created on first use)."""
+    for p, g, st in zip(params, grads, state):
+        if not st:
+            st.update(step=0, next_m=torch.zeros_like(p), next_v=torch.zeros_like(p))
+        g = g.clone()
+        if max_grad_norm > 0:                       # clip_grad_norm_(p, max_grad_norm): per tensor
+            total_norm = g.norm(2)
+            clip_coef = max_grad_norm / (total_norm + 1e-6)
+            if clip_coef < 1:
+                g.mul_(clip_coef)
+        st['next_m'].mul_(b1).add_(g, alpha=1 - b1)
+        st['next_v'].mul_(b2).addcmul_(g, g, value=1 - b2)
+        update = st['next_m'] / (st['next_v'].sqrt() + e)
+        if weight_decay > 0.0:
+            update = update + weight_decay * p
+        lr_scheduled = lr * bert_adam_schedule(st['step'], t_total, warmup, schedule)
+        p.add_(-(lr_scheduled * update))
+        st['step'] += 1

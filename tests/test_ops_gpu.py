@@ -436,3 +436,22 @@ def test_layer_mix():
     assert (oc.cpu() - out.detach()).abs().max() < 1e-5
     dw = ops.layer_mix_bwd(cuda(hid), cuda(w.detach()), cuda(dout))
     assert (dw.cpu() - w.grad).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize('N,E', [(2000, 1024), (37, 1024), (50, 256)])
+def test_layernorm_bf16_out(N, E):
+    """tt_ln_fwd16 (RoBERTa post-LN, bf16 output, padded rows zeroed): the one-CTA-per-row kernel
+    (E = 1024, more rows than the grid cap) and the warp-per-row kernel vs F.layer_norm; tolerance
+    = bf16 rounding of O(1) outputs (2^-8 relative)."""
+    from tell_b200 import ops
+    torch.manual_seed(11)
+    x = torch.randn(N, E) * 2 + 0.3
+    g = torch.randn(E) * 0.1 + 1
+    b = torch.randn(E) * 0.1
+    zero = (torch.rand(N) < 0.2).to(torch.uint8)
+    want = F.layer_norm(x, (E,), g, b, 1e-5) * (1 - zero.float()).unsqueeze(1)
+    out = torch.empty(N, E, dtype=torch.bfloat16, device='cuda')
+    ops.ln_fwd16(cuda(x), cuda(g), cuda(b), out, cuda(zero))
+    got = out.float().cpu()
+    assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6
+    assert torch.equal(got[zero.bool()], torch.zeros_like(got[zero.bool()]))

@@ -129,3 +129,32 @@ def test_tail_local_index_one_quirk():
     l_q, _, _ = restate.adaptive_loss(X, t_quirk, sd, [10, 20, 30])
     true_q = sum(full[i, t_quirk[0, i]] for i in range(3))
     assert l_q.item() < true_q.item() - 1e-3      # tail terms of local index 1 are dropped
+
+
+def test_bert_adam_restatement_known_answers():
+    """Hand-computed known answers for the BertAdam restatement (the optimizer behind
+    `type: bert_adam`, config.yaml:126-136; pytorch-pretrained-bert is absent here, so these pin
+    the arithmetic of the published algorithm rather than the package itself)."""
+    import restate
+    # schedule: warm-up is linear in progress, then linear decay to 0 at t_total, clamped after
+    assert restate.bert_adam_schedule(0, 1000, 0.05) == 0.0
+    assert abs(restate.bert_adam_schedule(25, 1000, 0.05) - 0.5) < 1e-12
+    assert abs(restate.bert_adam_schedule(500, 1000, 0.05) - 0.5 / 0.95) < 1e-12
+    assert restate.bert_adam_schedule(1500, 1000, 0.05) == 0.0
+    assert restate.bert_adam_schedule(7, -1, 0.05) == 1.0
+    assert restate.bert_adam_schedule(500, 1000, 0.05, 'warmup_constant') == 1.0
+    # one step on a scalar: clip 0.5 -> 0.1/(0.5+1e-6), m = 0.1 g, v = 0.001 g^2
+    p, g, st = [torch.tensor([1.0])], [torch.tensor([0.5])], [dict()]
+    restate.bert_adam_step(p, g, st, lr=1e-3, b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01,
+                           max_grad_norm=0.1)
+    gc = 0.5 * (0.1 / (0.5 + 1e-6))
+    m, v = 0.1 * gc, 0.001 * gc * gc
+    want = 1.0 - 1e-3 * (m / (v ** 0.5 + 1e-6) + 0.01 * 1.0)
+    assert abs(p[0].item() - want) < 1e-7 and st[0]['step'] == 1
+    assert abs(st[0]['next_m'].item() - m) < 1e-9 and abs(st[0]['next_v'].item() - v) < 1e-11
+    # unclipped small gradient, no decay: update is m / (sqrt(v) + e)
+    p, g, st = [torch.tensor([2.0])], [torch.tensor([1e-3])], [dict()]
+    restate.bert_adam_step(p, g, st, lr=1.0, b1=0.9, b2=0.98, e=1e-6, weight_decay=0.0,
+                           max_grad_norm=0.1)
+    want = 2.0 - (1e-4 / ((0.02 * 1e-6) ** 0.5 + 1e-6))
+    assert abs(p[0].item() - want) < 1e-5

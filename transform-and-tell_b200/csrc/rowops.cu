@@ -294,6 +294,128 @@ __global__ void nan_rows_kernel(float* __restrict__ x, uint8_t* __restrict__ mas
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide-row variants (E = 1024 with 256 threads): ONE CTA PER ROW, the row lives in registers (one
+// float4 per thread), block reductions through shared memory.  The decoder has only T*B = 800
+// rows: warp-per-row left 5 warps per SM and a chain of 8 dependent loads per pass; here every row
+// is a single round of memory latency and all SMs are busy.
+__device__ __forceinline__ float2 block_sum2_256(float a, float b, float2* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) red[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = lane < 8 ? red[lane] : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+    t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+  }
+  t.x = __shfl_sync(0xffffffffu, t.x, 0);
+  t.y = __shfl_sync(0xffffffffu, t.y, 0);
+  return t;
+}
+
+__global__ void __launch_bounds__(256) ln_fwd_row_kernel(
+    float* __restrict__ h, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ y, long long ldy, float* __restrict__ mean,
+    float* __restrict__ rstd, int N, float eps, float p, unsigned long long seed,
+    const unsigned long long* step_ptr) {
+  pdl_prologue();
+  __shared__ float2 red[8];
+  constexpr int E = 1024;
+  seed = mix_seed(seed, step_ptr);
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int c = threadIdx.x;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+  for (int r = blockIdx.x; r < N; r += gridDim.x) {
+    float4* hr = reinterpret_cast<float4*>(h + static_cast<long long>(r) * E);
+    float4 v = hr[c];
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) q = __ldg(reinterpret_cast<const float4*>(res + static_cast<long long>(r) * E) + c);
+    if (p > 0.f) {
+      const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
+      v.x *= dropout_scale(seed, base, p, inv_keep);
+      v.y *= dropout_scale(seed, base + 1, p, inv_keep);
+      v.z *= dropout_scale(seed, base + 2, p, inv_keep);
+      v.w *= dropout_scale(seed, base + 3, p, inv_keep);
+    }
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    hr[c] = v;
+    const float mu = block_sum2_256((v.x + v.y) + (v.z + v.w), 0.f, red).x * (1.f / E);
+    const float a = v.x - mu, b = v.y - mu, d = v.z - mu, e = v.w - mu;
+    const float var = block_sum2_256((a * a + b * b) + (d * d + e * e), 0.f, red).x * (1.f / E);
+    const float rs = rsqrtf(var + eps);
+    if (c == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+    float4 o;
+    o.x = a * rs * gm.x + bt.x;
+    o.y = b * rs * gm.y + bt.y;
+    o.z = d * rs * gm.z + bt.z;
+    o.w = e * rs * gm.w + bt.w;
+    reinterpret_cast<float4*>(y + static_cast<long long>(r) * ldy)[c] = o;
+  }
+}
+
+// Backward, wide rows: each thread owns 4 fixed columns, so dgamma/dbeta accumulate in registers
+// over the CTA's rows and leave with ONE global atomic per column per CTA.
+__global__ void __launch_bounds__(256) ln_bwd_row_kernel(
+    const float* __restrict__ dy, long long lddy, const float* __restrict__ x,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+    float* __restrict__ dx, float* __restrict__ dh, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, int N, float p, unsigned long long seed,
+    const unsigned long long* step_ptr) {
+  pdl_prologue();
+  __shared__ float2 red[8];
+  constexpr int E = 1024;
+  seed = mix_seed(seed, step_ptr);
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int c = threadIdx.x;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  for (int r = blockIdx.x; r < N; r += gridDim.x) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + static_cast<long long>(r) * lddy) + c);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E) + c);
+    const float mu = mean[r], rs = rstd[r];
+    float4 xh, g;
+    xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs; xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
+    g.x = d.x * gm.x; g.y = d.y * gm.y; g.z = d.z * gm.z; g.w = d.w * gm.w;
+    ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
+    ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+    const float2 s = block_sum2_256((g.x + g.y) + (g.z + g.w),
+                                    (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w), red);
+    const float s1 = s.x * (1.f / E), s2 = s.y * (1.f / E);
+    float4 o;
+    o.x = rs * (g.x - s1 - xh.x * s2);
+    o.y = rs * (g.y - s1 - xh.y * s2);
+    o.z = rs * (g.z - s1 - xh.z * s2);
+    o.w = rs * (g.w - s1 - xh.w * s2);
+    if (dx) reinterpret_cast<float4*>(dx + static_cast<long long>(r) * E)[c] = o;
+    if (dh) {
+      if (p > 0.f) {
+        const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
+        o.x *= dropout_scale(seed, base, p, inv_keep);
+        o.y *= dropout_scale(seed, base + 1, p, inv_keep);
+        o.z *= dropout_scale(seed, base + 2, p, inv_keep);
+        o.w *= dropout_scale(seed, base + 3, p, inv_keep);
+      }
+      reinterpret_cast<float4*>(dh + static_cast<long long>(r) * E)[c] = o;
+    }
+  }
+  if (dgamma) {
+    atomicAdd(dgamma + 4 * c, ag.x); atomicAdd(dgamma + 4 * c + 1, ag.y);
+    atomicAdd(dgamma + 4 * c + 2, ag.z); atomicAdd(dgamma + 4 * c + 3, ag.w);
+  }
+  if (dbeta) {
+    atomicAdd(dbeta + 4 * c, ab.x); atomicAdd(dbeta + 4 * c + 1, ab.y);
+    atomicAdd(dbeta + 4 * c + 2, ab.z); atomicAdd(dbeta + 4 * c + 3, ab.w);
+  }
+}
+
 static inline int flat_grid(long long n) {
   long long g = ceil_div_ll(n, 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -311,6 +433,12 @@ extern "C" int tt_ln_fwd(float* h, const float* res, const float* gamma, const f
   TT_REQUIRE(E > 0 && E % 4 == 0 && ldy % 4 == 0, "tt_ln_fwd: E and ldy must be multiples of 4");
   TT_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "tt_ln_fwd: bad dropout p");
   if (N <= 0) return TT_OK;
+  if (E == 1024) {      // production width: one CTA per row
+    const int grid = N < num_sms() * 8 ? N : num_sms() * 8;
+    launch_k(ln_fwd_row_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+        h, res, gamma, beta, y, ldy, mean, rstd, N, eps, p_drop, seed, rng_step_ptr());
+    return check_launch("ln_fwd_row_kernel");
+  }
   launch_k(ln_fwd_kernel, dim3(row_grid(N)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, 
       h, res, gamma, beta, y, ldy, mean, rstd, N, E, eps, p_drop, seed, rng_step_ptr());
   return check_launch("ln_fwd_kernel");
@@ -324,6 +452,12 @@ extern "C" int tt_ln_bwd(const float* dy, long long lddy, const float* x, const 
   TT_REQUIRE(E > 0 && E % 4 == 0 && E <= 1024 && lddy % 4 == 0,
              "tt_ln_bwd: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (N <= 0) return TT_OK;
+  if (E == 1024) {      // production width: one CTA per row, <= 2 CTAs per SM share the atomics
+    const int cap = num_sms() * 2;
+    launch_k(ln_bwd_row_kernel, dim3(N < cap ? N : cap), dim3(256), 0, (cudaStream_t)stream,
+        dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, p_drop, seed, rng_step_ptr());
+    return check_launch("ln_bwd_row_kernel");
+  }
   // fewer, fatter warps so the dgamma/dbeta atomics stay cheap
   int grid = row_grid(N);
   if (grid > num_sms()) grid = num_sms();
