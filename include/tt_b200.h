@@ -305,6 +305,22 @@ int tt_ln_fwd16(const float* x, const float* gamma, const float* beta, void* y16
  * -> out [B*S, H*D] bf16.  D must be 64. */
 int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_mask, void* out, int B, int S,
                        int H, int D, void* stream);
+/* Variable-length ("packed") RoBERTa forward: articles are padded to S with `pad`
+ * (tell/data/token_indexers/roberta_indexer.py:185-200) and every consumer of the encoder output
+ * masks the padding (transformer_faces_objects.py:366 article_padding_mask), so the encoder only
+ * has to compute the real tokens.  tt_varlen_prepare builds inv_map[B*S] (padded row -> packed row,
+ * -1 = padding) and cu_seqlens[B+1] (first packed row of each sample; cu_seqlens[B] = number of
+ * real tokens, the m_limit of the encoder GEMMs).  tt_flash_self_attn_varlen is the self-attention
+ * over the packed layout (sample b = rows cu[b]..cu[b+1]); tt_ln_fwd16_varlen is the LayerNorm that
+ * moves between the layouts (see encoders.cu) and writes zeros to the padding rows of the padded
+ * hidden-state buffer. */
+int tt_varlen_prepare(const long long* ids, int B, int S, int pad, int* inv_map, int* cu_seqlens,
+                      void* stream);
+int tt_flash_self_attn_varlen(const void* qkv, const int* cu_seqlens, void* out, int B, int S_max,
+                              int H, int D, void* stream);
+int tt_ln_fwd16_varlen(const float* x, int x_packed, const float* gamma, const float* beta,
+                       void* y_packed, void* y_padded, const int* inv_map, const int* count_ptr,
+                       int R, int E, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step: BertAdam as configured by

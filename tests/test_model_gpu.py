@@ -41,17 +41,24 @@ def test_resnet_matches_oracle():
     assert torch.equal(nhwc.permute(0, 3, 1, 2), out)
 
 
-def test_roberta_matches_oracle():
+@pytest.mark.parametrize('varlen', [False, True])
+def test_roberta_matches_oracle(varlen):
+    """Padded path and packed (variable-length) path against the fp32 restatement on the real
+    tokens; the packed path leaves the padding rows of every layer exactly zero."""
     import restate
     from tell_b200 import synth
     from tell_b200.models import RobertaEncoder
-    L, E, H, ffn, V, P = 2, 1024, 16, 512, 500, 80
+    L, E, H, ffn, V, P = 2, 1024, 16, 512, 500, 300
     sd = synth.roberta_state_dict(L, E, ffn, V, P, seed=2)
     enc = RobertaEncoder(L, E, H, ffn, V, P)
     enc.load_state_dict(sd, strict=True)
     enc = enc.cuda().eval()
+    enc.varlen = varlen
     rs = np.random.RandomState(1)
-    ids = synth.article_batch(3, 70, V, rs, min_len=20)
+    ids = synth.article_batch(5, 270, V, rs, min_len=20)     # > 2 query tiles, ragged lengths
+    ids[1, 1:] = 1                                           # a one-token sample
+    ids[2, 3:] = 1                                           # a 3-token sample
+    ids[3, :] = torch.from_numpy(rs.randint(4, V, size=270)) # a full-length sample
     ref = restate.roberta_forward(ids, sd, L, H, prefix='')
     outs = enc.extract_features(ids.cuda(), return_all_hiddens=True)
     assert len(outs) == L + 1
@@ -62,6 +69,16 @@ def test_roberta_matches_oracle():
         assert err < 6e-2 * max(1.0, r.abs().max().item()), err
     # padded rows of the embedding output are exactly zero (fairseq: x *= 1 - padding_mask)
     assert (outs[0].cpu()[~real] == 0).all()
+    if varlen:
+        for o in outs:
+            assert (o.cpu()[~real] == 0).all()
+        inv_map, cu = __import__('tell_b200').ops.varlen_prepare(ids.cuda(), 1)
+        lens = real.sum(1)
+        want_cu = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).int()
+        assert torch.equal(cu.cpu(), want_cu)
+        want_map = torch.full((ids.numel(),), -1, dtype=torch.int32)
+        want_map[real.view(-1)] = torch.arange(int(lens.sum()), dtype=torch.int32)
+        assert torch.equal(inv_map.cpu(), want_map)
 
 
 class _StubResNet(torch.nn.Module):

@@ -159,27 +159,122 @@ __global__ void ln_fwd16_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// E == 1024: one CTA per row, the row stays in registers (one float4 per thread) -- a single round of
-// memory latency per row instead of three dependent 8-load passes per warp.
-__global__ void __launch_bounds__(256) ln_fwd16_row_kernel(
-    const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-    __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ row_zero, int N, float eps) {
+// Variable-length packing of the article batch: inv_map[r] = index of padded row r = b*S + t among
+// the non-pad rows (sample-major order) or -1 for padding, cu[b] = first packed row of sample b,
+// cu[B] = total number of real tokens (used as the device-side row limit of every RoBERTa GEMM).
+// One CTA per sample: its offset is the number of real tokens in all earlier samples.
+__global__ void __launch_bounds__(256) varlen_prepare_kernel(const long long* __restrict__ ids, int B, int S,
+                                                             int pad, int* __restrict__ inv_map,
+                                                             int* __restrict__ cu) {
   pdl_prologue();
-  __shared__ float red[32];
-  constexpr int E = 1024;
-  const int c = threadIdx.x;
-  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
-  for (int r = blockIdx.x; r < N; r += gridDim.x) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E) + c);
-    const float mu = block_sum((v.x + v.y) + (v.z + v.w), red) * (1.f / E);
-    const float a = v.x - mu, b = v.y - mu, d = v.z - mu, e = v.w - mu;
-    const float rs = rsqrtf(block_sum((a * a + b * b) + (d * d + e * e), red) * (1.f / E) + eps);
-    const float keep = (row_zero && row_zero[r]) ? 0.f : 1.f;
-    uint2 u;
-    u.x = pack_bf16(keep * (a * rs * g.x + bt.x), keep * (b * rs * g.y + bt.y));
-    u.y = pack_bf16(keep * (d * rs * g.z + bt.z), keep * (e * rs * g.w + bt.w));
-    reinterpret_cast<uint2*>(y + static_cast<long long>(r) * E)[c] = u;
+  __shared__ int red[32];
+  __shared__ int wsum[8];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  auto block_total = [&](int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    int t = lane < 8 ? red[lane] : 0;
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  int before = 0;
+  for (long long j = threadIdx.x; j < static_cast<long long>(b) * S; j += 256) before += ids[j] != pad;
+  before = block_total(before);
+  // own sample: thread t owns the contiguous tokens [t*per, (t+1)*per)
+  const int per = (S + 255) / 256;
+  const int t0 = threadIdx.x * per;
+  const long long* row = ids + static_cast<long long>(b) * S;
+  int mine = 0;
+  for (int t = t0; t < t0 + per && t < S; ++t) mine += row[t] != pad;
+  int incl = mine;                                   // inclusive scan within the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < w; ++i) woff += wsum[i];
+  int pos = before + woff + incl - mine;
+  for (int t = t0; t < t0 + per && t < S; ++t) {
+    const bool real = row[t] != pad;
+    inv_map[static_cast<long long>(b) * S + t] = real ? pos : -1;
+    pos += real;
+  }
+  if (threadIdx.x == 255) {
+    cu[b] = before;
+    if (b == B - 1) cu[B] = pos;                     // thread 255 ends the scan: pos = total
+  }
+}
+
+// LayerNorm (fp32 in, bf16 out) between the packed and padded layouts.  One WARP per row, the row
+// lives in registers (MAXC float4 per lane, all loads issued back to back, shuffle reductions, no
+// block barrier): HBM-bound, 4 B read + 2 B (4 B when both layouts are written) per element.
+//   inv_map == null : rows i < *count:  y_packed[i] = LN(x[i])                  (mid-layer LN)
+//   inv_map != null : padded rows r < R: c = inv_map[r];
+//                       c < 0 : y_padded[r] = 0 (padding stays finite for the masked consumers)
+//                       else  : y = LN(x[x_packed ? c : r]) -> y_packed[c] and y_padded[r]
+template <int MAXC>   // E <= 128 * MAXC
+__global__ void __launch_bounds__(256) ln_fwd16_varlen_kernel(
+    const float* __restrict__ x, int x_packed, const float* __restrict__ gamma,
+    const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_packed,
+    __nv_bfloat16* __restrict__ y_padded, const int* __restrict__ inv_map,
+    const int* __restrict__ count, int R, int E, float eps) {
+  pdl_prologue();
+  const int E4 = E >> 2;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int limit = (inv_map == nullptr && count != nullptr) ? min(R, __ldg(count)) : R;
+  const float inv_e = 1.f / E;
+  for (int r = warp_global; r < limit; r += nwarps) {
+    int c = r, src = r;
+    if (inv_map != nullptr) {
+      c = inv_map[r];
+      if (c < 0) {
+        if (y_padded)
+          for (int i = lane; i < E4; i += 32)
+            reinterpret_cast<uint2*>(y_padded + static_cast<long long>(r) * E)[i] = make_uint2(0u, 0u);
+        continue;
+      }
+      src = x_packed ? c : r;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(src) * E);
+    float4 v[MAXC];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int i = lane + k * 32;
+      v[k] = i < E4 ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    const float mu = warp_sum(s) * inv_e;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      if (lane + k * 32 < E4) {
+        const float a = v[k].x - mu, b = v[k].y - mu, d = v[k].z - mu, e = v[k].w - mu;
+        ss += (a * a + b * b) + (d * d + e * e);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(ss) * inv_e + eps);
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int i = lane + k * 32;
+      if (i < E4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i);
+        uint2 u;
+        u.x = pack_bf16((v[k].x - mu) * rs * g.x + bt.x, (v[k].y - mu) * rs * g.y + bt.y);
+        u.y = pack_bf16((v[k].z - mu) * rs * g.z + bt.z, (v[k].w - mu) * rs * g.w + bt.w);
+        if (y_packed) reinterpret_cast<uint2*>(y_packed + static_cast<long long>(c) * E)[i] = u;
+        if (y_padded && inv_map) reinterpret_cast<uint2*>(y_padded + static_cast<long long>(r) * E)[i] = u;
+      }
+    }
   }
 }
 
@@ -237,7 +332,8 @@ constexpr int FA_QROWS = 128;
 
 __global__ void __launch_bounds__(FA_THREADS)
 flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ mask,
-                       __nv_bfloat16* __restrict__ out, int B, int S, int H) {
+                       __nv_bfloat16* __restrict__ out, int B, int S, int H,
+                       const int* __restrict__ cu) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t fa_smem[];
   typedef __nv_bfloat16 (*Tile)[FA_LD];
@@ -251,7 +347,16 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
   const long long ld = 3LL * E;
-  const __nv_bfloat16* qbase = qkv + static_cast<long long>(b) * S * ld + h * FA_D;
+  // padded layout: sample b owns rows [b*S, (b+1)*S) and `mask` flags its padding keys;
+  // packed (variable-length) layout: rows [cu[b], cu[b+1]) hold its real tokens only.
+  long long row0 = static_cast<long long>(b) * S;
+  int len = S;
+  if (cu != nullptr) {
+    row0 = cu[b];
+    len = cu[b + 1] - cu[b];
+    if (q0 >= len) return;
+  }
+  const __nv_bfloat16* qbase = qkv + row0 * ld + h * FA_D;
   const __nv_bfloat16* kbase = qbase + E;
   const __nv_bfloat16* vbase = qbase + 2 * E;
   constexpr float LOG2E = 1.4426950408889634f;
@@ -261,7 +366,7 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
     Tile sV = sV0 + buf * FA_BN;
     for (int i = threadIdx.x; i < FA_BN * (FA_D / 8); i += FA_THREADS) {
       const int r = i >> 3, c8 = i & 7;
-      const bool ok = j0 + r < S;
+      const bool ok = j0 + r < len;
       const long long row = ok ? (j0 + r) : 0;
       cp_async16(&sK[r][c8 * 8], kbase + row * ld + c8 * 8, ok);
       cp_async16(&sV[r][c8 * 8], vbase + row * ld + c8 * 8, ok);
@@ -269,13 +374,13 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
     if (threadIdx.x < FA_BN) {
       const int j = j0 + threadIdx.x;
       sMask[buf * FA_BN + threadIdx.x] =
-          (j < S && !(mask && mask[static_cast<long long>(b) * S + j])) ? 0.f : -INFINITY;
+          (j < len && !(mask && mask[static_cast<long long>(b) * S + j])) ? 0.f : -INFINITY;
     }
   };
 
   for (int i = threadIdx.x; i < FA_QROWS * (FA_D / 8); i += FA_THREADS) {
     const int r = i >> 3, c8 = i & 7;
-    const bool ok = q0 + r < S;
+    const bool ok = q0 + r < len;
     cp_async16(&sQ[r][c8 * 8], qbase + (ok ? (q0 + r) : 0) * ld + c8 * 8, ok);
   }
   load_kv(0, 0);
@@ -292,7 +397,7 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
   for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max in log2 units
 
-  const int ntiles = (S + FA_BN - 1) / FA_BN;
+  const int ntiles = (len + FA_BN - 1) / FA_BN;
   for (int t = 0; t < ntiles; ++t) {
     const int buf = t & 1;
     if (t + 1 < ntiles) load_kv(buf ^ 1, (t + 1) * FA_BN);   // prefetch next tile
@@ -373,11 +478,11 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __r
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int col = h * FA_D + n * 8 + 2 * tg;
-    if (r0 < S)
-      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * S + r0) * E + col) =
+    if (r0 < len)
+      *reinterpret_cast<uint32_t*>(out + (row0 + r0) * E + col) =
           pack_bf16(o[n][0] * i0, o[n][1] * i0);
-    if (r1 < S)
-      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * S + r1) * E + col) =
+    if (r1 < len)
+      *reinterpret_cast<uint32_t*>(out + (row0 + r1) * E + col) =
           pack_bf16(o[n][2] * i1, o[n][3] * i1);
   }
 }
@@ -444,12 +549,6 @@ extern "C" int tt_ln_fwd16(const float* x, const float* gamma, const float* beta
   TT_REQUIRE(x && gamma && beta && y16, "tt_ln_fwd16: null pointer");
   TT_REQUIRE(E % 4 == 0, "tt_ln_fwd16: E must be a multiple of 4");
   if (N <= 0) return TT_OK;
-  if (E == 1024) {
-    const int capr = num_sms() * 8;
-    launch_k(ln_fwd16_row_kernel, dim3(N < capr ? N : capr), dim3(256), 0, (cudaStream_t)stream,
-        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y16), row_zero, N, eps);
-    return check_launch("ln_fwd16_row_kernel");
-  }
   long long g = ceil_div_ll(N, 8);
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (g > cap) g = cap;
@@ -481,6 +580,52 @@ extern "C" int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_ma
   }
   launch_k(flash_self_attn_kernel, dim3(grid), dim3(FA_THREADS), FA_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), key_padding_mask,
-      reinterpret_cast<__nv_bfloat16*>(out), B, S, H);
+      reinterpret_cast<__nv_bfloat16*>(out), B, S, H, (const int*)nullptr);
   return check_launch("flash_self_attn_kernel");
+}
+
+extern "C" int tt_flash_self_attn_varlen(const void* qkv, const int* cu_seqlens, void* out, int B,
+                                         int S_max, int H, int D, void* stream) {
+  TT_REQUIRE(qkv && out && cu_seqlens, "tt_flash_self_attn_varlen: null pointer");
+  TT_REQUIRE(D == FA_D, "tt_flash_self_attn_varlen: head_dim must be %d (got %d)", FA_D, D);
+  if (B <= 0 || S_max <= 0) return TT_OK;
+  dim3 grid(ceil_div(S_max, FA_QROWS), B * H);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(flash_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    attr_set = true;
+  }
+  launch_k(flash_self_attn_kernel, dim3(grid), dim3(FA_THREADS), FA_SMEM, (cudaStream_t)stream,
+      reinterpret_cast<const __nv_bfloat16*>(qkv), (const uint8_t*)nullptr,
+      reinterpret_cast<__nv_bfloat16*>(out), B, S_max, H, cu_seqlens);
+  return check_launch("flash_self_attn_kernel");
+}
+
+extern "C" int tt_varlen_prepare(const long long* ids, int B, int S, int pad, int* inv_map,
+                                 int* cu_seqlens, void* stream) {
+  TT_REQUIRE(ids && inv_map && cu_seqlens, "tt_varlen_prepare: null pointer");
+  if (B <= 0 || S <= 0) return TT_OK;
+  launch_k(varlen_prepare_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, ids, B, S, pad, inv_map,
+           cu_seqlens);
+  return check_launch("varlen_prepare_kernel");
+}
+
+extern "C" int tt_ln_fwd16_varlen(const float* x, int x_packed, const float* gamma, const float* beta,
+                                  void* y_packed, void* y_padded, const int* inv_map,
+                                  const int* count_ptr, int R, int E, float eps, void* stream) {
+  TT_REQUIRE(x && gamma && beta && (y_packed || y_padded), "tt_ln_fwd16_varlen: null pointer");
+  TT_REQUIRE(E % 4 == 0 && E <= 1024, "tt_ln_fwd16_varlen: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  if (R <= 0) return TT_OK;
+  const int cap = num_sms() * 8;
+  const int want = ceil_div(R, 8);
+  const dim3 grid(want < cap ? want : cap);
+  if (E <= 256)
+    launch_k(ln_fwd16_varlen_kernel<2>, grid, dim3(256), 0, (cudaStream_t)stream, x, x_packed, gamma, beta,
+             reinterpret_cast<__nv_bfloat16*>(y_packed), reinterpret_cast<__nv_bfloat16*>(y_padded),
+             inv_map, count_ptr, R, E, eps);
+  else
+    launch_k(ln_fwd16_varlen_kernel<8>, grid, dim3(256), 0, (cudaStream_t)stream, x, x_packed, gamma, beta,
+             reinterpret_cast<__nv_bfloat16*>(y_packed), reinterpret_cast<__nv_bfloat16*>(y_padded),
+             inv_map, count_ptr, R, E, eps);
+  return check_launch("ln_fwd16_varlen_kernel");
 }

@@ -296,6 +296,12 @@ int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream) {
   if (p->N >= 256 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 256) >= pairs_max) bn = 256;
   else if (p->N >= 128 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 128) >= pairs_max) bn = 128;
   if (bn == 0) return 0;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TT_GEMM2_BN");     // experiments: force the pair kernel's tile width
+    forced = e ? atoi(e) : 0;
+  }
+  if ((forced == 128 || forced == 256) && p->N >= forced) bn = forced;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
   if (rc != TT_OK) return rc;

@@ -152,24 +152,28 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy,
       }
     }
   }
-  // CTA-level reduction in shared memory, then ONE global atomic per column per CTA
-  extern __shared__ float ln_red[];   // [2][E]
-  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) ln_red[i] = 0.f;
-  __syncthreads();
+  // CTA-level reduction: every warp parks its register accumulators in shared memory (plain
+  // float4 stores, one quantity at a time), the CTA adds the 8 copies and issues ONE global atomic
+  // per column.
+  extern __shared__ float ln_red[];   // [ROW_WARPS][E]
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = lane + 32 * i;
-    if (c < E4) {
-      atomicAdd(&ln_red[4 * c], acc_g[i].x); atomicAdd(&ln_red[4 * c + 1], acc_g[i].y);
-      atomicAdd(&ln_red[4 * c + 2], acc_g[i].z); atomicAdd(&ln_red[4 * c + 3], acc_g[i].w);
-      atomicAdd(&ln_red[E + 4 * c], acc_b[i].x); atomicAdd(&ln_red[E + 4 * c + 1], acc_b[i].y);
-      atomicAdd(&ln_red[E + 4 * c + 2], acc_b[i].z); atomicAdd(&ln_red[E + 4 * c + 3], acc_b[i].w);
+  for (int q = 0; q < 2; ++q) {
+    float* dst = q == 0 ? dgamma : dbeta;
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < E4) reinterpret_cast<float4*>(ln_red + warp * E)[c] = q == 0 ? acc_g[i] : acc_b[i];
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, ln_red[i]);
-    if (dbeta) atomicAdd(dbeta + i, ln_red[E + i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) t += ln_red[w * E + i];
+      atomicAdd(dst + i, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -361,61 +365,6 @@ __global__ void __launch_bounds__(256) ln_fwd_row_kernel(
   }
 }
 
-// Backward, wide rows: each thread owns 4 fixed columns, so dgamma/dbeta accumulate in registers
-// over the CTA's rows and leave with ONE global atomic per column per CTA.
-__global__ void __launch_bounds__(256) ln_bwd_row_kernel(
-    const float* __restrict__ dy, long long lddy, const float* __restrict__ x,
-    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-    float* __restrict__ dx, float* __restrict__ dh, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, int N, float p, unsigned long long seed,
-    const unsigned long long* step_ptr) {
-  pdl_prologue();
-  __shared__ float2 red[8];
-  constexpr int E = 1024;
-  seed = mix_seed(seed, step_ptr);
-  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  const int c = threadIdx.x;
-  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
-  for (int r = blockIdx.x; r < N; r += gridDim.x) {
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + static_cast<long long>(r) * lddy) + c);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E) + c);
-    const float mu = mean[r], rs = rstd[r];
-    float4 xh, g;
-    xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs; xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
-    g.x = d.x * gm.x; g.y = d.y * gm.y; g.z = d.z * gm.z; g.w = d.w * gm.w;
-    ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
-    ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
-    const float2 s = block_sum2_256((g.x + g.y) + (g.z + g.w),
-                                    (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w), red);
-    const float s1 = s.x * (1.f / E), s2 = s.y * (1.f / E);
-    float4 o;
-    o.x = rs * (g.x - s1 - xh.x * s2);
-    o.y = rs * (g.y - s1 - xh.y * s2);
-    o.z = rs * (g.z - s1 - xh.z * s2);
-    o.w = rs * (g.w - s1 - xh.w * s2);
-    if (dx) reinterpret_cast<float4*>(dx + static_cast<long long>(r) * E)[c] = o;
-    if (dh) {
-      if (p > 0.f) {
-        const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
-        o.x *= dropout_scale(seed, base, p, inv_keep);
-        o.y *= dropout_scale(seed, base + 1, p, inv_keep);
-        o.z *= dropout_scale(seed, base + 2, p, inv_keep);
-        o.w *= dropout_scale(seed, base + 3, p, inv_keep);
-      }
-      reinterpret_cast<float4*>(dh + static_cast<long long>(r) * E)[c] = o;
-    }
-  }
-  if (dgamma) {
-    atomicAdd(dgamma + 4 * c, ag.x); atomicAdd(dgamma + 4 * c + 1, ag.y);
-    atomicAdd(dgamma + 4 * c + 2, ag.z); atomicAdd(dgamma + 4 * c + 3, ag.w);
-  }
-  if (dbeta) {
-    atomicAdd(dbeta + 4 * c, ab.x); atomicAdd(dbeta + 4 * c + 1, ab.y);
-    atomicAdd(dbeta + 4 * c + 2, ab.z); atomicAdd(dbeta + 4 * c + 3, ab.w);
-  }
-}
-
 static inline int flat_grid(long long n) {
   long long g = ceil_div_ll(n, 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -452,16 +401,10 @@ extern "C" int tt_ln_bwd(const float* dy, long long lddy, const float* x, const 
   TT_REQUIRE(E > 0 && E % 4 == 0 && E <= 1024 && lddy % 4 == 0,
              "tt_ln_bwd: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (N <= 0) return TT_OK;
-  if (E == 1024) {      // production width: one CTA per row, <= 2 CTAs per SM share the atomics
-    const int cap = num_sms() * 2;
-    launch_k(ln_bwd_row_kernel, dim3(N < cap ? N : cap), dim3(256), 0, (cudaStream_t)stream,
-        dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, p_drop, seed, rng_step_ptr());
-    return check_launch("ln_bwd_row_kernel");
-  }
   // fewer, fatter warps so the dgamma/dbeta atomics stay cheap
   int grid = row_grid(N);
   if (grid > num_sms()) grid = num_sms();
-  const size_t smem = 2 * static_cast<size_t>(E) * sizeof(float);
+  const size_t smem = ROW_WARPS * static_cast<size_t>(E) * sizeof(float);
   if (E <= 256)
     launch_k(ln_bwd_kernel<2>, dim3(grid), dim3(ROW_WARPS * 32), smem, (cudaStream_t)stream, 
         dy, lddy, x, mean, rstd, gamma, dx, dh, dgamma, dbeta, N, E, p_drop, seed, rng_step_ptr());

@@ -67,6 +67,9 @@ class RobertaEncoder(nn.Module):
         self.n_layers, self.embed_dim, self.heads = n_layers, embed_dim, heads
         self.padding_idx = padding_idx
         self._prep = None
+        # Skip the padding: pack the real tokens of the batch and run every GEMM / attention /
+        # LayerNorm of the encoder on the packed rows only (all consumers mask the padding).
+        self.varlen = True
 
     def _apply(self, fn, *a, **k):
         self._prep = None
@@ -93,9 +96,12 @@ class RobertaEncoder(nn.Module):
 
     @torch.no_grad()
     def all_hiddens(self, ids):
-        """ids [B,S] int64 -> (bf16 [L+1, B*S, E], key padding mask uint8 [B*S])."""
+        """ids [B,S] int64 -> (bf16 [L+1, B*S, E], key padding mask uint8 [B*S]).
+        With `varlen` the rows of padding tokens are zero instead of the encoder's values there."""
         if self._prep is None:
             self.prepare()
+        if self.varlen:
+            return self._all_hiddens_packed(ids)
         se = self.decoder.sentence_encoder
         B, S = ids.shape
         E, H = self.embed_dim, self.heads
@@ -115,6 +121,43 @@ class RobertaEncoder(nn.Module):
             f = ops.gemm_tn(x16, p['w1'], bias=p['b1'], act=ops.ACT_GELU, want32=False, want16=True)
             ops.gemm_tn(f, p['w2'], out=tmp, bias=p['b2'], residual16=x16)
             ops.ln_fwd16(tmp, l.final_layer_norm.weight, l.final_layer_norm.bias, hid[i + 1])
+        return hid, is_pad
+
+    def _all_hiddens_packed(self, ids):
+        """Variable-length forward: row counts are device values (cu_seqlens[B] is the m_limit of
+        every GEMM), so there is no host sync and the whole thing captures into a CUDA graph; the
+        buffers are sized for the padded batch."""
+        se = self.decoder.sentence_encoder
+        B, S = ids.shape
+        E, H = self.embed_dim, self.heads
+        L = self.n_layers
+        dev = ids.device
+        R = B * S
+        ids = ids.contiguous()
+        hid = torch.empty((L + 1, R, E), dtype=torch.bfloat16, device=dev)
+        inv_map, cu = ops.varlen_prepare(ids, self.padding_idx)
+        ntok = cu[B:B + 1]
+        x, is_pad = ops.roberta_embed(ids, se.embed_tokens.weight, se.embed_positions.weight,
+                                      self.padding_idx)
+        h = [torch.empty((R, E), dtype=torch.bfloat16, device=dev) for _ in range(2)]   # packed
+        ops.ln_fwd16_varlen(x, se.emb_layer_norm.weight, se.emb_layer_norm.bias, y_packed=h[0],
+                            y_padded=hid[0], inv_map=inv_map, x_packed=False)
+        tmp = torch.zeros((R, E), dtype=torch.float32, device=dev)
+        x16 = torch.empty((R, E), dtype=torch.bfloat16, device=dev)
+        qkv = torch.empty((R, 3 * E), dtype=torch.bfloat16, device=dev)
+        f = torch.empty((R, se.layers[0].fc1.weight.shape[0]), dtype=torch.bfloat16, device=dev)
+        for i, (l, p) in enumerate(zip(se.layers, self._prep)):
+            h_in, h_out = h[i & 1], h[(i + 1) & 1]
+            ops.gemm_tn(h_in, p['wqkv'], out16=qkv, bias=p['bqkv'], want32=False, m_limit=ntok)
+            a = ops.flash_self_attn_varlen(qkv, cu, B, S, H, E // H)
+            ops.gemm_tn(a, p['wo'], out=tmp, bias=p['bo'], residual16=h_in, m_limit=ntok)
+            ops.ln_fwd16_varlen(tmp, l.self_attn_layer_norm.weight, l.self_attn_layer_norm.bias,
+                                y_packed=x16, count=ntok)
+            ops.gemm_tn(x16, p['w1'], out16=f, bias=p['b1'], act=ops.ACT_GELU, want32=False,
+                        m_limit=ntok)
+            ops.gemm_tn(f, p['w2'], out=tmp, bias=p['b2'], residual16=x16, m_limit=ntok)
+            ops.ln_fwd16_varlen(tmp, l.final_layer_norm.weight, l.final_layer_norm.bias,
+                                y_packed=h_out, y_padded=hid[i + 1], inv_map=inv_map)
         return hid, is_pad
 
     @torch.no_grad()

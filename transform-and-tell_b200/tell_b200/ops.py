@@ -486,3 +486,31 @@ def flash_self_attn(qkv, mask, B, S, H, D):
     _lib.call('tt_flash_self_attn', _ptr(qkv), _ptr(mask), _ptr(out), c_int(B), c_int(S), c_int(H),
               c_int(D), _stream())
     return out
+
+
+def varlen_prepare(ids, pad=1):
+    """ids [B,S] -> (inv_map int32 [B*S]: padded row -> packed row or -1, cu_seqlens int32 [B+1])."""
+    B, S = ids.shape
+    inv_map = torch.empty(B * S, dtype=torch.int32, device=ids.device)
+    cu = torch.empty(B + 1, dtype=torch.int32, device=ids.device)
+    _lib.call('tt_varlen_prepare', _ptr(ids), c_int(B), c_int(S), c_int(pad), _ptr(inv_map), _ptr(cu),
+              _stream())
+    return inv_map, cu
+
+
+def flash_self_attn_varlen(qkv, cu, B, S_max, H, D):
+    out = torch.empty((qkv.shape[0], H * D), dtype=torch.bfloat16, device=qkv.device)
+    _lib.call('tt_flash_self_attn_varlen', _ptr(qkv), _ptr(cu), _ptr(out), c_int(B), c_int(S_max),
+              c_int(H), c_int(D), _stream())
+    return out
+
+
+def ln_fwd16_varlen(x, gamma, beta, y_packed=None, y_padded=None, inv_map=None, count=None,
+                    x_packed=True, eps=1e-5):
+    """LayerNorm fp32 -> bf16 between the packed and padded layouts (tt_ln_fwd16_varlen)."""
+    E = x.shape[1]
+    R = inv_map.numel() if inv_map is not None else x.shape[0]
+    _lib.call('tt_ln_fwd16_varlen', _ptr(x), c_int(1 if x_packed else 0), _ptr(gamma), _ptr(beta),
+              _ptr(y_packed), _ptr(y_padded), _ptr(inv_map), _ptr(count), c_int(R), c_int(E),
+              c_float(eps), _stream())
+
