@@ -358,6 +358,34 @@ int tt_bertadam_step(const TtAdamSeg* segs_dev, int nsegs, int total_chunks,
                      const TtAdamHyper* hyper, long long* step_dev, const float* loss_dev,
                      float* partial, float* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Face encoders: InceptionResnetV1 "FaceNet"
+ * (tell/facenet/inception_resnet_v1.py:184-299) and the MTCNN P/R/O networks
+ * (tell/facenet/mtcnn.py:11-159).  Inference only, NHWC bf16 activations; convolutions are
+ * tt_im2col_nhwc_hw + tt_gemm_bf16_tn (folded BatchNorm / bias / residual scale / ReLU in the GEMM
+ * epilogue, branch outputs written straight into channel slices of the concatenation buffer).
+ * "pitch" = elements between consecutive pixels of an NHWC view (>= C, multiple of 8).
+ */
+/* nn.Conv2d / nn.MaxPool2d output extent (ceil_mode as in torch: the last window starts inside). */
+int tt_conv_out_size(int in, int k, int stride, int pad, int ceil_mode);
+/* im2col with rectangular kernels and per-axis padding (1x7 / 7x1 / 1x3 / 3x1 of Block17 / Block8,
+ * inception_resnet_v1.py:75-78,103-106). */
+int tt_im2col_nhwc_hw(const void* in, long long in_pitch, void* out, int B, int H, int W, int C,
+                      int KH, int KW, int stride, int pad_h, int pad_w, int Kp, void* stream);
+/* nn.MaxPool2d(k, stride, padding, ceil_mode) on NHWC bf16 (inception_resnet_v1.py:121,147,212;
+ * mtcnn.py:23,66,69,116,119,122). */
+int tt_maxpool_nhwc(const void* in, long long in_pitch, void* out, long long out_pitch, int B, int H,
+                    int W, int C, int k, int stride, int pad, int ceil_mode, void* stream);
+/* nn.AdaptiveAvgPool2d(1) (inception_resnet_v1.py:249): [B, HW, C] bf16 -> [B, C] fp32. */
+int tt_avgpool_nhwc(const void* in, float* out, int B, int HW, int C, void* stream);
+/* nn.PReLU(C) in place on bf16 rows (mtcnn.py:22-27 ...). */
+int tt_prelu_bf16(void* x, long long pitch, const float* slope, long long rows, int C, void* stream);
+/* F.normalize(x, p=2, dim=1) (inception_resnet_v1.py:296). */
+int tt_l2norm_rows(const float* x, float* y, int N, int D, float eps, void* stream);
+/* nn.Softmax(dim=1) over the two face / non-face logits stored in columns [c0, c0+2) of fp32 rows
+ * (mtcnn.py:29,75,126). */
+int tt_softmax2(float* x, long long ld, long long rows, int c0, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

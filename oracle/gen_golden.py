@@ -193,10 +193,58 @@ def op_goldens():
     print('ops ok')
 
 
+def facenet_goldens():
+    """tell/facenet: the reference's own InceptionResnetV1 (seeded synthetic weights -- the VGGFace2
+    checkpoint is a network download) and P/R/O-Net with BOTH seeded synthetic weights and the real
+    vendored checkpoints tell/facenet/data/{pnet,rnet,onet}.pt (copied into the fixture as data so
+    the GPU box, which has no /root/reference, can load them)."""
+    from tell.facenet.inception_resnet_v1 import InceptionResnetV1
+    from tell.facenet.mtcnn import ONet, PNet, RNet
+    g = {}
+    rs = np.random.RandomState(7)
+    net = InceptionResnetV1(num_classes=10).eval()
+    sd = synth.shaped_state_dict({k: v.shape for k, v in net.state_dict().items()}, seed=3)
+    net.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(rs.standard_normal((3, 3, 160, 160)).astype(np.float32))
+    x = x * torch.tensor([0.6, 1.0, 1.6]).view(3, 1, 1, 1) + torch.tensor([-0.5, 0.0, 0.7]).view(3, 1, 1, 1)
+    with torch.no_grad():
+        emb, logits = net(x)
+        o_emb, o_logits = restate.inception_resnet_v1_forward(x, sd)
+    assert (emb - o_emb).abs().max() < 1e-5 and (logits - o_logits).abs().max() < 1e-4
+    g.update(irv1_x=x.numpy(), irv1_emb=emb.numpy(), irv1_logits=logits.numpy())
+    sizes = {'pnet': (2, 3, 37, 53), 'rnet': (5, 3, 24, 24), 'onet': (4, 3, 48, 48)}
+    fwd = {'pnet': restate.pnet_forward, 'rnet': restate.rnet_forward, 'onet': restate.onet_forward}
+    for name, cls in (('pnet', PNet), ('rnet', RNet), ('onet', ONet)):
+        x = torch.from_numpy(rs.standard_normal(sizes[name]).astype(np.float32))
+        g[name + '_x'] = x.numpy()
+        for kind in ('synth', 'real'):
+            net = cls(pretrained=(kind == 'real')).eval()
+            if kind == 'synth':
+                sd = synth.shaped_state_dict({k: v.shape for k, v in net.state_dict().items()}, seed=5)
+                net.load_state_dict(sd, strict=True)
+            else:
+                sd = {k: v.clone() for k, v in net.state_dict().items()}
+                for k, v in sd.items():
+                    g['%s_real_w.%s' % (name, k)] = v.numpy()
+            with torch.no_grad():
+                outs = net(x)
+                o_outs = fwd[name](x, sd)
+            for i, (a, b) in enumerate(zip(outs, o_outs)):
+                assert (a - b).abs().max() < 1e-5, (name, kind, i)
+                g['%s_%s_out%d' % (name, kind, i)] = a.numpy()
+    np.savez_compressed(os.path.join(OUT, 'facenet.npz'), **g)
+    print('facenet goldens:', len(g), 'arrays')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if '--facenet-only' in sys.argv:
+        ref_loader.load()
+        facenet_goldens()
+        sys.exit(0)
     op_goldens()
     forward_glue_goldens()
     decoder_goldens(synth.CFG_TINY, 'faces_objects', 'tiny_faces_objects', gain=4.0)
     decoder_goldens(synth.CFG_TINY_NO_IMAGE, 'no_image', 'tiny_no_image', gain=4.0)
+    facenet_goldens()

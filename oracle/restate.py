@@ -414,3 +414,94 @@ def bert_adam_step(params, grads, state, lr, warmup=-1, t_total=-1, schedule='wa
         lr_scheduled = lr * bert_adam_schedule(st['step'], t_total, warmup, schedule)
         p.add_(-(lr_scheduled * update))
         st['step'] += 1
+
+
+# ------------------------------------------------------------------------------------- face encoders
+def _basic_conv(x, sd, p, stride=1, padding=0):
+    """BasicConv2d (tell/facenet/inception_resnet_v1.py:10-34): conv (no bias), BatchNorm eps 1e-3
+    in eval mode, ReLU."""
+    x = F.conv2d(x, sd[p + 'conv.weight'], None, stride, padding)
+    x = F.batch_norm(x, sd[p + 'bn.running_mean'], sd[p + 'bn.running_var'], sd[p + 'bn.weight'],
+                     sd[p + 'bn.bias'], False, 0.0, 1e-3)
+    return F.relu(x)
+
+
+def _res_block(x, sd, p, tails, scale, relu=True):
+    """Block35 / Block17 / Block8 (:37-119): branches -> cat -> 1x1 conv (bias) * scale + x -> ReLU."""
+    outs = [_basic_conv(x, sd, p + 'branch0.')]
+    for i, tail in enumerate(tails, start=1):
+        h = _basic_conv(x, sd, p + 'branch%d.0.' % i)
+        for j, pad in enumerate(tail, start=1):
+            h = _basic_conv(h, sd, p + 'branch%d.%d.' % (i, j), 1, pad)
+        outs.append(h)
+    out = F.conv2d(torch.cat(outs, 1), sd[p + 'conv2d.weight'], sd[p + 'conv2d.bias'])
+    out = out * scale + x
+    return F.relu(out) if relu else out
+
+
+def inception_resnet_v1_forward(x, sd):
+    """InceptionResnetV1.forward in eval mode (tell/facenet/inception_resnet_v1.py:264-299):
+    x [B,3,H,W] -> (l2-normalised embedding [B,512], logits)."""
+    x = _basic_conv(x, sd, 'conv2d_1a.', 2)
+    x = _basic_conv(x, sd, 'conv2d_2a.')
+    x = _basic_conv(x, sd, 'conv2d_2b.', 1, 1)
+    x = F.max_pool2d(x, 3, 2)
+    x = _basic_conv(x, sd, 'conv2d_3b.')
+    x = _basic_conv(x, sd, 'conv2d_4a.')
+    x = _basic_conv(x, sd, 'conv2d_4b.', 2)
+    for i in range(5):
+        x = _res_block(x, sd, 'repeat_1.%d.' % i, [[1], [1, 1]], 0.17)
+    x = torch.cat([_basic_conv(x, sd, 'mixed_6a.branch0.', 2),                     # Mixed_6a :122-144
+                   _basic_conv(_basic_conv(_basic_conv(x, sd, 'mixed_6a.branch1.0.'), sd,
+                                           'mixed_6a.branch1.1.', 1, 1), sd, 'mixed_6a.branch1.2.', 2),
+                   F.max_pool2d(x, 3, 2)], 1)
+    for i in range(10):
+        x = _res_block(x, sd, 'repeat_2.%d.' % i, [[(0, 3), (3, 0)]], 0.10)
+    b0 = _basic_conv(_basic_conv(x, sd, 'mixed_7a.branch0.0.'), sd, 'mixed_7a.branch0.1.', 2)   # :147-181
+    b1 = _basic_conv(_basic_conv(x, sd, 'mixed_7a.branch1.0.'), sd, 'mixed_7a.branch1.1.', 2)
+    b2 = _basic_conv(_basic_conv(_basic_conv(x, sd, 'mixed_7a.branch2.0.'), sd, 'mixed_7a.branch2.1.', 1, 1),
+                     sd, 'mixed_7a.branch2.2.', 2)
+    x = torch.cat([b0, b1, b2, F.max_pool2d(x, 3, 2)], 1)
+    for i in range(5):
+        x = _res_block(x, sd, 'repeat_3.%d.' % i, [[(0, 1), (1, 0)]], 0.20)
+    x = _res_block(x, sd, 'block8.', [[(0, 1), (1, 0)]], 1.0, relu=False)
+    x = x.mean(dim=(2, 3))
+    x = F.linear(x, sd['last_linear.weight'])
+    x = F.batch_norm(x, sd['last_bn.running_mean'], sd['last_bn.running_var'], sd['last_bn.weight'],
+                     sd['last_bn.bias'], False, 0.0, 1e-3)
+    x = F.normalize(x, p=2, dim=1)
+    return x, F.linear(x, sd['logits.weight'], sd['logits.bias'])
+
+
+def _conv_prelu(x, sd, i):
+    return F.prelu(F.conv2d(x, sd['conv%d.weight' % i], sd['conv%d.bias' % i]), sd['prelu%d.weight' % i])
+
+
+def pnet_forward(x, sd):
+    """PNet.forward (tell/facenet/mtcnn.py:40-51) -> (box regression, face probability)."""
+    x = F.max_pool2d(_conv_prelu(x, sd, 1), 2, 2, ceil_mode=True)
+    x = _conv_prelu(_conv_prelu(x, sd, 2), sd, 3)
+    a = F.softmax(F.conv2d(x, sd['conv4_1.weight'], sd['conv4_1.bias']), dim=1)
+    return F.conv2d(x, sd['conv4_2.weight'], sd['conv4_2.bias']), a
+
+
+def rnet_forward(x, sd):
+    """RNet.forward (mtcnn.py:86-101); note the (w, h, c) flatten before dense4."""
+    x = F.max_pool2d(_conv_prelu(x, sd, 1), 3, 2, ceil_mode=True)
+    x = F.max_pool2d(_conv_prelu(x, sd, 2), 3, 2, ceil_mode=True)
+    x = _conv_prelu(x, sd, 3).permute(0, 3, 2, 1).contiguous()
+    x = F.prelu(F.linear(x.view(x.shape[0], -1), sd['dense4.weight'], sd['dense4.bias']), sd['prelu4.weight'])
+    a = F.softmax(F.linear(x, sd['dense5_1.weight'], sd['dense5_1.bias']), dim=1)
+    return F.linear(x, sd['dense5_2.weight'], sd['dense5_2.bias']), a
+
+
+def onet_forward(x, sd):
+    """ONet.forward (mtcnn.py:136-159) -> (box, landmarks, probability)."""
+    x = F.max_pool2d(_conv_prelu(x, sd, 1), 3, 2, ceil_mode=True)
+    x = F.max_pool2d(_conv_prelu(x, sd, 2), 3, 2, ceil_mode=True)
+    x = F.max_pool2d(_conv_prelu(x, sd, 3), 2, 2, ceil_mode=True)
+    x = _conv_prelu(x, sd, 4).permute(0, 3, 2, 1).contiguous()
+    x = F.prelu(F.linear(x.view(x.shape[0], -1), sd['dense5.weight'], sd['dense5.bias']), sd['prelu5.weight'])
+    a = F.softmax(F.linear(x, sd['dense6_1.weight'], sd['dense6_1.bias']), dim=1)
+    return (F.linear(x, sd['dense6_2.weight'], sd['dense6_2.bias']),
+            F.linear(x, sd['dense6_3.weight'], sd['dense6_3.bias']), a)

@@ -158,3 +158,28 @@ def test_bert_adam_restatement_known_answers():
                            max_grad_norm=0.1)
     want = 2.0 - (1e-4 / ((0.02 * 1e-6) ** 0.5 + 1e-6))
     assert abs(p[0].item() - want) < 1e-5
+
+
+def test_face_encoder_restatements_match_reference_goldens():
+    """oracle/restate.py face encoders vs tests/golden/facenet.npz (outputs of the reference's own
+    InceptionResnetV1 / PNet / RNet / ONet modules, the latter also with the vendored checkpoints)."""
+    import restate
+    from tell_b200 import synth
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'facenet.npz'))
+    fwd = {'pnet': restate.pnet_forward, 'rnet': restate.rnet_forward, 'onet': restate.onet_forward}
+    with torch.no_grad():
+        for name in ('pnet', 'rnet', 'onet'):
+            keys = [k[len(name) + 8:] for k in g.files if k.startswith(name + '_real_w.')]
+            sd_real = {k: torch.from_numpy(g['%s_real_w.%s' % (name, k)]) for k in keys}
+            sd_synth = synth.shaped_state_dict({k: v.shape for k, v in sd_real.items()}, seed=5)
+            x = torch.from_numpy(g[name + '_x'])
+            for kind, sd in (('synth', sd_synth), ('real', sd_real)):
+                for i, o in enumerate(fwd[name](x, sd)):
+                    want = torch.from_numpy(g['%s_%s_out%d' % (name, kind, i)])
+                    assert (o - want).abs().max().item() < 1e-5, (name, kind, i)
+        from tell_b200.facenet import InceptionResnetV1
+        shapes = {k: v.shape for k, v in InceptionResnetV1(num_classes=10).state_dict().items()}
+        sd = synth.shaped_state_dict(shapes, seed=3)
+        emb, logits = restate.inception_resnet_v1_forward(torch.from_numpy(g['irv1_x']), sd)
+        assert (emb - torch.from_numpy(g['irv1_emb'])).abs().max().item() < 1e-5
+        assert (logits - torch.from_numpy(g['irv1_logits'])).abs().max().item() < 1e-4

@@ -514,3 +514,82 @@ def ln_fwd16_varlen(x, gamma, beta, y_packed=None, y_padded=None, inv_map=None, 
               _ptr(y_packed), _ptr(y_padded), _ptr(inv_map), _ptr(count), c_int(R), c_int(E),
               c_float(eps), _stream())
 
+
+
+# --------------------------------------------------------------------------- face encoders (convnets.cu)
+def conv_out_size(n, k, stride, pad, ceil_mode=False):
+    return int(_lib.lib().tt_conv_out_size(c_int(n), c_int(k), c_int(stride), c_int(pad),
+                                           c_int(1 if ceil_mode else 0)))
+
+
+def _nhwc_view(x):
+    """x: [B,H,W,C] bf16 view whose last dim is contiguous and whose pixels are evenly pitched
+    (a channel slice of a contiguous [B,H,W,Ctot] buffer).  Returns the pixel pitch."""
+    B, H, W, C = x.shape
+    pitch = x.stride(2)
+    assert x.dtype == torch.bfloat16 and x.stride(3) == 1
+    assert x.stride(1) == W * pitch and (B == 1 or x.stride(0) == H * W * pitch), x.stride()
+    return pitch
+
+
+def im2col_nhwc_hw(x, KH, KW, stride, pad_h, pad_w):
+    """x [B,H,W,C] bf16 (channel-slice views allowed) -> ([B*Ho*Wo, Kp] bf16, Ho, Wo)."""
+    _check_cuda(x)
+    B, H, W, C = x.shape
+    pitch = _nhwc_view(x)
+    Ho, Wo = (H + 2 * pad_h - KH) // stride + 1, (W + 2 * pad_w - KW) // stride + 1
+    Kp = (KH * KW * C + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_im2col_nhwc_hw', _ptr(x), c_ll(pitch), _ptr(out), c_int(B), c_int(H), c_int(W),
+              c_int(C), c_int(KH), c_int(KW), c_int(stride), c_int(pad_h), c_int(pad_w), c_int(Kp),
+              _stream())
+    return out, Ho, Wo
+
+
+def maxpool_nhwc(x, k, stride, pad=0, ceil_mode=False, out=None):
+    """nn.MaxPool2d on NHWC bf16; `out` may be a channel slice of a concatenation buffer."""
+    _check_cuda(x, out)
+    B, H, W, C = x.shape
+    Ho, Wo = conv_out_size(H, k, stride, pad, ceil_mode), conv_out_size(W, k, stride, pad, ceil_mode)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    assert out.shape == (B, Ho, Wo, C)
+    _lib.call('tt_maxpool_nhwc', _ptr(x), c_ll(_nhwc_view(x)), _ptr(out), c_ll(_nhwc_view(out)),
+              c_int(B), c_int(H), c_int(W), c_int(C), c_int(k), c_int(stride), c_int(pad),
+              c_int(1 if ceil_mode else 0), _stream())
+    return out
+
+
+def avgpool_nhwc(x):
+    """[B,H,W,C] bf16 contiguous -> [B,C] fp32."""
+    _check_cuda(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    _lib.call('tt_avgpool_nhwc', _ptr(x), _ptr(out), c_int(B), c_int(H * W), c_int(C), _stream())
+    return out
+
+
+def prelu_bf16_(x2d, slope):
+    """In-place PReLU on bf16 rows [R, C] (row pitch = x2d.stride(0))."""
+    _check_cuda(x2d, slope)
+    assert x2d.dtype == torch.bfloat16 and x2d.dim() == 2 and x2d.stride(1) == 1
+    _lib.call('tt_prelu_bf16', _ptr(x2d), c_ll(x2d.stride(0)), _ptr(slope), c_ll(x2d.shape[0]),
+              c_int(x2d.shape[1]), _stream())
+    return x2d
+
+
+def l2norm_rows(x, eps=1e-12):
+    _check_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.call('tt_l2norm_rows', _ptr(x), _ptr(y), c_int(x.shape[0]), c_int(x.shape[1]), c_float(eps),
+              _stream())
+    return y
+
+
+def softmax2_(x, c0=0):
+    _check_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    _lib.call('tt_softmax2', _ptr(x), c_ll(x.stride(0)), c_ll(x.shape[0]), c_int(c0), _stream())
+    return x

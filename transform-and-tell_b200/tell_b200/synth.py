@@ -245,3 +245,38 @@ def roberta_state_dict(n_layers, embed_dim, ffn, vocab, max_pos, seed=0):
         sd[lp + 'final_layer_norm.weight'] = 1 + 0.1 * n(E)
         sd[lp + 'final_layer_norm.bias'] = 0.05 * n(E)
     return sd
+
+
+def shaped_state_dict(shapes, seed=0):
+    """Seeded synthetic weights for a convnet given {key: shape} (the keys of the reference module's
+    state_dict): He-scaled conv / linear weights, near-identity BatchNorm with non-trivial running
+    statistics, PReLU slopes around 0.25.  Every tensor is drawn from its own RandomState seeded by
+    (seed, crc32(key)), so the result does not depend on iteration order or on which side (the
+    reference module or the B200 module) supplied the shapes."""
+    import zlib
+    sd = {}
+    for key in sorted(shapes):
+        shape = tuple(shapes[key])
+        rs = np.random.RandomState((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        leaf = key.rsplit('.', 1)[-1]
+        owner = key.rsplit('.', 2)[-2] if key.count('.') >= 1 else ''
+
+        def n(std=1.0):
+            return torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+        if leaf == 'num_batches_tracked':
+            t = torch.tensor(0, dtype=torch.long)
+        elif leaf == 'running_var':
+            t = torch.from_numpy((0.5 + rs.random_sample(shape)).astype(np.float32))
+        elif leaf == 'running_mean':
+            t = 0.1 * n()
+        elif owner.startswith('prelu'):
+            t = torch.from_numpy((0.1 + 0.3 * rs.random_sample(shape)).astype(np.float32))
+        elif owner.startswith('bn') or owner == 'last_bn':
+            t = 1 + 0.1 * n() if leaf == 'weight' else 0.05 * n()
+        elif leaf == 'weight':
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+            t = n(math.sqrt(2.0 / fan_in))
+        else:   # conv / linear bias
+            t = 0.05 * n()
+        sd[key] = t
+    return sd
