@@ -178,6 +178,12 @@ int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_stride, float*
 int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float* dx, float* dz,
                    int T, int B, int C, int H, int K, int softmax, float p_drop,
                    unsigned long long seed, void* stream);
+/* One incremental decoding step of DynamicConv1dTBC / LightweightConv1dTBC (dynamic.py:95-116,
+ * lightweight.py incremental branch) for T = 1: window [K-1,B,C] is the time-ordered input buffer
+ * (updated in place: shifted by one step, x_new appended), z [B, H*K] the new row's tap logits
+ * (z_b_stride = H*K, or 0 for taps shared by the batch), out [B,C]. */
+int tt_dynconv_step(float* window, const float* x_new, const float* z, long long z_b_stride,
+                    float* out, int B, int C, int H, int K, int softmax, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cross-attention core, tell/modules/attention/multi_head.py:355-466 (static_kv=True path).
@@ -263,6 +269,10 @@ int tt_embed_scatter_grad(const long long* ids, int B, int T, int tbc, const int
 /* make_positions (positional.py:231-268) + incremental start_pos (:196-198). */
 int tt_make_positions(const long long* ids, int B, int T, int pad, int left_pad, int start_pos,
                       int tbc, int* pos, void* stream);
+/* Same with a device-resident running position added to start_pos (incremental decoding inside a
+ * captured CUDA graph: positional.py:170-176 keeps the position in the incremental state). */
+int tt_make_positions_at(const long long* ids, int B, int T, int pad, int left_pad, int start_pos,
+                         const int* start_dev, int tbc, int* pos, void* stream);
 /* [A,B,C] -> [B,A,C] */
 int tt_transpose01(const float* in, float* out, int A, int B, int C, void* stream);
 

@@ -193,3 +193,49 @@ def test_greedy_decode_early_exit_and_padding():
     assert torch.equal(ids.cpu(), rids)
     assert (lp.cpu() - rlp).abs().max() < 1e-3
     assert ids.shape[1] < 101
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+def test_graphed_decode_equals_eager_decode(precision):
+    """The captured decode step (fixed-size DynamicConv buffers, device-side position / column
+    counters) emits exactly the tokens and log-probs of the eager loop, with and without early
+    exit."""
+    from tell_b200 import synth
+    cfg, sd, model = _tiny_model(precision, _StubResNet(None), _StubRoberta(None, 24))
+    cap, ctx = synth.decoder_inputs(cfg, 4, 9, 11, 3, 4, 5, seed=7)
+    cctx = {k: v.cuda() for k, v in ctx.items()}
+    model.eval()
+    for early in (True, False):
+        model.gen_len = 100 if early else 23
+        model.decode_graph = False
+        lp0, ids0, _ = model._generate(cap[:, 0:1].cuda(), cctx, early_exit=early)
+        model.decode_graph = True
+        lp1, ids1, _ = model._generate(cap[:, 0:1].cuda(), cctx, early_exit=early)
+        assert ids0.shape == ids1.shape and torch.equal(ids0, ids1)
+        assert (lp0 - lp1).abs().max().item() < 1e-5
+        if not early:
+            assert ids1.shape == (4, 24)
+
+
+def test_dynconv_decode_step_matches_full_convolution():
+    """tt_dynconv_step over T single steps == the full causal convolution (DynamicConv and
+    Lightweight), including the in-place shift of the [K-1,B,C] buffer."""
+    from tell_b200.modules import DynamicConv1dTBC, LightweightConv1dTBC
+    from tell_b200 import config
+    config.set_precision('bf16x3')
+    torch.manual_seed(3)
+    T, B, C, H = 12, 3, 64, 4
+    for K in (1, 3, 7):
+        for cls in (DynamicConv1dTBC, LightweightConv1dTBC):
+            m = cls(C, kernel_size=K, padding_l=K - 1, num_heads=H, weight_softmax=True).cuda().eval()
+            x = torch.randn(T, B, C, device='cuda')
+            with torch.no_grad():
+                full = m(x)
+                state = {}
+                steps = [m(x[t:t + 1], incremental_state=state) for t in range(T)]
+            got = torch.cat(steps, 0)
+            assert (got - full).abs().max().item() < 2e-5, (cls.__name__, K)
+            buf = [v for k, v in state.items() if k.endswith('.input_buffer')]
+            if K > 1:
+                assert buf[0].shape == (K - 1, B, C)
+                assert torch.equal(buf[0], x[T - K + 1:])

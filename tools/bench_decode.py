@@ -22,12 +22,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--steps', type=int, default=50)
 ap.add_argument('--reps', type=int, default=3)
+ap.add_argument('--eager', action='store_true', help='disable the captured decode step')
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
 config.set_precision('bf16')
 config.manual_seed(1234)
 model = bench.build_model(dev).eval()
 model.gen_len = args.steps
+model.decode_graph = not args.eager
 B = args.batch
 host = bench.make_batch(B)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -54,5 +56,6 @@ print(json.dumps({'metric': 'greedy decode latency', 'batch': B, 'steps': args.s
                   'ms_per_step': round(dec_ms / args.steps, 3),
                   'captions_per_s_decode_only': round(B / (dec_ms * 1e-3), 1),
                   'captions_per_s_incl_encoders': round(B / ((dec_ms + ctx_ms) * 1e-3), 1),
-                  'note': 'eager launches (no CUDA graph); first decoder step includes the one-off '
-                          'K|V projections of the four contexts'}))
+                  'decode_graph': bool(model.decode_graph),
+                  'note': 'steps 0-1 eager (one-off K|V projections of the four contexts, graph capture), '
+                          'steps 2.. replay one captured decode step'}))

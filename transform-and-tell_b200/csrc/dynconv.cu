@@ -83,6 +83,61 @@ dynconv_fwd_kernel(DynConvArgs a) {
   }
 }
 
+// One incremental decoding step (dynamic.py:95-116 with T = 1): the reference concatenates the
+// <= K-1 buffered inputs with the new one, recomputes the convolution over the whole window and keeps
+// the last row.  Here `window` is a fixed [K-1, B, C] time-ordered buffer (zero rows = the causal zero
+// padding of the first steps): one thread per (b, channel) column computes the single output that is
+// needed, then shifts its column by one step and appends the new input -- the state update and the
+// convolution are one pass over the window (HBM-bound: (K-1)*B*C*8 bytes per step).
+__global__ void __launch_bounds__(256)
+dynconv_step_kernel(float* __restrict__ window, const float* __restrict__ x_new,
+                    const float* __restrict__ z, long long z_b_stride, float* __restrict__ out, int B,
+                    int C, int H, int K, int softmax) {
+  pdl_prologue();
+  const long long BC = static_cast<long long>(B) * C;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= BC) return;
+  const int b = static_cast<int>(idx / C), c = static_cast<int>(idx - static_cast<long long>(b) * C);
+  const int h = c / (C / H);
+  const float* zr = z + b * z_b_stride + h * K;
+  float w[DC_MAXK];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < DC_MAXK; ++k) {
+    w[k] = k < K ? __ldg(zr + k) : -INFINITY;
+    m = fmaxf(m, w[k]);
+  }
+  if (softmax) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < DC_MAXK; ++k) {
+      w[k] = k < K ? expf(w[k] - m) : 0.f;
+      sum += w[k];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int k = 0; k < DC_MAXK; ++k) w[k] *= inv;
+  } else {
+#pragma unroll
+    for (int k = 0; k < DC_MAXK; ++k) w[k] = k < K ? w[k] : 0.f;
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < DC_MAXK - 1; ++k) {
+    if (k < K - 1) {
+      const float v = window[k * BC + idx];
+      acc += w[k] * v;
+      if (k > 0) window[(k - 1) * BC + idx] = v;      // shift: row k becomes row k-1
+    }
+  }
+  const float xn = __ldg(x_new + idx);
+#pragma unroll
+  for (int k = 0; k < DC_MAXK; ++k)
+    if (k == K - 1) acc += w[k] * xn;
+  if (K > 1) window[(K - 2) * BC + idx] = xn;
+  out[idx] = acc;
+}
+
 struct DynConvBwdArgs {
   const float* dout;  // [T,B,C]
   const float* x;     // [T,B,C]
@@ -205,4 +260,16 @@ extern "C" int tt_dynconv_bwd(const float* dout, const float* x, const float* pr
   dim3 grid(B * H, ceil_div(T, DC_TT));
   launch_k(dynconv_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("dynconv_bwd_kernel");
+}
+
+extern "C" int tt_dynconv_step(float* window, const float* x_new, const float* z, long long z_b_stride,
+                               float* out, int B, int C, int H, int K, int softmax, void* stream) {
+  TT_REQUIRE(x_new && z && out && (window || K == 1), "tt_dynconv_step: null pointer");
+  int rc = dynconv_check(1, B, C, H, K);
+  if (rc != TT_OK) return rc;
+  const long long BC = static_cast<long long>(B) * C;
+  if (BC == 0) return TT_OK;
+  launch_k(dynconv_step_kernel, dim3(static_cast<unsigned>(ceil_div_ll(BC, 256))), dim3(256), 0,
+           (cudaStream_t)stream, window, x_new, z, z_b_stride, out, B, C, H, K, softmax);
+  return check_launch("dynconv_step_kernel");
 }

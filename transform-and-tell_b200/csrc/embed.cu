@@ -62,9 +62,10 @@ __global__ void embed_scatter_kernel(const long long* __restrict__ ids, int B, i
 // positional.py:231-268: non-pad symbols -> pad+1+index (+start_pos), pads stay pad.
 // left_pad shifts positions so the last real token sits at the right edge.
 __global__ void make_positions_kernel(const long long* __restrict__ ids, int B, int T, int pad,
-                                      int left_pad, int start_pos, int tbc,
-                                      int* __restrict__ pos) {
+                                      int left_pad, int start_pos, const int* __restrict__ start_dev,
+                                      int tbc, int* __restrict__ pos) {
   pdl_prologue();
+  if (start_dev != nullptr) start_pos += *start_dev;   // running position kept on the device
   const int b = blockIdx.x;
   __shared__ int nonpad;
   if (threadIdx.x == 0) nonpad = 0;
@@ -144,7 +145,17 @@ extern "C" int tt_make_positions(const long long* ids, int B, int T, int pad, in
   TT_REQUIRE(ids && pos, "tt_make_positions: null pointer");
   if (B * T <= 0) return TT_OK;
   launch_k(make_positions_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, ids, B, T, pad, left_pad, start_pos,
-                                                            tbc, pos);
+           (const int*)nullptr, tbc, pos);
+  return check_launch("make_positions_kernel");
+}
+
+extern "C" int tt_make_positions_at(const long long* ids, int B, int T, int pad, int left_pad,
+                                    int start_pos, const int* start_dev, int tbc, int* pos,
+                                    void* stream) {
+  TT_REQUIRE(ids && pos, "tt_make_positions_at: null pointer");
+  if (B * T <= 0) return TT_OK;
+  launch_k(make_positions_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, ids, B, T, pad, left_pad, start_pos,
+           start_dev, tbc, pos);
   return check_launch("make_positions_kernel");
 }
 

@@ -142,6 +142,7 @@ class _CaptionModelBase(Model):
 
     # ------------------------------------------------------------------ _generate (:399-494)
     @torch.no_grad()
+    @torch.no_grad()
     def _generate(self, caption_ids, contexts, attn_idx=None, early_exit=True, sync_every=8):
         """Greedy decode (sampling_topk=1: multinomial over one candidate == argmax).  Device
         resident: all rows stay in the batch, finished rows are masked (emit pad / log-prob 0),
@@ -158,6 +159,15 @@ class _CaptionModelBase(Model):
         eos, pad = 2, self.padding_idx
         B = caption_ids.shape[0]
         dev = caption_ids.device
+        if self.decode_graph and dev.type == 'cuda' and self.gen_len > 2 \
+                and not torch.cuda.is_current_stream_capturing():
+            with torch.no_grad():
+                log_probs, token_ids = self._generate_graphed(caption_ids, contexts, early_exit,
+                                                              sync_every)
+            for l, n in zip(self.decoder.layers, need_attn):
+                l.need_attn = n
+            self.decoder.train(was_training)
+            return log_probs, token_ids, []
         state = {}
         prev = caption_ids[:, 0:1].contiguous()
         active = prev[:, 0] != eos
@@ -191,6 +201,80 @@ class _CaptionModelBase(Model):
             l.need_attn = n
         self.decoder.train(was_training)
         return log_probs, token_ids, []
+
+    decode_graph = True
+
+    def _generate_graphed(self, caption_ids, contexts, early_exit, sync_every):
+        """The greedy loop with ONE captured decode step replayed gen_len-1 times.
+
+        Step 0 runs eagerly (it projects the four contexts, allocates the fixed-size DynamicConv
+        input buffers and prepares the weight operands); every later step has identical shapes, so
+        a single CUDA graph holds it: previous token, finished-row mask, running position and the
+        output matrices are static device buffers the graph updates in place (the column written
+        is indexed by a device step counter).  The host only replays, and looks at the all-done
+        flag every `sync_every` steps."""
+        from ..modules.token_embedders import POSITION_DEV_KEY
+        eos, pad = 2, self.padding_idx
+        B = caption_ids.shape[0]
+        dev = caption_ids.device
+        n_max = self.gen_len
+        dec = self.decoder
+        ids_buf = torch.full((B, 1 + n_max), pad, dtype=torch.long, device=dev)
+        lp_buf = torch.zeros((B, n_max), dtype=torch.float32, device=dev)
+        flags = torch.zeros(n_max, dtype=torch.bool, device=dev)
+        prev = caption_ids[:, 0:1].contiguous().clone()
+        ids_buf[:, 0:1] = prev
+        active = prev[:, 0] != eos
+        pos = torch.zeros(1, dtype=torch.int32, device=dev)          # tokens fed so far
+        col = torch.zeros(1, dtype=torch.long, device=dev)           # output column of this step
+        state = {POSITION_DEV_KEY: pos}
+        for m in dec.modules():                                      # positional table for all steps
+            if hasattr(m, 'ensure_size') and hasattr(m, 'padding_idx'):
+                m.ensure_size(n_max + 2 + m.padding_idx)
+
+        def one_step():
+            X, _ = dec.forward_tbc({self.index: prev}, contexts, incremental_state=state)
+            tok, lp = dec.adaptive_softmax.greedy(X.view(B, -1))
+            lp = lp / self.sampling_temp
+            tok = torch.where(active, tok, torch.full_like(tok, pad))
+            lp = torch.where(active, lp, torch.zeros_like(lp))
+            ids_buf.index_copy_(1, col + 1, tok.view(B, 1))
+            lp_buf.index_copy_(1, col, lp.view(B, 1))
+            active.logical_and_(tok != eos)
+            flags.index_copy_(0, col, active.any().view(1))
+            prev.copy_(tok.view(B, 1))
+            pos.add_(1)
+            col.add_(1)
+
+        with dec.weight_scope(refresh=True):
+            one_step()                                               # step 0, eager
+        # Step 1 runs eagerly on the capture stream (warms every lazy path), then the same stream
+        # records the step.  capture_begin/capture_end directly: torch.cuda.graph() would also
+        # synchronise the device, run the Python GC and empty the allocator cache on every call.
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side), dec.weight_scope(refresh=False):
+            one_step()
+            graph.capture_begin()
+            try:
+                one_step()                       # recorded, not executed: steps 2.. are replays
+            finally:
+                graph.capture_end()
+        cur.wait_stream(side)
+        n_steps = n_max
+        for i in range(2, n_max):
+            graph.replay()
+            if early_exit and (i + 1) % sync_every == 0 and not bool(flags[i]):
+                n_steps = i + 1
+                break
+        if early_exit:
+            f = flags[:n_steps].cpu()
+            dead = (~f).nonzero()
+            if dead.numel() > 0:
+                n_steps = int(dead[0]) + 1       # the reference stops after the first all-done step
+        return lp_buf[:, :n_steps].clone(), ids_buf[:, :1 + n_steps].clone()
 
     # ------------------------------------------------------------------ generate (:142-309)
     @torch.no_grad()

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .. import config
+from .. import config, ops
 from .. import functional as Fn
 from ..utils import get_incremental_state, set_incremental_state
 from .linear import linear
@@ -15,6 +15,39 @@ class _WeightLinear(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_features, in_features))
         nn.init.xavier_uniform_(self.weight)
         self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+
+
+_OWNED = '__tt_owned_windows__'
+
+
+def _step_window(module, incremental_state, X):
+    """Fixed [K-1,B,C] time-ordered input buffer of an incremental decode (T = 1, no autograd).
+    The reference's buffer grows from 0 to K-1 rows (dynamic.py:95-99); zero rows are exactly the
+    causal zero padding it would apply, so a zero-initialised full-size buffer gives the same
+    numbers with step-independent shapes (which is what lets a decode step be captured in a CUDA
+    graph).  The buffer is owned by the state and updated in place by tt_dynconv_step."""
+    K = module.kernel_size
+    _, B, C = X.shape
+    buf = get_incremental_state(module, incremental_state, 'input_buffer')
+    owned_set = incremental_state.setdefault(_OWNED, set())   # buffers this module may overwrite
+    owned = buf is not None and buf.data_ptr() in owned_set
+    if K == 1:
+        return None
+    if buf is None:
+        buf = torch.zeros((K - 1, B, C), dtype=X.dtype, device=X.device)
+    elif buf.shape[0] < K - 1:
+        pad = torch.zeros((K - 1 - buf.shape[0], B, C), dtype=X.dtype, device=X.device)
+        buf = torch.cat([pad, buf], dim=0)
+    elif not owned or not buf.is_contiguous():
+        buf = buf.clone()            # may alias a caller's tensor (prefix fed with T > 1)
+    set_incremental_state(module, incremental_state, 'input_buffer', buf)
+    owned_set.add(buf.data_ptr())
+    return buf
+
+
+def _is_decode_step(X, incremental_state, query=None):
+    return (incremental_state is not None and X.shape[0] == 1 and query is None
+            and not torch.is_grad_enabled())
 
 
 class DynamicConv1dTBC(nn.Module):
@@ -44,6 +77,15 @@ class DynamicConv1dTBC(nn.Module):
         """X [T,B,C] -> [T,B,C]; with incremental_state the last K-1 inputs are buffered
         (dynamic.py:95-99) and only the new rows are returned (:115-116)."""
         assert X.dim() == 3 and X.shape[2] == self.input_size
+        if _is_decode_step(X, incremental_state, query) and not self.training:
+            # one new time step: only its own tap logits and its own output row are computed
+            _, B, C = X.shape
+            x_new = X[0].contiguous()
+            window = _step_window(self, incremental_state, X)
+            z = linear(x_new, self.weight_linear.weight, self.weight_linear.bias)
+            out = ops.dynconv_step(window, x_new, z.contiguous(), self.num_heads, self.kernel_size,
+                                   self.weight_softmax)
+            return out.view(1, B, C)
         prev = None
         if incremental_state is not None:
             prev = get_incremental_state(self, incremental_state, 'input_buffer')
@@ -90,6 +132,14 @@ class LightweightConv1dTBC(nn.Module):
         self.bias = nn.Parameter(torch.zeros(input_size)) if bias else None
 
     def forward(self, X, incremental_state=None, unfold=False):
+        if _is_decode_step(X, incremental_state) and not self.training:
+            _, B, C = X.shape
+            x_new = X[0].contiguous()
+            window = _step_window(self, incremental_state, X)
+            out = ops.dynconv_step(window, x_new, self.weight.view(self.num_heads, -1).contiguous(),
+                                   self.num_heads, self.kernel_size, self.weight_softmax,
+                                   broadcast=True)
+            return out.view(1, B, C)
         prev = None
         if incremental_state is not None:
             prev = get_incremental_state(self, incremental_state, 'input_buffer')

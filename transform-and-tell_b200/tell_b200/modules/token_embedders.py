@@ -69,6 +69,10 @@ class AdaptiveEmbedding(TokenEmbedder):
         return self.embed_size
 
 
+# incremental_state key holding the running position as a device tensor (see start_position)
+POSITION_DEV_KEY = '__tt_position_dev__'
+
+
 @TokenEmbedder.register('sinusoidal_positional')
 class SinusoidalPositionalEmbedding(TokenEmbedder):
     """positional.py:85-229; buffer `weights` [init_size+1, E], row padding_idx zero."""
@@ -98,6 +102,9 @@ class SinusoidalPositionalEmbedding(TokenEmbedder):
         """positional.py:170-176: running position kept in the incremental state."""
         if incremental_state is None:
             return 0
+        dev = incremental_state.get(POSITION_DEV_KEY)
+        if dev is not None:          # captured decode step: int32 [1] device tensor, advanced by the caller
+            return dev
         start = get_incremental_state(self, incremental_state, 'position') or 0
         set_incremental_state(self, incremental_state, 'position', start + seq_len)
         return start
@@ -110,7 +117,8 @@ class SinusoidalPositionalEmbedding(TokenEmbedder):
     def forward(self, X, incremental_state=None, timestep=None):
         B, T = X.shape
         start = self.start_position(incremental_state, T)
-        self.ensure_size(start + T + 1 + self.padding_idx)
+        if not torch.is_tensor(start):
+            self.ensure_size(start + T + 1 + self.padding_idx)
         pos = ops.make_positions(X, self.padding_idx, self.left_pad, start, tbc=False)
         return ops.gather_rows(self.weights, pos.view(-1)).view(B, T, -1)
 
@@ -183,7 +191,8 @@ class SumTextFieldEmbedder(TextFieldEmbedder):
         if pe.left_pad:
             raise NotImplementedError('left-padded targets are not used by the shipped configs')
         start = pe.start_position(incremental_state, ids.shape[1])
-        pe.ensure_size(start + ids.shape[1] + 1 + pe.padding_idx)
+        if not torch.is_tensor(start):
+            pe.ensure_size(start + ids.shape[1] + 1 + pe.padding_idx)
         return embed_tokens(ids, ad, pe, start), ids
 
     def forward(self, text_field_input, num_wrapping_dims=0, incremental_state=None):

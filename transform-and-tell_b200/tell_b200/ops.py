@@ -262,6 +262,20 @@ def dynconv_fwd(x, z, H, K, softmax=True, p=0.0, seed=0, broadcast=False):
     return out, probs
 
 
+def dynconv_step(window, x_new, z, H, K, softmax=True, broadcast=False):
+    """One incremental step: window [K-1,B,C] (updated in place), x_new [B,C], z [B,H*K] (or [H,K]
+    with broadcast) -> out [B,C]."""
+    _check_cuda(window, x_new, z)
+    B, C = x_new.shape
+    assert x_new.is_contiguous() and z.is_contiguous()
+    assert K == 1 or (window.is_contiguous() and window.shape == (K - 1, B, C))
+    out = torch.empty_like(x_new)
+    _lib.call('tt_dynconv_step', _ptr(window if K > 1 else None), _ptr(x_new), _ptr(z),
+              c_ll(0 if broadcast else H * K), _ptr(out), c_int(B), c_int(C), c_int(H), c_int(K),
+              c_int(1 if softmax else 0), _stream())
+    return out
+
+
 def dynconv_bwd(dout, x, probs, H, K, softmax=True, p=0.0, seed=0):
     T, B, C = x.shape
     dx = torch.empty_like(x)
@@ -412,8 +426,16 @@ def embed_scatter_grad(ids, cutoffs, grads, E, dA, padding_idx=0, tbc=True):
 
 
 def make_positions(ids, pad=1, left_pad=False, start_pos=0, tbc=False):
+    """start_pos: host int, or an int32 device tensor [1] (running position of a captured decode
+    step)."""
     B, T = ids.shape
     pos = torch.empty((T, B) if tbc else (B, T), dtype=torch.int32, device=ids.device)
+    if torch.is_tensor(start_pos):
+        assert start_pos.dtype == torch.int32 and start_pos.is_cuda
+        _lib.call('tt_make_positions_at', _ptr(ids), c_int(B), c_int(T), c_int(pad),
+                  c_int(1 if left_pad else 0), c_int(0), _ptr(start_pos), c_int(1 if tbc else 0),
+                  _ptr(pos), _stream())
+        return pos
     _lib.call('tt_make_positions', _ptr(ids), c_int(B), c_int(T), c_int(pad),
               c_int(1 if left_pad else 0), c_int(start_pos), c_int(1 if tbc else 0), _ptr(pos),
               _stream())
