@@ -221,6 +221,21 @@ int tt_attn_bwd_tc(const float* dout, const float* q, const float* k, const floa
                    float* dbias_k, float* dbias_v, int T, int B, int S, int H, int D, long long ldq,
                    long long ldkv, long long ldo, int zero_row, float p_drop,
                    unsigned long long seed, void* stream);
+/* Variants whose projected keys|values are bf16 in HBM (the K|V projection GEMM writes bf16
+ * directly: half the bytes of these HBM-bound kernels) and whose dL/dk, dL/dv are written as bf16
+ * -- exactly the operand the projection's weight-gradient GEMM consumes.  ldkv in bf16 elements,
+ * multiple of 8; k16/v16 16-byte aligned. */
+int tt_attn_fwd_tc_kv16(const float* q, const void* k16, const void* v16, const float* bias_k,
+                        const float* bias_v, const uint8_t* key_padding_mask, float* out,
+                        float* lse, int T, int B, int S, int H, int D, long long ldq,
+                        long long ldkv, long long ldo, int zero_row, float p_drop,
+                        unsigned long long seed, void* stream);
+int tt_attn_bwd_tc_kv16(const float* dout, const float* q, const void* k16, const void* v16,
+                        const float* bias_k, const float* bias_v,
+                        const uint8_t* key_padding_mask, const float* out, const float* lse,
+                        float* dq, void* dk16, void* dv16, float* dbias_k, float* dbias_v, int T,
+                        int B, int S, int H, int D, long long ldq, long long ldkv, long long ldo,
+                        int zero_row, float p_drop, unsigned long long seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Adaptive softmax / loss, tell/modules/softmax.py:144-222, criteria/adaptive_loss.py:27-73.
@@ -279,6 +294,9 @@ int tt_transpose01(const float* in, float* out, int A, int B, int C, void* strea
 /* out[c] = scale * sum_r x[r,c] (+ out[c] when accumulate): bias gradients. */
 int tt_colsum(const float* x, long long ld, int M, int N, float* out, float scale, int accumulate,
               void* stream);
+/* Same for a bf16 matrix (fp32 accumulation); N, ld multiples of 4. */
+int tt_colsum_bf16(const void* x, long long ld, int M, int N, float* out, float scale,
+                   int accumulate, void* stream);
 /* dx = dy * (y > 0): backward of the ReLU fused into fc1's GEMM epilogue. */
 int tt_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
 /* RoBERTa layer mix, transformer_faces_objects.py:355-364: out = sum_l softmax(w)[l] * h_l.

@@ -280,6 +280,45 @@ def test_attention_tensor_core_path(T, B, S):
             assert close(x, y, 3e-2)
 
 
+@pytest.mark.parametrize('T,B,S', [(50, 2, 130), (50, 3, 512), (1, 4, 70), (9, 2, 5)])
+def test_attention_bf16_keys_values(T, B, S):
+    """kv16 kernels: keys|values stored as bf16 in a strided [S*B, 2E] buffer, dL/dk|dL/dv written as
+    bf16.  On bf16-representable k/v the forward and dQ are bit-identical to the fp32-storage
+    kernels (same staged bf16 tile); dK/dV equal the fp32 kernels' output rounded to bf16.  Dropout
+    on, so the regenerated masks are covered too."""
+    from tell_b200 import ops
+    torch.manual_seed(100 + S)
+    H, D = 4, 64
+    E = H * D
+    q = torch.randn(T * B, E, device='cuda') * D ** -0.5
+    kv16 = torch.randn(S * B, 2 * E, device='cuda').to(torch.bfloat16)
+    kv32 = kv16.float()
+    bk, bv = torch.randn(E, device='cuda') * 0.5, torch.randn(E, device='cuda') * 0.5
+    mask = torch.zeros(B, S, dtype=torch.uint8, device='cuda')
+    mask[0, S // 2:] = 1
+    do = torch.randn(T * B, E, device='cuda')
+    for p_drop in (0.0, 0.2):
+        kw = dict(p=p_drop, seed=11, tc=True)
+        o32, l32 = ops.attn_fwd(q, kv32[:, :E], kv32[:, E:], bk, bv, mask, T, B, S, H, D, **kw)
+        o16, l16 = ops.attn_fwd(q, kv16[:, :E], kv16[:, E:], bk, bv, mask, T, B, S, H, D, **kw)
+        assert torch.equal(o32, o16) and torch.equal(l32, l16)
+        g32 = [torch.empty_like(q), torch.empty_like(kv32), torch.zeros(E, device='cuda'),
+               torch.zeros(E, device='cuda')]
+        g16 = [torch.empty_like(q), torch.empty_like(kv16), torch.zeros(E, device='cuda'),
+               torch.zeros(E, device='cuda')]
+        ops.attn_bwd(do, q, kv32[:, :E], kv32[:, E:], bk, bv, mask, o32, l32, g32[0], g32[1][:, :E],
+                     g32[1][:, E:], g32[2], g32[3], T, B, S, H, D, **kw)
+        ops.attn_bwd(do, q, kv16[:, :E], kv16[:, E:], bk, bv, mask, o16, l16, g16[0], g16[1][:, :E],
+                     g16[1][:, E:], g16[2], g16[3], T, B, S, H, D, **kw)
+        assert torch.equal(g32[0], g16[0])
+        assert torch.equal(g32[1].to(torch.bfloat16), g16[1])
+        assert (g32[2] - g16[2]).abs().max().item() < 1e-3 and (g32[3] - g16[3]).abs().max().item() < 1e-3
+    x = torch.randn(300, 512, device='cuda').to(torch.bfloat16)
+    got = ops.colsum(x[:, 128:384], scale=2.0)
+    want = x[:, 128:384].double().sum(0).float() * 2.0
+    assert (got - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
+
+
 def test_attention_strided_and_dropout():
     from tell_b200 import ops
     torch.manual_seed(5)

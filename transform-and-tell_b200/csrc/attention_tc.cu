@@ -56,11 +56,28 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ base, long 
 // Key/value tile j0..j0+63 of the extended key set [ctx rows ; bias row ; zero row] + additive mask,
 // split into a load phase (global -> registers; lets the caller prefetch the next tile while the
 // tensor cores work on the current one) and a store phase (registers -> bf16 smem).
-struct KvRegs {
+// KV16: the projected keys|values live in HBM as bf16 (the K|V projection GEMM writes bf16
+// directly): half the bytes of this HBM-bound kernel, no conversion on the way to shared memory.
+template <bool KV16> struct KvRegs {
   float4 k[TC_ST], v[TC_ST];
   float mask;     // threads 0..63: additive mask of key j0 + threadIdx.x
 };
-__device__ __forceinline__ void load_kv(const AttnArgs& a, int b, int h, int j0, int L, KvRegs& R) {
+template <> struct KvRegs<true> {
+  uint4 k[TC_ST / 2], v[TC_ST / 2];    // 8 bf16 per 16-byte chunk
+  float mask;
+};
+__device__ __forceinline__ float kv_mask(const AttnArgs& a, int b, int j0, int L) {
+  float m = 0.f;
+  if (threadIdx.x < 64) {
+    const int j = j0 + threadIdx.x;
+    bool ok;
+    if (j < a.S) ok = !(a.mask && a.mask[static_cast<long long>(b) * a.S + j]);
+    else ok = j < L;
+    m = ok ? 0.f : -INFINITY;
+  }
+  return m;
+}
+__device__ __forceinline__ void load_kv(const AttnArgs& a, int b, int h, int j0, int L, KvRegs<false>& R) {
   const bool has_bias = a.bias_k != nullptr;
 #pragma unroll
   for (int it = 0; it < TC_ST; ++it) {
@@ -78,27 +95,54 @@ __device__ __forceinline__ void load_kv(const AttnArgs& a, int b, int h, int j0,
       R.v[it] = __ldg(reinterpret_cast<const float4*>(a.bias_v + h * TC_D) + c4);
     }
   }
-  R.mask = 0.f;
-  if (threadIdx.x < 64) {
-    const int j = j0 + threadIdx.x;
-    bool ok;
-    if (j < a.S) ok = !(a.mask && a.mask[static_cast<long long>(b) * a.S + j]);
-    else ok = j < L;
-    R.mask = ok ? 0.f : -INFINITY;
-  }
+  R.mask = kv_mask(a, b, j0, L);
 }
-__device__ __forceinline__ void store_kv(const KvRegs& R, __nv_bfloat16 (*sK)[TC_LD],
+__device__ __forceinline__ uint4 pack8_bf16(const float* p) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  uint4 u;
+  u.x = pack_bf16(x.x, x.y); u.y = pack_bf16(x.z, x.w);
+  u.z = pack_bf16(y.x, y.y); u.w = pack_bf16(y.z, y.w);
+  return u;
+}
+__device__ __forceinline__ void load_kv(const AttnArgs& a, int b, int h, int j0, int L, KvRegs<true>& R) {
+  const bool has_bias = a.bias_k != nullptr;
+  const __nv_bfloat16* k16 = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* v16 = reinterpret_cast<const __nv_bfloat16*>(a.v);
+#pragma unroll
+  for (int it = 0; it < TC_ST / 2; ++it) {
+    const int i = threadIdx.x + it * TC_THREADS;
+    const int r = i >> 3, c8 = i & 7;
+    const int j = j0 + r;
+    R.k[it] = make_uint4(0u, 0u, 0u, 0u);
+    R.v[it] = R.k[it];
+    if (j < a.S) {
+      const long long off = (static_cast<long long>(j) * a.B + b) * a.ldkv + h * TC_D;
+      R.k[it] = __ldg(reinterpret_cast<const uint4*>(k16 + off) + c8);
+      R.v[it] = __ldg(reinterpret_cast<const uint4*>(v16 + off) + c8);
+    } else if (has_bias && j == a.S) {
+      R.k[it] = pack8_bf16(a.bias_k + h * TC_D + c8 * 8);
+      R.v[it] = pack8_bf16(a.bias_v + h * TC_D + c8 * 8);
+    }
+  }
+  R.mask = kv_mask(a, b, j0, L);
+}
+__device__ __forceinline__ void store_kv(const KvRegs<false>& R, __nv_bfloat16 (*sK)[TC_LD],
                                          __nv_bfloat16 (*sV)[TC_LD], float* sMask) {
   store_tile(R.k, sK);
   store_tile(R.v, sV);
   if (threadIdx.x < 64) sMask[threadIdx.x] = R.mask;
 }
-__device__ __forceinline__ void stage_kv(const AttnArgs& a, int b, int h, int j0, int L,
-                                         __nv_bfloat16 (*sK)[TC_LD], __nv_bfloat16 (*sV)[TC_LD],
-                                         float* sMask) {
-  KvRegs R;
-  load_kv(a, b, h, j0, L, R);
-  store_kv(R, sK, sV, sMask);
+__device__ __forceinline__ void store_kv(const KvRegs<true>& R, __nv_bfloat16 (*sK)[TC_LD],
+                                         __nv_bfloat16 (*sV)[TC_LD], float* sMask) {
+#pragma unroll
+  for (int it = 0; it < TC_ST / 2; ++it) {
+    const int i = threadIdx.x + it * TC_THREADS;
+    const int r = i >> 3, c8 = i & 7;
+    *reinterpret_cast<uint4*>(&sK[r][c8 * 8]) = R.k[it];
+    *reinterpret_cast<uint4*>(&sV[r][c8 * 8]) = R.v[it];
+  }
+  if (threadIdx.x < 64) sMask[threadIdx.x] = R.mask;
 }
 
 // A fragments (16 rows x 64 k) of the warp's row block from a [64][TC_LD] tile.
@@ -153,6 +197,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
+template <bool KV16>
 __global__ void __launch_bounds__(128)
 attn_fwd_tc_kernel(AttnArgs a) {
   pdl_prologue();
@@ -166,7 +211,7 @@ attn_fwd_tc_kernel(AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  KvRegs nxt;
+  KvRegs<KV16> nxt;
   {
     float4 qreg[TC_ST];
     load_tile(a.q, a.ldq, a.B, b, h, q0, a.T, qreg);
@@ -279,6 +324,7 @@ __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h,
 }
 
 // ------------------------------------------------------------------------------------------ dQ
+template <bool KV16>
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_tc_kernel(AttnArgs a) {
   pdl_prologue();
@@ -293,7 +339,7 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int L = a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  KvRegs nxt;
+  KvRegs<KV16> nxt;
   {
     float4 qreg[TC_ST], doreg[TC_ST];
     load_tile(a.q, a.ldq, a.B, b, h, q0, a.T, qreg);
@@ -359,6 +405,7 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ dK, dV
+template <bool KV16>
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_tc_kernel(AttnArgs a) {
   pdl_prologue();
@@ -375,7 +422,7 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   {
-    KvRegs kv;
+    KvRegs<KV16> kv;
     float4 qreg[TC_ST], doreg[TC_ST];
     load_kv(a, b, h, j0, L, kv);                      // all loads of the first round in flight
     load_tile(a.q, a.ldq, a.B, b, h, 0, a.T, qreg);
@@ -437,16 +484,26 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
     const int c = n * 8 + 2 * tg;
     if (ja < a.S) {
       const long long off = (static_cast<long long>(ja) * a.B + b) * a.ldkv + h * TC_D + c;
-      *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][0], dk[n][1]);
-      *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][0], dv[n][1]);
+      if (KV16) {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][0], dk[n][1]);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][0], dv[n][1]);
+      } else {
+        *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][0], dk[n][1]);
+        *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][0], dv[n][1]);
+      }
     } else if (has_bias && ja == a.S) {
       if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][0]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][1]); }
       if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][0]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][1]); }
     }
     if (jb < a.S) {
       const long long off = (static_cast<long long>(jb) * a.B + b) * a.ldkv + h * TC_D + c;
-      *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][2], dk[n][3]);
-      *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][2], dv[n][3]);
+      if (KV16) {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][2], dk[n][3]);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][2], dv[n][3]);
+      } else {
+        *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][2], dk[n][3]);
+        *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][2], dv[n][3]);
+      }
     } else if (has_bias && jb == a.S) {
       if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][2]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][3]); }
       if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][2]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][3]); }
@@ -454,11 +511,69 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   }
 }
 
-static int tc_check(const AttnArgs& a, int D) {
+static int tc_check(const AttnArgs& a, int D, bool kv16 = false) {
   TT_REQUIRE(D == TC_D, "attention (tensor-core path): head_dim must be %d (got %d)", TC_D, D);
-  TT_REQUIRE(a.ldq % 4 == 0 && a.ldkv % 4 == 0 && a.ldo % 4 == 0,
-             "attention (tensor-core path): row strides must be multiples of 4");
+  TT_REQUIRE(a.ldq % 4 == 0 && a.ldkv % (kv16 ? 8 : 4) == 0 && a.ldo % 4 == 0,
+             "attention (tensor-core path): row strides must be multiples of 4 (8 for bf16 k/v)");
+  TT_REQUIRE(!kv16 || ((reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0,
+             "attention (tensor-core path): bf16 k/v must be 16-byte aligned");
   return TT_OK;
+}
+
+static int attn_fwd_tc_impl(const float* q, const void* k, const void* v, const float* bias_k,
+                            const float* bias_v, const uint8_t* key_padding_mask, float* out,
+                            float* lse, int T, int B, int S, int H, int D, long long ldq,
+                            long long ldkv, long long ldo, int zero_row, float p_drop,
+                            unsigned long long seed, void* stream, bool kv16) {
+  TT_REQUIRE(q && out && lse, "tt_attn_fwd_tc: null pointer");
+  TT_REQUIRE(S == 0 || (k && v), "tt_attn_fwd_tc: null k/v with S > 0");
+  TT_REQUIRE((bias_k == nullptr) == (bias_v == nullptr), "tt_attn_fwd_tc: bias_k/bias_v mismatch");
+  TT_REQUIRE(S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0) > 0, "tt_attn_fwd_tc: empty key set");
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgs a{};
+  a.q = q; a.k = reinterpret_cast<const float*>(k); a.v = reinterpret_cast<const float*>(v);
+  a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
+  a.out = out; a.lse = lse; a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row;
+  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo;
+  a.p_drop = p_drop; a.seed = seed; a.step_ptr = rng_step_ptr();
+  int rc = tc_check(a, D, kv16 && S > 0);
+  if (rc != TT_OK) return rc;
+  dim3 grid(B * H, ceil_div(T, TC_BM));
+  if (kv16) launch_k(attn_fwd_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  else launch_k(attn_fwd_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+static int attn_bwd_tc_impl(const float* dout, const float* q, const void* k, const void* v,
+                            const float* bias_k, const float* bias_v,
+                            const uint8_t* key_padding_mask, const float* out, const float* lse,
+                            float* dq, void* dk, void* dv, float* dbias_k, float* dbias_v,
+                            int T, int B, int S, int H, int D, long long ldq, long long ldkv,
+                            long long ldo, int zero_row, float p_drop, unsigned long long seed,
+                            void* stream, bool kv16) {
+  TT_REQUIRE(dout && q && out && lse && dq, "tt_attn_bwd_tc: null pointer");
+  TT_REQUIRE(S == 0 || (k && v && dk && dv), "tt_attn_bwd_tc: null k/v/dk/dv with S > 0");
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgs a{};
+  a.q = q; a.k = reinterpret_cast<const float*>(k); a.v = reinterpret_cast<const float*>(v);
+  a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
+  a.out = const_cast<float*>(out); a.lse = const_cast<float*>(lse);
+  a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row; a.p_drop = p_drop; a.seed = seed;
+  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo; a.step_ptr = rng_step_ptr();
+  a.dout = dout; a.dq = dq; a.dk = reinterpret_cast<float*>(dk); a.dv = reinterpret_cast<float*>(dv);
+  a.dbias_k = dbias_k; a.dbias_v = dbias_v;
+  int rc = tc_check(a, D, kv16 && S > 0);
+  if (rc != TT_OK) return rc;
+  const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+  dim3 grid(B * H, ceil_div(T, TC_BM));
+  if (kv16) launch_k(attn_bwd_dq_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  else launch_k(attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  rc = check_launch("attn_bwd_dq_tc_kernel");
+  if (rc != TT_OK) return rc;
+  dim3 grid2(B * H, ceil_div(L, TC_BN));
+  if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
+  else launch_k(attn_bwd_dkv_tc_kernel<false>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
+  return check_launch("attn_bwd_dkv_tc_kernel");
 }
 
 }  // namespace tt
@@ -470,21 +585,17 @@ extern "C" int tt_attn_fwd_tc(const float* q, const float* k, const float* v, co
                               float* lse, int T, int B, int S, int H, int D, long long ldq,
                               long long ldkv, long long ldo, int zero_row, float p_drop,
                               unsigned long long seed, void* stream) {
-  TT_REQUIRE(q && out && lse, "tt_attn_fwd_tc: null pointer");
-  TT_REQUIRE(S == 0 || (k && v), "tt_attn_fwd_tc: null k/v with S > 0");
-  TT_REQUIRE((bias_k == nullptr) == (bias_v == nullptr), "tt_attn_fwd_tc: bias_k/bias_v mismatch");
-  TT_REQUIRE(S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0) > 0, "tt_attn_fwd_tc: empty key set");
-  if (T <= 0 || B <= 0) return TT_OK;
-  AttnArgs a{};
-  a.q = q; a.k = k; a.v = v; a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
-  a.out = out; a.lse = lse; a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row;
-  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo;
-  a.p_drop = p_drop; a.seed = seed; a.step_ptr = rng_step_ptr();
-  int rc = tc_check(a, D);
-  if (rc != TT_OK) return rc;
-  dim3 grid(B * H, ceil_div(T, TC_BM));
-  launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
-  return check_launch("attn_fwd_tc_kernel");
+  return attn_fwd_tc_impl(q, k, v, bias_k, bias_v, key_padding_mask, out, lse, T, B, S, H, D, ldq, ldkv,
+                          ldo, zero_row, p_drop, seed, stream, false);
+}
+
+extern "C" int tt_attn_fwd_tc_kv16(const float* q, const void* k16, const void* v16, const float* bias_k,
+                                   const float* bias_v, const uint8_t* key_padding_mask, float* out,
+                                   float* lse, int T, int B, int S, int H, int D, long long ldq,
+                                   long long ldkv, long long ldo, int zero_row, float p_drop,
+                                   unsigned long long seed, void* stream) {
+  return attn_fwd_tc_impl(q, k16, v16, bias_k, bias_v, key_padding_mask, out, lse, T, B, S, H, D, ldq,
+                          ldkv, ldo, zero_row, p_drop, seed, stream, true);
 }
 
 extern "C" int tt_attn_bwd_tc(const float* dout, const float* q, const float* k, const float* v,
@@ -494,23 +605,18 @@ extern "C" int tt_attn_bwd_tc(const float* dout, const float* q, const float* k,
                               int T, int B, int S, int H, int D, long long ldq, long long ldkv,
                               long long ldo, int zero_row, float p_drop, unsigned long long seed,
                               void* stream) {
-  TT_REQUIRE(dout && q && out && lse && dq, "tt_attn_bwd_tc: null pointer");
-  TT_REQUIRE(S == 0 || (k && v && dk && dv), "tt_attn_bwd_tc: null k/v/dk/dv with S > 0");
-  if (T <= 0 || B <= 0) return TT_OK;
-  AttnArgs a{};
-  a.q = q; a.k = k; a.v = v; a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
-  a.out = const_cast<float*>(out); a.lse = const_cast<float*>(lse);
-  a.T = T; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row; a.p_drop = p_drop; a.seed = seed;
-  a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo; a.step_ptr = rng_step_ptr();
-  a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv; a.dbias_k = dbias_k; a.dbias_v = dbias_v;
-  int rc = tc_check(a, D);
-  if (rc != TT_OK) return rc;
-  const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
-  dim3 grid(B * H, ceil_div(T, TC_BM));
-  launch_k(attn_bwd_dq_tc_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
-  rc = check_launch("attn_bwd_dq_tc_kernel");
-  if (rc != TT_OK) return rc;
-  dim3 grid2(B * H, ceil_div(L, TC_BN));
-  launch_k(attn_bwd_dkv_tc_kernel, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
-  return check_launch("attn_bwd_dkv_tc_kernel");
+  return attn_bwd_tc_impl(dout, q, k, v, bias_k, bias_v, key_padding_mask, out, lse, dq, dk, dv, dbias_k,
+                          dbias_v, T, B, S, H, D, ldq, ldkv, ldo, zero_row, p_drop, seed, stream, false);
+}
+
+extern "C" int tt_attn_bwd_tc_kv16(const float* dout, const float* q, const void* k16, const void* v16,
+                                   const float* bias_k, const float* bias_v,
+                                   const uint8_t* key_padding_mask, const float* out, const float* lse,
+                                   float* dq, void* dk16, void* dv16, float* dbias_k, float* dbias_v,
+                                   int T, int B, int S, int H, int D, long long ldq, long long ldkv,
+                                   long long ldo, int zero_row, float p_drop, unsigned long long seed,
+                                   void* stream) {
+  return attn_bwd_tc_impl(dout, q, k16, v16, bias_k, bias_v, key_padding_mask, out, lse, dq, dk16, dv16,
+                          dbias_k, dbias_v, T, B, S, H, D, ldq, ldkv, ldo, zero_row, p_drop, seed, stream,
+                          true);
 }

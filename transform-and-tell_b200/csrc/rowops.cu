@@ -543,6 +543,42 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict
     atomicAdd(out + c + threadIdx.y, t * scale);
   }
 }
+// Same tiling for a bf16 matrix (the bf16 dL/d(k|v) slab of the cross-attention backward): 4 bf16
+// (8 bytes) per thread per row, fp32 accumulation.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                          int M, int N, float* __restrict__ out,
+                                                          float scale, int rows_per_cta) {
+  pdl_prologue();
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  auto add = [](float4& a, uint2 u) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    a.x += __low2float(h[0]); a.y += __high2float(h[0]);
+    a.z += __low2float(h[1]); a.w += __high2float(h[1]);
+  };
+  if (c < N) {
+    const __nv_bfloat16* xc = x + c;
+    int r = r0 + threadIdx.y;
+    for (; r + 8 < r1; r += 16) {
+      const uint2 v0 = __ldg(reinterpret_cast<const uint2*>(xc + (long long)r * ld));
+      const uint2 v1 = __ldg(reinterpret_cast<const uint2*>(xc + (long long)(r + 8) * ld));
+      add(a0, v0);
+      add(a1, v1);
+    }
+    for (; r < r1; r += 8) add(a0, __ldg(reinterpret_cast<const uint2*>(xc + (long long)r * ld)));
+  }
+  red[threadIdx.y][threadIdx.x] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+  __syncthreads();
+  if (threadIdx.y < 4 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += reinterpret_cast<const float*>(&red[i][threadIdx.x])[threadIdx.y];
+    atomicAdd(out + c + threadIdx.y, t * scale);
+  }
+}
 // dx = dy * (y > 0)
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                 float* __restrict__ dx, long long n) {
@@ -661,6 +697,28 @@ extern "C" int tt_colsum(const float* x, long long ld, int M, int N, float* out,
   dim3 block(32, 8), grid(ceil_div(N, 32), ceil_div(M, COLSUM_ROWS));
   launch_k(colsum_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, x, ld, M, N, out, scale);
   return check_launch("colsum_kernel");
+}
+
+extern "C" int tt_colsum_bf16(const void* x, long long ld, int M, int N, float* out, float scale,
+                              int accumulate, void* stream) {
+  TT_REQUIRE(x && out, "tt_colsum_bf16: null pointer");
+  TT_REQUIRE(N % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+             "tt_colsum_bf16: N and ld must be multiples of 4, x 8-byte aligned");
+  if (N <= 0) return TT_OK;
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream);
+  if (M <= 0) return TT_OK;
+  const int strips = ceil_div(N, 128);
+  int slabs = ceil_div(4 * num_sms(), strips);
+  const int max_slabs = ceil_div(M, 32);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 65535) slabs = 65535;
+  int rows_per_cta = ceil_div(M, slabs);
+  rows_per_cta = ceil_div(rows_per_cta, 8) * 8;
+  slabs = ceil_div(M, rows_per_cta);
+  launch_k(colsum_bf16_kernel, dim3(strips, slabs), dim3(32, 8), 0, (cudaStream_t)stream,
+           reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out, scale, rows_per_cta);
+  return check_launch("colsum_bf16_kernel");
 }
 
 namespace tt {

@@ -97,6 +97,18 @@ def wgrad_join(local=False):
         st.keep = []
 
 
+def kv16_ok(head_dim, need_weights=False):
+    """Projected keys|values (and their gradients) as bf16 in HBM: throughput mode with the
+    tensor-core attention kernels (head_dim 64); the head-averaged attention weights of eval mode
+    are computed by an fp32 kernel, so that path keeps fp32 keys."""
+    return config.precision == 'bf16' and config.kv_bf16 and head_dim == 64 and not need_weights
+
+
+def _as_operand(d):
+    """A gradient that is already a bf16 GEMM operand (bf16 dL/dkv slab) is used as it is."""
+    return d if d.dtype == torch.bfloat16 else operand(d, 'a')
+
+
 def _fast():
     """bf16 throughput mode: backward GEMMs read the forward's bf16 operands in place through
     MN-major UMMA descriptors (trans_a / trans_b) -- no transposed copies, no weight re-casts.
@@ -163,10 +175,10 @@ class KVProjFn(Function):
     GEMM whose output the attention kernels read with stride 2E (multi_head.py:500-518)."""
 
     @staticmethod
-    def forward(ctx, x, wk, wv, bias_kv):
+    def forward(ctx, x, wk, wv, bias_kv, kv16=False):
         a16 = operand(x, 'a')
         w16 = concat_rows_operand([wk, wv], 'b', x.device)          # [2E, kdim]
-        kv = ops.gemm_tn(a16, w16, bias=bias_kv)
+        kv = ops.gemm_tn(a16, w16, bias=bias_kv, want32=not kv16, want16=kv16)
         ctx.has_bias, ctx.fast, ctx.E = bias_kv is not None, _fast(), wk.shape[0]
         if ctx.fast:
             ctx.save_for_backward(a16, w16)
@@ -182,7 +194,7 @@ class KVProjFn(Function):
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         if ctx.fast:
             x, w = ctx.saved_tensors
-            d16 = operand(dkv, 'a')
+            d16 = _as_operand(dkv)
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(d16, w, trans_b=True)
             if need_w:
@@ -195,7 +207,7 @@ class KVProjFn(Function):
                 dW = ops.gemm_tn(operand(dkv, 'a', transpose=True), operand(x, 'b', transpose=True))
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = ops.colsum(dkv)
-        return dx, (dW[:E] if dW is not None else None), (dW[E:] if dW is not None else None), db
+        return dx, (dW[:E] if dW is not None else None), (dW[E:] if dW is not None else None), db, None
 
 
 class GradSlab:
@@ -204,14 +216,14 @@ class GradSlab:
     backward is one operand cast + one dW GEMM (+ one dx GEMM) over all layers, with no
     gather copies.  Allocated lazily by the first attention backward that needs it."""
 
-    def __init__(self, rows, width, n, device):
-        self.rows, self.width, self.n, self.device = rows, width, n, device
+    def __init__(self, rows, width, n, device, dtype=torch.float32):
+        self.rows, self.width, self.n, self.device, self.dtype = rows, width, n, device, dtype
         self.buf = None
         self.written = set()
 
     def block(self, l):
         if self.buf is None:
-            self.buf = torch.empty((self.rows, self.n * self.width), dtype=torch.float32,
+            self.buf = torch.empty((self.rows, self.n * self.width), dtype=self.dtype,
                                    device=self.device)
         self.written.add(l)
         return self.buf[:, l * self.width:(l + 1) * self.width]
@@ -225,7 +237,7 @@ class AllLayerKVProjFn(Function):
     8192 x 2048 x 1024 GEMMs).  Returns L views [R, 2E] (row stride L*2E), read by stride."""
 
     @staticmethod
-    def forward(ctx, x, L, slab, *args):
+    def forward(ctx, x, L, slab, kv16, *args):
         wks, wvs, biases = args[:L], args[L:2 * L], args[2 * L:3 * L]
         E = wks[0].shape[0]
         a16 = operand(x, 'a')
@@ -234,7 +246,7 @@ class AllLayerKVProjFn(Function):
             mats += [wks[l], wvs[l]]
         w16 = concat_rows_operand(mats, 'b', x.device)                  # [L*2E, kdim]
         bias = torch.cat([b.reshape(-1) for b in biases]) if biases[0] is not None else None
-        KV = ops.gemm_tn(a16, w16, bias=bias)
+        KV = ops.gemm_tn(a16, w16, bias=bias, want32=not kv16, want16=kv16)
         ctx.cfg = (L, E, bias is not None, _fast())
         ctx.slab = slab
         if ctx.cfg[3]:
@@ -256,10 +268,10 @@ class AllLayerKVProjFn(Function):
         slab.buf = None                       # the buffer belongs to this backward only
         slab.written = set()
         dx = dW = None
-        need_w = any(ctx.needs_input_grad[3:3 + 2 * L])
+        need_w = any(ctx.needs_input_grad[4:4 + 2 * L])
         if fast:
             a16, w16 = ctx.saved_tensors
-            d16 = operand(D, 'a')
+            d16 = _as_operand(D)
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(d16, w16, trans_b=True)
             if need_w:
@@ -276,7 +288,7 @@ class AllLayerKVProjFn(Function):
         if has_bias:
             db = ops.colsum(D)
             dbs = tuple(db[l * 2 * E:(l + 1) * 2 * E] for l in range(L))
-        return (dx, None, None) + dwk + dwv + dbs
+        return (dx, None, None, None) + dwk + dwv + dbs
 
 
 class WeightNormFn(Function):

@@ -113,7 +113,7 @@ class DynamicConvDecoderLayer(DecoderLayer):
             if kv_cache is not None and nm in kv_cache:
                 kv = kv_cache[nm]
             else:
-                kv = mha.project_kv(contexts[nm])
+                kv = mha.project_kv(contexts[nm], need_weights=(not self.training) and self.need_attn)
                 if kv_cache is not None:
                     kv_cache[nm] = kv
             kvs.append(kv)
@@ -265,9 +265,13 @@ class _DynamicConvDecoderBase(Decoder):
             ws = [m._weights() for m in mhas]
             E = mhas[0].embed_dim
             biases = [m.in_proj_bias[E:] if m.in_proj_bias is not None else None for m in mhas]
-            slab = Fn.GradSlab(S * B, 2 * E, L, key.device) if torch.is_grad_enabled() else None
-            kvs = Fn.AllLayerKVProjFn.apply(key.reshape(S * B, kd), L, slab, *[w[1] for w in ws],
-                                            *[w[2] for w in ws], *biases)
+            need_w = (not self.training) and any(layer.need_attn for layer in self.layers)
+            kv16 = Fn.kv16_ok(mhas[0].head_dim, need_w)
+            slab = Fn.GradSlab(S * B, 2 * E, L, key.device,
+                               torch.bfloat16 if kv16 else torch.float32) \
+                if torch.is_grad_enabled() else None
+            kvs = Fn.AllLayerKVProjFn.apply(key.reshape(S * B, kd), L, slab, kv16,
+                                            *[w[1] for w in ws], *[w[2] for w in ws], *biases)
             for l in range(L):
                 caches[l][nm] = kvs[l]
                 if slab is not None:

@@ -60,7 +60,7 @@ class MultiHeadAttention(nn.Module):
         bq = self.in_proj_bias[:self.embed_dim] if self.in_proj_bias is not None else None
         return Fn.LinearFn.apply(query2d, wq, bq, self.scaling)      # q *= scaling (:353)
 
-    def project_kv(self, key):
+    def project_kv(self, key, need_weights=True):
         """key [S,B,kdim] -> fused [S*B, 2E] (k | v).  Returns None for an empty context
         ([.,.,0]: multi_head.py:349-352)."""
         if key.shape[2] == 0 or key.shape[0] == 0:
@@ -68,7 +68,8 @@ class MultiHeadAttention(nn.Module):
         _, wk, wv = self._weights()
         bkv = self.in_proj_bias[self.embed_dim:] if self.in_proj_bias is not None else None
         S, B, kd = key.shape
-        return Fn.KVProjFn.apply(key.reshape(S * B, kd), wk, wv, bkv)
+        return Fn.KVProjFn.apply(key.reshape(S * B, kd), wk, wv, bkv,
+                                 Fn.kv16_ok(self.head_dim, need_weights))
 
     def attend(self, query, kv, key_padding_mask, need_weights=False):
         """query [T,B,E]; kv from project_kv.  Returns (out_proj input [T*B,E], weights)."""
@@ -95,7 +96,7 @@ class MultiHeadAttention(nn.Module):
                                       '(incremental_state=None, attn_mask=None) is implemented')
         if value is not key and not (value.shape == key.shape and value.data_ptr() == key.data_ptr()):
             raise NotImplementedError('key and value must be the same context tensor')
-        kv = self.project_kv(key)
+        kv = self.project_kv(key, need_weights)
         a, weights = self.attend(query, kv, key_padding_mask, need_weights)
         out = linear(a, self.out_proj.weight, self.out_proj.bias).view(T, B, -1)
         return out, weights

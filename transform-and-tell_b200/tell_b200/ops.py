@@ -222,8 +222,9 @@ def colsum(x, scale=1.0, out=None, accumulate=False):
             out, accumulate = zeros_f32((N,), x), True      # pre-zeroed: skip the memset node
         else:
             out = _f32(N, like=x)
-    _lib.call('tt_colsum', _ptr(x), c_ll(x.stride(0)), c_int(M), c_int(N), _ptr(out),
-              c_float(scale), c_int(1 if accumulate else 0), _stream())
+    _lib.call('tt_colsum_bf16' if x.dtype == torch.bfloat16 else 'tt_colsum', _ptr(x),
+              c_ll(x.stride(0)), c_int(M), c_int(N), _ptr(out), c_float(scale),
+              c_int(1 if accumulate else 0), _stream())
     return out
 
 
@@ -295,7 +296,10 @@ def attn_fwd(q, k, v, bias_k, bias_v, mask, T, B, S, H, D, zero_row=True, p=0.0,
     if out is None:
         out = _f32(T * B, E, like=q)
     lse = _f32(B, H, T, like=q)
-    _lib.call('tt_attn_fwd_tc' if tc else 'tt_attn_fwd', _ptr(q), _ptr(k if S > 0 else None),
+    kv16 = S > 0 and k.dtype == torch.bfloat16
+    assert not kv16 or tc, 'bf16 keys|values need the tensor-core attention kernels'
+    _lib.call(('tt_attn_fwd_tc_kv16' if kv16 else 'tt_attn_fwd_tc') if tc else 'tt_attn_fwd',
+              _ptr(q), _ptr(k if S > 0 else None),
               _ptr(v if S > 0 else None),
               _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out), _ptr(lse), c_int(T), c_int(B),
               c_int(S), c_int(H), c_int(D), c_ll(q.stride(0)),
@@ -311,7 +315,10 @@ def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k,
     assert dout.stride(0) == out.stride(0) and dq.stride(0) == q.stride(0)
     if S > 0:
         assert dk.stride(0) == k.stride(0) and dv.stride(0) == k.stride(0)
-    _lib.call('tt_attn_bwd_tc' if tc else 'tt_attn_bwd', _ptr(dout), _ptr(q),
+    kv16 = S > 0 and k.dtype == torch.bfloat16
+    assert not kv16 or (tc and dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16)
+    _lib.call(('tt_attn_bwd_tc_kv16' if kv16 else 'tt_attn_bwd_tc') if tc else 'tt_attn_bwd',
+              _ptr(dout), _ptr(q),
               _ptr(k if S > 0 else None),
               _ptr(v if S > 0 else None), _ptr(bias_k), _ptr(bias_v), _ptr(mask), _ptr(out),
               _ptr(lse), _ptr(dq), _ptr(dk if S > 0 else None), _ptr(dv if S > 0 else None),
