@@ -56,6 +56,6 @@ print(json.dumps({'metric': 'greedy decode latency', 'batch': B, 'steps': args.s
                   'ms_per_step': round(dec_ms / args.steps, 3),
                   'captions_per_s_decode_only': round(B / (dec_ms * 1e-3), 1),
                   'captions_per_s_incl_encoders': round(B / ((dec_ms + ctx_ms) * 1e-3), 1),
-                  'decode_graph': bool(model.decode_graph),
+                  'decode_graph': bool(model.decode_graph), 'decode_ms_reps': [round(r[1], 1) for r in res],
                   'note': 'steps 0-1 eager (one-off K|V projections of the four contexts, graph capture), '
                           'steps 2.. replay one captured decode step'}))

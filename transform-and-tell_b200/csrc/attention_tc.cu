@@ -511,6 +511,140 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ decode (T = 1)
+// One query row per (b, h): the 64-query tensor-core tile would spend 63/64 of its MMAs and
+// exponentials on padding rows, so incremental decoding gets a bandwidth-shaped kernel instead.
+// CTA = (b, group of HG heads), one WARP per head, everything per head is warp-local (no block
+// barrier).  The projected keys|values of one (key, batch) row hold all heads side by side, so the
+// HG warps of a CTA read HG*128 contiguous bytes per key: DRAM-friendly bursts instead of isolated
+// 128-byte lines 16 KB apart.
+//   phase 1: lane = key (32 keys per pass), 64-dim dot with q (shared memory broadcast)
+//   phase 2: warp softmax over the L scores kept in shared memory
+//   phase 3: lane = 2 of the 64 value dims, loop over keys (coalesced 128-byte row reads)
+// K and V are read exactly once: 2*L*64*sizeof(kv) bytes per (b, h).
+__device__ __forceinline__ float dot4(float acc, float x0, float x1, float x2, float x3, const float* q) {
+  return fmaf(x3, q[3], fmaf(x2, q[2], fmaf(x1, q[1], fmaf(x0, q[0], acc))));
+}
+constexpr int DEC_HG = 8;      // heads (warps) per CTA
+template <bool KV16>
+__global__ void __launch_bounds__(DEC_HG * 32)
+attn_decode_kernel(AttnArgs a, int Lp) {
+  pdl_prologue();
+  extern __shared__ float dsm[];        // [DEC_HG][Lp] scores -> probabilities
+  __shared__ float sq_all[DEC_HG][TC_D];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.y * DEC_HG + warp;
+  if (h >= a.H) return;                 // warp-uniform; no block barrier below
+  const bool has_bias = a.bias_k != nullptr;
+  const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
+  float* sp = dsm + warp * Lp;
+  float* sq = sq_all[warp];
+  {
+    const float2 q2 = *reinterpret_cast<const float2*>(a.q + static_cast<long long>(b) * a.ldq + h * TC_D + 2 * lane);
+    sq[2 * lane] = q2.x;
+    sq[2 * lane + 1] = q2.y;
+  }
+  __syncwarp();
+  // ---- phase 1: scores
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    float sc;
+    if (j < a.S) {
+      const long long off = (static_cast<long long>(j) * a.B + b) * a.ldkv + h * TC_D;
+      float acc = 0.f;
+      if (KV16) {
+        const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.k) + off);
+        uint4 u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __ldg(kr + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {       // same association order as the fp32-storage branch
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+          acc = dot4(acc, __low2float(h2[0]), __high2float(h2[0]), __low2float(h2[1]), __high2float(h2[1]),
+                     sq + 8 * i);
+          acc = dot4(acc, __low2float(h2[2]), __high2float(h2[2]), __low2float(h2[3]), __high2float(h2[3]),
+                     sq + 8 * i + 4);
+        }
+      } else {
+        const float4* kr = reinterpret_cast<const float4*>(a.k + off);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const float4 v = __ldg(kr + i);
+          acc = dot4(acc, v.x, v.y, v.z, v.w, sq + 4 * i);
+        }
+      }
+      sc = (a.mask && a.mask[static_cast<long long>(b) * a.S + j]) ? -INFINITY : acc;
+    } else if (has_bias && j == a.S) {
+      float acc = 0.f;
+      for (int i = 0; i < TC_D; ++i) acc = fmaf(__ldg(a.bias_k + h * TC_D + i), sq[i], acc);
+      sc = acc;
+    } else {
+      sc = 0.f;                       // add_zero_attn: an all-zero key
+    }
+    sp[j] = sc;
+    m = fmaxf(m, sc);
+  }
+  m = warp_max(m);
+  // ---- phase 2: softmax
+  const float base = (m == -INFINITY) ? 0.f : m;
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float e = __expf(sp[j] - base);
+    sp[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // ---- phase 3: out = sum_j p_j v_j.  8 lanes cover one 64-dim value row with 16-byte loads, the
+  // warp takes 4 keys per pass (x4 unrolled: 16 rows in flight), the 4 key groups meet by shuffle.
+  const int kq = lane >> 3, c8 = lane & 7;         // key slot within a pass, 8-dim chunk of the row
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  const long long vstep = static_cast<long long>(a.B) * a.ldkv;
+  if (KV16) {
+    const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(b) * a.ldkv +
+                              h * TC_D + c8 * 8;
+#pragma unroll 4
+    for (int j = kq; j < a.S; j += 4) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(vp + j * vstep));
+      const float pj = sp[j];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[2 * e] = fmaf(pj, __low2float(h2[e]), o[2 * e]);
+        o[2 * e + 1] = fmaf(pj, __high2float(h2[e]), o[2 * e + 1]);
+      }
+    }
+  } else {
+    const float* vp = a.v + static_cast<long long>(b) * a.ldkv + h * TC_D + c8 * 8;
+#pragma unroll 4
+    for (int j = kq; j < a.S; j += 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(vp + j * vstep));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(vp + j * vstep) + 1);
+      const float pj = sp[j];
+      o[0] = fmaf(pj, x.x, o[0]); o[1] = fmaf(pj, x.y, o[1]); o[2] = fmaf(pj, x.z, o[2]); o[3] = fmaf(pj, x.w, o[3]);
+      o[4] = fmaf(pj, y.x, o[4]); o[5] = fmaf(pj, y.y, o[5]); o[6] = fmaf(pj, y.z, o[6]); o[7] = fmaf(pj, y.w, o[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (kq == 0) {
+    const float inv = 1.f / sum;
+    float bvv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bvv[i] = has_bias ? sp[a.S] * __ldg(a.bias_v + h * TC_D + c8 * 8 + i) : 0.f;
+    float4* op = reinterpret_cast<float4*>(a.out + static_cast<long long>(b) * a.ldo + h * TC_D + c8 * 8);
+    op[0] = make_float4((o[0] + bvv[0]) * inv, (o[1] + bvv[1]) * inv, (o[2] + bvv[2]) * inv, (o[3] + bvv[3]) * inv);
+    op[1] = make_float4((o[4] + bvv[4]) * inv, (o[5] + bvv[5]) * inv, (o[6] + bvv[6]) * inv, (o[7] + bvv[7]) * inv);
+  }
+  if (lane == 0 && a.lse) a.lse[b * a.H + h] = base + logf(sum);
+}
+
 static int tc_check(const AttnArgs& a, int D, bool kv16 = false) {
   TT_REQUIRE(D == TC_D, "attention (tensor-core path): head_dim must be %d (got %d)", TC_D, D);
   TT_REQUIRE(a.ldq % 4 == 0 && a.ldkv % (kv16 ? 8 : 4) == 0 && a.ldo % 4 == 0,
@@ -538,6 +672,17 @@ static int attn_fwd_tc_impl(const float* q, const void* k, const void* v, const 
   a.p_drop = p_drop; a.seed = seed; a.step_ptr = rng_step_ptr();
   int rc = tc_check(a, D, kv16 && S > 0);
   if (rc != TT_OK) return rc;
+  if (T == 1 && p_drop == 0.f) {      // incremental decoding: one query row per (b, h)
+    const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+    const int Lp = (L + 3) & ~3;
+    const size_t smem = static_cast<size_t>(DEC_HG) * Lp * sizeof(float);
+    if (smem <= 40 * 1024) {
+      const dim3 grid(B, ceil_div(H, DEC_HG));
+      if (kv16) launch_k(attn_decode_kernel<true>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, a, Lp);
+      else launch_k(attn_decode_kernel<false>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, a, Lp);
+      return check_launch("attn_decode_kernel");
+    }
+  }
   dim3 grid(B * H, ceil_div(T, TC_BM));
   if (kv16) launch_k(attn_fwd_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
   else launch_k(attn_fwd_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);

@@ -257,12 +257,21 @@ class _CaptionModelBase(Model):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.stream(side), dec.weight_scope(refresh=False):
             one_step()
-            graph.capture_begin()
+            # one allocator pool for every decode graph of this model: the blocks of a finished
+            # call's graph are reused by the next capture instead of cudaMalloc / cudaFree per call
+            # (a pool lives as long as a graph captured into it: the previous call's graph is kept
+            # until this capture has joined its pool)
+            keep = getattr(self, '_decode_graph_keep', None)
+            if keep is not None:
+                graph.capture_begin(pool=keep.pool())
+            else:
+                graph.capture_begin()
             try:
                 one_step()                       # recorded, not executed: steps 2.. are replays
             finally:
                 graph.capture_end()
         cur.wait_stream(side)
+        object.__setattr__(self, '_decode_graph_keep', graph)
         n_steps = n_max
         for i in range(2, n_max):
             graph.replay()
