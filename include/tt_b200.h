@@ -414,6 +414,19 @@ int tt_l2norm_rows(const float* x, float* y, int N, int D, float eps, void* stre
  * (mtcnn.py:29,75,126). */
 int tt_softmax2(float* x, long long ld, long long rows, int c0, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batch collation.  The reference pads each field on the host and uploads
+ * one tensor per field (allennlp TextField.as_tensor via tell/data/token_indexers/
+ * roberta_indexer.py:185-200; ArrayField(padding_value=nan) for face / object features,
+ * tell/data/dataset_readers/nytimes_faces_ner_matched.py:213-217).  Here the ragged rows of a field
+ * are one flat buffer + row offsets [B+1] and the padding happens on the device:
+ *   out[b, i, :] = i < n_b ? flat[(row_offsets[b] + i) * width + :] : fill.
+ */
+int tt_pad_ragged_f32(const float* flat, const long long* row_offsets, float* out, int B,
+                      int max_rows, int width, float fill, void* stream);
+int tt_pad_ragged_i64(const long long* flat, const long long* row_offsets, long long* out, int B,
+                      int max_rows, long long fill, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

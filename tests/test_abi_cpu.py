@@ -90,3 +90,29 @@ def test_registry_builds_reference_model_block():
     bad = dict(block, bogus_key=1)
     with pytest.raises(ConfigurationError):
         Decoder.from_params(bad)
+
+
+def test_collator_host_packing_and_generations_writer(tmp_path):
+    """Host half of the batch-dict producer (no GPU): ragged packing + offsets, and the
+    generations.jsonl wire format of tell/commands/evaluate.py:196-215."""
+    import json
+    import numpy as np
+    from tell_b200.data import Collator, write_generations_jsonl
+    arrs, off, max_len = Collator.pack_tokens([[0, 5, 2], [0, 2], []])
+    assert off.tolist() == [0, 3, 5, 5] and max_len == 3 and [a.tolist() for a in arrs][1] == [0, 2]
+    flat, off, max_rows, width = Collator.pack_arrays([np.ones((2, 4)), np.array([[]]), np.zeros((3, 4))])
+    assert off.tolist() == [0, 2, 2, 5] and max_rows == 3 and width == 4 and flat[1].size == 0
+    flat, off, max_rows, width = Collator.pack_arrays([np.array([[]]), np.array([[]])])
+    assert (max_rows, width) == (1, 0)
+    with pytest.raises(ValueError):
+        Collator.pack_arrays([np.ones((1, 4)), np.ones((1, 5))])
+    out = {'captions': ['a cap'], 'generations': ['a gen'], 'copied_texts': ['cp'],
+           'metadata': [{'caption': 'A Cap', 'web_url': 'http://x', 'image_path': '/i.jpg', 'context': 'ctx'}]}
+    path = str(tmp_path / 'generations.jsonl')
+    assert write_generations_jsonl(path, out) == 1
+    assert write_generations_jsonl(path, out, nlp=lambda t: {'names': [t.upper()]}) == 1
+    assert write_generations_jsonl(path, {'loss': 1.0}) == 0
+    rows = [json.loads(l) for l in open(path)]
+    assert rows[0] == {'caption': 'a cap', 'raw_caption': 'A Cap', 'generation': 'a gen', 'copied_texts': 'cp',
+                       'web_url': 'http://x', 'image_path': '/i.jpg', 'context': 'ctx', 'copied_text': 'cp'}
+    assert rows[1]['generated_names'] == ['A GEN'] and rows[1]['context_names'] == ['CTX']

@@ -170,3 +170,53 @@ extern "C" int tt_transpose01(const float* in, float* out, int A, int B, int C, 
   launch_k(transpose01_kernel, dim3((int)g), dim3(256), 0, (cudaStream_t)stream, in, out, A, B, C / 4);
   return check_launch("transpose01_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Batch collation: the reference pads every field on the host
+// (allennlp TextField / ArrayField(padding_value=nan) as_tensor, roberta_indexer.py:185-200,
+// nytimes_faces_ner_matched.py:213-217) and uploads one tensor per field.  Here the ragged rows of
+// a field travel as ONE flat pinned buffer + row offsets and are padded on the device.
+namespace tt {
+// out[b, i, :] = i < n_b ? flat[(off[b] + i) * width + :] : fill     (n_b = off[b+1] - off[b])
+template <typename T>
+__global__ void pad_ragged_kernel(const T* __restrict__ flat, const long long* __restrict__ off,
+                                  T* __restrict__ out, int B, int max_rows, int width, T fill) {
+  pdl_prologue();
+  const long long per = static_cast<long long>(max_rows) * width;
+  const long long total = per * B;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per);
+    const long long r = i - static_cast<long long>(b) * per;
+    const int row = static_cast<int>(r / width);
+    const int c = static_cast<int>(r - static_cast<long long>(row) * width);
+    const long long o0 = off[b], n = off[b + 1] - o0;
+    out[i] = row < n ? flat[(o0 + row) * width + c] : fill;
+  }
+}
+template <typename T>
+static int pad_ragged(const T* flat, const long long* off, T* out, int B, int max_rows, int width,
+                      T fill, void* stream, const char* what) {
+  if (!(off && out) || (!flat && max_rows > 0 && width > 0)) {
+    set_error("%s: null pointer", what);
+    return TT_ERR_INVALID;
+  }
+  const long long total = static_cast<long long>(B) * max_rows * width;
+  if (total <= 0) return TT_OK;
+  long long g = ceil_div_ll(total, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  launch_k(pad_ragged_kernel<T>, dim3(static_cast<unsigned>(g)), dim3(256), 0, (cudaStream_t)stream, flat,
+           off, out, B, max_rows, width, fill);
+  return check_launch(what);
+}
+}  // namespace tt
+
+extern "C" int tt_pad_ragged_f32(const float* flat, const long long* row_offsets, float* out, int B,
+                                 int max_rows, int width, float fill, void* stream) {
+  return tt::pad_ragged<float>(flat, row_offsets, out, B, max_rows, width, fill, stream, "tt_pad_ragged_f32");
+}
+extern "C" int tt_pad_ragged_i64(const long long* flat, const long long* row_offsets, long long* out,
+                                 int B, int max_rows, long long fill, void* stream) {
+  return tt::pad_ragged<long long>(flat, row_offsets, out, B, max_rows, 1, fill, stream, "tt_pad_ragged_i64");
+}
