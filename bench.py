@@ -183,6 +183,7 @@ def run_b200(args):
     config.enable_device_step(dev)
     config.enable_zero_arena(dev)     # the step below consumes gradients before the next forward
     config.enable_wgrad_stream(args.wgrad)   # weight-gradient GEMMs as a parallel graph branch
+    config.encoder_overlap = bool(args.encoder_overlap)
     B = args.batch
     model = build_model(dev)
     # the flat gradient buffer only exists where there is a collective to feed
@@ -190,111 +191,146 @@ def run_b200(args):
     params = [p for p in model.parameters() if p.requires_grad]
     host = make_batch(B, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
-    static = {k: v.to(dev) for k, v in host.items()}        # buffers the step reads (and mutates)
-    pristine = {k: v.clone() for k, v in static.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     loss_host = torch.zeros(1).pin_memory()
     out_loss = torch.zeros(1, device=dev)
+    pristine = {k: v.to(dev) for k, v in host.items()}
 
     grad16 = None
     if fg is not None and args.grad_dtype == 'bf16':
         grad16 = torch.zeros(fg.flat.numel(), dtype=torch.bfloat16, device=dev)
-    enc = {}
 
-    def encode():
-        """Frozen encoders (ResNet-152 + RoBERTa-large forward): no trainable weight involved."""
-        enc['v'] = model.encode({'roberta': static['article']}, static['image'])
+    class StepSet:
+        """One set of step buffers: the input tensors the step reads (and mutates), the frozen
+        encoders' outputs, and the two CUDA graphs captured over them.  Two sets make a software
+        pipeline: the frozen encoders of step i+1 (set B) run while the decoder forward/backward of
+        step i (set A) is still in flight -- they read no trainable weight (Model.encode)."""
 
-    def train_part():
-        """Decoder forward + loss + full backward (+ gradient packing for the all-reduce)."""
-        from tell_b200 import ops
-        for p in params:          # backward then WRITES each gradient (no accumulate kernels)
-            p.grad = None
-        config.advance_device_step()
-        out = model(context={'roberta': static['article']}, image=static['image'],
-                    caption={'roberta': static['caption']}, face_embeds=static['faces'],
-                    obj_embeds=static['objs'], metadata=None, encoded=enc['v'])
-        out['loss'].backward()
-        out_loss.copy_(out['loss'].detach().view(1))
-        if fg is not None:
-            fg.pack()             # one batched copy into the flat all-reduce buffer
-            if grad16 is not None:
-                ops.cast_bf16(fg.flat.view(1, -1), out=grad16.view(1, -1))
+        def __init__(self):
+            self.static = {k: v.clone() for k, v in pristine.items()}
+            self.enc = None
+            self.g1 = self.g2 = None
+            self.enc_done = torch.cuda.Event()
+            self.train_done = torch.cuda.Event()
+            self.busy = False
 
-    def fwd_bwd():
-        encode()
-        train_part()
+        def restore(self):
+            for k in ('faces', 'objs'):   # forward() zeroes NaN rows in place, like the reference
+                self.static[k].copy_(pristine[k])
 
-    def restore():
-        for k in ('faces', 'objs'):       # forward() zeroes NaN rows in place, like the reference
-            static[k].copy_(pristine[k])
+        def encode(self):
+            """Frozen encoders (ResNet-152 + RoBERTa-large forward): no trainable weight involved."""
+            st = self.static
+            self.enc = model.encode({'roberta': st['article']}, st['image'])
+
+        def train_part(self):
+            """Decoder forward + loss + full backward (+ gradient packing for the all-reduce)."""
+            from tell_b200 import ops
+            st = self.static
+            for p in params:          # backward then WRITES each gradient (no accumulate kernels)
+                p.grad = None
+            config.advance_device_step()
+            out = model(context={'roberta': st['article']}, image=st['image'],
+                        caption={'roberta': st['caption']}, face_embeds=st['faces'],
+                        obj_embeds=st['objs'], metadata=None, encoded=self.enc)
+            out['loss'].backward()
+            out_loss.copy_(out['loss'].detach().view(1))
+            if fg is not None:
+                fg.pack()             # one batched copy into the flat all-reduce buffer
+                if grad16 is not None:
+                    ops.cast_bf16(fg.flat.view(1, -1), out=grad16.view(1, -1))
+
+        def fwd_bwd(self):
+            self.encode()
+            self.train_part()
+
+    n_sets = 2 if (args.pipeline and not args.no_graph) else 1
+    sets = [StepSet() for _ in range(n_sets)]
 
     # ---- warm-up (eager): lazy weight folding, cudaFuncSetAttribute, allocator pools
     stream = torch.cuda.Stream()
     stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup) if args.no_graph else 3):
-            restore()
-            fwd_bwd()
+            sets[0].restore()
+            sets[0].fwd_bwd()
     torch.cuda.current_stream().wait_stream(stream)
     torch.cuda.synchronize()
-    # ---- count launches of OUR kernels in one step, then capture the step in two CUDA graphs:
-    #      G1 = frozen encoders, G2 = decoder fwd + loss + bwd.  The split lets the gradient
-    #      all-reduce of step i (side stream) overlap G1 of step i+1.
+    # ---- count launches of OUR kernels in one step, then capture the step in two CUDA graphs per
+    #      set: G1 = frozen encoders, G2 = decoder fwd + loss + bwd.
     _lib.reset_launch_count()
-    restore()
-    fwd_bwd()
+    sets[0].restore()
+    sets[0].fwd_bwd()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count()
-    g1 = g2 = None
     if not args.no_graph:
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        restore()
-        with torch.cuda.graph(g1):
-            encode()
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            train_part()
-        torch.cuda.synchronize()
-    graph = g1
-    side = torch.cuda.Stream() if world > 1 else None
+        for st in sets:
+            st.g1, st.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            st.restore()
+            with torch.cuda.graph(st.g1):
+                st.encode()
+            with torch.cuda.graph(st.g2, pool=st.g1.pool()):
+                st.train_part()
+            torch.cuda.synchronize()
+    graph = sets[0].g1
+    s_enc, s_train = torch.cuda.Stream(), torch.cuda.Stream()      # encoder / train pipeline stages
+    s_ar = torch.cuda.Stream() if world > 1 else None
     ev_bwd, ev_ar = torch.cuda.Event(), torch.cuda.Event()
     ar_pending = [False]
+    counter = [0]
 
     def step(e2e):
-        main = torch.cuda.current_stream()
-        if e2e:
-            for k in static:
-                static[k].copy_(pinned[k], non_blocking=True)
-        else:
-            restore()
-        if g1 is not None:
-            g1.replay()
-        else:
-            encode()
-        if ar_pending[0]:
-            main.wait_event(ev_ar)        # previous step's all-reduce must be done before the
-            ar_pending[0] = False         # gradient buffers are overwritten
-        if g2 is not None:
-            g2.replay()
-        else:
-            train_part()
+        st = sets[counter[0] % n_sets]
+        counter[0] += 1
+        # stage 1 (stream s_enc): inputs + frozen encoders of this step.  With two sets this runs
+        # while the previous step's stage 2 is still executing on s_train.
+        with torch.cuda.stream(s_enc):
+            if st.busy:
+                s_enc.wait_event(st.train_done)   # the step that last used this set has finished
+            if e2e:
+                for k in st.static:
+                    st.static[k].copy_(pinned[k], non_blocking=True)
+            else:
+                st.restore()
+            if st.g1 is not None:
+                st.g1.replay()
+            else:
+                st.encode()
+            st.enc_done.record(s_enc)
+        # stage 2 (stream s_train): decoder forward + loss + backward
+        with torch.cuda.stream(s_train):
+            s_train.wait_event(st.enc_done)
+            if ar_pending[0]:
+                s_train.wait_event(ev_ar)     # previous step's all-reduce must be done before the
+                ar_pending[0] = False         # gradient buffers are overwritten
+            if st.g2 is not None:
+                st.g2.replay()
+            else:
+                st.train_part()
+            if e2e:
+                loss_host.copy_(out_loss, non_blocking=True)
+            st.train_done.record(s_train)
+            st.busy = True
+            if world > 1:
+                ev_bwd.record(s_train)
         if world > 1:
-            ev_bwd.record(main)
-            side.wait_event(ev_bwd)
-            with torch.cuda.stream(side):
+            s_ar.wait_event(ev_bwd)
+            with torch.cuda.stream(s_ar):
                 buf = grad16 if grad16 is not None else fg.flat
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-                ev_ar.record(side)
+                ev_ar.record(s_ar)
             ar_pending[0] = True
-        if e2e:
-            loss_host.copy_(out_loss, non_blocking=True)
 
     def drain():
+        main = torch.cuda.current_stream()
+        main.wait_stream(s_enc)
+        main.wait_stream(s_train)
         if ar_pending[0]:
-            torch.cuda.current_stream().wait_event(ev_ar)
+            main.wait_event(ev_ar)
             ar_pending[0] = False
 
     def timed(e2e, steps, warmup):
+        main = torch.cuda.current_stream()
         for _ in range(warmup):
             step(e2e)
         drain()
@@ -303,11 +339,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        s.record(main)                    # the pipeline is empty here: every timed step's encoders
+        s_enc.wait_event(s)               # AND train part run inside [s, e]
+        s_train.wait_event(s)
         for _ in range(steps):
             step(e2e)
         drain()
-        e.record()
+        e.record(main)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -354,8 +392,8 @@ def run_b200(args):
         _lib.PROFILE, _lib.GEMM_FLOPS[:] = [], []
         n_prof = 2
         for _ in range(n_prof):
-            restore()
-            fwd_bwd()
+            sets[0].restore()
+            sets[0].fwd_bwd()
         torch.cuda.synchronize()
         ops.gemm_tn = orig_gemm
         agg, total = {}, 0.0
@@ -369,7 +407,9 @@ def run_b200(args):
         breakdown = {k: {'ms_per_step': round(v[0] / n_prof, 4), 'launches': v[1] // n_prof}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
         share = agg['tt_gemm_bf16_tn'][0] / total
-        del pristine, static
+        for st in sets:
+            st.g1 = st.g2 = st.enc = st.static = None
+        sets.clear()
         model.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
         gemm_us, gemm_flop, gemm_calls = replay_gemm_signatures(sigs, n_prof, dev)
@@ -404,6 +444,10 @@ def run_b200(args):
                                'T=50, S=512, F=4, O=16, dropout on, fwd+bwd (no optimizer step)',
                    'global_batch': world * B, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
+                   'encoder_overlap': bool(args.encoder_overlap),
+                   'pipeline': ('2 step-buffer sets: frozen encoders of step i+1 overlap the decoder '
+                                'fwd+bwd of step i; all K encoder and K train passes run inside the '
+                                'timed region' if n_sets == 2 else None),
                    'grad_allreduce': (None if world == 1 else args.grad_dtype + ', one flat buffer, '
                                       'overlapped with the next step\'s frozen-encoder forward'),
                    'l2': 'working set per step (weights + activations, >2 GB) exceeds the 126 MB L2'},
@@ -557,6 +601,11 @@ def main():
     ap.add_argument('--wgrad', type=int, default=0, choices=[0, 1, 2],
                     help='weight-gradient stream: 0 off (fastest measured: graph branch fork/join edges cost '
                          'more than the overlap wins), 1 weight-bank dW only, 2 + per-function forks')
+    ap.add_argument('--pipeline', type=int, default=1, choices=[0, 1],
+                    help='two step-buffer sets: frozen encoders of step i+1 overlap the decoder '
+                         'forward/backward of step i')
+    ap.add_argument('--encoder-overlap', type=int, default=1, choices=[0, 1],
+                    help='ResNet as a parallel stream branch beside RoBERTa')
     ap.add_argument('--grad-dtype', default='fp32', choices=['bf16', 'fp32'],
                     help='dtype of the gradient all-reduce payload (N > 1)')
     args = ap.parse_args()

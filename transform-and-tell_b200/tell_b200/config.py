@@ -15,6 +15,8 @@ precision = 'bf16'
 # weight gradients on a second stream (functional.wgrad); opt-in, throughput mode only
 # projected keys|values of the cross-attentions (and dL/dk, dL/dv) as bf16 in HBM (throughput mode)
 kv_bf16 = True
+# run the ResNet encoder as a parallel stream branch beside RoBERTa in Model.encode()
+encoder_overlap = True
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks
 
 _seed_base = 0x5EED

@@ -20,6 +20,16 @@ from .resnet import resnet152
 from .roberta import RobertaEncoder
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class Model(nn.Module, Registrable):
     pass
 
@@ -73,6 +83,17 @@ class _CaptionModelBase(Model):
         RoBERTa hidden states (bf16 [L+1, B*S, E]).  It depends on no trainable weight, so a
         data-parallel trainer may run it for step i+1 while step i's gradient all-reduce is still
         in flight; pass the result to forward(..., encoded=...)."""
+        if self.USES_IMAGE and config.encoder_overlap and image.is_cuda:
+            # the two frozen encoders are independent: ResNet's ~200 small latency-bound launches
+            # run as a parallel branch (one fork, one join) beside RoBERTa's large GEMMs
+            cur = torch.cuda.current_stream(image.device)
+            side = _side_stream(image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                feats = self.resnet.features_nhwc(image)
+            hid, _ = self.roberta.all_hiddens(context[self.index])
+            cur.wait_stream(side)
+            return feats, hid
         feats = self.resnet.features_nhwc(image) if self.USES_IMAGE else None
         hid, _ = self.roberta.all_hiddens(context[self.index])
         return feats, hid
