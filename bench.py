@@ -176,6 +176,8 @@ def run_b200(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # stdout carries exactly one JSON line: NCCL's banner / debug output goes to a file
         os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/nccl_bench_%h_%p.log')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'     # level VERSION printf()s its banner to stdout
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
     config.set_precision('bf16')
