@@ -341,12 +341,13 @@ int tt_flash_self_attn(const void* qkv, const uint8_t* key_padding_mask, void* o
  * real tokens, the m_limit of the encoder GEMMs).  tt_flash_self_attn_varlen is the self-attention
  * over the packed layout (sample b = rows cu[b]..cu[b+1]); tt_ln_fwd16_varlen is the LayerNorm that
  * moves between the layouts (see encoders.cu) and writes zeros to the padding rows of the padded
- * hidden-state buffer. */
+ * hidden-state buffer; its input rows are fp32 (embedding sum) or bf16 (x_bf16 != 0: the pre-norm
+ * residual sums the encoder GEMMs write). */
 int tt_varlen_prepare(const long long* ids, int B, int S, int pad, int* inv_map, int* cu_seqlens,
                       void* stream);
 int tt_flash_self_attn_varlen(const void* qkv, const int* cu_seqlens, void* out, int B, int S_max,
                               int H, int D, void* stream);
-int tt_ln_fwd16_varlen(const float* x, int x_packed, const float* gamma, const float* beta,
+int tt_ln_fwd16_varlen(const void* x, int x_bf16, int x_packed, const float* gamma, const float* beta,
                        void* y_packed, void* y_padded, const int* inv_map, const int* count_ptr,
                        int R, int E, float eps, void* stream);
 

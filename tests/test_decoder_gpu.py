@@ -154,3 +154,38 @@ def test_full_size_decoder_matches_oracle():
         assert torch.equal(torch.cat(toks, 1).cpu(), rids[:, 1:])
     del dec
     torch.cuda.empty_cache()
+
+
+def test_long_article_stress_shapes_match_oracle():
+    """BASELINE configs[4] shapes (2048-token article context fed as embeddings, 8 faces, 16
+    objects) on the full-size architecture, batch 2: throughput-mode (bf16, bf16 K|V, tensor-core
+    attention over 33 key tiles) decoder output and loss against the fp32 CPU oracle -- tolerance
+    0.15 abs on outputs of O(1..10) as for the other bf16 tests -- and the T = 1 decode step with
+    a key set too long for the dedicated decode kernel's shared-memory budget."""
+    import restate
+    from tell_b200 import config, synth
+    from tell_b200.models import DynamicConvFacesObjectsDecoder
+    from tell_b200.testing import build_decoder
+    config.set_precision('bf16')
+    cfg = synth.CFG_FULL
+    sd = synth.decoder_state_dict(cfg, seed=2, logit_gain=2.0)
+    dec = build_decoder(cfg, DynamicConvFacesObjectsDecoder, sd).cuda().eval()
+    for l in dec.layers:
+        l.need_attn = False
+    cap, ctx = synth.decoder_inputs(cfg, B=2, T=50, S=2048, F=8, O=16, P=49, seed=5)
+    inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    cctx = {k: v.cuda() for k, v in ctx.items()}
+    ocfg = synth.oracle_cfg(cfg)
+    with torch.no_grad():
+        out, _ = dec({'roberta': inp.cuda()}, cctx)
+        loss, ntok = dec.adaptive_softmax.fused_loss(out, tgt.cuda())
+        ref, _ = restate.decoder_forward(inp, ctx, sd, ocfg)
+        _, n, ref_loss = restate.adaptive_loss(ref, tgt, sd, ocfg['cutoffs'])
+        assert (out.cpu() - ref).abs().max().item() < 0.15
+        assert int(ntok) == n and abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+        # one incremental step == first position of the full forward
+        X, _ = dec.forward_tbc({'roberta': inp[:, 0:1].cuda()}, cctx, incremental_state={})
+        assert (X.view(2, -1).cpu() - ref[:, 0]).abs().max().item() < 0.15
+    config.set_precision('bf16x3')
+    del dec
+    torch.cuda.empty_cache()

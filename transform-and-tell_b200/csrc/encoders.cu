@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(256) varlen_prepare_kernel(const long long* __
 //   inv_map != null : padded rows r < R: c = inv_map[r];
 //                       c < 0 : y_padded[r] = 0 (padding stays finite for the masked consumers)
 //                       else  : y = LN(x[x_packed ? c : r]) -> y_packed[c] and y_padded[r]
-template <int MAXC>   // E <= 128 * MAXC
+template <int MAXC, bool X16>   // E <= 128 * MAXC; X16: the input rows are bf16
 __global__ void __launch_bounds__(256) ln_fwd16_varlen_kernel(
-    const float* __restrict__ x, int x_packed, const float* __restrict__ gamma,
+    const void* __restrict__ xv, int x_packed, const float* __restrict__ gamma,
     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_packed,
     __nv_bfloat16* __restrict__ y_padded, const int* __restrict__ inv_map,
     const int* __restrict__ count, int R, int E, float eps) {
@@ -242,13 +242,30 @@ __global__ void __launch_bounds__(256) ln_fwd16_varlen_kernel(
       }
       src = x_packed ? c : r;
     }
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(src) * E);
     float4 v[MAXC];
     float s = 0.f;
+    if (X16) {
+      const uint2* xr = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xv) +
+                                                       static_cast<long long>(src) * E);
+      uint2 u[MAXC];
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int i = lane + k * 32;
-      v[k] = i < E4 ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < MAXC; ++k) {
+        const int i = lane + k * 32;
+        u[k] = i < E4 ? __ldg(xr + i) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < MAXC; ++k) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+        v[k] = make_float4(__low2float(h2[0]), __high2float(h2[0]), __low2float(h2[1]), __high2float(h2[1]));
+      }
+    } else {
+      const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) +
+                                                         static_cast<long long>(src) * E);
+#pragma unroll
+      for (int k = 0; k < MAXC; ++k) {
+        const int i = lane + k * 32;
+        v[k] = i < E4 ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
@@ -610,7 +627,7 @@ extern "C" int tt_varlen_prepare(const long long* ids, int B, int S, int pad, in
   return check_launch("varlen_prepare_kernel");
 }
 
-extern "C" int tt_ln_fwd16_varlen(const float* x, int x_packed, const float* gamma, const float* beta,
+extern "C" int tt_ln_fwd16_varlen(const void* x, int x_bf16, int x_packed, const float* gamma, const float* beta,
                                   void* y_packed, void* y_padded, const int* inv_map,
                                   const int* count_ptr, int R, int E, float eps, void* stream) {
   TT_REQUIRE(x && gamma && beta && (y_packed || y_padded), "tt_ln_fwd16_varlen: null pointer");
@@ -619,13 +636,14 @@ extern "C" int tt_ln_fwd16_varlen(const float* x, int x_packed, const float* gam
   const int cap = num_sms() * 8;
   const int want = ceil_div(R, 8);
   const dim3 grid(want < cap ? want : cap);
-  if (E <= 256)
-    launch_k(ln_fwd16_varlen_kernel<2>, grid, dim3(256), 0, (cudaStream_t)stream, x, x_packed, gamma, beta,
-             reinterpret_cast<__nv_bfloat16*>(y_packed), reinterpret_cast<__nv_bfloat16*>(y_padded),
-             inv_map, count_ptr, R, E, eps);
-  else
-    launch_k(ln_fwd16_varlen_kernel<8>, grid, dim3(256), 0, (cudaStream_t)stream, x, x_packed, gamma, beta,
-             reinterpret_cast<__nv_bfloat16*>(y_packed), reinterpret_cast<__nv_bfloat16*>(y_padded),
-             inv_map, count_ptr, R, E, eps);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_packed);
+  __nv_bfloat16* yd = reinterpret_cast<__nv_bfloat16*>(y_padded);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TT_LN_VARLEN(MAXC, X16) \
+  launch_k(ln_fwd16_varlen_kernel<MAXC, X16>, grid, dim3(256), 0, st, x, x_packed, gamma, beta, yp, yd, inv_map, \
+           count_ptr, R, E, eps)
+  if (E <= 256) { if (x_bf16) TT_LN_VARLEN(2, true); else TT_LN_VARLEN(2, false); }
+  else { if (x_bf16) TT_LN_VARLEN(8, true); else TT_LN_VARLEN(8, false); }
+#undef TT_LN_VARLEN
   return check_launch("ln_fwd16_varlen_kernel");
 }

@@ -142,7 +142,7 @@ class RobertaEncoder(nn.Module):
         h = [torch.empty((R, E), dtype=torch.bfloat16, device=dev) for _ in range(2)]   # packed
         ops.ln_fwd16_varlen(x, se.emb_layer_norm.weight, se.emb_layer_norm.bias, y_packed=h[0],
                             y_padded=hid[0], inv_map=inv_map, x_packed=False)
-        tmp = torch.zeros((R, E), dtype=torch.float32, device=dev)
+        tmp = torch.empty((R, E), dtype=torch.bfloat16, device=dev)      # pre-norm residual sums
         x16 = torch.empty((R, E), dtype=torch.bfloat16, device=dev)
         qkv = torch.empty((R, 3 * E), dtype=torch.bfloat16, device=dev)
         f = torch.empty((R, se.layers[0].fc1.weight.shape[0]), dtype=torch.bfloat16, device=dev)
@@ -150,12 +150,14 @@ class RobertaEncoder(nn.Module):
             h_in, h_out = h[i & 1], h[(i + 1) & 1]
             ops.gemm_tn(h_in, p['wqkv'], out16=qkv, bias=p['bqkv'], want32=False, m_limit=ntok)
             a = ops.flash_self_attn_varlen(qkv, cu, B, S, H, E // H)
-            ops.gemm_tn(a, p['wo'], out=tmp, bias=p['bo'], residual16=h_in, m_limit=ntok)
+            ops.gemm_tn(a, p['wo'], out16=tmp, bias=p['bo'], residual16=h_in, want32=False,
+                        m_limit=ntok)
             ops.ln_fwd16_varlen(tmp, l.self_attn_layer_norm.weight, l.self_attn_layer_norm.bias,
                                 y_packed=x16, count=ntok)
             ops.gemm_tn(x16, p['w1'], out16=f, bias=p['b1'], act=ops.ACT_GELU, want32=False,
                         m_limit=ntok)
-            ops.gemm_tn(f, p['w2'], out=tmp, bias=p['b2'], residual16=x16, m_limit=ntok)
+            ops.gemm_tn(f, p['w2'], out16=tmp, bias=p['b2'], residual16=x16, want32=False,
+                        m_limit=ntok)
             ops.ln_fwd16_varlen(tmp, l.final_layer_norm.weight, l.final_layer_norm.bias,
                                 y_packed=h_out, y_padded=hid[i + 1], inv_map=inv_map)
         return hid, is_pad

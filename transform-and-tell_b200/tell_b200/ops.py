@@ -539,7 +539,8 @@ def ln_fwd16_varlen(x, gamma, beta, y_packed=None, y_padded=None, inv_map=None, 
     """LayerNorm fp32 -> bf16 between the packed and padded layouts (tt_ln_fwd16_varlen)."""
     E = x.shape[1]
     R = inv_map.numel() if inv_map is not None else x.shape[0]
-    _lib.call('tt_ln_fwd16_varlen', _ptr(x), c_int(1 if x_packed else 0), _ptr(gamma), _ptr(beta),
+    _lib.call('tt_ln_fwd16_varlen', _ptr(x), c_int(1 if x.dtype == torch.bfloat16 else 0),
+              c_int(1 if x_packed else 0), _ptr(gamma), _ptr(beta),
               _ptr(y_packed), _ptr(y_padded), _ptr(inv_map), _ptr(count), c_int(R), c_int(E),
               c_float(eps), _stream())
 
