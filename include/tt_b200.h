@@ -236,6 +236,18 @@ int tt_attn_bwd_tc_kv16(const float* dout, const float* q, const void* k16, cons
                         float* dq, void* dk16, void* dv16, float* dbias_k, float* dbias_v, int T,
                         int B, int S, int H, int D, long long ldq, long long ldkv, long long ldo,
                         int zero_row, float p_drop, unsigned long long seed, void* stream);
+/* Incremental decoding (transformer_faces_objects.py:399-494 recomputes every K|V projection per
+ * step; here they are projected once and cached).  tt_kv_repack_heads turns the token-major bf16
+ * projection ([S*B, ldkv] rows, key j of batch b at row j*B+b) into head-major K, V [B,H,S,64];
+ * tt_attn_decode_hm is the T = 1 attention over that cache: q [B, H*64] (row stride ldq, already
+ * scaled), extended key set [S keys ; bias row ; zero row] as in multi_head.py:355-425,
+ * out [B, H*64] (row stride ldo), lse [B,H] optional. */
+int tt_kv_repack_heads(const void* k16, const void* v16, long long ldkv, void* k_out, void* v_out,
+                       int S, int B, int H, int D, void* stream);
+int tt_attn_decode_hm(const float* q, const void* k_hm, const void* v_hm, const float* bias_k,
+                      const float* bias_v, const uint8_t* key_padding_mask, float* out, float* lse,
+                      int B, int S, int H, int D, long long ldq, long long ldo, int zero_row,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Adaptive softmax / loss, tell/modules/softmax.py:144-222, criteria/adaptive_loss.py:27-73.

@@ -29,6 +29,9 @@ struct AttnArgs {
   float* dbias_v;
   // head-averaged weights (eval): [B,T,L]
   float* avg_w;
+  // decode kernel only: element strides of k/v between keys, batch rows and heads
+  // (token-major projection buffer: B*ldkv, ldkv, 64; head-major decode cache: 64, H*S*64, S*64)
+  long long kv_j_stride, kv_b_stride, kv_h_stride;
 };
 
 }  // namespace tt

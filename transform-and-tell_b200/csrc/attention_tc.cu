@@ -551,7 +551,7 @@ attn_decode_kernel(AttnArgs a, int Lp) {
   for (int j = lane; j < L; j += 32) {
     float sc;
     if (j < a.S) {
-      const long long off = (static_cast<long long>(j) * a.B + b) * a.ldkv + h * TC_D;
+      const long long off = j * a.kv_j_stride + b * a.kv_b_stride + h * a.kv_h_stride;
       float acc = 0.f;
       if (KV16) {
         const uint4* kr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.k) + off);
@@ -602,10 +602,10 @@ attn_decode_kernel(AttnArgs a, int Lp) {
   float o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
-  const long long vstep = static_cast<long long>(a.B) * a.ldkv;
+  const long long vstep = a.kv_j_stride;
+  const long long vbase = b * a.kv_b_stride + h * a.kv_h_stride + c8 * 8;
   if (KV16) {
-    const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(b) * a.ldkv +
-                              h * TC_D + c8 * 8;
+    const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + vbase;
 #pragma unroll 4
     for (int j = kq; j < a.S; j += 4) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(vp + j * vstep));
@@ -618,7 +618,7 @@ attn_decode_kernel(AttnArgs a, int Lp) {
       }
     }
   } else {
-    const float* vp = a.v + static_cast<long long>(b) * a.ldkv + h * TC_D + c8 * 8;
+    const float* vp = a.v + vbase;
 #pragma unroll 4
     for (int j = kq; j < a.S; j += 4) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(vp + j * vstep));
@@ -643,6 +643,29 @@ attn_decode_kernel(AttnArgs a, int Lp) {
     op[1] = make_float4((o[4] + bvv[4]) * inv, (o[5] + bvv[5]) * inv, (o[6] + bvv[6]) * inv, (o[7] + bvv[7]) * inv);
   }
   if (lane == 0 && a.lse) a.lse[b * a.H + h] = base + logf(sum);
+}
+
+// Token-major projected keys|values ([S*B, ld] rows, one 64-dim slice per head) -> head-major decode
+// cache K, V [B, H, S, 64]: one (batch, head) slice becomes S*128 contiguous bytes, so the decode
+// kernel streams it instead of touching isolated 128-byte lines 16 KB apart.  One 16-byte chunk per
+// thread, done once per generate() call.
+__global__ void kv_repack_heads_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                                       long long ld, __nv_bfloat16* __restrict__ ko,
+                                       __nv_bfloat16* __restrict__ vo, int S, int B, int H) {
+  pdl_prologue();
+  const long long total = static_cast<long long>(S) * B * H * 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i & 7);
+    long long t = i >> 3;
+    const int h = static_cast<int>(t % H); t /= H;
+    const int b = static_cast<int>(t % B);
+    const int j = static_cast<int>(t / B);
+    const long long src = (static_cast<long long>(j) * B + b) * ld + h * TC_D + c8 * 8;
+    const long long dst = ((static_cast<long long>(b) * H + h) * S + j) * TC_D + c8 * 8;
+    *reinterpret_cast<uint4*>(ko + dst) = __ldg(reinterpret_cast<const uint4*>(k + src));
+    *reinterpret_cast<uint4*>(vo + dst) = __ldg(reinterpret_cast<const uint4*>(v + src));
+  }
 }
 
 static int tc_check(const AttnArgs& a, int D, bool kv16 = false) {
@@ -672,6 +695,7 @@ static int attn_fwd_tc_impl(const float* q, const void* k, const void* v, const 
   a.p_drop = p_drop; a.seed = seed; a.step_ptr = rng_step_ptr();
   int rc = tc_check(a, D, kv16 && S > 0);
   if (rc != TT_OK) return rc;
+  a.kv_j_stride = static_cast<long long>(B) * ldkv; a.kv_b_stride = ldkv; a.kv_h_stride = TC_D;
   if (T == 1 && p_drop == 0.f) {      // incremental decoding: one query row per (b, h)
     const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
     const int Lp = (L + 3) & ~3;
@@ -764,4 +788,44 @@ extern "C" int tt_attn_bwd_tc_kv16(const float* dout, const float* q, const void
   return attn_bwd_tc_impl(dout, q, k16, v16, bias_k, bias_v, key_padding_mask, out, lse, dq, dk16, dv16,
                           dbias_k, dbias_v, T, B, S, H, D, ldq, ldkv, ldo, zero_row, p_drop, seed, stream,
                           true);
+}
+
+extern "C" int tt_kv_repack_heads(const void* k16, const void* v16, long long ldkv, void* k_out,
+                                  void* v_out, int S, int B, int H, int D, void* stream) {
+  TT_REQUIRE(k16 && v16 && k_out && v_out, "tt_kv_repack_heads: null pointer");
+  TT_REQUIRE(D == TC_D && ldkv % 8 == 0, "tt_kv_repack_heads: head_dim must be %d, ldkv a multiple of 8", TC_D);
+  const long long total = static_cast<long long>(S) * B * H * 8;
+  if (total <= 0) return TT_OK;
+  long long g = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  launch_k(kv_repack_heads_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, (cudaStream_t)stream,
+           reinterpret_cast<const __nv_bfloat16*>(k16), reinterpret_cast<const __nv_bfloat16*>(v16), ldkv,
+           reinterpret_cast<__nv_bfloat16*>(k_out), reinterpret_cast<__nv_bfloat16*>(v_out), S, B, H);
+  return check_launch("kv_repack_heads_kernel");
+}
+
+extern "C" int tt_attn_decode_hm(const float* q, const void* k_hm, const void* v_hm, const float* bias_k,
+                                 const float* bias_v, const uint8_t* key_padding_mask, float* out,
+                                 float* lse, int B, int S, int H, int D, long long ldq, long long ldo,
+                                 int zero_row, void* stream) {
+  TT_REQUIRE(q && out && k_hm && v_hm && S > 0, "tt_attn_decode_hm: null pointer / empty cache");
+  TT_REQUIRE(D == TC_D, "tt_attn_decode_hm: head_dim must be %d (got %d)", TC_D, D);
+  TT_REQUIRE((bias_k == nullptr) == (bias_v == nullptr), "tt_attn_decode_hm: bias_k/bias_v mismatch");
+  TT_REQUIRE(ldq % 2 == 0 && ldo % 4 == 0, "tt_attn_decode_hm: ldq must be even, ldo a multiple of 4");
+  if (B <= 0) return TT_OK;
+  AttnArgs a{};
+  a.q = q; a.k = reinterpret_cast<const float*>(k_hm); a.v = reinterpret_cast<const float*>(v_hm);
+  a.bias_k = bias_k; a.bias_v = bias_v; a.mask = key_padding_mask;
+  a.out = out; a.lse = lse; a.T = 1; a.B = B; a.S = S; a.H = H; a.zero_row = zero_row;
+  a.ldq = ldq; a.ldo = ldo; a.ldkv = 0;
+  a.kv_j_stride = TC_D; a.kv_b_stride = static_cast<long long>(H) * S * TC_D;
+  a.kv_h_stride = static_cast<long long>(S) * TC_D;
+  const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+  const int Lp = (L + 3) & ~3;
+  const size_t smem = static_cast<size_t>(DEC_HG) * Lp * sizeof(float);
+  TT_REQUIRE(smem <= 40 * 1024, "tt_attn_decode_hm: key set too long for the decode kernel (L=%d)", L);
+  launch_k(attn_decode_kernel<true>, dim3(B, ceil_div(H, DEC_HG)), dim3(DEC_HG * 32), smem,
+           (cudaStream_t)stream, a, Lp);
+  return check_launch("attn_decode_kernel");
 }

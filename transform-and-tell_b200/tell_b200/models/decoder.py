@@ -127,11 +127,29 @@ class DynamicConvDecoderLayer(DecoderLayer):
         seeds_a = tuple(self._seed(p_att) for _ in range(n))
         slabs = tuple(kv_cache.get(nm + '/slab') if kv_cache is not None else None for nm in names)
         extra = (slabs,) if any(s_ is not None for s_ in slabs) else ()
-        res = Fn.MultiCtxAttentionFn.apply(Q_all, T, B, mhas[0].num_heads, mhas[0].add_zero_attn, p_att,
-                                           seeds_a, need_w, n, *kvs, *[m.bias_k for m in mhas],
-                                           *[m.bias_v for m in mhas], *masks, *extra)
-        A_all = res[0]
-        attns = {nm: w for nm, w in zip(names, res[1:])} if need_w else {}
+        hm = [kv_cache.get(nm + '/hm') if kv_cache is not None else None for nm in names]
+        if T == 1 and not need_w and not torch.is_grad_enabled() and \
+                all(h_ is not None or kv is None for h_, kv in zip(hm, kvs)) and any(h_ is not None for h_ in hm):
+            # incremental decoding over the head-major K|V cache (built once by the generate loop)
+            A_all = torch.empty_like(Q_all)
+            for c, (mha, kv) in enumerate(zip(mhas, kvs)):
+                sl = slice(c * E_, (c + 1) * E_)
+                bk = mha.bias_k.view(-1) if mha.bias_k is not None else None
+                bv = mha.bias_v.view(-1) if mha.bias_v is not None else None
+                if kv is None:        # empty context: only the bias / zero rows
+                    ops.attn_fwd(Q_all[:, sl], None, None, bk, bv, None, 1, B, 0, mha.num_heads,
+                                 mha.head_dim, mha.add_zero_attn, tc=True, out=A_all[:, sl])
+                else:
+                    ops.attn_decode_hm(Q_all[:, sl], hm[c][0], hm[c][1], bk, bv, masks[c], A_all[:, sl],
+                                       mha.add_zero_attn)
+            attns = {}
+        else:
+            res = Fn.MultiCtxAttentionFn.apply(Q_all, T, B, mhas[0].num_heads, mhas[0].add_zero_attn,
+                                               p_att, seeds_a, need_w, n, *kvs,
+                                               *[m.bias_k for m in mhas], *[m.bias_v for m in mhas],
+                                               *masks, *extra)
+            A_all = res[0]
+            attns = {nm: w for nm, w in zip(names, res[1:])} if need_w else {}
         hs = Fn.FusedOutProjFn.apply(A_all, n, *[m.out_proj.weight for m in mhas],
                                      *[m.out_proj.bias for m in mhas])
         lns = [self.context_attn_lns[nm] for nm in names]
@@ -277,6 +295,29 @@ class _DynamicConvDecoderBase(Decoder):
                 if slab is not None:
                     caches[l][nm + '/slab'] = (slab, l)
 
+    def build_decode_cache(self, incremental_state):
+        """After the first incremental step: repack every projected context of every layer from the
+        token-major [S*B, 2E] bf16 views into head-major K, V [B,H,S,64] (tt_kv_repack_heads).  Returns
+        the number of caches built (0 when keys|values are not bf16 / head_dim is not 64)."""
+        caches = incremental_state.get(_KV_KEY) if incremental_state is not None else None
+        if not caches:
+            return 0
+        built = 0
+        for layer, cache in zip(self.layers, caches):
+            for nm in layer.context_names:
+                kv = cache.get(nm)
+                mha = layer.context_attns[nm]
+                if kv is None or kv.dtype != torch.bfloat16 or mha.head_dim != 64 or nm + '/hm' in cache:
+                    continue
+                E = mha.embed_dim
+                B = cache['/B']
+                S = kv.shape[0] // B
+                if (S + 2) * 8 * 4 > 40 * 1024:          # key set beyond the decode kernel's budget
+                    continue
+                cache[nm + '/hm'] = ops.kv_repack_heads(kv[:, :E], kv[:, E:], S, B, mha.num_heads, 64)
+                built += 1
+        return built
+
     def _forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
         X2, ids = self.embedder.embed_tbc(prev_target, incremental_state)
         B, T = ids.shape
@@ -289,6 +330,8 @@ class _DynamicConvDecoderBase(Decoder):
             caches = incremental_state.setdefault(_KV_KEY, [dict() for _ in self.layers])
         else:
             caches = [dict() for _ in self.layers]
+        for c_ in caches:
+            c_['/B'] = B
         if self.batch_kv_layers and not use_layers:
             self._project_contexts_all_layers(contexts, caches)
         for i, layer in enumerate(self.layers):

@@ -327,6 +327,26 @@ def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k,
               c_int(1 if zero_row else 0), c_float(p), _ull(seed), _stream())
 
 
+def kv_repack_heads(k, v, S, B, H, D):
+    """Token-major bf16 k, v views ([S*B, H*D], shared row stride) -> head-major K, V [B,H,S,D]."""
+    _check_cuda(k, v)
+    assert k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and k.stride(0) == v.stride(0)
+    ko = torch.empty((B, H, S, D), dtype=torch.bfloat16, device=k.device)
+    vo = torch.empty_like(ko)
+    _lib.call('tt_kv_repack_heads', _ptr(k), _ptr(v), c_ll(k.stride(0)), _ptr(ko), _ptr(vo), c_int(S),
+              c_int(B), c_int(H), c_int(D), _stream())
+    return ko, vo
+
+
+def attn_decode_hm(q, k_hm, v_hm, bias_k, bias_v, mask, out, zero_row=True):
+    """T = 1 attention over the head-major decode cache; q/out are [B, H*D] views (row-strided)."""
+    B, H, S, D = k_hm.shape
+    _lib.call('tt_attn_decode_hm', _ptr(q), _ptr(k_hm), _ptr(v_hm), _ptr(bias_k), _ptr(bias_v),
+              _ptr(mask), _ptr(out), _ptr(None), c_int(B), c_int(S), c_int(H), c_int(D),
+              c_ll(q.stride(0)), c_ll(out.stride(0)), c_int(1 if zero_row else 0), _stream())
+    return out
+
+
 def attn_avg_weights(q, k, bias_k, mask, lse, T, B, S, H, D, zero_row=True):
     L = S + (1 if bias_k is not None else 0) + (1 if zero_row else 0)
     w = torch.zeros((B, T, L), dtype=torch.float32, device=q.device)
