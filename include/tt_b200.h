@@ -359,6 +359,11 @@ int tt_varlen_prepare(const long long* ids, int B, int S, int pad, int* inv_map,
                       void* stream);
 int tt_flash_self_attn_varlen(const void* qkv, const int* cu_seqlens, void* out, int B, int S_max,
                               int H, int D, void* stream);
+/* The same self-attention on tcgen05 tensor cores (TMEM accumulators, TMA tiles straight out of the
+ * qkv matrix, flash_tc5.cu).  `rows` = allocated rows of qkv/out (>= cu_seqlens[B]); rows of qkv
+ * beyond cu_seqlens[B] must hold finite values (masked keys still enter P.V with weight 0). */
+int tt_flash_self_attn_varlen_tc5(const void* qkv, const int* cu_seqlens, void* out, int B, int S_max,
+                                  int H, int D, long long rows, void* stream);
 int tt_ln_fwd16_varlen(const void* x, int x_bf16, int x_packed, const float* gamma, const float* beta,
                        void* y_packed, void* y_padded, const int* inv_map, const int* count_ptr,
                        int R, int E, float eps, void* stream);

@@ -494,3 +494,34 @@ def test_layernorm_bf16_out(N, E):
     got = out.float().cpu()
     assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6
     assert torch.equal(got[zero.bool()], torch.zeros_like(got[zero.bool()]))
+
+
+@pytest.mark.parametrize('lens', [[512, 300, 1, 129, 128, 257], [37], [512] * 3])
+def test_flash_attention_tcgen05_matches_fp32(lens):
+    """RoBERTa self-attention on the packed layout: the tcgen05/TMEM kernel (flash_tc5.cu) and the
+    mma.sync kernel against an fp32 softmax(QK^T)V per sample.  Tolerance: bf16 probabilities and
+    bf16 output, 2e-2 of the largest output.  Rows beyond the packed count hold finite junk."""
+    from tell_b200 import ops
+    torch.manual_seed(len(lens))
+    H, D = 16, 64
+    E = H * D
+    B, S = len(lens), 512
+    n = sum(lens)
+    R = B * S
+    qkv = torch.randn(R, 3 * E) * 0.7
+    qkv[:, :E] *= D ** -0.5
+    qkv16 = qkv.to(torch.bfloat16)
+    cu = torch.cat([torch.zeros(1, dtype=torch.long), torch.tensor(lens).cumsum(0)]).int()
+    want = torch.zeros(n, E)
+    x = qkv16.float()
+    for b in range(B):
+        r0, r1 = int(cu[b]), int(cu[b + 1])
+        q = x[r0:r1, :E].view(-1, H, D).transpose(0, 1)
+        k = x[r0:r1, E:2 * E].view(-1, H, D).transpose(0, 1)
+        v = x[r0:r1, 2 * E:].view(-1, H, D).transpose(0, 1)
+        p = torch.softmax(q @ k.transpose(1, 2), dim=-1)
+        want[r0:r1] = (p @ v).transpose(0, 1).reshape(-1, E)
+    for tc5 in (False, True):
+        got = ops.flash_self_attn_varlen(qkv16.cuda(), cu.cuda(), B, S, H, D, tc5=tc5)[:n].float().cpu()
+        err = (got - want).abs().max().item()
+        assert err < 2e-2 * want.abs().max().item(), (tc5, err)

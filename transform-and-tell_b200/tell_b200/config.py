@@ -8,6 +8,7 @@ precision
               error, used for the "fp32 logits within 1e-3 / token-exact greedy" parity gate.
 """
 import itertools
+import os
 
 import torch
 
@@ -15,6 +16,8 @@ precision = 'bf16'
 # weight gradients on a second stream (functional.wgrad); opt-in, throughput mode only
 # projected keys|values of the cross-attentions (and dL/dk, dL/dv) as bf16 in HBM (throughput mode)
 kv_bf16 = True
+# RoBERTa self-attention on tcgen05 tensor cores (flash_tc5.cu) instead of the mma.sync kernel
+flash_tc5 = os.environ.get('TT_FLASH_TC5', '1') == '1'
 # run the ResNet encoder as a parallel stream branch beside RoBERTa in Model.encode()
 encoder_overlap = True
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks

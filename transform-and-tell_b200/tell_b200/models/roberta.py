@@ -144,7 +144,9 @@ class RobertaEncoder(nn.Module):
                             y_padded=hid[0], inv_map=inv_map, x_packed=False)
         tmp = torch.empty((R, E), dtype=torch.bfloat16, device=dev)      # pre-norm residual sums
         x16 = torch.empty((R, E), dtype=torch.bfloat16, device=dev)
-        qkv = torch.empty((R, 3 * E), dtype=torch.bfloat16, device=dev)
+        # zeros: rows beyond the packed token count are masked keys of the last sample, and a masked
+        # key still enters P.V with weight 0 (0 * garbage NaN would poison the row)
+        qkv = torch.zeros((R, 3 * E), dtype=torch.bfloat16, device=dev)
         f = torch.empty((R, se.layers[0].fc1.weight.shape[0]), dtype=torch.bfloat16, device=dev)
         for i, (l, p) in enumerate(zip(se.layers, self._prep)):
             h_in, h_out = h[i & 1], h[(i + 1) & 1]

@@ -547,8 +547,16 @@ def varlen_prepare(ids, pad=1):
     return inv_map, cu
 
 
-def flash_self_attn_varlen(qkv, cu, B, S_max, H, D):
+def flash_self_attn_varlen(qkv, cu, B, S_max, H, D, tc5=None):
+    """Packed self-attention.  tc5 (default config.flash_tc5): the tcgen05/TMEM kernel, which needs
+    finite values in every allocated row of qkv; otherwise the mma.sync kernel."""
+    from . import config
     out = torch.empty((qkv.shape[0], H * D), dtype=torch.bfloat16, device=qkv.device)
+    if config.flash_tc5 if tc5 is None else tc5:
+        assert qkv.is_contiguous() and qkv.shape[1] == 3 * H * D
+        _lib.call('tt_flash_self_attn_varlen_tc5', _ptr(qkv), _ptr(cu), _ptr(out), c_int(B),
+                  c_int(S_max), c_int(H), c_int(D), c_ll(qkv.shape[0]), _stream())
+        return out
     _lib.call('tt_flash_self_attn_varlen', _ptr(qkv), _ptr(cu), _ptr(out), c_int(B), c_int(S_max),
               c_int(H), c_int(D), _stream())
     return out
