@@ -40,30 +40,41 @@ __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
     reinterpret_cast<uint4*>(out)[i] = v;
   }
 }
-// First layer: NCHW fp32 image, scalar path (C = 3).  K index = (kh*KW + kw)*C + c.
+// First layer: NCHW fp32 image (C = 3).  K index = (kh*KW + kw)*C + c.  One thread builds 8
+// consecutive k of one output pixel (a 16-byte store); the gathers hit the L1/L2-resident image.
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                        int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
                                        int stride, int pad, int Kp) {
   pdl_prologue();
-  const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
+  const int chunks = Kp >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * chunks;
   const int K = KH * KW * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % Kp);
-    const long long row = i / Kp;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % C, tap = k / C;
-      const int kh = tap / KW, kw = tap - kh * KW;
-      const int wo = static_cast<int>(row % Wo);
-      const long long t = row / Wo;
-      const int ho = static_cast<int>(t % Ho);
-      const int b = static_cast<int>(t / Ho);
-      const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-        v = __ldg(in + ((static_cast<long long>(b) * C + c) * H + hi) * W + wi);
+    const int ch = static_cast<int>(i % chunks);
+    const long long row = i / chunks;
+    const int wo = static_cast<int>(row % Wo);
+    const long long t = row / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = ch * 8 + e;
+      v[e] = 0.f;
+      if (k < K) {
+        const int c = k % C, tap = k / C;
+        const int kh = tap / KW, kw = tap - kh * KW;
+        const int hi = h0 + kh, wi = w0 + kw;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+          v[e] = __ldg(in + ((static_cast<long long>(b) * C + c) * H + hi) * W + wi);
+      }
     }
-    out[i] = __float2bfloat16_rn(v);
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[i] = u;
   }
 }
 
@@ -531,9 +542,9 @@ extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, in
 extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int W, int C, int KH,
                                   int KW, int stride, int pad, int Kp, void* stream) {
   TT_REQUIRE(in && out, "tt_im2col_nchw_f32: null pointer");
-  TT_REQUIRE(Kp >= KH * KW * C, "tt_im2col_nchw_f32: Kp too small");
+  TT_REQUIRE(Kp >= KH * KW * C && Kp % 8 == 0, "tt_im2col_nchw_f32: Kp must cover KH*KW*C and be a multiple of 8");
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * Kp;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
   if (total <= 0) return TT_OK;
   launch_k(im2col_nchw_f32_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
       in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);

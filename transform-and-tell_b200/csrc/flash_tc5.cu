@@ -33,6 +33,31 @@ constexpr int FT_OFF_BAR = 6 * FT_TILE;              // barriers + TMEM slot
 constexpr int FT_SMEM = 6 * FT_TILE + 64 + 1024 + 1024;   // + barriers, row exchange, alignment slack
 constexpr int FT_TMEM_COLS = 256;                    // S: 128, PV: 64 (power of two >= 192)
 
+// Barrier wait that parks in hardware: try_wait with a suspend-time hint instead of a tight poll
+// loop, so the waiting lanes of one CTA do not take issue slots from the other CTA's softmax.
+__device__ __forceinline__ void ft_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if ((clock64() - t0) > 4000000000LL) __trap();     // protocol bug -> trapped kernel, never a hang
+  }
+}
+__device__ __forceinline__ void ft_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) ft_wait(bar, parity);
+  __syncwarp();
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {     // ex2.approx.ftz(-inf) = +0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -131,8 +156,8 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   };
 
   if (threadIdx.x == 0) {
-    mbar_wait(bar_q, 0);
-    mbar_wait(bar_k, 0);
+    ft_wait(bar_q, 0);
+    ft_wait(bar_k, 0);
     tcgen05_fence_after();
     issue_s();
   }
@@ -141,7 +166,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   //   PV(t-1) is collected in the middle of tile t, PV(t) is issued at its end.
   for (int t = 0; t < ntiles; ++t) {
     const uint32_t ph = t & 1;               // phase of the once-per-tile barriers
-    mbar_wait_warp(bar_s, ph);
+    ft_wait_warp(bar_s, ph);
     tcgen05_fence_after();
     if (threadIdx.x == 0 && t + 1 < ntiles) {          // S(t) retired: the K buffer is free
       mbar_arrive_expect_tx(bar_k, FT_TILE);
@@ -167,14 +192,14 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     tcgen05_fence_before();
     __syncthreads();                         // every thread holds S(t): the S columns are free
     if (threadIdx.x == 0 && t + 1 < ntiles) {
-      mbar_wait(bar_k, ph ^ 1);              // K(t+1) landed
+      ft_wait(bar_k, ph ^ 1);              // K(t+1) landed
       tcgen05_fence_after();
       issue_s();
     }
     const float mn = fmaxf(m, fmaxf(tm, xch[(half ^ 1) * 128 + r]) * LOG2E);   // finite: key 0 of
     const float alpha = ex2_approx(m - mn);                                     // the tile is valid
     if (t > 0) {                             // collect PV(t-1) (o is still in the scale of m_{t-1})
-      mbar_wait_warp(bar_pv, ph ^ 1);
+      ft_wait_warp(bar_pv, ph ^ 1);
       tcgen05_fence_after();
       add_pv();
       if (threadIdx.x == 0 && t + 1 < ntiles) {        // PV(t-1) retired: its V buffer takes V(t+1)
@@ -210,7 +235,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     __syncthreads();
     // ---- PV(t) = P . V(t), collected during the next tile (or after the loop)
     if (threadIdx.x == 0) {
-      mbar_wait(&bar_v[t & 1], (t >> 1) & 1);
+      ft_wait(&bar_v[t & 1], (t >> 1) & 1);
       tcgen05_fence_after();
       const uint64_t dv = dv0 + static_cast<uint64_t>(((t & 1) * FT_TILE) >> 4);
 #pragma unroll
@@ -221,7 +246,7 @@ flash_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       umma_commit(bar_pv);
     }
   }
-  mbar_wait_warp(bar_pv, (ntiles - 1) & 1);
+  ft_wait_warp(bar_pv, (ntiles - 1) & 1);
   tcgen05_fence_after();
   add_pv();
   // ---- epilogue: the two threads of a row add their partial sums, each writes its 32 dims
