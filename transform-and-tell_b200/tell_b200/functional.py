@@ -28,6 +28,14 @@ def _c(x):
     return x if x.is_contiguous() else x.contiguous()
 
 
+# Gradients of tied matrices produced earlier in the running backward (AdaptiveLossFn: the adaptive
+# softmax shares its word matrices with the adaptive input embedding, tie_adaptive_weights).  A later
+# backward node that contributes to the same parameter (EmbedFn) accumulates INTO that tensor and
+# returns None instead of materialising a second dense gradient that autograd would then have to
+# zero-fill and add (206 MB of fills + 600 MB of add traffic per step for the 50265 x 1024 tables).
+_TIED_GRADS = {}
+
+
 class _WGradState:
     stream = None      # the weight-gradient stream of this process
     main = None        # stream the running backward was forked from
@@ -761,9 +769,19 @@ class EmbedFn(Function):
                             out=dA[:, i * E:(i + 1) * E], alpha=scale)
                 dprojs.append(ops.gemm_tn(d16T, operand(A[:, i * E:(i + 1) * E], 'b', transpose=True),
                                           alpha=scale))
-        dtables = [torch.zeros_like(t) for t in tables]
+        dtables, ret = [], []
+        for t in tables:
+            g = _TIED_GRADS.pop(t.data_ptr(), None)
+            if g is not None and g.shape == t.shape and g.is_contiguous() and g.dtype == torch.float32:
+                dtables.append(g)        # tied: add into the softmax's gradient of the same matrix
+                ret.append(None)
+            else:
+                g = torch.zeros_like(t)
+                dtables.append(g)
+                ret.append(g)
+        _TIED_GRADS.clear()
         ops.embed_scatter_grad(ids, cutoffs, dtables, E, dA, padding_idx=0, tbc=True)
-        return (None,) * 7 + tuple(dtables) + tuple(dprojs)
+        return (None,) * 7 + tuple(ret) + tuple(dprojs)
 
 
 class LayerMixFn(Function):
@@ -809,12 +827,16 @@ class AdaptiveLossFn(Function):
             xg16, proj16 = operand(Xg, 'a'), operand(proj, 'b')
             P = ops.gemm_tn(xg16, proj16, m_limit=cnt)
             p16, words16 = operand(P, 'a'), operand(words, 'b')
-            logits = ops.gemm_tn(p16, words16, m_limit=cnt)
+            # rows >= cnt of the logits are never read (ce_fwd stops at cnt, ce_bwd zeroes them):
+            # no zero fill of the [N, V_tail] buffer
+            logits = ops.gemm_tn(p16, words16, m_limit=cnt,
+                                 out=torch.empty((N, words.shape[0]), dtype=torch.float32, device=X.device))
             lse, _ = ops.ce_fwd(logits, tail_local[i], cnt, pad_idx, row_loss[i + 1])
             saved_tail += ([xg16, p16, proj16, words16, logits, lse] if fast
                            else [Xg, P, proj, words, logits, lse])
         loss, scale = ops.loss_finalize(row_loss, ntok)
         ctx.cfg = (cutoffs, pad_idx, nt, fast)
+        ctx.tied_ptrs = (word0.data_ptr(),) + tuple(tails[2 * i + 1].data_ptr() for i in range(nt))
         head_saved = (x16, hw16) if fast else (X, word0, class_proj)
         ctx.n_head = len(head_saved)
         ctx.save_for_backward(*head_saved, head_logits, head_lse, head_t, tail_idx, tail_local,
@@ -862,4 +884,8 @@ class AdaptiveLossFn(Function):
                 dproj = ops.gemm_tn(operand(dP, 'a', transpose=True), operand(Xg, 'b', transpose=True))
             ops.scatter_add_rows(dXg, tail_idx[i], dX, cnt)
             dtails += [dproj, dwords]
+        _TIED_GRADS.clear()
+        _TIED_GRADS[ctx.tied_ptrs[0]] = dW_head[:c0]
+        for i in range(nt):
+            _TIED_GRADS[ctx.tied_ptrs[1 + i]] = dtails[2 * i + 1]
         return (dX, None, None, None, dW_head[:c0], dW_head[c0:]) + tuple(dtails)
