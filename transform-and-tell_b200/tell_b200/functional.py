@@ -299,6 +299,43 @@ class AllLayerKVProjFn(Function):
         return (dx, None, None, None) + dwk + dwv + dbs
 
 
+class InProjSplitFn(Function):
+    """in_proj_weight [3E,E] -> (Wq, Wk, Wv) and in_proj_bias [3E] -> (bq, bk|bv) as views
+    (multi_head.py:491-518 slices them per projection).  Done with plain autograd slicing every
+    slice costs a zero-filled full-size gradient, a copy and an add (SliceBackward + accumulation:
+    ~100 tiny launches per step for the 16 attention modules); here the backward assembles each
+    parameter's gradient with ONE concatenation."""
+
+    @staticmethod
+    def forward(ctx, w, b, E):
+        outs = []
+        if w is not None:
+            outs += [w[:E], w[E:2 * E], w[2 * E:]]
+        if b is not None:
+            outs += [b[:E], b[E:]]
+        ctx.cfg = (w is not None, b is not None, E)
+        ctx.meta = (w.shape[1] if w is not None else 0, (w if w is not None else b).device)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        has_w, has_b, E = ctx.cfg
+        K, dev = ctx.meta
+        dw = db = None
+        i = 0
+        if has_w:
+            parts = [g if g is not None else torch.zeros((E, K), dtype=torch.float32, device=dev)
+                     for g in grads[0:3]]
+            dw = torch.cat(parts, 0)
+            i = 3
+        if has_b:
+            sizes = (E, 2 * E)
+            parts = [g.reshape(-1) if g is not None else torch.zeros(n, dtype=torch.float32, device=dev)
+                     for g, n in zip(grads[i:i + 2], sizes)]
+            db = torch.cat(parts, 0)
+        return dw, db, None
+
+
 class WeightNormFn(Function):
     """w = g * v / ||v||_row  (nn.utils.weight_norm dim=0; linear.py:30-34)."""
 

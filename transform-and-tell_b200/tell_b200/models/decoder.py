@@ -121,7 +121,7 @@ class DynamicConvDecoderLayer(DecoderLayer):
             masks.append(m.to(torch.uint8).contiguous() if (m is not None and kv is not None) else None)
         E_ = self.embed_dim
         q_ws = [mha._weights()[0] for mha in mhas]
-        q_bs = [mha.in_proj_bias[:E_] if mha.in_proj_bias is not None else None for mha in mhas]
+        q_bs = [mha._bias_q() for mha in mhas]
         Q_all = Fn.FusedQProjFn.apply(X2, mhas[0].scaling, n, *q_ws, *q_bs)
         p_att = self._p(mhas[0].dropout)
         seeds_a = tuple(self._seed(p_att) for _ in range(n))
@@ -282,7 +282,7 @@ class _DynamicConvDecoderBase(Decoder):
             mhas = [layer.context_attns[nm] for layer in self.layers]
             ws = [m._weights() for m in mhas]
             E = mhas[0].embed_dim
-            biases = [m.in_proj_bias[E:] if m.in_proj_bias is not None else None for m in mhas]
+            biases = [m._bias_kv() for m in mhas]
             need_w = (not self.training) and any(layer.need_attn for layer in self.layers)
             kv16 = Fn.kv16_ok(mhas[0].head_dim, need_w)
             slab = Fn.GradSlab(S * B, 2 * E, L, key.device,
@@ -319,6 +319,9 @@ class _DynamicConvDecoderBase(Decoder):
         return built
 
     def _forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
+        for layer in self.layers:            # parameter splits belong to one forward's autograd graph
+            for mha in layer.context_attns.values():
+                mha.begin_step()
         X2, ids = self.embedder.embed_tbc(prev_target, incremental_state)
         B, T = ids.shape
         p = self.dropout if self.training else 0.0

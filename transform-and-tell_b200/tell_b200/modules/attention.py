@@ -48,16 +48,44 @@ class MultiHeadAttention(nn.Module):
         self.add_zero_attn = add_zero_attn
 
     # -- projections (multi_head.py:491-518)
-    def _weights(self):
+    def begin_step(self):
+        """Forget the parameter split of the previous forward (it belongs to that autograd graph)."""
+        self._split = None
+
+    def _splits(self):
+        """(Wq, Wk, Wv, bq, bkv).  With autograd on, the slices of in_proj_weight / in_proj_bias come
+        from ONE InProjSplitFn node per forward (see functional.InProjSplitFn)."""
         E = self.embed_dim
-        if self.qkv_same_dim:
-            w = self.in_proj_weight
-            return w[:E], w[E:2 * E], w[2 * E:]
-        return self.q_proj_weight, self.k_proj_weight, self.v_proj_weight
+        w = self.in_proj_weight if self.qkv_same_dim else None
+        b = self.in_proj_bias
+        need = torch.is_grad_enabled() and ((w is not None and w.requires_grad) or
+                                            (b is not None and b.requires_grad))
+        if not need:
+            ws = (w[:E], w[E:2 * E], w[2 * E:]) if w is not None else \
+                (self.q_proj_weight, self.k_proj_weight, self.v_proj_weight)
+            return ws + ((b[:E], b[E:]) if b is not None else (None, None))
+        sp = getattr(self, '_split', None)
+        if sp is None:
+            outs = list(Fn.InProjSplitFn.apply(w, b, E))
+            ws = tuple(outs[:3]) if w is not None else \
+                (self.q_proj_weight, self.k_proj_weight, self.v_proj_weight)
+            bs = tuple(outs[-2:]) if b is not None else (None, None)
+            sp = ws + bs
+            object.__setattr__(self, '_split', sp)
+        return sp
+
+    def _weights(self):
+        return self._splits()[:3]
+
+    def _bias_q(self):
+        return self._splits()[3]
+
+    def _bias_kv(self):
+        return self._splits()[4]
 
     def project_q(self, query2d):
         wq = self._weights()[0]
-        bq = self.in_proj_bias[:self.embed_dim] if self.in_proj_bias is not None else None
+        bq = self._bias_q()
         return Fn.LinearFn.apply(query2d, wq, bq, self.scaling)      # q *= scaling (:353)
 
     def project_kv(self, key, need_weights=True):
@@ -66,7 +94,7 @@ class MultiHeadAttention(nn.Module):
         if key.shape[2] == 0 or key.shape[0] == 0:
             return None
         _, wk, wv = self._weights()
-        bkv = self.in_proj_bias[self.embed_dim:] if self.in_proj_bias is not None else None
+        bkv = self._bias_kv()
         S, B, kd = key.shape
         return Fn.KVProjFn.apply(key.reshape(S * B, kd), wk, wv, bkv,
                                  Fn.kv16_ok(self.head_dim, need_weights))
@@ -91,6 +119,7 @@ class MultiHeadAttention(nn.Module):
         Returns (attn [T,B,E], head-averaged weights [B,T,S+2] or None)."""
         T, B, E = query.shape
         assert E == self.embed_dim
+        self.begin_step()
         if incremental_state is not None or attn_mask is not None:
             raise NotImplementedError('only the static_kv cross-attention mode of the decoder '
                                       '(incremental_state=None, attn_mask=None) is implemented')
