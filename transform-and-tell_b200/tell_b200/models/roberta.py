@@ -73,6 +73,7 @@ class RobertaEncoder(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._prep = None
+        object.__setattr__(self, '_qkv_key', None)
         return super()._apply(fn, *a, **k)
 
     def prepare(self):
@@ -146,7 +147,17 @@ class RobertaEncoder(nn.Module):
         x16 = torch.empty((R, E), dtype=torch.bfloat16, device=dev)
         # zeros: rows beyond the packed token count are masked keys of the last sample, and a masked
         # key still enters P.V with weight 0 (0 * garbage NaN would poison the row)
-        qkv = torch.zeros((R, 3 * E), dtype=torch.bfloat16, device=dev)
+        # persistent: zero-filled once, afterwards every row only ever holds finite GEMM outputs, so
+        # the step does not pay a 50 MB memset (callers on two streams must not share one encoder)
+        key = (R, str(dev))
+        if getattr(self, '_qkv_key', None) == key:
+            qkv = self._qkv_buf
+        elif torch.cuda.is_current_stream_capturing():
+            qkv = torch.zeros((R, 3 * E), dtype=torch.bfloat16, device=dev)   # graph-private, not kept
+        else:
+            qkv = torch.zeros((R, 3 * E), dtype=torch.bfloat16, device=dev)
+            object.__setattr__(self, '_qkv_buf', qkv)
+            object.__setattr__(self, '_qkv_key', key)
         f = torch.empty((R, se.layers[0].fc1.weight.shape[0]), dtype=torch.bfloat16, device=dev)
         for i, (l, p) in enumerate(zip(se.layers, self._prep)):
             h_in, h_out = h[i & 1], h[(i + 1) & 1]

@@ -40,7 +40,7 @@ def cast_bf16(x, transpose=False, split=0, out=None, seg_stride=0):
         ld = (shape[1] + 7) // 8 * 8
         buf = torch.empty((shape[0], ld), dtype=torch.bfloat16, device=x.device)
         if ld != shape[1]:
-            buf.zero_()
+            buf[:, shape[1]:].zero_()      # only the pad columns (outside every TMA extent anyway)
         out = buf[:, :shape[1]]
     _lib.call('tt_cast_bf16', _ptr(x), c_ll(x.stride(0)), _ptr(out), c_ll(out.stride(0)),
               c_int(rows), c_int(cols), c_int(1 if transpose else 0), c_int(split),
