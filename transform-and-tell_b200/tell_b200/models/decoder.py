@@ -117,8 +117,10 @@ class DynamicConvDecoderLayer(DecoderLayer):
                 if kv_cache is not None:
                     kv_cache[nm] = kv
             kvs.append(kv)
-            m = contexts[nm + '_mask']
-            masks.append(m.to(torch.uint8).contiguous() if (m is not None and kv is not None) else None)
+            m = contexts.get(nm + '_mask/u8')      # converted once per forward by the decoder
+            if m is None and contexts[nm + '_mask'] is not None:
+                m = contexts[nm + '_mask'].to(torch.uint8).contiguous()
+            masks.append(m if kv is not None else None)
         E_ = self.embed_dim
         q_ws = [mha._weights()[0] for mha in mhas]
         q_bs = [mha._bias_q() for mha in mhas]
@@ -335,6 +337,11 @@ class _DynamicConvDecoderBase(Decoder):
             caches = [dict() for _ in self.layers]
         for c_ in caches:
             c_['/B'] = B
+        contexts = dict(contexts)            # key-padding masks as uint8, once for all layers
+        for nm in self.layers[0].context_names:
+            m = contexts.get(nm + '_mask')
+            if m is not None and nm + '_mask/u8' not in contexts:
+                contexts[nm + '_mask/u8'] = m.to(torch.uint8).contiguous()
         if self.batch_kv_layers and not use_layers:
             self._project_contexts_all_layers(contexts, caches)
         for i, layer in enumerate(self.layers):
