@@ -82,6 +82,9 @@ typedef struct {
    * consume the forward's operands in place instead of materialising transposes. */
   int trans_a;
   int trans_b;
+  /* Host-side estimate of *m_limit (0 = unknown).  Scheduling hint only: it picks the tile shape
+   * whose tile count quantises best into waves of the machine; results never depend on it. */
+  int m_hint;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
 /* Debug hook: when non-NULL, every CTA of the 1-CTA GEMM kernel writes 8 %globaltimer stamps (

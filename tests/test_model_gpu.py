@@ -95,7 +95,7 @@ class _StubRoberta(torch.nn.Module):
         super().__init__()
         self.h, self.n_layers = hid, n_layers
 
-    def all_hiddens(self, ids):
+    def all_hiddens(self, ids, n_real_tokens=0):
         return self.h, (ids == 1).to(torch.uint8).view(-1)
 
 

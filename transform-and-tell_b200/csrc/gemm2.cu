@@ -296,6 +296,16 @@ int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream) {
   if (p->N >= 256 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 256) >= pairs_max) bn = 256;
   else if (p->N >= 128 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 128) >= pairs_max) bn = 128;
   if (bn == 0) return 0;
+  if (bn == 256 && p->m_limit != nullptr && p->m_hint > 0 && p->m_hint < p->M) {
+    // Row-limited problem (packed RoBERTa batch): the host's estimate of the row count tells how
+    // the tiles quantise into waves of 74 CTA pairs.  128-wide tiles run ~15 % below 256-wide ones
+    // per FLOP (measured), so they are chosen only when they save more than that in idle waves:
+    // 5957 x 1024 is 96 wide tiles = 2 waves (second one 30 % full) but 192 narrow tiles = 3 waves.
+    const int mt = ceil_div(p->m_hint, 2 * BM);
+    const double cost256 = static_cast<double>(ceil_div(mt * ceil_div(p->N, 256), pairs_max)) * 256.0;
+    const double cost128 = static_cast<double>(ceil_div(mt * ceil_div(p->N, 128), pairs_max)) * 128.0 * 1.15;
+    if (cost128 < cost256) bn = 128;
+  }
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("TT_GEMM2_BN");     // experiments: force the pair kernel's tile width

@@ -96,13 +96,15 @@ class RobertaEncoder(nn.Module):
         return self
 
     @torch.no_grad()
-    def all_hiddens(self, ids):
+    def all_hiddens(self, ids, n_real_tokens=0):
         """ids [B,S] int64 -> (bf16 [L+1, B*S, E], key padding mask uint8 [B*S]).
-        With `varlen` the rows of padding tokens are zero instead of the encoder's values there."""
+        With `varlen` the rows of padding tokens are zero instead of the encoder's values there.
+        n_real_tokens: optional host-side count of non-padding tokens (the data loader knows it);
+        a GEMM tile-scheduling hint only."""
         if self._prep is None:
             self.prepare()
         if self.varlen:
-            return self._all_hiddens_packed(ids)
+            return self._all_hiddens_packed(ids, int(n_real_tokens))
         se = self.decoder.sentence_encoder
         B, S = ids.shape
         E, H = self.embed_dim, self.heads
@@ -124,7 +126,7 @@ class RobertaEncoder(nn.Module):
             ops.ln_fwd16(tmp, l.final_layer_norm.weight, l.final_layer_norm.bias, hid[i + 1])
         return hid, is_pad
 
-    def _all_hiddens_packed(self, ids):
+    def _all_hiddens_packed(self, ids, hint=0):
         """Variable-length forward: row counts are device values (cu_seqlens[B] is the m_limit of
         every GEMM), so there is no host sync and the whole thing captures into a CUDA graph; the
         buffers are sized for the padded batch."""
@@ -161,16 +163,16 @@ class RobertaEncoder(nn.Module):
         f = torch.empty((R, se.layers[0].fc1.weight.shape[0]), dtype=torch.bfloat16, device=dev)
         for i, (l, p) in enumerate(zip(se.layers, self._prep)):
             h_in, h_out = h[i & 1], h[(i + 1) & 1]
-            ops.gemm_tn(h_in, p['wqkv'], out16=qkv, bias=p['bqkv'], want32=False, m_limit=ntok)
+            ops.gemm_tn(h_in, p['wqkv'], out16=qkv, bias=p['bqkv'], want32=False, m_limit=ntok, m_hint=hint)
             a = ops.flash_self_attn_varlen(qkv, cu, B, S, H, E // H)
             ops.gemm_tn(a, p['wo'], out16=tmp, bias=p['bo'], residual16=h_in, want32=False,
-                        m_limit=ntok)
+                        m_limit=ntok, m_hint=hint)
             ops.ln_fwd16_varlen(tmp, l.self_attn_layer_norm.weight, l.self_attn_layer_norm.bias,
                                 y_packed=x16, count=ntok)
             ops.gemm_tn(x16, p['w1'], out16=f, bias=p['b1'], act=ops.ACT_GELU, want32=False,
-                        m_limit=ntok)
+                        m_limit=ntok, m_hint=hint)
             ops.gemm_tn(f, p['w2'], out16=tmp, bias=p['b2'], residual16=x16, want32=False,
-                        m_limit=ntok)
+                        m_limit=ntok, m_hint=hint)
             ops.ln_fwd16_varlen(tmp, l.final_layer_norm.weight, l.final_layer_norm.bias,
                                 y_packed=h_out, y_padded=hid[i + 1], inv_map=inv_map)
         return hid, is_pad

@@ -78,7 +78,7 @@ class _CaptionModelBase(Model):
 
     # ------------------------------------------------------------------ frozen encoders
     @torch.no_grad()
-    def encode(self, context, image):
+    def encode(self, context, image, n_real_tokens=0):
         """The gradient-free part of _forward (:332, :352-353): ResNet features (NHWC bf16) and all
         RoBERTa hidden states (bf16 [L+1, B*S, E]).  It depends on no trainable weight, so a
         data-parallel trainer may run it for step i+1 while step i's gradient all-reduce is still
@@ -91,11 +91,11 @@ class _CaptionModelBase(Model):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 feats = self.resnet.features_nhwc(image)
-            hid, _ = self.roberta.all_hiddens(context[self.index])
+            hid, _ = self.roberta.all_hiddens(context[self.index], n_real_tokens)
             cur.wait_stream(side)
             return feats, hid
         feats = self.resnet.features_nhwc(image) if self.USES_IMAGE else None
-        hid, _ = self.roberta.all_hiddens(context[self.index])
+        hid, _ = self.roberta.all_hiddens(context[self.index], n_real_tokens)
         return feats, hid
 
     # ------------------------------------------------------------------ _forward (:311-397)
