@@ -61,6 +61,7 @@ def replay_gemm_signatures(sigs, n_prof, dev):
     """Device time of every GEMM of one step: replay each unique signature from a CUDA graph."""
     from tell_b200 import ops
     tot_us, tot_flop, calls = 0.0, 0.0, 0
+    big_us, big_flop, big_calls = 0.0, 0.0, 0      # launches of >= 10 GFLOP (the CTA-pair kernel's diet)
     for key, cnt in sigs.items():
         M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha, hinted = key
         cnt = cnt // n_prof
@@ -102,10 +103,15 @@ def replay_gemm_signatures(sigs, n_prof, dev):
         torch.cuda.synchronize()
         us = s.elapsed_time(e) * 1e3 / 48
         tot_us += us * cnt
-        tot_flop += 2.0 * (min(lim, M) if lim else M) * N * K * cnt
+        flop = 2.0 * (min(lim, M) if lim else M) * N * K
+        tot_flop += flop * cnt
         calls += cnt
+        if flop >= 1e10:
+            big_us += us * cnt
+            big_flop += flop * cnt
+            big_calls += cnt
         del g, A, Bm, kw
-    return tot_us, tot_flop, calls
+    return tot_us, tot_flop, calls, (big_us, big_flop, big_calls)
 
 
 class ClockSampler(threading.Thread):
@@ -416,7 +422,7 @@ def run_b200(args):
         sets.clear()
         model.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
-        gemm_us, gemm_flop, gemm_calls = replay_gemm_signatures(sigs, n_prof, dev)
+        gemm_us, gemm_flop, gemm_calls, big = replay_gemm_signatures(sigs, n_prof, dev)
         peak_tf, peak_bw, src = peaks()
         achieved = gemm_flop / (gemm_us * 1e-6) / 1e12
         roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_kernel (tcgen05.mma + TMA)',
@@ -426,6 +432,10 @@ def run_b200(args):
                 'flop_per_step': gemm_flop, 'device_ms_per_step': round(gemm_us / 1e3, 3),
                 'avg_launch_us': round(gemm_us / max(1, gemm_calls), 2),
                 'share_of_step_kernel_time': round(share, 4),
+                'large_launches': {'min_gflop': 10, 'launches_per_step': big[2],
+                                   'device_ms_per_step': round(big[0] / 1e3, 3),
+                                   'achieved': round(big[1] / max(big[0], 1e-9) / 1e6, 1),
+                                   'frac': round(big[1] / max(big[0], 1e-9) / 1e6 / peak_tf, 4)},
                 'method': 'each unique GEMM signature of the step replayed from a CUDA graph between '
                           'CUDA events; algorithmic FLOP = sum 2*M*N*K with M = the rows actually '
                           'computed (device-side row limits of the packed RoBERTa batch and the '
