@@ -104,6 +104,9 @@ def replay_gemm_signatures(sigs, n_prof, dev):
         us = s.elapsed_time(e) * 1e3 / 48
         tot_us += us * cnt
         flop = 2.0 * (min(lim, M) if lim else M) * N * K
+        if os.environ.get('TT_GEMM_TABLE'):      # per-signature table on stderr (debugging aid)
+            print('gemm M=%-6d N=%-6d K=%-6d ta=%d tb=%d lim=%-5d x%-3d %7.1f us %7.1f TFLOP/s  %6.1f us/step'
+                  % (M, N, K, ta, tb, lim, cnt, us, flop / us / 1e6, us * cnt), file=sys.stderr)
         tot_flop += flop * cnt
         calls += cnt
         if flop >= 1e10:

@@ -113,7 +113,10 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
               }
             }
           }
-          if (g.act != TT_ACT_NONE) {
+          if (g.act == TT_ACT_GELU && g.C == nullptr) {        // bf16-only output: bf16-accurate GELU
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_bf16(v[j]);
+          } else if (g.act != TT_ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
           }
