@@ -63,7 +63,7 @@ def replay_gemm_signatures(sigs, n_prof, dev):
     tot_us, tot_flop, calls = 0.0, 0.0, 0
     big_us, big_flop, big_calls = 0.0, 0.0, 0      # launches of >= 10 GFLOP (the CTA-pair kernel's diet)
     for key, cnt in sigs.items():
-        M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha, hinted = key
+        M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha, hinted, klim = key
         cnt = cnt // n_prof
         if cnt == 0 or M == 0:
             continue
@@ -87,6 +87,8 @@ def replay_gemm_signatures(sigs, n_prof, dev):
         if lim:       # lim = the device-side row count observed in the profiled step
             kw['m_limit'] = torch.tensor([lim], dtype=torch.int32, device=dev)
             kw['m_hint'] = lim if hinted else 0
+        if klim:      # device-side contraction limit observed in the profiled step
+            kw['k_limit'] = torch.tensor([klim], dtype=torch.int32, device=dev)
         for i in range(2):
             ops.gemm_tn(A[i], Bm[i], **kw)
         torch.cuda.synchronize()
@@ -103,7 +105,8 @@ def replay_gemm_signatures(sigs, n_prof, dev):
         torch.cuda.synchronize()
         us = s.elapsed_time(e) * 1e3 / 48
         tot_us += us * cnt
-        flop = 2.0 * (min(lim, M) if lim else M) * N * K
+        k_eff = min(K, (klim + 63) // 64 * 64) if klim else K
+        flop = 2.0 * (min(lim, M) if lim else M) * N * k_eff
         if os.environ.get('TT_GEMM_TABLE'):      # per-signature table on stderr (debugging aid)
             print('gemm M=%-6d N=%-6d K=%-6d ta=%d tb=%d lim=%-5d x%-3d %7.1f us %7.1f TFLOP/s  %6.1f us/step'
                   % (M, N, K, ta, tb, lim, cnt, us, flop / us / 1e6, us * cnt), file=sys.stderr)
@@ -398,7 +401,8 @@ def run_b200(args):
                    kw.get('bias') is not None, kw.get('act', 0), kw.get('residual') is not None,
                    kw.get('residual16') is not None, bool(kw.get('accumulate')),
                    int(kw['m_limit'].item()) if kw.get('m_limit') is not None else 0,
-                   float(kw.get('alpha', 1.0)) != 1.0, bool(kw.get('m_hint', 0)))
+                   float(kw.get('alpha', 1.0)) != 1.0, bool(kw.get('m_hint', 0)),
+                   int(kw['k_limit'].item()) if kw.get('k_limit') is not None else 0)
             sigs[key] = sigs.get(key, 0) + 1
             return orig_gemm(a, b, out=out, out16=out16, **kw)
         ops.gemm_tn = rec_gemm

@@ -85,6 +85,10 @@ typedef struct {
   /* Host-side estimate of *m_limit (0 = unknown).  Scheduling hint only: it picks the tile shape
    * whose tile count quantises best into waves of the machine; results never depend on it. */
   int m_hint;
+  /* Device int, optional: the caller guarantees that both operands are ZERO for contraction
+   * indices k >= *k_limit (e.g. the rows of a gradient beyond a device-side row count), so the
+   * kernel may stop its K loop there (rounded up to whole 64-wide k-blocks, at least one). */
+  const int* k_limit;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
 /* Debug hook: when non-NULL, every CTA of the 1-CTA GEMM kernel writes 8 %globaltimer stamps (

@@ -83,7 +83,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (g.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (g.K + BK - 1) / BK;
+  int Keff = g.K;
+  if (g.k_limit != nullptr) Keff = min(Keff, max(__ldg(g.k_limit), 1));   // >= 1 block: zeros give zeros
+  const int num_k = (Keff + BK - 1) / BK;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -322,6 +324,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.residual16 = reinterpret_cast<const __nv_bfloat16*>(p->residual16); g.ldr16 = p->ldr16;
   g.alpha = p->alpha; g.act = p->act; g.accumulate = p->accumulate;
   g.m_limit = p->m_limit;
+  g.k_limit = p->k_limit;
   bool vec = true;
   if (p->C) vec = vec && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0 && (p->ldc % 4 == 0);
   if (p->C16) vec = vec && (reinterpret_cast<uintptr_t>(p->C16) & 15) == 0 && (p->ldc16 % 8 == 0);

@@ -163,7 +163,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_m = (M + 2 * BM - 1) / (2 * BM);   // 256-row tiles
   const int num_n = (g.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (g.K + BK - 1) / BK;
+  int Keff = g.K;
+  if (g.k_limit != nullptr) Keff = min(Keff, max(__ldg(g.k_limit), 1));
+  const int num_k = (Keff + BK - 1) / BK;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

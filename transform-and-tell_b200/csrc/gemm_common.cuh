@@ -24,6 +24,7 @@ struct GemmArgs {
   int act;
   int accumulate;
   const int* m_limit;
+  const int* k_limit;   // device int, optional: operand rows/cols k >= *k_limit are known to be zero
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
   long long* trace;  // debug: [grid, 8] globaltimer stamps (tt_gemm_set_trace), normally null
 };

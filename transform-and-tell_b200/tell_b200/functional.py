@@ -909,10 +909,12 @@ class AdaptiveLossFn(Function):
             if fast:
                 xg16, p16, proj16, words16 = a0, a1, a2, a3
                 dP = ops.gemm_tn(dl16, words16, m_limit=cnt, trans_b=True)
-                dwords = ops.gemm_tn(dl16, p16, trans_a=True, trans_b=True)
+                # contraction over the cluster's rows: rows >= cnt of dl / dP are zero, so the K loop
+                # stops at the device-side row count (23-120 of the 800 rows for the tail clusters)
+                dwords = ops.gemm_tn(dl16, p16, trans_a=True, trans_b=True, k_limit=cnt)
                 dP16 = operand(dP, 'a')
                 dXg = ops.gemm_tn(dP16, proj16, m_limit=cnt, trans_b=True)
-                dproj = ops.gemm_tn(dP16, xg16, trans_a=True, trans_b=True)
+                dproj = ops.gemm_tn(dP16, xg16, trans_a=True, trans_b=True, k_limit=cnt)
             else:
                 Xg, P, proj, words = a0, a1, a2, a3
                 dP = ops.gemm_tn(dl16, operand(words, 'b', transpose=True), m_limit=cnt)

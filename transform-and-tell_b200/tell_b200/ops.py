@@ -62,7 +62,7 @@ def scalar_mul(a, b):
 
 def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act=ACT_NONE,
             accumulate=False, m_limit=None, want32=True, want16=False, residual16=None,
-            trans_a=False, trans_b=False, m_hint=0):
+            trans_a=False, trans_b=False, m_hint=0, k_limit=None):
     """C[M,N] = act(alpha * (a[M,K] @ b[N,K]^T + bias) + residual), bf16 operands, fp32 accumulate."""
     _check_cuda(a, b, out, out16, bias, residual)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -105,6 +105,9 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
         assert m_limit.dtype == torch.int32
         p.m_limit = m_limit.data_ptr()
         p.m_hint = int(m_hint)
+    if k_limit is not None:      # operands are zero for k >= *k_limit (device int32)
+        assert k_limit.dtype == torch.int32
+        p.k_limit = k_limit.data_ptr()
     if _lib.PROFILE is not None:
         _lib.GEMM_FLOPS.append(0.0 if m_limit is not None else 2.0 * M * N * K)
     _lib.call('tt_gemm_bf16_tn', ctypes.byref(p), _stream())
