@@ -132,3 +132,29 @@ def test_gemm_mn_major_operands(M, N, K, ta, tb):
     ref = a.float() @ b.float().t()
     err = (c - ref).abs().max().item()
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K, ta, tb, err)
+
+
+@pytest.mark.parametrize('M,N,K,lim', [(256, 1024, 4096, 256), (800, 1024, 30265, 23), (130, 256, 2104, 97),
+                                       (800, 1024, 15000, 300)])
+def test_gemm_split_k(M, N, K, lim):
+    """Row-limited, few-tile / long-K problems that carry a row-count hint run as split-K (partials
+    added atomically into a zeroed C): checked against a float64 reference, with bias + residual
+    entering exactly once, and with a device row limit smaller AND larger than the hint."""
+    from tell_b200 import ops
+    torch.manual_seed(K)
+    a32 = (torch.randn(M, K) * 0.1).to(torch.bfloat16).float()
+    a16 = ops.cast_bf16(a32.cuda())                          # row pitch padded to a multiple of 8
+    a = a32
+    w = (torch.randn(K, N) * 0.1).to(torch.bfloat16)        # stored [K, N]: MN-major B (trans_b)
+    bias = torch.randn(N)
+    res = torch.randn(M, N)
+    want = (a.double() @ w.double() + bias.double()) * 0.5 + res.double()
+    kw = {}
+    if lim is not None:
+        kw = dict(m_limit=torch.tensor([lim], dtype=torch.int32, device='cuda'), m_hint=128)
+    out = ops.gemm_tn(a16, w.cuda(), bias=bias.cuda(), residual=res.cuda(), alpha=0.5, trans_b=True, **kw)
+    rows = M if lim is None else lim
+    err = (out[:rows].cpu().double() - want[:rows]).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+    if lim is not None:
+        assert torch.equal(out[lim:].cpu(), torch.zeros(M - lim, N))

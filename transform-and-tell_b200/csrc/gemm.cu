@@ -82,10 +82,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (g.m_limit != nullptr) M = min(M, __ldg(g.m_limit));
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (g.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_mn = num_m * num_n;
   int Keff = g.K;
   if (g.k_limit != nullptr) Keff = min(Keff, max(__ldg(g.k_limit), 1));   // >= 1 block: zeros give zeros
   const int num_k = (Keff + BK - 1) / BK;
+  // split-K: tile index = (k split, n block, m block); split ks owns k-blocks [ks*kper, +kper).
+  // Few-tile / long-K problems (the adaptive-softmax tail back-projections: one m block x 16 n
+  // blocks x 473 k-blocks on 16 SMs) spread over the machine; partials meet in C through atomics.
+  const int splits = g.splits > 1 ? g.splits : 1;
+  const int kper = (num_k + splits - 1) / splits;
+  const int num_tiles = num_mn * splits;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -97,8 +103,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), full_u = smem_u32(full_bar);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
-      for (int kb = 0; kb < num_k; ++kb) {
+      const int ks = tile / num_mn, mn = tile - ks * num_mn;
+      const int m_blk = mn % num_m, n_blk = mn / num_m;
+      const int kb_end = min(num_k, (ks + 1) * kper);
+      for (int kb = ks * kper; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           const uint32_t bar = full_u + stage * 8;
@@ -117,7 +125,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c = 0; c < BN / 64; ++c)
               tma_load_2d_u(sB_u + stage * Cfg::B_BYTES + c * 8192, &tmB, bar, n_blk * BN + c * 64, kb * BK);
           }
-          if (kb == 0 && tile == blockIdx.x) trace_stamp(g, 2);
+          if (kb == ks * kper && tile == blockIdx.x) trace_stamp(g, 2);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -139,21 +147,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile / num_mn;
+      const int kb0 = ks * kper, kb_end = min(num_k, (ks + 1) * kper);
+      if (kb0 >= kb_end) continue;            // empty split (num_k not a multiple): no accumulator
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < num_k; ++kb) {
+      for (int kb = kb0; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint64_t da = da0 + static_cast<uint64_t>((stage * Cfg::A_BYTES) >> 4);
         const uint64_t db = db0 + static_cast<uint64_t>((stage * Cfg::B_BYTES) >> 4);
         if (elect_one()) {
-          if (kb == 0 && tile == blockIdx.x) trace_stamp(g, 3);
+          if (kb == kb0 && tile == blockIdx.x) trace_stamp(g, 3);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d_tmem, da + k * KA, db + k * KB, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, da + k * KA, db + k * KB, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit_u(empty_u + stage * 8);  // frees the smem slot when these MMAs retire
-          if (kb == num_k - 1) {
+          if (kb == kb_end - 1) {
             umma_commit_u(tfull_u + acc * 8);
             if (tile == blockIdx.x) trace_stamp(g, 4);
           }
@@ -180,15 +191,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int ks = tile / num_mn, mn = tile - ks * num_mn;
+      const int m_blk = mn % num_m, n_blk = mn / num_m;
+      if (ks * kper >= min(num_k, (ks + 1) * kper)) continue;     // empty split
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 5);
       const long long row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < M;
-      epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BN),
-                          half, row, row_ok, n_blk * BN);
+      if (splits > 1) {
+        GemmArgs ge = g;                      // partial product: bias / residual enter once (split 0)
+        ge.atomic = 1;
+        if (ks > 0) { ge.bias = nullptr; ge.residual = nullptr; ge.residual16 = nullptr; }
+        epilogue_chunks<BN>(ge, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                    static_cast<uint32_t>(acc * BN),
+                            half, row, row_ok, n_blk * BN);
+      } else {
+        epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN),
+                            half, row, row_ok, n_blk * BN);
+      }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 6);
@@ -335,15 +357,44 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   if (p->bias) vec = vec && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
   g.vec_ok = vec ? 1 : 0;
   g.trace = gemm_trace_ptr();
+  g.splits = 1;
+  g.atomic = 0;
 
   {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
     const int r2 = gemm2_try(p, g, reinterpret_cast<cudaStream_t>(stream));
     if (r2 != 0) return r2 > 0 ? TT_OK : r2;
   }
 
-  const int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
-  const int grid = tiles < sms ? tiles : sms;
+  int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // split-K for few-tile, long-K problems with a plain fp32 epilogue
+    static int sk = -1;
+    if (sk < 0) {
+      const char* e = getenv("TT_GEMM_SPLITK");
+      sk = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int num_k = ceil_div(p->K, BK);
+    if (p->m_limit != nullptr && p->m_hint > 0 && p->m_hint < p->M)     // expected rows (a hint)
+      tiles = ceil_div(p->m_hint, BM) * ceil_div(p->N, bn);
+    // Opt-in through m_hint (row-limited training GEMMs): atomics make the fp32 summation order
+    // run-dependent, which the backward already tolerates (LayerNorm / column-sum / scatter
+    // atomics) but greedy decoding must not -- its GEMMs never set a hint and stay bit-reproducible.
+    if (sk && p->m_limit != nullptr && p->m_hint > 0 && p->C != nullptr && p->C16 == nullptr &&
+        p->act == TT_ACT_NONE && !p->accumulate && tiles * 2 <= sms && num_k >= 32) {
+      int sp = sms / tiles;
+      if (sp > num_k / 8) sp = num_k / 8;     // at least 8 k-blocks per split
+      if (sp > 1) {
+        g.splits = sp;
+        cudaMemset2DAsync(p->C, static_cast<size_t>(p->ldc) * sizeof(float), 0,
+                          static_cast<size_t>(p->N) * sizeof(float), static_cast<size_t>(p->M), s);
+        tiles *= sp;
+      }
+    }
+    if (g.splits == 1) tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
+    else tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * g.splits;
+  }
+  const int grid = tiles < sms ? tiles : sms;
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, g, grid, ta, tb, s);
     case 128: return launch_gemm<128>(tmA, tmB, g, grid, ta, tb, s);

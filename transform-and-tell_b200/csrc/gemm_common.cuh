@@ -25,6 +25,8 @@ struct GemmArgs {
   int accumulate;
   const int* m_limit;
   const int* k_limit;   // device int, optional: operand rows/cols k >= *k_limit are known to be zero
+  int splits;           // split-K factor (1-CTA kernel): partial products are added atomically into C
+  int atomic;           // epilogue adds into C with atomics (set per tile by the split-K kernel)
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
   long long* trace;  // debug: [grid, 8] globaltimer stamps (tt_gemm_set_trace), normally null
 };
@@ -123,16 +125,22 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
           }
           if (g.C != nullptr) {
             float4* cp = reinterpret_cast<float4*>(g.C + row * g.ldc + col0);
-            if (g.accumulate) {
+            if (g.atomic) {               // split-K partial: C was zeroed by the host wrapper
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = cp[j];
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              for (int j = 0; j < 8; ++j)
+                atomicAdd(cp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            } else {
+              if (g.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = cp[j];
+                  v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
               }
-            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j)
+                cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
           }
           if (g.C16 != nullptr) {
             uint4* hp = reinterpret_cast<uint4*>(g.C16 + row * g.ldc16 + col0);
@@ -160,8 +168,12 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
               o = apply_act(o, g.act);
               if (g.C != nullptr) {
                 float* cp = g.C + row * g.ldc + col;
-                if (g.accumulate) o += *cp;
-                *cp = o;
+                if (g.atomic) {
+                  atomicAdd(cp, o);
+                } else {
+                  if (g.accumulate) o += *cp;
+                  *cp = o;
+                }
               }
               if (g.C16 != nullptr) g.C16[row * g.ldc16 + col] = __float2bfloat16_rn(o);
             }

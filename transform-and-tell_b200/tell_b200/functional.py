@@ -908,7 +908,9 @@ class AdaptiveLossFn(Function):
             dl16 = operand(dl, 'a')
             if fast:
                 xg16, p16, proj16, words16 = a0, a1, a2, a3
-                dP = ops.gemm_tn(dl16, words16, m_limit=cnt, trans_b=True)
+                # few rows x the whole tail vocabulary as the contraction: split-K (m_hint = the
+                # expected row count lets the dispatcher see how few tiles there really are)
+                dP = ops.gemm_tn(dl16, words16, m_limit=cnt, trans_b=True, m_hint=max(128, dl16.shape[0] // 8))
                 # contraction over the cluster's rows: rows >= cnt of dl / dP are zero, so the K loop
                 # stops at the device-side row count (23-120 of the 800 rows for the tail clusters)
                 dwords = ops.gemm_tn(dl16, p16, trans_a=True, trans_b=True, k_limit=cnt)
