@@ -63,7 +63,7 @@ def replay_gemm_signatures(sigs, n_prof, dev):
     tot_us, tot_flop, calls = 0.0, 0.0, 0
     big_us, big_flop, big_calls = 0.0, 0.0, 0      # launches of >= 10 GFLOP (the CTA-pair kernel's diet)
     for key, cnt in sigs.items():
-        M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha, hinted, klim = key
+        M, N, K, ta, tb, o16, o32, bias, act, res, res16, accum, lim, _alpha, hinted, klim, padded = key
         cnt = cnt // n_prof
         if cnt == 0 or M == 0:
             continue
@@ -75,7 +75,7 @@ def replay_gemm_signatures(sigs, n_prof, dev):
         Bm = mk(K, N) if tb else mk(N, K)
         kw = dict(trans_a=ta, trans_b=tb, act=act, accumulate=accum, want32=False)
         if o32:
-            kw['out'] = torch.zeros(M, N, device=dev)
+            kw['out'] = ops.f32_padded(M, N, A[0], zero=True) if padded else torch.zeros(M, N, device=dev)
         if o16:
             kw['out16'] = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         if bias:
@@ -402,7 +402,8 @@ def run_b200(args):
                    kw.get('residual16') is not None, bool(kw.get('accumulate')),
                    int(kw['m_limit'].item()) if kw.get('m_limit') is not None else 0,
                    float(kw.get('alpha', 1.0)) != 1.0, bool(kw.get('m_hint', 0)),
-                   int(kw['k_limit'].item()) if kw.get('k_limit') is not None else 0)
+                   int(kw['k_limit'].item()) if kw.get('k_limit') is not None else 0,
+                   out is not None and out.stride(0) != N)
             sigs[key] = sigs.get(key, 0) + 1
             return orig_gemm(a, b, out=out, out16=out16, **kw)
         ops.gemm_tn = rec_gemm

@@ -853,7 +853,7 @@ class AdaptiveLossFn(Function):
                                                                               pad_idx)
         hw16 = concat_rows_operand([word0, class_proj], 'b', X.device)
         x16 = operand(X, 'a')
-        head_logits = ops.gemm_tn(x16, hw16)
+        head_logits = ops.gemm_tn(x16, hw16, out=ops.f32_padded(N, hw16.shape[0], X))
         row_loss = torch.empty((nt + 1, N), dtype=torch.float32, device=X.device)
         head_lse, _ = ops.ce_fwd(head_logits, head_t, None, pad_idx, row_loss[0])
         saved_tail = []
@@ -866,8 +866,7 @@ class AdaptiveLossFn(Function):
             p16, words16 = operand(P, 'a'), operand(words, 'b')
             # rows >= cnt of the logits are never read (ce_fwd stops at cnt, ce_bwd zeroes them):
             # no zero fill of the [N, V_tail] buffer
-            logits = ops.gemm_tn(p16, words16, m_limit=cnt,
-                                 out=torch.empty((N, words.shape[0]), dtype=torch.float32, device=X.device))
+            logits = ops.gemm_tn(p16, words16, m_limit=cnt, out=ops.f32_padded(N, words.shape[0], X))
             lse, _ = ops.ce_fwd(logits, tail_local[i], cnt, pad_idx, row_loss[i + 1])
             saved_tail += ([xg16, p16, proj16, words16, logits, lse] if fast
                            else [Xg, P, proj, words, logits, lse])

@@ -123,12 +123,14 @@ class AdaptiveSoftmax(nn.Module):
         c0, nt = self.cutoff[0], len(self.cutoff) - 1
         hw16 = Fn.concat_rows_operand([self.head.word_proj.weight, self.head.class_proj.weight],
                                       'b', X2.device)
-        head = ops.gemm_tn(a16, hw16)
+        M = X2.shape[0]
+        head = ops.gemm_tn(a16, hw16, out=ops.f32_padded(M, hw16.shape[0], X2))
         tails = []
         tw = self._tail_weights()
         for i in range(nt):
             h = ops.gemm_tn(a16, Fn.operand(tw[2 * i], 'b'))
-            tails.append(ops.gemm_tn(Fn.operand(h, 'a'), Fn.operand(tw[2 * i + 1], 'b')))
+            tails.append(ops.gemm_tn(Fn.operand(h, 'a'), Fn.operand(tw[2 * i + 1], 'b'),
+                                     out=ops.f32_padded(M, tw[2 * i + 1].shape[0], X2)))
         return head, tails
 
     @torch.no_grad()
