@@ -1,0 +1,91 @@
+"""BASELINE.json configs[4] / SURVEY.md 8d cfg 5, one GPU's share: long-article stress -- 2048-token
+article context fed as EMBEDDINGS (RoBERTa bypassed: 2048 > its 512 positions), 8 faces, 16 objects,
+batch 4 per GPU, ResNet-152 on the image, decoder forward + loss + backward, dropout on.
+
+    python tools/bench_cfg5.py [--batch 4] [--steps 20]
+
+One JSON line (samples/s per GPU; the 8-GPU figure is 8 x this minus the all-reduce, see bench.py)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'transform-and-tell_b200'))
+import bench  # noqa: E402
+from tell_b200 import config, ops, synth  # noqa: E402
+from tell_b200 import functional as Fn  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--batch', type=int, default=4)
+ap.add_argument('--steps', type=int, default=20)
+args = ap.parse_args()
+dev = torch.device('cuda', 0)
+config.set_precision('bf16')
+config.manual_seed(1234)
+config.enable_device_step(dev)
+config.enable_zero_arena(dev)
+model = bench.build_model(dev)
+dec = model.decoder
+params = [p for p in dec.parameters() if p.requires_grad]
+B, T, S, F, O = args.batch, 50, 2048, 8, 16
+rs = np.random.RandomState(1234)
+cap = synth.caption_batch(B, T + 1, 50265, rs, min_len=20).to(dev)
+image = torch.from_numpy(rs.standard_normal((B, 3, 224, 224)).astype(np.float32)).to(dev)
+article = torch.from_numpy(rs.standard_normal((S, B, 1024)).astype(np.float32)).to(dev)
+lens = rs.randint(S // 2, S + 1, size=B)
+art_mask = (torch.arange(S).view(1, S) >= torch.from_numpy(lens).view(B, 1)).to(dev)
+faces0 = synth.nan_padded(B, F, 512, rs, 'faces').to(dev)
+objs0 = synth.nan_padded(B, O, 2048, rs, 'obj').to(dev)
+faces, objs = faces0.clone(), objs0.clone()
+out_loss = torch.zeros(1, device=dev)
+
+
+def step():
+    for p in params:
+        p.grad = None
+    config.advance_device_step()
+    faces.copy_(faces0)
+    objs.copy_(objs0)
+    feats = model.resnet.features_nhwc(image)
+    X_image = ops.bf16_to_f32(feats).view(B, 49, 2048)
+    fm, om = ops.nan_rows_(faces), ops.nan_rows_(objs)
+    ctx = {'image': Fn.Transpose01Fn.apply(X_image), 'image_mask': torch.zeros((B, 49), dtype=torch.bool, device=dev),
+           'article': article, 'article_mask': art_mask,
+           'faces': Fn.Transpose01Fn.apply(faces), 'faces_mask': fm,
+           'obj': Fn.Transpose01Fn.apply(objs), 'obj_mask': om}
+    X, _ = dec.forward_tbc({'roberta': cap[:, :-1].contiguous()}, ctx)
+    loss, _ = dec.adaptive_softmax.fused_loss(X.view(T * B, -1), cap[:, 1:].t().contiguous())
+    loss.backward()
+    out_loss.copy_(loss.detach().view(1))
+
+
+s = torch.cuda.Stream()
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    for _ in range(3):
+        step()
+torch.cuda.current_stream().wait_stream(s)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    step()
+for _ in range(3):
+    g.replay()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(args.steps):
+    g.replay()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / args.steps
+print(json.dumps({'metric': 'caption samples/sec (train fwd+bwd), long-article stress', 'batch_per_gpu': B,
+                  'article_tokens': S, 'faces': F, 'objects': O, 'ms_per_step': round(ms, 3),
+                  'samples_per_s_per_gpu': round(B / (ms * 1e-3), 1), 'loss': float(out_loss.item()),
+                  'note': 'ResNet-152 + decoder fwd + loss + bwd in one CUDA graph, RoBERTa bypassed '
+                          '(article embeddings are the input), dropout on'}))
