@@ -64,3 +64,42 @@ def test_collator_matches_host_padding():
     assert batch['face_embeds'].shape == (3, 1, 0) and 'obj_embeds' not in batch
     with pytest.raises(Exception):
         Collator('cpu')
+
+
+def test_collated_batch_drives_model_forward():
+    """Instances -> Collator -> Model.forward: same loss as the batch padded by hand on the host
+    (NaN-padded face / object arrays, right-padded ids)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_model_gpu as tm
+    from tell_b200 import synth
+    from tell_b200.data import Collator
+    rs = np.random.RandomState(3)
+    B, S, L, P = 3, 14, 5, 2
+    cfg = synth.CFG_TINY
+    feats = torch.from_numpy(rs.standard_normal((B, P, P, 2048)).astype(np.float32)).bfloat16()
+    insts = []
+    for b in range(B):
+        nf, no = rs.randint(0, 4), rs.randint(1, 5)
+        insts.append({'context': [0] + list(rs.randint(4, cfg['vocab'], size=rs.randint(4, S - 2))) + [2],
+                      'caption': [0] + list(rs.randint(4, cfg['vocab'], size=rs.randint(3, 8))) + [2],
+                      'image': np.zeros((3, 8, 8), dtype=np.float32),
+                      'face_embeds': rs.standard_normal((nf, 512)).astype(np.float32) if nf else np.array([[]]),
+                      'obj_embeds': rs.standard_normal((no, 2048)).astype(np.float32),
+                      'metadata': {}})
+    insts[0]['face_embeds'] = rs.standard_normal((2, 512)).astype(np.float32)      # at least one face
+    S_pad = max(len(i['context']) for i in insts)
+    hid = torch.from_numpy(rs.standard_normal((L, B * S_pad, 1024)).astype(np.float32)).bfloat16()
+    _, _, model = tm._tiny_model('bf16x3', tm._StubResNet(feats.cuda()), tm._StubRoberta(hid.cuda(), L - 1))
+    model.eval()
+    batch = Collator('cuda')(insts)
+    out = model(context=batch['context'], image=batch['image'], caption=batch['caption'],
+                face_embeds=batch['face_embeds'], obj_embeds=batch['obj_embeds'], metadata=batch['metadata'])
+    loss = out['loss'].item()
+    ctx_ids = _ref_pad_tokens([i['context'] for i in insts], 1).cuda()
+    cap_ids = _ref_pad_tokens([i['caption'] for i in insts], 1).cuda()
+    out2 = model(context={'roberta': ctx_ids}, image=torch.zeros(B, 3, 8, 8).cuda(), caption={'roberta': cap_ids},
+                 face_embeds=_ref_pad_arrays([i['face_embeds'] for i in insts]).cuda(),
+                 obj_embeds=_ref_pad_arrays([i['obj_embeds'] for i in insts]).cuda(), metadata=[{}] * B)
+    assert np.isfinite(loss) and abs(loss - out2['loss'].item()) < 1e-6
