@@ -188,6 +188,61 @@ struct LogProbArgs {
   float* argmax_lp;      // [M] or null
   int M;
 };
+// Block-wide arg-max of (value, index) pairs, ties -> lowest index (torch.topk on CPU returns the
+// first maximal element).  Result valid in every thread.
+__device__ __forceinline__ void block_argmax_256(float& v, int& i, float* sv, int* si) {
+  __syncthreads();
+  sv[threadIdx.x] = v;
+  si[threadIdx.x] = i;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = sv[threadIdx.x + o];
+      const int i2 = si[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = v2;
+        si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  v = sv[0];
+  i = si[0];
+}
+
+// One cluster of logits x[0..n): maximum, arg-max (lowest index among ties) and sum exp(x - max).
+// The arg-max of the log-probabilities of a cluster is the arg-max of its raw logits (the
+// normaliser is constant within the cluster), so greedy decoding needs two passes, not three.
+// 16-byte loads when the row is aligned (the logits buffers have a padded pitch).
+__device__ __forceinline__ void cluster_stats(const float* __restrict__ x, int n, float* red, float* sv,
+                                              int* si, float& mx, int& amax, float& sumexp) {
+  float v = -INFINITY;
+  int vi = 0x7fffffff;
+  const bool al = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int n4 = al ? (n >> 2) : 0;
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(x) + j);
+    if (q.x > v) { v = q.x; vi = 4 * j; }
+    if (q.y > v) { v = q.y; vi = 4 * j + 1; }
+    if (q.z > v) { v = q.z; vi = 4 * j + 2; }
+    if (q.w > v) { v = q.w; vi = 4 * j + 3; }
+  }
+  for (int j = 4 * n4 + threadIdx.x; j < n; j += blockDim.x) {
+    const float q = x[j];
+    if (q > v) { v = q; vi = j; }
+  }
+  block_argmax_256(v, vi, sv, si);
+  mx = v;
+  amax = vi;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(x) + j);
+    s += (expf(q.x - v) + expf(q.y - v)) + (expf(q.z - v) + expf(q.w - v));
+  }
+  for (int j = 4 * n4 + threadIdx.x; j < n; j += blockDim.x) s += expf(x[j] - v);
+  sumexp = block_sum(s, red);
+}
+
 __global__ void __launch_bounds__(256)
 adaptive_logprob_kernel(const LogProbArgs a) {
   pdl_prologue();
@@ -200,58 +255,47 @@ adaptive_logprob_kernel(const LogProbArgs a) {
   const int vocab = a.cut.cutoff[a.cut.n_clusters - 1];
   const int head_n = c0 + n_tails;
   const float* h = a.head + r * a.ld_head;
-  float m = -INFINITY;
-  for (int j = threadIdx.x; j < head_n; j += blockDim.x) m = fmaxf(m, h[j]);
-  m = block_max(m, red);
+  // head: the softmax runs over the c0 words AND the cluster priors; the arg-max candidates are
+  // the words only
+  float wm, ws_unused;
+  int wi;
+  cluster_stats(h, c0, red, best_v, best_i, wm, wi, ws_unused);
+  float m = wm;
+  for (int i = 0; i < n_tails; ++i) m = fmaxf(m, h[c0 + i]);
   float s = 0.f;
-  for (int j = threadIdx.x; j < head_n; j += blockDim.x) s += expf(h[j] - m);
+  {
+    const bool al = (reinterpret_cast<uintptr_t>(h) & 15) == 0;
+    const int n4 = al ? (head_n >> 2) : 0;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(h) + j);
+      s += (expf(q.x - m) + expf(q.y - m)) + (expf(q.z - m) + expf(q.w - m));
+    }
+    for (int j = 4 * n4 + threadIdx.x; j < head_n; j += blockDim.x) s += expf(h[j] - m);
+  }
   s = block_sum(s, red);
   const float head_lse = m + logf(s);
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int j = threadIdx.x; j < c0; j += blockDim.x) {
-    const float lp = h[j] - head_lse;
-    if (a.log_probs) a.log_probs[static_cast<long long>(r) * vocab + j] = lp;
-    if (lp > bv) { bv = lp; bi = j; }
-  }
+  float bv = wm - head_lse;
+  int bi = wi;
+  if (a.log_probs)
+    for (int j = threadIdx.x; j < c0; j += blockDim.x)
+      a.log_probs[static_cast<long long>(r) * vocab + j] = h[j] - head_lse;
   for (int i = 0; i < n_tails; ++i) {
     const int Vi = a.cut.cutoff[i + 1] - a.cut.cutoff[i];
     const float* t = a.tail[i] + r * a.ld_tail[i];
-    float tm = -INFINITY;
-    for (int j = threadIdx.x; j < Vi; j += blockDim.x) tm = fmaxf(tm, t[j]);
-    tm = block_max(tm, red);
-    float ts = 0.f;
-    for (int j = threadIdx.x; j < Vi; j += blockDim.x) ts += expf(t[j] - tm);
-    ts = block_sum(ts, red);
+    float tm, ts;
+    int ti;
+    cluster_stats(t, Vi, red, best_v, best_i, tm, ti, ts);
     const float prior = h[c0 + i] - head_lse;
     const float off = prior - (tm + logf(ts));
-    for (int j = threadIdx.x; j < Vi; j += blockDim.x) {
-      const float lp = t[j] + off;
-      const int id = a.cut.cutoff[i] + j;
-      if (a.log_probs) a.log_probs[static_cast<long long>(r) * vocab + id] = lp;
-      if (lp > bv) { bv = lp; bi = id; }
-    }
+    const float lp = tm + off;
+    if (lp > bv) { bv = lp; bi = a.cut.cutoff[i] + ti; }      // ties keep the lower (earlier) id
+    if (a.log_probs)
+      for (int j = threadIdx.x; j < Vi; j += blockDim.x)
+        a.log_probs[static_cast<long long>(r) * vocab + a.cut.cutoff[i] + j] = t[j] + off;
   }
-  if (a.argmax_id || a.argmax_lp) {
-    best_v[threadIdx.x] = bv;
-    best_i[threadIdx.x] = bi;
-    __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        const float v2 = best_v[threadIdx.x + o];
-        const int i2 = best_i[threadIdx.x + o];
-        // ties -> lowest index (torch.topk on CPU returns the first maximal element)
-        if (v2 > best_v[threadIdx.x] || (v2 == best_v[threadIdx.x] && i2 < best_i[threadIdx.x])) {
-          best_v[threadIdx.x] = v2;
-          best_i[threadIdx.x] = i2;
-        }
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      if (a.argmax_id) a.argmax_id[r] = best_i[0];
-      if (a.argmax_lp) a.argmax_lp[r] = best_v[0];
-    }
+  if (threadIdx.x == 0) {
+    if (a.argmax_id) a.argmax_id[r] = bi;
+    if (a.argmax_lp) a.argmax_lp[r] = bv;
   }
 }
 
