@@ -565,7 +565,8 @@ def flash_self_attn_varlen(qkv, cu, B, S_max, H, D, tc5=None):
     finite values in every allocated row of qkv; otherwise the mma.sync kernel."""
     from . import config
     out = torch.empty((qkv.shape[0], H * D), dtype=torch.bfloat16, device=qkv.device)
-    if config.flash_tc5 if tc5 is None else tc5:
+    use_tc5 = config.flash_tc5 if tc5 is None else tc5
+    if use_tc5 and qkv.shape[0] >= 128 and D == 64:     # TMA boxes are 128 rows tall
         assert qkv.is_contiguous() and qkv.shape[1] == 3 * H * D
         _lib.call('tt_flash_self_attn_varlen_tc5', _ptr(qkv), _ptr(cu), _ptr(out), c_int(B),
                   c_int(S_max), c_int(H), c_int(D), c_ll(qkv.shape[0]), _stream())
