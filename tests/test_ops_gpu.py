@@ -525,3 +525,21 @@ def test_flash_attention_tcgen05_matches_fp32(lens):
         got = ops.flash_self_attn_varlen(qkv16.cuda(), cu.cuda(), B, S, H, D, tc5=tc5)[:n].float().cpu()
         err = (got - want).abs().max().item()
         assert err < 2e-2 * want.abs().max().item(), (tc5, err)
+
+
+@pytest.mark.parametrize('B,H,W,C,k,s,p', [(2, 14, 14, 256, 3, 1, 1), (3, 9, 11, 64, 3, 2, 1),
+                                           (2, 8, 8, 128, 1, 2, 0), (1, 7, 6, 24, 3, 1, 1),
+                                           (2, 5, 5, 40, 7, 2, 3), (1, 1, 1, 8, 3, 1, 1)])
+def test_im2col_nhwc_bit_exact(B, H, W, C, k, s, p):
+    """ResNet im2col (resnet.py:92-117 convs as GEMMs): a pure gather, so every bit must match
+    F.unfold re-ordered to (kh, kw, c) columns; covers power-of-two and other channel counts,
+    stride 2, 1x1 taps, K padding (C = 24, 40) and a single-pixel image."""
+    from tell_b200 import ops
+    torch.manual_seed(B * 100 + C + k)
+    x = torch.randn(B, H, W, C).bfloat16()
+    cols, Ho, Wo = ops.im2col_nhwc(cuda(x), k, k, s, p)
+    u = F.unfold(x.permute(0, 3, 1, 2).float(), k, padding=p, stride=s)          # [B, C*k*k, L]
+    u = u.view(B, C, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * C)
+    assert cols.shape == (B * Ho * Wo, (k * k * C + 7) // 8 * 8)
+    assert torch.equal(cols[:, :k * k * C].float().cpu(), u)
+    assert (cols[:, k * k * C:] == 0).all()

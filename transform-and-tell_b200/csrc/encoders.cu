@@ -5,6 +5,8 @@
 //     embedding + LayerNorm, fp32->bf16 LayerNorm, flash self-attention on mma.sync bf16 tensor cores.
 #include <mma.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "runtime.h"
 
@@ -12,51 +14,102 @@ namespace tt {
 
 // ------------------------------------------------------------------------------------------ im2col
 // out[(b,ho,wo), (kh,kw,c)] = in[b, ho*s - p + kh, wo*s - p + kw, c]  (zero outside), K padded to Kp.
-// NHWC bf16 input, 8 channels (16 B) per thread.
+// NHWC bf16 input, 8 channels (16 B) per thread.  The index arithmetic is the cost of this kernel
+// (one load + one store per element): idx_t = unsigned whenever the element count fits (64-bit
+// div/mod made it issue-bound at 1.3 TB/s), and two elements per iteration are in flight.
+template <typename idx_t>
+__device__ __forceinline__ uint4 im2col_gather(const __nv_bfloat16* __restrict__ in, idx_t i, int H, int W,
+                                               int C, int C8, int Ho, int Wo, int KH, int KW, int stride,
+                                               int pad, idx_t chunks_per_row) {
+  const int ch = static_cast<int>(i % chunks_per_row);
+  const idx_t row = i / chunks_per_row;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  const int tap = ch / C8;
+  if (tap < KH * KW) {
+    const int c8 = ch - tap * C8;
+    const int kh = tap / KW, kw = tap - kh * KW;
+    const int wo = static_cast<int>(row % static_cast<idx_t>(Wo));
+    const idx_t t = row / static_cast<idx_t>(Wo);
+    const int ho = static_cast<int>(t % static_cast<idx_t>(Ho));
+    const long long b = static_cast<long long>(t / static_cast<idx_t>(Ho));
+    const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((b * H + hi) * W + wi) * C) + c8);
+  }
+  return v;
+}
+
+template <typename idx_t>
 __global__ void im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                    int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
                                    int stride, int pad, int Kp) {
   pdl_prologue();
   const int C8 = C >> 3;
-  const int chunks_per_row = Kp >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * chunks_per_row;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % chunks_per_row);
-    const long long row = i / chunks_per_row;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    const int tap = ch / C8;
-    if (tap < KH * KW) {
-      const int c8 = ch - tap * C8;
-      const int kh = tap / KW, kw = tap - kh * KW;
-      const int wo = static_cast<int>(row % Wo);
-      const long long t = row / Wo;
-      const int ho = static_cast<int>(t % Ho);
-      const int b = static_cast<int>(t / Ho);
-      const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + hi) * W + wi) * C) + c8);
+  const idx_t chunks_per_row = static_cast<idx_t>(Kp >> 3);
+  const idx_t total = static_cast<idx_t>(B) * Ho * Wo * chunks_per_row;
+  const idx_t step = static_cast<idx_t>(gridDim.x) * blockDim.x;
+  idx_t i = blockIdx.x * static_cast<idx_t>(blockDim.x) + threadIdx.x;
+  uint4* o = reinterpret_cast<uint4*>(out);
+  for (; i < total && total - i > step; i += 2 * step) {       // i and i + step both in range
+    const uint4 v0 = im2col_gather<idx_t>(in, i, H, W, C, C8, Ho, Wo, KH, KW, stride, pad, chunks_per_row);
+    const uint4 v1 = im2col_gather<idx_t>(in, i + step, H, W, C, C8, Ho, Wo, KH, KW, stride, pad, chunks_per_row);
+    o[i] = v0;
+    o[i + step] = v1;
+  }
+  if (i < total) o[i] = im2col_gather<idx_t>(in, i, H, W, C, C8, Ho, Wo, KH, KW, stride, pad, chunks_per_row);
+}
+// Warp-per-output-row form (every ResNet layer): the (b, ho, wo) decomposition is paid once per
+// row, the lanes walk the row's 16-byte chunks -- contiguous 512 B loads and stores per warp
+// instruction -- and tap -> (kh, kw) is a multiply-shift (kw_inv = 65536 / KW + 1, exact for
+// tap < 65536 / KW), so no division is left in the element loop.
+template <bool POW2>
+__global__ void im2col_nhwc_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                        int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
+                                        int stride, int pad, int Kp, int c8_shift, int kw_inv) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int warps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  const int cpr = Kp >> 3, C8 = C >> 3, taps = KH * KW;
+  const int rows = B * Ho * Wo;
+  for (int row = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+    const int wo = row % Wo, t = row / Wo;
+    const int ho = t % Ho, b = t / Ho;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const __nv_bfloat16* src = in + static_cast<long long>(b) * H * W * C;
+    uint4* dst = reinterpret_cast<uint4*>(out) + static_cast<long long>(row) * cpr;
+#pragma unroll 4
+    for (int ch = lane; ch < cpr; ch += 32) {
+      const int tap = POW2 ? (ch >> c8_shift) : (ch / C8);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (tap < taps) {
+        const int c8 = ch - tap * C8;
+        const int kh = (tap * kw_inv) >> 16, kw = tap - kh * KW;
+        const int hi = h0 + kh, wi = w0 + kw;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+          v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<long long>(hi) * W + wi) * C) + c8);
+      }
+      dst[ch] = v;
     }
-    reinterpret_cast<uint4*>(out)[i] = v;
   }
 }
 // First layer: NCHW fp32 image (C = 3).  K index = (kh*KW + kw)*C + c.  One thread builds 8
 // consecutive k of one output pixel (a 16-byte store); the gathers hit the L1/L2-resident image.
+template <typename idx_t>
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                        int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
                                        int stride, int pad, int Kp) {
   pdl_prologue();
-  const int chunks = Kp >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * chunks;
+  const idx_t chunks = static_cast<idx_t>(Kp >> 3);
+  const idx_t total = static_cast<idx_t>(B) * Ho * Wo * chunks;
   const int K = KH * KW * C;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (idx_t i = blockIdx.x * static_cast<idx_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<idx_t>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % chunks);
-    const long long row = i / chunks;
-    const int wo = static_cast<int>(row % Wo);
-    const long long t = row / Wo;
-    const int ho = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+    const idx_t row = i / chunks;
+    const int wo = static_cast<int>(row % static_cast<idx_t>(Wo));
+    const idx_t t = row / static_cast<idx_t>(Wo);
+    const int ho = static_cast<int>(t % static_cast<idx_t>(Ho));
+    const int b = static_cast<int>(t / static_cast<idx_t>(Ho));
     const int h0 = ho * stride - pad, w0 = wo * stride - pad;
     float v[8];
 #pragma unroll
@@ -533,9 +586,39 @@ extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, in
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
   if (total <= 0) return TT_OK;
-  launch_k(im2col_nhwc_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
-      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
-      Ho, Wo, KH, KW, stride, pad, Kp);
+  const int C8 = C / 8;
+  static int rows_form = -1;
+  if (rows_form < 0) {
+    const char* e = getenv("TT_IM2COL_ROWS");
+    rows_form = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (rows_form && total < (1ll << 31) && KH * KW < 65536 / KW) {
+    const long long rows = static_cast<long long>(B) * Ho * Wo;
+    long long ctas = ceil_div_ll(rows, 8);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (ctas > cap) ctas = cap;
+    const bool pow2 = (C8 & (C8 - 1)) == 0;
+    int sh = 0;
+    while ((1 << sh) < C8) ++sh;
+    const int kw_inv = 65536 / KW + 1;
+    if (pow2) {
+      launch_k(im2col_nhwc_rows_kernel<true>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
+          reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+          Ho, Wo, KH, KW, stride, pad, Kp, sh, kw_inv);
+    } else {
+      launch_k(im2col_nhwc_rows_kernel<false>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
+          reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+          Ho, Wo, KH, KW, stride, pad, Kp, sh, kw_inv);
+    }
+  } else if (total < (1ll << 31) - (1ll << 24)) {        // headroom: i + 2 * step must not wrap
+    launch_k(im2col_nhwc_kernel<unsigned>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+        reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+        Ho, Wo, KH, KW, stride, pad, Kp);
+  } else {
+    launch_k(im2col_nhwc_kernel<long long>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+        reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
+        Ho, Wo, KH, KW, stride, pad, Kp);
+  }
   return check_launch("im2col_nhwc_kernel");
 }
 
@@ -546,8 +629,13 @@ extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int 
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
   if (total <= 0) return TT_OK;
-  launch_k(im2col_nchw_f32_kernel, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream, 
-      in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
+  if (total < (1ll << 31) - (1ll << 24)) {
+    launch_k(im2col_nchw_f32_kernel<unsigned>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+        in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
+  } else {
+    launch_k(im2col_nchw_f32_kernel<long long>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+        in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
+  }
   return check_launch("im2col_nchw_f32_kernel");
 }
 
