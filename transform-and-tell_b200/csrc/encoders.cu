@@ -590,7 +590,7 @@ extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, in
   static int rows_form = -1;
   if (rows_form < 0) {
     const char* e = getenv("TT_IM2COL_ROWS");
-    rows_form = (e && e[0] == '1') ? 1 : 0;
+    rows_form = (e && e[0] == '0') ? 0 : 1;       // TT_IM2COL_ROWS=0: flat form (experiments)
   }
   if (rows_form && total < (1ll << 31) && KH * KW < 65536 / KW) {
     const long long rows = static_cast<long long>(B) * Ho * Wo;
