@@ -279,6 +279,13 @@ int tt_ce_fwd(const float* logits, long long ld, const int* target, const int* c
 /* in place: logits <- (softmax - onehot) * *scale_ptr ; ignored / inactive rows <- 0. */
 int tt_ce_bwd(float* logits, long long ld, const int* target, const int* count_ptr, int M, int V,
               int ignore_index, const float* lse, const float* scale_ptr, void* stream);
+/* The same gradient (adaptive_loss.py:47-58 backward of F.cross_entropy) written as the bf16 operand
+ * of the backward GEMMs: out16 [M, ld16] <- bf16((softmax - onehot) * *scale_ptr); logits are not
+ * modified.  zero_round > 0 with count_ptr: rows >= max(round_up(*count_ptr, zero_round), zero_round) are NOT
+ * written (their consumers are limited to *count_ptr rows); zero_round = 0 zeroes every inactive row. */
+int tt_ce_bwd_bf16(const float* logits, long long ld, const int* target, const int* count_ptr,
+                   int M, int V, int ignore_index, const float* lse, const float* scale_ptr,
+                   void* out16, long long ld16, int zero_round, void* stream);
 /* loss = sum(row_loss)/ln2/ntokens, scale = 1/(ln2*ntokens). transformer_faces_objects.py:85-90 */
 int tt_loss_finalize(const float* row_loss, long long n, const int* ntokens, float* loss,
                      float* scale, void* stream);

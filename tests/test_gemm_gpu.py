@@ -94,6 +94,19 @@ def test_cast(transpose, split):
     assert torch.equal(y, exp)
 
 
+@pytest.mark.parametrize('cols', [102, 101, 7, 3])
+def test_cast_odd_width_padded_pitch(cols):
+    """fp32 rows with a 16-byte-aligned pitch but a width that is not a multiple of 4 (the 5002-way
+    adaptive-softmax head): vector body + per-row leftover columns, exact bf16 rounding."""
+    from tell_b200 import ops
+    torch.manual_seed(cols)
+    x = ops.f32_padded(70, cols, torch.zeros(1, device='cuda'))
+    x.copy_(torch.randn(70, cols, device='cuda'))
+    y = ops.cast_bf16(x)
+    assert torch.equal(y, x.bfloat16())
+    assert (y.as_strided((70, y.stride(0)), (y.stride(0), 1))[:, cols:] == 0).all()
+
+
 def test_gemm_split_precision():
     """bf16x3 operands recover ~fp32 accuracy (parity mode)."""
     from tell_b200 import ops

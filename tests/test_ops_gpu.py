@@ -543,3 +543,37 @@ def test_im2col_nhwc_bit_exact(B, H, W, C, k, s, p):
     assert cols.shape == (B * Ho * Wo, (k * k * C + 7) // 8 * 8)
     assert torch.equal(cols[:, :k * k * C].float().cpu(), u)
     assert (cols[:, k * k * C:] == 0).all()
+
+
+@pytest.mark.parametrize('V', [12, 37, 5002])
+def test_ce_bwd_bf16_operand_equals_fp32_pass_plus_cast(V):
+    """tt_ce_bwd_bf16 (adaptive_loss.py:47-58 backward as a bf16 GEMM operand) must be bit-identical
+    to the in-place fp32 gradient followed by the bf16 cast it replaces, on padded (vector path) and
+    plain (scalar path) logits; with zero_round, rows in [count, round_up) are zero, later rows are
+    left alone, and a zero count still zeroes one round of rows."""
+    from tell_b200 import ops
+    torch.manual_seed(V)
+    M = 300
+    target = torch.randint(0, V, (M,), dtype=torch.int32, device='cuda')
+    target[::7] = 1                                   # ignored rows
+    scale = torch.tensor([0.013], device='cuda')
+    for padded in (True, False):
+        logits = ops.f32_padded(M, V, scale) if padded else torch.empty(M, V, device='cuda')
+        logits.copy_(torch.randn(M, V, device='cuda') * 3)
+        keep = logits.clone()
+        lse, _ = ops.ce_fwd(logits, target)
+        ref_lse = torch.logsumexp(keep.double(), 1).float()
+        assert (lse - ref_lse).abs().max() < 1e-5
+        d16 = ops.ce_bwd16(logits, target, lse, scale)
+        assert torch.equal(logits, keep)              # logits untouched
+        d32 = ops.ce_bwd_(logits.clone(), target, lse, scale)
+        assert torch.equal(d16, d32.bfloat16())
+        for c in (0, 5, 128, 131):
+            cnt = torch.tensor([c], dtype=torch.int32, device='cuda')
+            lse_c, _ = ops.ce_fwd(logits, target, count=cnt)
+            buf = ops.ce_bwd16(logits, target, lse_c, scale, count=cnt, zero_round=128)
+            edge = max((c + 127) // 128, 1) * 128
+            assert torch.equal(buf[:c], d16[:c])
+            assert (buf[c:min(edge, M)] == 0).all()
+            full = ops.ce_bwd16(logits, target, lse_c, scale, count=cnt)      # zero_round = 0
+            assert torch.equal(full[:c], d16[:c]) and (full[c:] == 0).all()

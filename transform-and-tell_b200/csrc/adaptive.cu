@@ -110,6 +110,10 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int
 }
 
 // F.cross_entropy(logits, target, ignore_index, reduction='sum') per row + saved lse.
+// VEC: 16-byte loads (row pitch a multiple of 4 floats, aligned base -- ops.f32_padded); the
+// 30265-wide tail cluster has only a few dozen active rows, so per-thread trip count is what
+// bounds it.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const float* __restrict__ logits, long long ld, const int* __restrict__ target,
               const int* __restrict__ count_ptr, int M, int V, int ignore_index,
@@ -123,11 +127,21 @@ ce_fwd_kernel(const float* __restrict__ logits, long long ld, const int* __restr
     return;
   }
   const float* x = logits + r * ld;
+  const int nv = VEC ? (V >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
   float m = -INFINITY;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) m = fmaxf(m, x[j]);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    const float4 v = x4[j];
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int j = nv * 4 + threadIdx.x; j < V; j += blockDim.x) m = fmaxf(m, x[j]);
   m = block_max(m, red);
   float s = 0.f;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(x[j] - m);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    const float4 v = x4[j];
+    s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
+  }
+  for (int j = nv * 4 + threadIdx.x; j < V; j += blockDim.x) s += expf(x[j] - m);
   s = block_sum(s, red);
   if (threadIdx.x == 0) {
     const float l = m + logf(s);
@@ -157,6 +171,59 @@ ce_bwd_kernel(float* __restrict__ logits, long long ld, const int* __restrict__ 
     float g = expf(x[j] - l);
     if (j == t) g -= 1.f;
     x[j] = g * sc;
+  }
+}
+
+// Same gradient written straight as the bf16 GEMM operand of the backward GEMMs (throughput mode):
+// out16 <- bf16((softmax - onehot) * scale), logits untouched.  Replaces the in-place fp32 pass plus
+// a separate fp32 -> bf16 cast of the whole [M, V] matrix.  With zero_round > 0 and a device-side
+// row count, rows >= round_up(count, zero_round) are left unwritten: the row-limited GEMMs that
+// consume the operand (m_limit / k_limit = the same count) never read them, which saves ~145 MB of
+// zero fill per step for the two tail clusters.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+ce_bwd16_kernel(const float* __restrict__ logits, long long ld, const int* __restrict__ target,
+                const int* __restrict__ count_ptr, int M, int V, int ignore_index,
+                const float* __restrict__ lse, const float* __restrict__ scale_ptr,
+                __nv_bfloat16* __restrict__ out, long long ld16, int zero_round) {
+  pdl_prologue();
+  const int r = blockIdx.x;
+  const int count = count_ptr ? min(*count_ptr, M) : M;
+  const float* x = logits + r * ld;
+  __nv_bfloat16* o = out + r * ld16;
+  const int nv = VEC ? (V >> 2) : 0;
+  const int t = r < count ? target[r] : ignore_index;
+  if (r >= count || t == ignore_index) {
+    // at least one zero_round of rows is always zeroed: a k_limit GEMM reads one k-block even
+    // when the count is 0
+    if (r >= count && zero_round > 0 && count_ptr != nullptr &&
+        r >= max((count + zero_round - 1) / zero_round, 1) * zero_round)
+      return;
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) reinterpret_cast<uint2*>(o)[j] = make_uint2(0u, 0u);
+    for (int j = nv * 4 + threadIdx.x; j < V; j += blockDim.x) o[j] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float l = lse[r];
+  const float sc = scale_ptr ? *scale_ptr : 1.f;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    const float4 v = x4[j];
+    float g[4] = {expf(v.x - l), expf(v.y - l), expf(v.z - l), expf(v.w - l)};
+    const int d = t - 4 * j;
+    if (d >= 0 && d < 4) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e == d) g[e] -= 1.f;
+    }
+    uint2 u;
+    u.x = pack_bf16(g[0] * sc, g[1] * sc);
+    u.y = pack_bf16(g[2] * sc, g[3] * sc);
+    reinterpret_cast<uint2*>(o)[j] = u;
+  }
+  for (int j = nv * 4 + threadIdx.x; j < V; j += blockDim.x) {
+    float g = expf(x[j] - l);
+    if (j == t) g -= 1.f;
+    o[j] = __float2bfloat16_rn(g * sc);
   }
 }
 
@@ -354,9 +421,33 @@ extern "C" int tt_ce_fwd(const float* logits, long long ld, const int* target,
                          float* row_loss, void* stream) {
   TT_REQUIRE(logits && target && lse && row_loss, "tt_ce_fwd: null pointer");
   if (M <= 0) return TT_OK;
-  launch_k(ce_fwd_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target, count_ptr, M, V,
-                                                     ignore_index, lse, row_loss);
+  const bool vec = (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+  if (vec)
+    launch_k(ce_fwd_kernel<true>, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target, count_ptr,
+             M, V, ignore_index, lse, row_loss);
+  else
+    launch_k(ce_fwd_kernel<false>, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target, count_ptr,
+             M, V, ignore_index, lse, row_loss);
   return check_launch("ce_fwd_kernel");
+}
+
+extern "C" int tt_ce_bwd_bf16(const float* logits, long long ld, const int* target,
+                              const int* count_ptr, int M, int V, int ignore_index,
+                              const float* lse, const float* scale_ptr, void* out16,
+                              long long ld16, int zero_round, void* stream) {
+  TT_REQUIRE(logits && target && lse && out16, "tt_ce_bwd_bf16: null pointer");
+  TT_REQUIRE(ld >= V && ld16 >= V && zero_round >= 0, "tt_ce_bwd_bf16: bad pitch / zero_round");
+  if (M <= 0) return TT_OK;
+  const bool vec = (ld % 4 == 0) && (ld16 % 4 == 0) && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out16) & 7) == 0;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out16);
+  if (vec)
+    launch_k(ce_bwd16_kernel<true>, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target,
+             count_ptr, M, V, ignore_index, lse, scale_ptr, o, ld16, zero_round);
+  else
+    launch_k(ce_bwd16_kernel<false>, dim3(M), dim3(256), 0, (cudaStream_t)stream, logits, ld, target,
+             count_ptr, M, V, ignore_index, lse, scale_ptr, o, ld16, zero_round);
+  return check_launch("ce_bwd16_kernel");
 }
 
 extern "C" int tt_ce_bwd(float* logits, long long ld, const int* target, const int* count_ptr,

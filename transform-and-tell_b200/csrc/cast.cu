@@ -20,17 +20,32 @@ __device__ __forceinline__ void seg_values(float x, __nv_bfloat16 (&o)[3]) {
 }
 
 template <int SPLIT>
+__device__ __forceinline__ void cast_store1(float x, __nv_bfloat16* __restrict__ d, long long seg) {
+  if (SPLIT == 0) {
+    d[0] = __float2bfloat16_rn(x);
+  } else {
+    __nv_bfloat16 o[3];
+    seg_values<SPLIT>(x, o);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) d[s * seg] = o[s];
+  }
+}
+
+// One thread per 4 consecutive columns (16 B load, 8 B stores); the cols % 4 leftover columns of
+// each row (the 5002-wide adaptive-softmax head) are done one element per thread afterwards.
+// idx_t = unsigned whenever rows * cols fits: the row/column split is the only arithmetic here.
+template <int SPLIT, typename idx_t>
 __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src,
                                  __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
                                  int cols, long long seg) {
   pdl_prologue();
-  // one thread per 4 consecutive columns
-  const int c4 = cols >> 2;
-  const long long total = static_cast<long long>(rows) * c4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / c4);
-    const int c = static_cast<int>(i - static_cast<long long>(r) * c4) << 2;
+  const idx_t c4 = static_cast<idx_t>(cols >> 2);
+  const idx_t total = static_cast<idx_t>(rows) * c4;
+  const idx_t step = static_cast<idx_t>(gridDim.x) * blockDim.x;
+  const idx_t first = blockIdx.x * static_cast<idx_t>(blockDim.x) + threadIdx.x;
+  for (idx_t i = first; i < total; i += step) {
+    const idx_t r = i / c4;
+    const int c = static_cast<int>(i - r * c4) << 2;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c));
     const float x[4] = {v.x, v.y, v.z, v.w};
     if (SPLIT == 0) {
@@ -53,6 +68,16 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, long long ld_src
         u.y = *reinterpret_cast<uint32_t*>(&p1);
         *reinterpret_cast<uint2*>(dst + r * ld_dst + s * seg + c) = u;
       }
+    }
+  }
+  const int rem = cols & 3;
+  if (rem) {
+    const int cbase = cols - rem;
+    const idx_t tail = static_cast<idx_t>(rows) * rem;
+    for (idx_t i = first; i < tail; i += step) {
+      const idx_t r = i / static_cast<idx_t>(rem);
+      const int c = cbase + static_cast<int>(i - r * rem);
+      cast_store1<SPLIT>(src[r * ld_src + c], dst + r * ld_dst + c, seg);
     }
   }
 }
@@ -116,7 +141,7 @@ static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst,
     launch_k(cast_transpose_kernel<SPLIT>, dim3(grid), dim3(block), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
     return check_launch("cast_transpose_kernel");
   }
-  const bool vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && (seg % 4 == 0) &&
+  const bool vec = (cols >= 4) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && (SPLIT == 0 || seg % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
   const long long work = vec ? static_cast<long long>(rows) * (cols / 4)
@@ -124,8 +149,10 @@ static int cast_dispatch(const float* src, long long ld_src, __nv_bfloat16* dst,
   long long blocks = ceil_div_ll(work, 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  if (vec)
-    launch_k(cast_rows_kernel<SPLIT>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
+  if (vec && static_cast<long long>(rows) * cols < (1ll << 31) - (1ll << 24))
+    launch_k(cast_rows_kernel<SPLIT, unsigned>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
+  else if (vec)
+    launch_k(cast_rows_kernel<SPLIT, long long>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols, seg);
   else
     launch_k(cast_rows_scalar_kernel<SPLIT>, dim3((int)blocks), dim3(256), 0, s, src, ld_src, dst, ld_dst, rows, cols,
                                                                seg);

@@ -889,8 +889,11 @@ class AdaptiveLossFn(Function):
         saved_tail = s[7:]
         c0 = cutoffs[0]
         gscale = ops.scalar_mul(scale, _c(dloss).view(1))       # upstream grad stays on device
-        dlog = ops.ce_bwd_(head_logits, head_t, head_lse, gscale, None, pad_idx)   # in place
-        dlog16 = operand(dlog, 'a')
+        if fast:        # gradient written directly as the bf16 operand (no fp32 pass + cast)
+            dlog16 = ops.ce_bwd16(head_logits, head_t, head_lse, gscale, None, pad_idx)
+        else:
+            dlog = ops.ce_bwd_(head_logits, head_t, head_lse, gscale, None, pad_idx)   # in place
+            dlog16 = operand(dlog, 'a')
         if fast:
             x16, hw16 = head_saved
             dX = ops.gemm_tn(dlog16, hw16, trans_b=True)
@@ -903,8 +906,11 @@ class AdaptiveLossFn(Function):
         for i in range(nt):
             a0, a1, a2, a3, logits, lse = saved_tail[6 * i:6 * i + 6]
             cnt = tail_count[i:i + 1]
-            dl = ops.ce_bwd_(logits, tail_local[i], lse, gscale, cnt, pad_idx)   # rows >= cnt := 0
-            dl16 = operand(dl, 'a')
+            if fast:    # rows >= round_up(cnt, 128) are never read by the cnt-limited GEMMs below
+                dl16 = ops.ce_bwd16(logits, tail_local[i], lse, gscale, cnt, pad_idx, zero_round=128)
+            else:
+                dl = ops.ce_bwd_(logits, tail_local[i], lse, gscale, cnt, pad_idx)   # rows >= cnt := 0
+                dl16 = operand(dl, 'a')
             if fast:
                 xg16, p16, proj16, words16 = a0, a1, a2, a3
                 # few rows x the whole tail vocabulary as the contraction: split-K (m_hint = the

@@ -425,6 +425,19 @@ def ce_bwd_(logits, target, lse, scale, count=None, ignore_index=1):
     return logits
 
 
+def ce_bwd16(logits, target, lse, scale, count=None, ignore_index=1, zero_round=0):
+    """(softmax - onehot) * scale as a bf16 GEMM operand [M, V] (row pitch padded to 8 elements);
+    logits stay intact.  zero_round > 0: rows >= round_up(count, zero_round) are left unwritten --
+    only for consumers limited to `count` rows (m_limit / k_limit)."""
+    M, V = logits.shape
+    ld = (V + 7) // 8 * 8
+    out = torch.empty((M, ld), dtype=torch.bfloat16, device=logits.device)[:, :V]
+    _lib.call('tt_ce_bwd_bf16', _ptr(logits), c_ll(logits.stride(0)), _ptr(target), _ptr(count),
+              c_int(M), c_int(V), c_int(ignore_index), _ptr(lse), _ptr(scale), _ptr(out),
+              c_ll(ld), c_int(zero_round), _stream())
+    return out
+
+
 def loss_finalize(row_loss, ntokens):
     loss, scale = _f32(1, like=row_loss), _f32(1, like=row_loss)
     _lib.call('tt_loss_finalize', _ptr(row_loss), c_ll(row_loss.numel()), _ptr(ntokens),
