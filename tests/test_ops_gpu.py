@@ -577,3 +577,21 @@ def test_ce_bwd_bf16_operand_equals_fp32_pass_plus_cast(V):
             assert (buf[c:min(edge, M)] == 0).all()
             full = ops.ce_bwd16(logits, target, lse_c, scale, count=cnt)      # zero_round = 0
             assert torch.equal(full[:c], d16[:c]) and (full[c:] == 0).all()
+
+
+@pytest.mark.parametrize('B,C,H,W,k,s,p', [(2, 3, 32, 40, 7, 2, 3), (1, 3, 9, 9, 7, 2, 3),
+                                           (2, 5, 12, 10, 3, 1, 1), (1, 3, 8, 8, 3, 2, 1)])
+def test_im2col_nchw_f32_exact(B, C, H, W, k, s, p):
+    """Stem im2col (resnet.py:95 conv1 as a GEMM): fp32 NCHW image -> bf16 [pixels, Kp] with
+    k = (kh*KW + kw)*C + c; the 7x7x3 stem takes the compile-time-constant instantiation, other
+    shapes the generic one.  bf16 rounding of a gathered fp32 value: bit-exact."""
+    from tell_b200 import ops
+    torch.manual_seed(C * 10 + k)
+    x = torch.randn(B, C, H, W)
+    K = k * k * C
+    Kp = (K + 7) // 8 * 8
+    cols, Ho, Wo = ops.im2col_nchw_f32(cuda(x), k, k, s, p, Kp)
+    u = F.unfold(x, k, padding=p, stride=s)                                      # [B, C*k*k, L]
+    u = u.view(B, C, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, K)
+    assert torch.equal(cols[:, :K].cpu(), u.bfloat16())
+    assert (cols[:, K:] == 0).all()

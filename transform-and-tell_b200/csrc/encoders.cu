@@ -94,10 +94,14 @@ __global__ void im2col_nhwc_rows_kernel(const __nv_bfloat16* __restrict__ in, __
 }
 // First layer: NCHW fp32 image (C = 3).  K index = (kh*KW + kw)*C + c.  One thread builds 8
 // consecutive k of one output pixel (a 16-byte store); the gathers hit the L1/L2-resident image.
-template <typename idx_t>
+// CC / CKW > 0: compile-time channel count / kernel width (the 7x7, 3-channel ResNet stem), so the
+// per-element k -> (tap, c) -> (kh, kw) decode is multiply-shift instead of runtime division.
+template <typename idx_t, int CC, int CKW>
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                       int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
+                                       int B, int H, int W, int C_rt, int Ho, int Wo, int KH, int KW_rt,
                                        int stride, int pad, int Kp) {
+  const int C = CC > 0 ? CC : C_rt;
+  const int KW = CKW > 0 ? CKW : KW_rt;
   pdl_prologue();
   const idx_t chunks = static_cast<idx_t>(Kp >> 3);
   const idx_t total = static_cast<idx_t>(B) * Ho * Wo * chunks;
@@ -629,11 +633,14 @@ extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int 
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (Kp / 8);
   if (total <= 0) return TT_OK;
-  if (total < (1ll << 31) - (1ll << 24)) {
-    launch_k(im2col_nchw_f32_kernel<unsigned>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+  if (total < (1ll << 31) - (1ll << 24) && C == 3 && KW == 7) {
+    launch_k(im2col_nchw_f32_kernel<unsigned, 3, 7>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+        in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
+  } else if (total < (1ll << 31) - (1ll << 24)) {
+    launch_k(im2col_nchw_f32_kernel<unsigned, 0, 0>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
         in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
   } else {
-    launch_k(im2col_nchw_f32_kernel<long long>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
+    launch_k(im2col_nchw_f32_kernel<long long, 0, 0>, dim3(flat_grid3(total)), dim3(256), 0, (cudaStream_t)stream,
         in, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, Ho, Wo, KH, KW, stride, pad, Kp);
   }
   return check_launch("im2col_nchw_f32_kernel");
