@@ -39,6 +39,16 @@ def test_invalid_arguments_fail_loudly_without_a_gpu():
     assert rc == -1 and b'null params' in lib.tt_last_error()
     rc = lib.tt_glu_fwd(None, None, ctypes.c_longlong(4), ctypes.c_int(8), None)
     assert rc == -1
+    # argument validation happens before any launch, so it is observable without a device
+    ll, ci = ctypes.c_longlong, ctypes.c_int
+    rc = lib.tt_ce_bwd_bf16(None, ll(8), None, None, ci(4), ci(8), ci(1), None, None, None, ll(8),
+                            ci(0), None)
+    assert rc == -1 and b'tt_ce_bwd_bf16' in lib.tt_last_error()
+    rc = lib.tt_im2col_nhwc(None, None, ci(1), ci(4), ci(4), ci(8), ci(3), ci(3), ci(1), ci(1), ci(72),
+                            None)
+    assert rc == -1 and b'tt_im2col_nhwc' in lib.tt_last_error()
+    rc = lib.tt_cast_bf16(None, ll(8), None, ll(8), ci(4), ci(8), ci(0), ci(0), ll(0), None)
+    assert rc == -1 and b'tt_cast_bf16' in lib.tt_last_error()
 
 
 def test_ops_refuse_cpu_tensors():
