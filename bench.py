@@ -12,6 +12,7 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -379,6 +380,8 @@ def run_b200(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
     loss_val = float(loss_host.item())
+    if not math.isfinite(loss_val):
+        raise RuntimeError('bench: non-finite loss %r from the timed steps' % loss_val)
 
     # ---- live per-kernel timing (rank 0)
     # (1) kernel_breakdown: CUDA events around every C-ABI call of two eager steps.  Eager launches
