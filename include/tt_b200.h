@@ -436,6 +436,19 @@ int tt_im2col_nhwc_hw(const void* in, long long in_pitch, void* out, int B, int 
  * mtcnn.py:23,66,69,116,119,122). */
 int tt_maxpool_nhwc(const void* in, long long in_pitch, void* out, long long out_pitch, int B, int H,
                     int W, int C, int k, int stride, int pad, int ceil_mode, void* stream);
+/* Train-mode nn.BatchNorm2d of the frozen ResNet (tell/models/resnet.py:35,92-117 under model.train(),
+ * callback_apex_trainer.py:259; torchvision Bottleneck bn1/bn2/bn3/downsample.1): batch statistics.
+ * x: raw convolution output, bf16 NHWC rows [M = B*H*W, C] (row pitch in elements).
+ * tt_bn_stats_bf16: stats[0..C) += sum over rows, stats[C..2C) += sum of squares (fp32; the caller
+ *   zeroes `stats` -- one memset for all layers of a forward).
+ * tt_bn_apply_bf16: in place x = relu?((x - mean) * rsqrt(var_biased + eps) * gamma + beta + residual?);
+ *   when running_mean/var are given they move by `momentum` towards the batch mean / UNBIASED batch
+ *   variance and *num_batches_tracked (may be NULL) is incremented, as F.batch_norm(training=True). */
+int tt_bn_stats_bf16(const void* x, long long pitch, long long M, int C, float* stats, void* stream);
+int tt_bn_apply_bf16(void* x, long long pitch, long long M, int C, const float* stats, const float* gamma,
+                     const float* beta, float eps, const void* residual, long long rpitch, int relu,
+                     float* running_mean, float* running_var, float momentum,
+                     long long* num_batches_tracked, void* stream);
 /* nn.AdaptiveAvgPool2d(1) (inception_resnet_v1.py:249): [B, HW, C] bf16 -> [B, C] fp32. */
 int tt_avgpool_nhwc(const void* in, float* out, int B, int HW, int C, void* stream);
 /* nn.PReLU(C) in place on bf16 rows (mtcnn.py:22-27 ...). */

@@ -312,12 +312,30 @@ def greedy_generate(seed_ids, contexts, sd, cfg, gen_len=100, eos=2, padding_idx
 
 
 # ------------------------------------------------------------------------------------- encoders
-def resnet152_forward(image, sd, prefix='resnet.', bn_eps=1e-5, blocks=(3, 8, 36, 3)):
-    """models/resnet.py:92-108 (torchvision Bottleneck stack, eval-mode BatchNorm): [B,3,224,224]
-    -> [B,2048,7,7].  Third-party block definition (torchvision 0.6.1): parity unpinned."""
+def resnet152_forward(image, sd, prefix='resnet.', bn_eps=1e-5, blocks=(3, 8, 36, 3),
+                      bn_mode='running', return_stats=False, momentum=0.1):
+    """models/resnet.py:92-108 (torchvision Bottleneck stack): [B,3,224,224] -> [B,2048,7,7].
+    bn_mode 'running' = eval() semantics (evaluate / demo); 'batch' = train() semantics -- what the
+    reference's training step runs on the frozen backbone (callback_apex_trainer.py:259 calls
+    model.train(); only the PARAMETERS are frozen, config.yaml `no_grad`): every BatchNorm normalises
+    with the biased batch variance and moves its running statistics by `momentum` towards the batch
+    mean / UNBIASED batch variance (returned as `stats` when return_stats).
+    Pinned by tests/golden/resnet152.npz (the reference's own ResNetFeatureExtractor, both modes)."""
+    stats = {}
+
     def bn(x, p):
-        return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'],
-                            sd[p + 'bias'], False, 0.0, bn_eps)
+        if bn_mode == 'running':
+            return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'],
+                                sd[p + 'bias'], False, 0.0, bn_eps)
+        n = x.numel() // x.shape[1]
+        mean = x.mean(dim=(0, 2, 3))
+        var = x.var(dim=(0, 2, 3), unbiased=False)
+        name = p[len(prefix):]
+        stats[name + 'running_mean'] = (1 - momentum) * sd[p + 'running_mean'] + momentum * mean
+        stats[name + 'running_var'] = ((1 - momentum) * sd[p + 'running_var']
+                                       + momentum * var * n / max(n - 1, 1))
+        y = (x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + bn_eps).view(1, -1, 1, 1)
+        return y * sd[p + 'weight'].view(1, -1, 1, 1) + sd[p + 'bias'].view(1, -1, 1, 1)
     x = F.conv2d(image, sd[prefix + 'conv1.weight'], stride=2, padding=3)
     x = F.relu(bn(x, prefix + 'bn1.'))
     x = F.max_pool2d(x, 3, 2, 1)
@@ -333,7 +351,7 @@ def resnet152_forward(image, sd, prefix='resnet.', bn_eps=1e-5, blocks=(3, 8, 36
                 idn = bn(F.conv2d(x, sd[p + 'downsample.0.weight'], stride=stride),
                          p + 'downsample.1.')
             x = F.relu(o + idn)
-    return x
+    return (x, stats) if return_stats else x
 
 
 def roberta_forward(ids, sd, n_layers, heads, prefix='roberta.', padding_idx=1, eps=1e-5):

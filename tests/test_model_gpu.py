@@ -157,6 +157,44 @@ def test_model_forward_glue_loss_and_bert_weight_grad():
     assert (model.bert_weight.grad.cpu() - bwr.grad).abs().max() < 2e-3 * max(1e-2, bwr.grad.abs().max().item())
 
 
+def test_model_forward_and_generate_with_zero_width_faces_and_objects():
+    """A batch where no sample has a face or an object arrives as [B,1,0] arrays (the reference
+    reader's np.array([[]])); multi_head.py:349-368 then attends over bias_k / the zero row only.
+    forward() and generate() must agree with the oracle fed the same empty contexts."""
+    import restate
+    from tell_b200 import synth
+    rs = np.random.RandomState(5)
+    B, S, L, P = 2, 9, 3, 2
+    cfg = synth.CFG_TINY
+    cap = synth.caption_batch(B, 8, cfg['vocab'], rs, cutoffs=cfg['cutoffs'])
+    art = synth.article_batch(B, S, cfg['vocab'], rs)
+    feats = torch.from_numpy(rs.standard_normal((B, P, P, 2048)).astype(np.float32)).bfloat16()
+    hid = torch.from_numpy(rs.standard_normal((L, B * S, 1024)).astype(np.float32)).bfloat16()
+    cfg, sd, model = _tiny_model('bf16x3', _StubResNet(feats.cuda()), _StubRoberta(hid.cuda(), L - 1))
+    model.eval()
+    faces = torch.zeros(B, 1, 0)
+    objs = torch.zeros(B, 1, 0)
+    with torch.no_grad():
+        out = model(context={'roberta': art.cuda()}, image=torch.zeros(B, 3, 8, 8).cuda(),
+                    caption={'roberta': cap.clone().cuda()}, face_embeds=faces.cuda(),
+                    obj_embeds=objs.cuda(), metadata=[{}] * B)
+        hid_list = [h.float().view(B, S, 1024) for h in hid]
+        ctx = restate.build_contexts(feats.float().permute(0, 3, 1, 2), hid_list,
+                                     model.bert_weight.detach().cpu(), art, faces.clone(), objs.clone())
+        inp, tgt = restate.shift_caption(cap)
+        ocfg = synth.oracle_cfg(cfg)
+        ro, _ = restate.decoder_forward(inp, ctx, sd, ocfg)
+        _, n, rl = restate.adaptive_loss(ro, tgt, sd, ocfg['cutoffs'])
+        assert int(out['sample_size']) == n
+        assert abs(out['loss'].item() - rl.item()) < 1e-3
+        model.gen_len = 12
+        gen = model.generate({'roberta': art.cuda()}, torch.zeros(B, 3, 8, 8).cuda(), faces.cuda(),
+                             objs.cuda(), metadata=[{}] * B)
+        rids, rlp = restate.greedy_generate(torch.zeros(B, 1, dtype=torch.long), ctx, sd, ocfg, gen_len=12)
+        assert torch.equal(gen['generated_indices'].cpu(), rids)
+        assert (gen['log_probs'].cpu() - rlp).abs().max() < 1e-3
+
+
 def test_greedy_decode_token_exact_vs_reference():
     """Token ids emitted by the reference's own _generate (golden) are reproduced exactly; log-probs
     within 1e-3 (north_star).  bf16x3 precision."""

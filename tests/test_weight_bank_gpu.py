@@ -147,3 +147,33 @@ def test_wgrad_stream_gradients_match(level):
             assert _close(held[n], g0[n], 1e-4), ('graph', n)
     finally:
         config.enable_wgrad_stream(0)
+
+
+def test_bank_gradient_accumulation_over_two_backwards():
+    """p.grad adopted from the bank's persistent dv / dg buffers must survive the next backward:
+    two backwards without zeroing give g1 + g2 (== 2 g for the same batch), not 2 * g2."""
+    dec, cap, ctx = _build(True)
+    _step(dec, cap, ctx)                       # recording step
+    _, _, g1 = _step(dec, cap, ctx)
+    inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    # second batch: another caption, so that g2 != g1 and "2 * g2" is distinguishable from g1 + g2
+    cap2 = cap.clone()
+    cap2[:, 1:4] = cap.flip(0)[:, 1:4]
+    _, _, g2 = _step(dec, cap2, ctx)
+    for p in dec.parameters():
+        p.grad = None
+    for c in (cap, cap2):                      # accumulate: no zeroing in between
+        i, t = c[:, :-1].contiguous(), c[:, 1:].contiguous()
+        with dec.weight_scope():
+            X, _ = dec.forward_tbc({'roberta': i}, ctx)
+            T, B, E = X.shape
+            loss, _ = dec.adaptive_softmax.fused_loss(X.view(T * B, E), t.t().contiguous())
+        loss.backward()
+    checked = 0
+    for n, p in dec.named_parameters():
+        if n.endswith('weight_v') or n.endswith('weight_g'):
+            want = g1[n] + g2[n]
+            assert _close(p.grad, want, 1e-4), n
+            assert not _close(p.grad, 2 * g2[n], 1e-3) or _close(g1[n], g2[n], 1e-3), n
+            checked += 1
+    assert checked >= 10

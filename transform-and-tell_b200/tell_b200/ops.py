@@ -205,7 +205,12 @@ def wnorm_bwd(dw, v, g, norm):
 def nan_rows_(x):
     """In place: zero NaN rows of x [..., D]; returns the bool row mask."""
     D = x.shape[-1]
-    R = x.numel() // D if D > 0 else int(torch.Size(x.shape[:-1]).numel())
+    if x.numel() == 0:
+        # a batch without any face / object is [B,1,0] (np.array([[]]) in the reference reader):
+        # isnan(x).any(-1) over an empty axis is all False (transformer_faces_objects.py:374-379)
+        _check_cuda(x)
+        return torch.zeros(x.shape[:-1], dtype=torch.bool, device=x.device)
+    R = x.numel() // D
     mask = torch.empty(x.shape[:-1], dtype=torch.uint8, device=x.device)
     assert x.is_contiguous()
     _lib.call('tt_nan_rows', _ptr(x), _ptr(mask), c_int(R), c_int(D), _stream())
@@ -678,3 +683,30 @@ def softmax2_(x, c0=0):
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     _lib.call('tt_softmax2', _ptr(x), c_ll(x.stride(0)), c_ll(x.shape[0]), c_int(c0), _stream())
     return x
+
+
+def bn_stats(x2d, stats):
+    """Per-channel sum / sum of squares of bf16 rows [M, C] accumulated into fp32 stats [2*C]."""
+    _check_cuda(x2d, stats)
+    assert x2d.dtype == torch.bfloat16 and x2d.dim() == 2 and x2d.stride(1) == 1
+    assert stats.dtype == torch.float32 and stats.numel() == 2 * x2d.shape[1]
+    _lib.call('tt_bn_stats_bf16', _ptr(x2d), c_ll(x2d.stride(0)), c_ll(x2d.shape[0]),
+              c_int(x2d.shape[1]), _ptr(stats), _stream())
+    return stats
+
+
+def bn_apply_(x2d, stats, gamma, beta, eps, residual=None, relu=True, running_mean=None,
+              running_var=None, momentum=0.1, num_batches_tracked=None):
+    """Train-mode BatchNorm (+ identity, + ReLU) in place on bf16 rows [M, C] from bn_stats' sums."""
+    _check_cuda(x2d, stats, gamma, beta)
+    assert x2d.dtype == torch.bfloat16 and x2d.dim() == 2 and x2d.stride(1) == 1
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == x2d.shape and residual.stride(1) == 1
+    _lib.call('tt_bn_apply_bf16', _ptr(x2d), c_ll(x2d.stride(0)), c_ll(x2d.shape[0]), c_int(x2d.shape[1]),
+              _ptr(stats), _ptr(gamma), _ptr(beta), c_float(eps),
+              _ptr(residual) if residual is not None else None,
+              c_ll(residual.stride(0) if residual is not None else 0), c_int(1 if relu else 0),
+              _ptr(running_mean) if running_mean is not None else None,
+              _ptr(running_var) if running_var is not None else None, c_float(momentum),
+              _ptr(num_batches_tracked) if num_batches_tracked is not None else None, _stream())
+    return x2d

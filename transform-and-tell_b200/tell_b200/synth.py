@@ -179,8 +179,11 @@ def decoder_inputs(cfg, B, T, S, F=4, O=16, P=49, seed=1234):
     return cap, contexts
 
 
-def resnet_state_dict(layers=(3, 8, 36, 3), seed=0):
-    """torchvision-keyed ResNet weights with non-trivial BatchNorm statistics."""
+def resnet_state_dict(layers=(3, 8, 36, 3), seed=0, bn3_gain=0.5):
+    """torchvision-keyed ResNet weights with non-trivial BatchNorm statistics.  With running
+    statistics that do not track the activations the residual stream grows by about
+    sqrt(1 + bn3_gain^2) per block in eval mode (0.5 -> ~1e5 after 50 blocks; the full-depth golden
+    uses 0.25)."""
     rs = np.random.RandomState(seed)
 
     def n(*shape, std=1.0):
@@ -207,7 +210,7 @@ def resnet_state_dict(layers=(3, 8, 36, 3), seed=0):
             stride = 2 if (li > 0 and bi == 0) else 1
             conv(p + 'conv1', planes, inplanes, 1); bn(p + 'bn1', planes)
             conv(p + 'conv2', planes, planes, 3); bn(p + 'bn2', planes)
-            conv(p + 'conv3', planes * 4, planes, 1); bn(p + 'bn3', planes * 4, gain=0.5)
+            conv(p + 'conv3', planes * 4, planes, 1); bn(p + 'bn3', planes * 4, gain=bn3_gain)
             if bi == 0 and (stride != 1 or inplanes != planes * 4):
                 conv(p + 'downsample.0', planes * 4, inplanes, 1); bn(p + 'downsample.1', planes * 4)
             inplanes = planes * 4

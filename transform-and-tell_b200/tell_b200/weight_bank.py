@@ -247,6 +247,16 @@ class _BankWNormFn(Function):
             elif dw.data_ptr() != e.dw.data_ptr():
                 e.dw.copy_(dw)
         bank.claimed.clear()
+        # The gradients returned below are views of the bank's persistent dv / dg buffers, which
+        # AccumulateGrad adopts as p.grad without a copy.  If a previous backward's gradient is still
+        # there (gradient accumulation, zero_grad(set_to_none=False), two forwards before one step),
+        # the launch below would overwrite it and autograd would then add the new gradient to
+        # itself: move the old value out of the bank first so that `p.grad += new` is what it says.
+        for e in bank.wn:
+            for p_, buf in ((e.v, e.dv), (e.g, e.dg)):
+                g_ = p_.grad
+                if g_ is not None and g_.untyped_storage().data_ptr() == buf.untyped_storage().data_ptr():
+                    p_.grad = g_.clone()
         bank.wnorm_bwd()
         grads = []
         for e in bank.wn:
