@@ -312,45 +312,87 @@ def greedy_generate(seed_ids, contexts, sd, cfg, gen_len=100, eos=2, padding_idx
 
 
 # ------------------------------------------------------------------------------------- encoders
+def _resnet_bn(x, sd, p, prefix, bn_mode, bn_eps, momentum, stats, storage=None):
+    """nn.BatchNorm2d in eval() ('running') or train() ('batch') mode on a raw convolution output.
+    storage (tests only): models where the CUDA path keeps bf16 -- the raw convolution in batch
+    mode (running mode folds the scale into the weights, see _resnet_conv_bn)."""
+    if bn_mode == 'running':
+        return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'],
+                            sd[p + 'bias'], False, 0.0, bn_eps)
+    if storage is not None:
+        x = storage(x)
+    n = x.numel() // x.shape[1]
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    name = p[len(prefix):]
+    stats[name + 'running_mean'] = (1 - momentum) * sd[p + 'running_mean'] + momentum * mean
+    stats[name + 'running_var'] = ((1 - momentum) * sd[p + 'running_var']
+                                   + momentum * var * n / max(n - 1, 1))
+    y = (x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + bn_eps).view(1, -1, 1, 1)
+    return y * sd[p + 'weight'].view(1, -1, 1, 1) + sd[p + 'bias'].view(1, -1, 1, 1)
+
+
+def _resnet_conv_bn(x, sd, conv, bn, prefix, bn_mode, bn_eps, momentum, stats, storage, **kw):
+    w = sd[conv + 'weight']
+    if storage is None:
+        return _resnet_bn(F.conv2d(x, w, **kw), sd, bn, prefix, bn_mode, bn_eps, momentum, stats)
+    if bn_mode == 'running':       # the CUDA path rounds the FOLDED weight, bias stays fp32
+        scale = sd[bn + 'weight'] / torch.sqrt(sd[bn + 'running_var'] + bn_eps)
+        bias = sd[bn + 'bias'] - sd[bn + 'running_mean'] * scale
+        return F.conv2d(x, storage(w * scale.view(-1, 1, 1, 1)), **kw) + bias.view(1, -1, 1, 1)
+    return _resnet_bn(F.conv2d(x, storage(w), **kw), sd, bn, prefix, bn_mode, bn_eps, momentum,
+                      stats, storage)
+
+
+def resnet_bottleneck(x, sd, p, stride, prefix='', bn_mode='running', bn_eps=1e-5, momentum=0.1,
+                      stats=None, storage=None):
+    """torchvision Bottleneck.forward (v1.5: the stride sits on the 3x3 convolution)."""
+    stats = {} if stats is None else stats
+    st = storage if storage is not None else (lambda t: t)
+    a = (sd, None, None, prefix, bn_mode, bn_eps, momentum, stats, storage)
+
+    def cb(x, conv, bn, **kw):
+        return _resnet_conv_bn(x, sd, p + conv, p + bn, prefix, bn_mode, bn_eps, momentum, stats,
+                               storage, **kw)
+    idn = x
+    o = st(F.relu(cb(x, 'conv1.', 'bn1.')))
+    o = st(F.relu(cb(o, 'conv2.', 'bn2.', stride=stride, padding=1)))
+    o = cb(o, 'conv3.', 'bn3.')
+    if (p + 'downsample.0.weight') in sd:
+        idn = st(cb(x, 'downsample.0.', 'downsample.1.', stride=stride))
+    return st(F.relu(o + idn))
+
+
 def resnet152_forward(image, sd, prefix='resnet.', bn_eps=1e-5, blocks=(3, 8, 36, 3),
-                      bn_mode='running', return_stats=False, momentum=0.1):
+                      bn_mode='running', return_stats=False, momentum=0.1, storage=None,
+                      collect=None):
     """models/resnet.py:92-108 (torchvision Bottleneck stack): [B,3,224,224] -> [B,2048,7,7].
     bn_mode 'running' = eval() semantics (evaluate / demo); 'batch' = train() semantics -- what the
     reference's training step runs on the frozen backbone (callback_apex_trainer.py:259 calls
     model.train(); only the PARAMETERS are frozen, config.yaml `no_grad`): every BatchNorm normalises
     with the biased batch variance and moves its running statistics by `momentum` towards the batch
     mean / UNBIASED batch variance (returned as `stats` when return_stats).
-    Pinned by tests/golden/resnet152.npz (the reference's own ResNetFeatureExtractor, both modes)."""
+    Pinned by tests/golden/resnet152.npz (the reference's own ResNetFeatureExtractor, both modes).
+    storage: None = the reference arithmetic (fp32 throughout).  A rounding function (e.g.
+    lambda t: t.bfloat16().float()) is applied wherever the CUDA path keeps a value in bf16 -- image,
+    (folded) weights, raw convolutions in batch mode, every block-internal activation -- giving the
+    "same algorithm, bf16 storage" model the tests use to separate storage precision from mistakes.
+    collect: optional list receiving (name, input, output) of the stem and of every block."""
     stats = {}
-
-    def bn(x, p):
-        if bn_mode == 'running':
-            return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'],
-                                sd[p + 'bias'], False, 0.0, bn_eps)
-        n = x.numel() // x.shape[1]
-        mean = x.mean(dim=(0, 2, 3))
-        var = x.var(dim=(0, 2, 3), unbiased=False)
-        name = p[len(prefix):]
-        stats[name + 'running_mean'] = (1 - momentum) * sd[p + 'running_mean'] + momentum * mean
-        stats[name + 'running_var'] = ((1 - momentum) * sd[p + 'running_var']
-                                       + momentum * var * n / max(n - 1, 1))
-        y = (x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var + bn_eps).view(1, -1, 1, 1)
-        return y * sd[p + 'weight'].view(1, -1, 1, 1) + sd[p + 'bias'].view(1, -1, 1, 1)
-    x = F.conv2d(image, sd[prefix + 'conv1.weight'], stride=2, padding=3)
-    x = F.relu(bn(x, prefix + 'bn1.'))
-    x = F.max_pool2d(x, 3, 2, 1)
+    st = storage if storage is not None else (lambda t: t)
+    x = _resnet_conv_bn(st(image), sd, prefix + 'conv1.', prefix + 'bn1.', prefix, bn_mode, bn_eps,
+                        momentum, stats, storage, stride=2, padding=3)
+    x = F.max_pool2d(st(F.relu(x)), 3, 2, 1)
+    if collect is not None:
+        collect.append(('stem', image, x))
     for li, n in enumerate(blocks):
         for bi in range(n):
             p = prefix + 'layer%d.%d.' % (li + 1, bi)
             stride = 2 if (li > 0 and bi == 0) else 1
-            idn = x
-            o = F.relu(bn(F.conv2d(x, sd[p + 'conv1.weight']), p + 'bn1.'))
-            o = F.relu(bn(F.conv2d(o, sd[p + 'conv2.weight'], stride=stride, padding=1), p + 'bn2.'))
-            o = bn(F.conv2d(o, sd[p + 'conv3.weight']), p + 'bn3.')
-            if (p + 'downsample.0.weight') in sd:
-                idn = bn(F.conv2d(x, sd[p + 'downsample.0.weight'], stride=stride),
-                         p + 'downsample.1.')
-            x = F.relu(o + idn)
+            y = resnet_bottleneck(x, sd, p, stride, prefix, bn_mode, bn_eps, momentum, stats, storage)
+            if collect is not None:
+                collect.append((p[len(prefix):-1], x, y))
+            x = y
     return (x, stats) if return_stats else x
 
 

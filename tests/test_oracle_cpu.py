@@ -183,3 +183,68 @@ def test_face_encoder_restatements_match_reference_goldens():
         emb, logits = restate.inception_resnet_v1_forward(torch.from_numpy(g['irv1_x']), sd)
         assert (emb - torch.from_numpy(g['irv1_emb'])).abs().max().item() < 1e-5
         assert (logits - torch.from_numpy(g['irv1_logits'])).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------ full-size goldens (round 2)
+def test_resnet152_restatement_vs_reference_golden_both_bn_modes():
+    """restate.resnet152_forward at [3,8,36,3] / 224x224 against the output of the reference's own
+    ResNetFeatureExtractor (tests/golden/resnet152.npz) in eval() and train() BatchNorm modes, and
+    the running statistics the train-mode forward leaves behind."""
+    g = np.load(os.path.join(GOLD, 'resnet152.npz'))
+    sd = synth.resnet_state_dict((3, 8, 36, 3), seed=3, bn3_gain=0.25)
+    img = T_(np.random.RandomState(11).standard_normal((2, 3, 224, 224)).astype(np.float32))
+    with torch.no_grad():
+        y = restate.resnet152_forward(img, sd, prefix='')
+        ref = T_(g['y_eval'])
+        assert (y - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
+        y, stats = restate.resnet152_forward(img, sd, prefix='', bn_mode='batch', return_stats=True)
+        ref = T_(g['y_train'])
+        # train-mode BN on random weights amplifies fp32 summation-order noise (fp32 vs fp64: 3e-4)
+        assert (y - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    for k in g.files:
+        if k.startswith('after_train/'):
+            assert torch.allclose(stats[k[len('after_train/'):]], T_(g[k]), rtol=1e-3, atol=1e-5), k
+
+
+def test_roberta_restatement_vs_hf_golden():
+    """restate.roberta_forward at roberta.large size against HF RobertaModel's hidden states
+    (tests/golden/roberta_large.npz): pins the stand-in oracle of SURVEY 8c."""
+    g = np.load(os.path.join(GOLD, 'roberta_large.npz'))
+    L, E, H = 24, 1024, 16
+    sd = synth.roberta_state_dict(L, E, 4096, 50265, 514, seed=5)
+    rs = np.random.RandomState(21)
+    ids = synth.article_batch(3, 200, 50265, rs, min_len=40)
+    ids[1, 7:] = 1
+    ids[1, 6] = 2
+    with torch.no_grad():
+        hs = torch.stack(restate.roberta_forward(ids, sd, L, H, prefix=''))     # [25,B,S,E]
+    pos = g['sample_pos']
+    got = torch.stack([hs[:, b, pos[b]] for b in range(3)], 1)
+    assert (got - T_(g['hidden_at_pos'])).abs().max().item() < 2e-4
+    real = (ids != 1)
+    norms = ((hs * real.unsqueeze(0).unsqueeze(-1)) ** 2).sum(dim=(2, 3)).sqrt()
+    assert ((norms - T_(g['layer_norms'])).abs() / T_(g['layer_norms'])).max().item() < 1e-4
+    w = torch.softmax(T_(g['bert_weight']), 0)
+    mix = (hs * w.view(-1, 1, 1, 1)).sum(0) * real.unsqueeze(-1)
+    assert (mix - T_(g['mix']).float()).abs().max().item() < 2e-3       # golden stored as fp16
+
+
+def test_decoder_restatement_vs_reference_full_size_golden():
+    """restate.decoder_forward / adaptive_loss / adaptive_log_prob at the cfg-2 architecture and
+    shapes (B=4, T=50, S=512) against the reference decoder's own output."""
+    g = np.load(os.path.join(GOLD, 'decoder_full.npz'))
+    cfg = synth.CFG_FULL
+    sd = synth.decoder_state_dict(cfg, seed=1, logit_gain=2.0)
+    cap, ctx = synth.decoder_inputs(cfg, B=4, T=50, S=512, F=4, O=16, P=49, seed=4247)
+    inp, tgt = cap[:, :-1].contiguous(), cap[:, 1:].contiguous()
+    ocfg = synth.oracle_cfg(cfg)
+    with torch.no_grad():
+        out, extra = restate.decoder_forward(inp, ctx, sd, ocfg)
+        assert (out - T_(g['dec_out'])).abs().max().item() < 5e-5
+        loss_sum, n, loss = restate.adaptive_loss(out, tgt, sd, ocfg['cutoffs'])
+        assert n == int(g['ntokens'][0])
+        assert abs(loss.item() - float(g['loss'][0])) < 1e-4 * float(g['loss'][0])
+        lp = restate.adaptive_log_prob(out[:, -1:], sd, ocfg['cutoffs'])
+        assert (lp - T_(g['log_probs_last'])).abs().max().item() < 1e-4
+    assert float(g['greedy_margin_min'][0]) > 2e-3      # the stored greedy path is decidable at 1e-3
+    assert g['greedy_ids'].shape == (4, 101)

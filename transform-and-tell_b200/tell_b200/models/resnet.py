@@ -120,85 +120,88 @@ class ResNetFeatureExtractor(nn.Module):
     def uses_batch_stats(self):
         return self.bn_mode == 'batch' or (self.bn_mode == 'auto' and self.training)
 
+    # ------------------------------------------------------------------ one convolution + BN
+    def _operands(self, batch_stats):
+        if batch_stats:
+            if self._plain is None:
+                self.prepare(fold=False)
+            self._folded = None            # running statistics are about to move
+            return self._plain
+        if self._folded is None:
+            self.prepare()
+        return self._folded
+
+    class _Pass:
+        """Per-forward state: which BN mode, and (batch mode) the zeroed arena of per-channel sums
+        -- ONE memset for all 155 BatchNorm layers of a forward."""
+
+        def __init__(self, net, device, batch_stats):
+            self.net, self.batch = net, batch_stats
+            self.f = net._operands(batch_stats)
+            self.off = 0
+            self.arena = (torch.zeros(net._n_stats, dtype=torch.float32, device=device)
+                          if batch_stats else None)
+
+        def conv_bn(self, cols, wb, bn, relu=True, residual=None):
+            """cols [M,K] bf16 (im2col rows or the NHWC activation itself for 1x1) -> [M,Cout] bf16."""
+            w, b = wb
+            if not self.batch:
+                return ops.gemm_tn(cols, w, bias=b, residual16=residual,
+                                   act=ops.ACT_RELU if relu else ops.ACT_NONE, want32=False, want16=True)
+            y = ops.gemm_tn(cols, w, want32=False, want16=True)
+            C = y.shape[1]
+            st = self.arena[self.off:self.off + 2 * C]
+            self.off = (self.off + 2 * C) % self.arena.numel()
+            ops.bn_stats(y, st)
+            return ops.bn_apply_(y, st, bn.weight, bn.bias, bn.eps, residual=residual, relu=relu,
+                                 running_mean=bn.running_mean, running_var=bn.running_var,
+                                 momentum=self.net.momentum, num_batches_tracked=bn.num_batches_tracked)
+
+    def _stem(self, ps, image):
+        B = image.shape[0]
+        w = ps.f['stem'][0]
+        cols, Ho, Wo = ops.im2col_nchw_f32(image.contiguous(), 7, 7, 2, 3, w.shape[1])
+        x = ps.conv_bn(cols, ps.f['stem'], self.bn1)
+        return ops.maxpool3x3s2_nhwc(x.view(B, Ho, Wo, 64))
+
+    def _block(self, ps, x, li, bi):
+        blk = getattr(self, 'layer%d' % li)[bi]
+        c1, c2, c3, ds = ps.f[(li, bi)]
+        Bx, H, W, C = x.shape
+        x2 = x.view(Bx * H * W, C)
+        planes = c1[0].shape[0]
+        o = ps.conv_bn(x2, c1, blk.bn1)
+        cols, Ho, Wo = ops.im2col_nhwc(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1)
+        o = ps.conv_bn(cols, c2, blk.bn2)
+        if ds is not None:
+            if blk.conv2.stride != 1:
+                idc, _, _ = ops.im2col_nhwc(x, 1, 1, blk.conv2.stride, 0)
+            else:
+                idc = x2
+            idn = ps.conv_bn(idc, ds, blk.downsample[1], relu=False)
+        else:
+            idn = x2
+        return ps.conv_bn(o, c3, blk.bn3, residual=idn).view(Bx, Ho, Wo, planes * 4)
+
     @torch.no_grad()
     def features_nhwc(self, image):
         """image [B,3,H,W] fp32 -> [B, H/32, W/32, 2048] bf16 (NHWC)."""
-        if self.uses_batch_stats():
-            return self._features_batch_stats(image)
-        if self._folded is None:
-            self.prepare()
-        f = self._folded
-        B = image.shape[0]
-        w, b = f['stem']
-        cols, Ho, Wo = ops.im2col_nchw_f32(image.contiguous(), 7, 7, 2, 3, w.shape[1])
-        x = ops.gemm_tn(cols, w, bias=b, act=ops.ACT_RELU, want32=False, want16=True)
-        x = ops.maxpool3x3s2_nhwc(x.view(B, Ho, Wo, 64))
+        ps = self._Pass(self, image.device, self.uses_batch_stats())
+        x = self._stem(ps, image)
         for li in range(1, 5):
-            for bi, blk in enumerate(getattr(self, 'layer%d' % li)):
-                (w1, b1), (w2, b2), (w3, b3), ds = f[(li, bi)]
-                Bx, H, W, C = x.shape
-                x2 = x.view(Bx * H * W, C)
-                o = ops.gemm_tn(x2, w1, bias=b1, act=ops.ACT_RELU, want32=False, want16=True)
-                planes = w1.shape[0]
-                cols, Ho, Wo = ops.im2col_nhwc(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1)
-                o = ops.gemm_tn(cols, w2, bias=b2, act=ops.ACT_RELU, want32=False, want16=True)
-                if ds is not None:
-                    if blk.conv2.stride != 1:
-                        idc, _, _ = ops.im2col_nhwc(x, 1, 1, blk.conv2.stride, 0)
-                    else:
-                        idc = x2
-                    idn = ops.gemm_tn(idc, ds[0], bias=ds[1], want32=False, want16=True)
-                else:
-                    idn = x2
-                x = ops.gemm_tn(o, w3, bias=b3, residual16=idn, act=ops.ACT_RELU, want32=False,
-                                want16=True).view(Bx, Ho, Wo, planes * 4)
+            for bi in range(len(getattr(self, 'layer%d' % li))):
+                x = self._block(ps, x, li, bi)
         return x
 
-    def _features_batch_stats(self, image):
-        """Train-mode forward (batch statistics; running statistics move, as in the reference's
-        training step).  The folded running-statistics operands become stale and are dropped."""
-        if self._plain is None:
-            self.prepare(fold=False)
-        self._folded = None
-        f = self._plain
-        B = image.shape[0]
-        arena = torch.zeros(self._n_stats, dtype=torch.float32, device=image.device)
-        off = [0]
+    @torch.no_grad()
+    def stem_nhwc(self, image):
+        """conv1 + bn1 + relu + maxpool alone (tests: per-stage parity)."""
+        return self._stem(self._Pass(self, image.device, self.uses_batch_stats()), image)
 
-        def bn_(y2d, bn, residual=None, relu=True):
-            C = y2d.shape[1]
-            st = arena[off[0]:off[0] + 2 * C]
-            off[0] += 2 * C
-            ops.bn_stats(y2d, st)
-            return ops.bn_apply_(y2d, st, bn.weight, bn.bias, bn.eps, residual=residual, relu=relu,
-                                 running_mean=bn.running_mean, running_var=bn.running_var,
-                                 momentum=self.momentum, num_batches_tracked=bn.num_batches_tracked)
-
-        w, _ = f['stem']
-        cols, Ho, Wo = ops.im2col_nchw_f32(image.contiguous(), 7, 7, 2, 3, w.shape[1])
-        x = bn_(ops.gemm_tn(cols, w, want32=False, want16=True), self.bn1)
-        x = ops.maxpool3x3s2_nhwc(x.view(B, Ho, Wo, 64))
-        for li in range(1, 5):
-            for bi, blk in enumerate(getattr(self, 'layer%d' % li)):
-                (w1, _), (w2, _), (w3, _), ds = f[(li, bi)]
-                Bx, H, W, C = x.shape
-                x2 = x.view(Bx * H * W, C)
-                o = bn_(ops.gemm_tn(x2, w1, want32=False, want16=True), blk.bn1)
-                planes = w1.shape[0]
-                cols, Ho, Wo = ops.im2col_nhwc(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1)
-                o = bn_(ops.gemm_tn(cols, w2, want32=False, want16=True), blk.bn2)
-                if ds is not None:
-                    if blk.conv2.stride != 1:
-                        idc, _, _ = ops.im2col_nhwc(x, 1, 1, blk.conv2.stride, 0)
-                    else:
-                        idc = x2
-                    idn = bn_(ops.gemm_tn(idc, ds[0], want32=False, want16=True), blk.downsample[1],
-                              relu=False)
-                else:
-                    idn = x2
-                x = bn_(ops.gemm_tn(o, w3, want32=False, want16=True), blk.bn3,
-                        residual=idn).view(Bx, Ho, Wo, planes * 4)
-        return x
+    @torch.no_grad()
+    def block_nhwc(self, x, li, bi):
+        """One Bottleneck (layer `li` in 1..4, block `bi`) on an NHWC bf16 activation."""
+        return self._block(self._Pass(self, x.device, self.uses_batch_stats()), x.contiguous(), li, bi)
 
     def forward(self, x, pool=False):
         """resnet.py:92-117 API: [B,3,224,224] -> [B,2048,7,7] fp32 (or pooled [B,2048])."""
