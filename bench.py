@@ -52,10 +52,9 @@ def make_batch(B, T=50, S=512, F=4, O=16, vocab=50265, seed=1234):
     return dict(caption=cap, article=art, image=image, faces=faces, objs=objs)
 
 
-# dram__bytes_read+write of one ncu --set full capture of the largest GEMM of the step (RoBERTa fc1,
-# M=8192 N=4096 K=1024, bf16 out): see profiles/r1_gemm_8192x4096x1024_full.txt.  Algorithmic bytes
-# of that launch: (8192*1024 + 4096*1024 + 8192*4096) * 2 B = 92.3 MB.
-GEMM_TRAFFIC_NOTE = 41630720   # bytes per launch of that GEMM (25.36 MB read + 16.27 MB written)
+# roofline.traffic is null: the roofline entry aggregates ~400 launches of ~60 GEMM signatures per
+# step, so there is no single per-launch DRAM figure; per-kernel dram__bytes of one ncu pass over a
+# step are in profiles/ (r1_kernel_hbm_tensor.txt).
 
 
 def replay_gemm_signatures(sigs, n_prof, dev):
@@ -155,7 +154,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------ B200 arm
-def build_model(device):
+def build_model(device, bn_mode='batch'):
     from tell_b200.models import (DynamicConvFacesObjectsDecoder, RobertaEncoder,
                                   TransformerFacesObjectModel, resnet152)
     from tell_b200.modules import AdaptiveLoss
@@ -172,7 +171,33 @@ def build_model(device):
         if hasattr(m, 'running_var'):
             m.running_var.uniform_(0.5, 1.5)
             m.running_mean.normal_(0, 0.1)
+    # 'batch' = what the reference's training step does: model.train() leaves the frozen ResNet's
+    # BatchNorm on batch statistics (callback_apex_trainer.py:259); 'running' = eval() semantics
+    model.resnet.bn_mode = bn_mode
     return model.to(device).train()
+
+
+def real_token_gflop(article_ids, B):
+    """Algorithmic GFLOP of ONE step with the RoBERTa encoder counted on the real (packed) tokens:
+    per token 24 layers x (4 E^2 + 2 E FFN) MACs of projections, per sample 24 x 2 x len^2 x E MACs
+    of attention; decoder fwd+bwd 66.2 and ResNet 23.1 GFLOP per sample."""
+    E, FFN, L = 1024, 4096, 24
+    lens = (article_ids != 1).sum(1).double()
+    macs = float(lens.sum()) * L * (4 * E * E + 2 * E * FFN) + float((lens ** 2).sum()) * L * 2 * E
+    return 2.0 * macs / 1e9 + B * (66.2 + 23.1)
+
+
+def run_extra(script, *extra, timeout=240):
+    """Runs a tools/ benchmark in its own process (own CUDA context) and returns its one JSON line."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', script)] + list(extra),
+                           capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in r.stdout.strip().splitlines() if l.startswith('{')]
+        if r.returncode != 0 or not lines:
+            return {'error': (r.stderr or r.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except Exception as ex:       # noqa: BLE001 -- an extra must never take the headline line down
+        return {'error': repr(ex)[:300]}
 
 
 def run_b200(args):
@@ -201,7 +226,7 @@ def run_b200(args):
     config.enable_wgrad_stream(args.wgrad)   # weight-gradient GEMMs as a parallel graph branch
     config.encoder_overlap = bool(args.encoder_overlap)
     B = args.batch
-    model = build_model(dev)
+    model = build_model(dev, args.bn_mode)
     # the flat gradient buffer only exists where there is a collective to feed
     fg = FlatGradients(model.parameters(), attach=False) if world > 1 else None
     params = [p for p in model.parameters() if p.requires_grad]
@@ -383,6 +408,65 @@ def run_b200(args):
     if not math.isfinite(loss_val):
         raise RuntimeError('bench: non-finite loss %r from the timed steps' % loss_val)
 
+    # ---- parity mode: the SAME step with the decoder (forward, loss, backward) in 'bf16x3' -- the
+    #      precision in which tests/ hold the north-star gate (fp32 logits within 1e-3, greedy tokens
+    #      exact vs the reference).  Own step-buffer set and graphs, single stream, rank 0 only.
+    parity = None
+    if rank == 0 and not args.skip_parity_mode:
+        config.set_precision('bf16x3')
+        try:
+            ps = StepSet()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    ps.restore()
+                    ps.fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            _lib.reset_launch_count()
+            ps.restore()
+            ps.fwd_bwd()
+            torch.cuda.synchronize()
+            p_launches = _lib.launch_count()
+            ps.g1, ps.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            ps.restore()
+            with torch.cuda.graph(ps.g1):
+                ps.encode()
+            with torch.cuda.graph(ps.g2, pool=ps.g1.pool()):
+                ps.train_part()
+            torch.cuda.synchronize()
+
+            def p_step():
+                ps.restore()
+                ps.g1.replay()
+                ps.g2.replay()
+            for _ in range(3):
+                p_step()
+            torch.cuda.synchronize()
+            n_p = max(5, args.steps // 2)
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(n_p):
+                p_step()
+            e_.record()
+            torch.cuda.synchronize()
+            p_ms = s_.elapsed_time(e_) / n_p
+            p_loss = float(out_loss.item())
+            parity = {'precision': 'bf16x3', 'samples_per_s': round(B / (p_ms * 1e-3), 2),
+                      'ms_per_step': round(p_ms, 4), 'steps': n_p, 'gpu_launches_per_step': int(p_launches),
+                      'loss': p_loss,
+                      'what': 'decoder forward + loss + backward with error-compensated (hi/lo split) bf16 '
+                              'tensor-core GEMMs and fp32 attention; the frozen encoders have one precision '
+                              '(bf16 activations).  Single stream, no step pipelining, inputs resident'}
+            ps.g1 = ps.g2 = ps.enc = ps.static = None
+            del ps
+        finally:
+            config.set_precision('bf16')
+            for p_ in params:
+                p_.grad = None
+            torch.cuda.empty_cache()
+
     # ---- live per-kernel timing (rank 0)
     # (1) kernel_breakdown: CUDA events around every C-ABI call of two eager steps.  Eager launches
     #     are CPU-bound, so these include launch gaps: use them for SHARES of the step.
@@ -436,10 +520,12 @@ def run_b200(args):
         gemm_us, gemm_flop, gemm_calls, big = replay_gemm_signatures(sigs, n_prof, dev)
         peak_tf, peak_bw, src = peaks()
         achieved = gemm_flop / (gemm_us * 1e-6) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_kernel (tcgen05.mma + TMA)',
+        roof = {'bound': 'tensor',
+                'kernel': 'tcgen05 GEMM family: gemm2_bf16_kernel<BN> (CTA pair, large K-major problems) + '
+                          'gemm_bf16_tn_kernel<BN,TA,TB> (single CTA, small-M / transposed operands)',
                 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': round(achieved / peak_tf, 4), 'peak_source': src + ' bf16_tflops_sustained',
-                'traffic': GEMM_TRAFFIC_NOTE, 'launches_per_step': gemm_calls,
+                'traffic': None, 'launches_per_step': gemm_calls,
                 'flop_per_step': gemm_flop, 'device_ms_per_step': round(gemm_us / 1e3, 3),
                 'avg_launch_us': round(gemm_us / max(1, gemm_calls), 2),
                 'share_of_step_kernel_time': round(share, 4),
@@ -457,6 +543,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     peak_tf, _, src = peaks()
+    step_gflop = real_token_gflop(host['article'], B)
     value = world * B / (ms_value * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
     line = {
@@ -466,7 +553,14 @@ def run_b200(args):
         'data': 'synthetic', 'impl': 'b200',
         'config': {'workload': 'cfg2: full transform-and-tell (ResNet-152 + RoBERTa-large + 4-layer '
                                'DynamicConv decoder, image+article+faces+objects), batch 16/GPU, '
-                               'T=50, S=512, F=4, O=16, dropout on, fwd+bwd (no optimizer step)',
+                               'T=50, S=512, F=4, O=16, dropout on, fwd+bwd (no optimizer step); frozen '
+                               'ResNet BatchNorm on %s' % (
+                                   'BATCH statistics with running-stat updates (the reference training '
+                                   'step: model.train(), callback_apex_trainer.py:259)'
+                                   if args.bn_mode == 'batch' else
+                                   'RUNNING statistics folded into the convolutions (eval() semantics; the '
+                                   'reference training step uses batch statistics: --bn-mode batch)'),
+                   'bn_mode': args.bn_mode,
                    'global_batch': world * B, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
                    'encoder_overlap': bool(args.encoder_overlap),
@@ -484,15 +578,28 @@ def run_b200(args):
         'article_tokens': {'real': int((host['article'] != 1).sum()), 'padded': int(host['article'].numel()),
                            'note': 'the RoBERTa encoder runs on the real tokens only (packed rows); '
                                    'GFLOP/sample below is the padded-batch figure of SURVEY 8d'},
-        'step_roofline': {'gflop_per_sample': GFLOP_PER_SAMPLE,
-                          'achieved_tflops': round(value / world * GFLOP_PER_SAMPLE / 1e3, 1),
-                          'frac_of_peak': round(value / world * GFLOP_PER_SAMPLE / 1e3 / peak_tf, 4),
-                          'peak_source': src},
-        'roofline': roof, 'kernel_breakdown': breakdown,
+        'step_roofline': {'gflop_per_step_real_tokens': round(step_gflop, 1),
+                          'gflop_per_step_padded': round(GFLOP_PER_SAMPLE * B, 1),
+                          'achieved_tflops': round(step_gflop / ms_value, 1),
+                          'frac_of_peak': round(step_gflop / ms_value / peak_tf, 4),
+                          'peak_source': src,
+                          'note': 'algorithmic FLOP of one step with RoBERTa counted on the real (packed) '
+                                  'article tokens, divided by the timed ms_per_step'},
+        'parity_mode': parity,
+        'roofline': roof,
+        'kernel_breakdown': breakdown,
+        'kernel_breakdown_note': 'CUDA events around every C-ABI call of two EAGER steps: CPU-bound launches, '
+                                 'gaps included -- read as shares of the step, not as device time',
         'clocks': sampler.summary() if sampler else None,
     }
+    if world == 1 and not args.skip_extras:
+        # BASELINE.json configs[3] (greedy decode latency, batch 256, 50 steps) and configs[4] (long
+        # article, one GPU's share), each in its own process (a few GB beside this one's)
+        torch.cuda.empty_cache()
+        line['decode'] = run_extra('bench_decode.py', '--reps', '2')
+        line['cfg5'] = run_extra('bench_cfg5.py')
     if not args.skip_cpu_baseline and world == 1:
-        line['cpu_baseline'] = cpu_baseline(budget_s=25.0)
+        line['cpu_baseline'] = cpu_baseline(budget_s=25.0, bn_mode=args.bn_mode)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -526,12 +633,12 @@ def _oracle_state(seed=0):
     return dec, rob, res
 
 
-def _oracle_step(batch, dec, rob, res, bert_weight, ocfg):
+def _oracle_step(batch, dec, rob, res, bert_weight, ocfg, bn_mode='batch'):
     """One reference train step (forward + loss.backward(), no optimizer) on the CPU oracle:
     transformer_faces_objects.py:67-90 with frozen encoders under no_grad."""
     import restate
     with torch.no_grad():
-        feats = restate.resnet152_forward(batch['image'], res, prefix='')
+        feats = restate.resnet152_forward(batch['image'], res, prefix='', bn_mode=bn_mode)
         hid = restate.roberta_forward(batch['article'], rob, 24, 16, prefix='')
     ctx = restate.build_contexts(feats, hid, bert_weight, batch['article'], batch['faces'].clone(),
                                  batch['objs'].clone())
@@ -556,7 +663,7 @@ def _prepare_oracle(B):
     return dec, rob, res, bw, synth.oracle_cfg(synth.CFG_FULL), make_batch(B)
 
 
-def cpu_baseline(budget_s=25.0, B=2):
+def cpu_baseline(budget_s=25.0, B=4, bn_mode='batch'):
     """The oracle (kind 'port': the reference modules are Python and cannot travel to the GPU box;
     oracle/restate.py is pinned to them by golden vectors) timed on the host cores on a bounded
     sample of the same workload."""
@@ -564,16 +671,17 @@ def cpu_baseline(budget_s=25.0, B=2):
     torch.set_num_threads(cores)
     dec, rob, res, bw, ocfg, batch = _prepare_oracle(B)
     t0 = time.time()
-    _oracle_step(batch, dec, rob, res, bw, ocfg)          # warm-up
+    _oracle_step(batch, dec, rob, res, bw, ocfg, bn_mode)          # warm-up
     warm = time.time() - t0
     n = max(1, min(5, int((budget_s - warm) / max(warm, 1e-3))))
     t0 = time.time()
     for _ in range(n):
-        _oracle_step(batch, dec, rob, res, bw, ocfg)
+        _oracle_step(batch, dec, rob, res, bw, ocfg, bn_mode)
     dt = (time.time() - t0) / n
     return {'value': round(B / dt, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d timed step(s) of batch %d (same shapes: T=50, S=512, F=4, O=16; fp32; '
-                      'eval-free dropout-off oracle; %.1f s/step)' % (n, B, dt)}
+            'sample': '%d timed step(s) of batch %d (BASELINE.md section 4; same shapes: T=50, S=512, F=4, '
+                      'O=16; fp32; dropout off; ResNet BatchNorm on %s statistics; %.1f s/step)'
+                      % (n, B, bn_mode, dt)}
 
 
 def run_reference(args):
@@ -582,19 +690,20 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = 2
+    B = 4                       # the reference CPU arm runs batch 4
+    bn = args.bn_mode
     dec, rob, res, bw, ocfg, batch = _prepare_oracle(B)
     budget = 150.0
     t0 = time.time()
-    _oracle_step(batch, dec, rob, res, bw, ocfg)
+    _oracle_step(batch, dec, rob, res, bw, ocfg, bn)
     first = time.time() - t0
     warm = max(0, min(args.warmup, int(0.2 * budget / max(first, 1e-3))) - 1)
     for _ in range(warm):
-        _oracle_step(batch, dec, rob, res, bw, ocfg)
+        _oracle_step(batch, dec, rob, res, bw, ocfg, bn)
     steps = max(1, min(args.steps, int(0.7 * budget / max(first, 1e-3))))
     t0 = time.time()
     for _ in range(steps):
-        _oracle_step(batch, dec, rob, res, bw, ocfg)
+        _oracle_step(batch, dec, rob, res, bw, ocfg, bn)
     dt = (time.time() - t0) / steps
     value = B / dt
     sample = ('%d timed step(s) of batch %d per step (of %d requested), T=50, S=512, F=4, O=16, '
@@ -605,7 +714,10 @@ def run_reference(args):
             'data': 'synthetic', 'impl': 'reference',
             'config': {'workload': 'cfg2: full transform-and-tell (ResNet-152 + RoBERTa-large + 4-layer '
                                    'DynamicConv decoder), reference algorithm (oracle port) on host CPU, '
-                                   'batch %d per step, fwd+bwd' % B},
+                                   'batch %d per step (per-step time does not depend on the GPU arm\'s batch '
+                                   'of 16: samples/s is the unit), T=50, S=512, F=4, O=16, dropout off, ResNet '
+                                   'BatchNorm on %s statistics, fwd+bwd' % (B, bn),
+                       'bn_mode': bn},
             'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': sample},
             'e2e': {'value': round(value, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0,
@@ -631,6 +743,13 @@ def main():
                          'forward/backward of step i')
     ap.add_argument('--encoder-overlap', type=int, default=1, choices=[0, 1],
                     help='ResNet as a parallel stream branch beside RoBERTa')
+    ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
+                    help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
+                         "model.train()) or 'running' statistics folded into the convolutions (eval())")
+    ap.add_argument('--skip-parity-mode', action='store_true',
+                    help='skip the bf16x3 (1e-3-parity precision) throughput measurement')
+    ap.add_argument('--skip-extras', action='store_true',
+                    help='skip the decode-latency (configs[3]) and long-article (configs[4]) sub-records')
     ap.add_argument('--grad-dtype', default='fp32', choices=['bf16', 'fp32'],
                     help='dtype of the gradient all-reduce payload (N > 1)')
     args = ap.parse_args()

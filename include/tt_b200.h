@@ -95,6 +95,11 @@ int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
  * (entry, setup done, first TMA issued, first tile landed, last MMA issued, accumulator ready,
  * epilogue done, exit) to dev_ptr[cta*8 ..]; NULL (default) disables it. */
 void tt_gemm_set_trace(long long* dev_ptr);
+/* Experiment / test switch: 0 forces the register-level (row-per-thread) epilogue for every problem,
+ * non-zero (default; also env TT_GEMM_TMA_EPI) lets bf16-only outputs with N % 32 == 0 take the staged
+ * epilogue (shared-memory tile + cp.async.bulk.tensor store, bf16 residual by TMA load).  Both paths
+ * produce bit-identical results. */
+void tt_gemm_set_staged_epilogue(int on);
 
 /* fp32 [rows, cols] (row stride ld_src) -> bf16 operand for tt_gemm_bf16_tn.
  *   transpose==0: dst is [rows, cols*rep]   transpose!=0: dst is [cols, rows*rep]

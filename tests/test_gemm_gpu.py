@@ -171,3 +171,67 @@ def test_gemm_split_k(M, N, K, lim):
     assert err < 2e-3 * max(1.0, want.abs().max().item()), err
     if lim is not None:
         assert torch.equal(out[lim:].cpu(), torch.zeros(M - lim, N))
+
+
+def _staged(on):
+    from tell_b200 import _lib
+    _lib.lib().tt_gemm_set_staged_epilogue(1 if on else 0)
+
+
+@pytest.mark.parametrize('M,N,K,bias,res,act,alpha', [
+    (8192, 3072, 1024, True, False, 1, 1.0),     # CTA-pair kernel, 256-wide tiles, bias + ReLU
+    (8192, 4096, 1024, True, False, 2, 1.0),     # RoBERTa fc1: GELU
+    (8192, 1024, 4096, True, True, 0, 1.0),      # RoBERTa fc2: bf16 residual
+    (3136, 1024, 256, True, True, 1, 1.0),       # ResNet stage-3 expanding 1x1 conv + identity + ReLU
+    (12544, 512, 128, True, True, 1, 1.0),
+    (50176, 64, 64, True, False, 1, 1.0),        # N < every tile width except 64
+    (800, 1024, 1024, False, False, 0, 0.5),     # decoder-sized, alpha
+    (777, 96, 200, True, True, 1, 1.0),          # ragged M (last warp rows take the register path), N = 3 chunks
+    (40, 32, 64, False, True, 0, 1.0),           # one chunk, one staged warp + one ragged warp
+    (5000, 2048, 512, True, True, 2, 1.0)])
+def test_gemm_staged_epilogue_bit_identical_to_register_epilogue(M, N, K, bias, res, act, alpha):
+    """The staged epilogue (shared-memory tile + TMA store, bf16 residual by TMA load) must produce
+    exactly the bits of the row-per-thread register epilogue, and both must match torch fp32."""
+    from tell_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device='cuda') / 8).bfloat16()
+    b = (torch.randn(N, K, device='cuda') / 4).bfloat16()
+    bv = torch.randn(N, device='cuda') if bias else None
+    r16 = torch.randn(M, N, device='cuda').bfloat16() if res else None
+    outs = []
+    try:
+        for on in (False, True):
+            _staged(on)
+            c16 = torch.full((M, N), 7.0, dtype=torch.bfloat16, device='cuda')
+            ops.gemm_tn(a, b, out16=c16, bias=bv, residual16=r16, act=act, alpha=alpha, want32=False)
+            torch.cuda.synchronize()
+            outs.append(c16)
+    finally:
+        _staged(True)
+    assert torch.equal(outs[0], outs[1])
+    ref = _ref(a, b, bv, r16.float() if res else None, alpha, act)
+    err = (outs[1].float() - ref).abs().max().item()
+    assert err <= 1.2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_staged_epilogue_row_limit_and_strided_output():
+    """Device-side row limit: rows >= m_limit keep their previous contents (the ragged 32-row group
+    takes the register path); the output may be a column slice of a wider buffer (ldc16 > N)."""
+    from tell_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 4096, 1024, 512
+    a = (torch.randn(M, K, device='cuda') / 8).bfloat16()
+    b = (torch.randn(N, K, device='cuda') / 4).bfloat16()
+    bias = torch.randn(N, device='cuda')
+    r16 = torch.randn(M, N, device='cuda').bfloat16()
+    for lim in (4096, 2977, 1, 64):
+        m_limit = torch.tensor([lim], dtype=torch.int32, device='cuda')
+        wide = torch.full((M, 2 * N + 64), 3.0, dtype=torch.bfloat16, device='cuda')
+        out = wide[:, 64:64 + N]
+        ops.gemm_tn(a, b, out16=out, bias=bias, residual16=r16, act=1, want32=False, m_limit=m_limit,
+                    m_hint=lim)
+        torch.cuda.synchronize()
+        ref = _ref(a[:lim], b, bias, r16[:lim].float(), 1.0, 1)
+        assert (out[:lim].float() - ref).abs().max().item() <= 1.2e-2 * max(1.0, ref.abs().max().item())
+        assert (out[lim:] == 3.0).all()
+        assert (wide[:, :64] == 3.0).all() and (wide[:, 64 + N:] == 3.0).all()

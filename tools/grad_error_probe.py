@@ -25,11 +25,11 @@ sd_r = {}
 for k, v in sd.items():
     if v.is_floating_point() and 'version' not in k and '_float_tensor' not in k and 'position' not in k:
         if id(v) not in clones:
-            clones[id(v)] = v.double().clone().requires_grad_(True)
+            clones[id(v)] = v.clone().requires_grad_(True)
         sd_r[k] = clones[id(v)]
     else:
-        sd_r[k] = v.double() if v.is_floating_point() else v
-ctx_r = {k: (v.double().requires_grad_(k == 'article') if v.is_floating_point() else v) for k, v in ctx.items()}
+        sd_r[k] = v
+ctx_r = {k: (v.clone().requires_grad_(k == 'article') if v.is_floating_point() else v) for k, v in ctx.items()}
 ro, _ = restate.decoder_forward(inp, ctx_r, sd_r, ocfg)
 _, n, rl = restate.adaptive_loss(ro, tgt, sd_r, ocfg['cutoffs'])
 rl.backward()

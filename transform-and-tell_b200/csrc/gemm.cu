@@ -24,12 +24,14 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 512;   // staged-epilogue tiles (512 B aligned)
+  static constexpr int SMEM_BYTES = EPI_OFF + EPI_SMEM_BYTES + 1024;   // + barriers + align slack
 };
 
 template <int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -43,6 +45,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
+  uint8_t* epi = smem + Cfg::EPI_OFF;
 
   // shuffled so the compiler knows the role index is warp-uniform (uniform-datapath code)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -54,12 +58,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_epi) tma_prefetch_desc(&tmC);
+    if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], GEMM_THREADS - 128);
@@ -190,16 +197,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    EpiWarp ew;
+    ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
+    ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
+    ew.res_bar = smem_u32(&res_bar[warp - 4]);
+    ew.res_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ks = tile / num_mn, mn = tile - ks * num_mn;
       const int m_blk = mn % num_m, n_blk = mn / num_m;
       if (ks * kper >= min(num_k, (ks + 1) * kper)) continue;     // empty split
+      const int row0 = m_blk * BM + q * 32;
+      // staged (TMA) epilogue for warps whose 32 rows are all valid (never with split-K: the host
+      // only sets tma_epi for plain bf16-output problems)
+      const bool staged = g.tma_epi != 0 && row0 + 32 <= M;
+      if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
+        epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 5);
-      const long long row = m_blk * BM + q * 32 + lane;
+      const long long row = row0 + lane;
       const bool row_ok = row < M;
-      if (splits > 1) {
+      if (staged) {
+        epilogue_chunks_tma<BN>(g, &tmC, &tmR, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                                   static_cast<uint32_t>(acc * BN),
+                                half, row0, n_blk * BN, ew);
+      } else if (splits > 1) {
         GemmArgs ge = g;                      // partial product: bias / residual enter once (split 0)
         ge.atomic = 1;
         if (ks > 0) { ge.bias = nullptr; ge.residual = nullptr; ge.residual16 = nullptr; }
@@ -219,6 +241,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_phase ^= 1;
       }
     }
+    if (g.tma_epi != 0 && lane == 0) bulk_wait_group0();   // staged stores performed before exit
   }
 
   tcgen05_fence_before();
@@ -231,8 +254,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN, bool TA, bool TB>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
-                         cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                         const CUtensorMap& tmR, const GemmArgs& g, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -246,24 +269,26 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
     }
     attr_set = true;
   }
-  launch_k(gemm_bf16_tn_kernel<BN, TA, TB>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, g);
+  launch_k(gemm_bf16_tn_kernel<BN, TA, TB>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC,
+           tmR, g);
   return check_launch("gemm_bf16_tn_kernel");
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int grid,
-                       bool ta, bool tb, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, const GemmArgs& g, int grid, bool ta, bool tb,
+                       cudaStream_t stream) {
   if (ta) {
     if (tb) {
-      if constexpr (BN >= 64) return launch_gemm_t<BN, true, true>(tmA, tmB, g, grid, stream);
+      if constexpr (BN >= 64) return launch_gemm_t<BN, true, true>(tmA, tmB, tmC, tmR, g, grid, stream);
     } else {
-      return launch_gemm_t<BN, true, false>(tmA, tmB, g, grid, stream);
+      return launch_gemm_t<BN, true, false>(tmA, tmB, tmC, tmR, g, grid, stream);
     }
   } else {
     if (tb) {
-      if constexpr (BN >= 64) return launch_gemm_t<BN, false, true>(tmA, tmB, g, grid, stream);
+      if constexpr (BN >= 64) return launch_gemm_t<BN, false, true>(tmA, tmB, tmC, tmR, g, grid, stream);
     } else {
-      return launch_gemm_t<BN, false, false>(tmA, tmB, g, grid, stream);
+      return launch_gemm_t<BN, false, false>(tmA, tmB, tmC, tmR, g, grid, stream);
     }
   }
   set_error("tt_gemm_bf16_tn: transposed B needs a tile width >= 64");
@@ -295,14 +320,17 @@ static int pick_bn(int M, int N, int sms) {
   return 64;
 }
 
-int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream);  // gemm2.cu
+int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR,
+              cudaStream_t stream);  // gemm2.cu
 
+static int g_staged = -1;    // staged (TMA) epilogue switch: -1 = read TT_GEMM_TMA_EPI on first use
 static long long* g_trace = nullptr;
 long long* gemm_trace_ptr() { return g_trace; }
 
 }  // namespace tt
 
 extern "C" void tt_gemm_set_trace(long long* dev_ptr) { tt::g_trace = dev_ptr; }
+extern "C" void tt_gemm_set_staged_epilogue(int on) { tt::g_staged = on ? 1 : 0; }
 
 extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   using namespace tt;
@@ -360,8 +388,30 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.splits = 1;
   g.atomic = 0;
 
+  // Staged epilogue (gemm_common.cuh): bf16-only output whose rows the TMA engine can address.
+  CUtensorMap tmC = tmA, tmR = tmA;
+  g.tma_epi = 0;
+  {
+    if (g_staged < 0) {
+      const char* e = getenv("TT_GEMM_TMA_EPI");        // experiments: 0 = register epilogue everywhere
+      g_staged = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (g_staged && p->C16 != nullptr && p->C == nullptr && p->residual == nullptr && !p->accumulate && vec &&
+        p->N % 32 == 0 && p->M >= 32) {
+      rc = make_tmap_bf16_2d_sw(&tmC, p->C16, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldc16, 32, 32, 64);
+      if (rc != TT_OK) return rc;
+      g.tma_epi = 1;
+      if (p->residual16 != nullptr) {
+        rc = make_tmap_bf16_2d_sw(&tmR, p->residual16, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldr16, 32, 32,
+                                  64);
+        if (rc != TT_OK) return rc;
+        g.tma_epi = 2;
+      }
+    }
+  }
+
   {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
-    const int r2 = gemm2_try(p, g, reinterpret_cast<cudaStream_t>(stream));
+    const int r2 = gemm2_try(p, g, tmC, tmR, reinterpret_cast<cudaStream_t>(stream));
     if (r2 != 0) return r2 > 0 ? TT_OK : r2;
   }
 
@@ -396,9 +446,9 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   }
   const int grid = tiles < sms ? tiles : sms;
   switch (bn) {
-    case 256: return launch_gemm<256>(tmA, tmB, g, grid, ta, tb, s);
-    case 128: return launch_gemm<128>(tmA, tmB, g, grid, ta, tb, s);
-    case 64: return launch_gemm<64>(tmA, tmB, g, grid, ta, tb, s);
-    default: return launch_gemm<32>(tmA, tmB, g, grid, ta, tb, s);
+    case 256: return launch_gemm<256>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);
+    case 128: return launch_gemm<128>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);
+    case 64: return launch_gemm<64>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);
+    default: return launch_gemm<32>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);
   }
 }

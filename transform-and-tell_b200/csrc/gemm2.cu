@@ -29,7 +29,8 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;               // double-buffered 128 x BN accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 512;   // staged-epilogue tiles (512 B aligned)
+  static constexpr int SMEM_BYTES = EPI_OFF + EPI_SMEM_BYTES + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -110,6 +111,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const GemmArgs g) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -123,6 +125,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
+  uint8_t* epi = smem + Cfg::EPI_OFF;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -135,6 +139,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_epi) tma_prefetch_desc(&tmC);
+    if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -145,6 +151,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[s], 1);              // one multicast commit per tile
       mbar_init(&tmem_empty[s], 2 * 8);         // leader: 8 epilogue warps of each CTA
     }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -237,15 +244,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    EpiWarp ew;
+    ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
+    ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
+    ew.res_bar = smem_u32(&res_bar[warp - 4]);
+    ew.res_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + q * 32;
+      // staged (TMA) epilogue for warps whose 32 rows are all valid; the ragged last rows of a
+      // row-limited problem keep the register path (rows beyond the limit stay untouched)
+      const bool staged = g.tma_epi != 0 && row0 + 32 <= M;
+      if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
+        epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const long long row = static_cast<long long>(m_blk) * 2 * BM + rank * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BN),
-                          half, row, row_ok, n_blk * BN);
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if (staged) {
+        epilogue_chunks_tma<BN>(g, &tmC, &tmR, tacc, half, row0, n_blk * BN, ew);
+      } else {
+        const long long row = static_cast<long long>(row0) + lane;
+        epilogue_chunks<BN>(g, tacc, half, row, row < M, n_blk * BN);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // report to the leader's barrier
@@ -254,6 +274,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1;
       }
     }
+    if (g.tma_epi != 0 && lane == 0) bulk_wait_group0();   // staged stores performed before exit
   }
 
   tcgen05_fence_before();
@@ -266,8 +287,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int BN>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, int pairs,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                        const CUtensorMap& tmR, const GemmArgs& g, int pairs, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -279,13 +300,15 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     }
     attr_set = true;
   }
-  launch_k(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, g);
+  launch_k(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR,
+           g);
   return check_launch("gemm2_bf16_kernel");
 }
 
 // Called by tt_gemm_bf16_tn for large K-major problems.  Returns 1 if it took the problem, 0 if
 // the caller should use the 1-CTA kernel, <0 on error.
-int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream) {
+int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR,
+              cudaStream_t stream) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("TT_GEMM_2CTA");
@@ -321,8 +344,8 @@ int gemm2_try(const TtGemmParams* p, const GemmArgs& g, cudaStream_t stream) {
   if (rc != TT_OK) return rc;
   const int tiles = ceil_div(p->M, 2 * BM) * ceil_div(p->N, bn);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  rc = (bn == 256) ? launch_gemm2<256>(tmA, tmB, g, pairs, stream)
-                   : launch_gemm2<128>(tmA, tmB, g, pairs, stream);
+  rc = (bn == 256) ? launch_gemm2<256>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                   : launch_gemm2<128>(tmA, tmB, tmC, tmR, g, pairs, stream);
   return rc == TT_OK ? 1 : rc;
 }
 

@@ -28,6 +28,7 @@ struct GemmArgs {
   int splits;           // split-K factor (1-CTA kernel): partial products are added atomically into C
   int atomic;           // epilogue adds into C with atomics (set per tile by the split-K kernel)
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
+  int tma_epi;  // staged epilogue (bf16-only output, N % 32 == 0): 1 = TMA store of C16, 2 = + TMA load of residual16
   long long* trace;  // debug: [grid, 8] globaltimer stamps (tt_gemm_set_trace), normally null
 };
 
@@ -180,6 +181,126 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
           }
         }
       }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staged epilogue for bf16-only outputs (g.tma_epi != 0; host guarantees N % 32 == 0, 16-byte aligned
+// rows, no fp32 output / fp32 residual / accumulate / atomics).
+//
+// The register-level epilogue above is row-per-thread: every 16-byte global load / store instruction
+// of a warp touches 32 different cache lines, and that LSU work (not the round trip) is what the
+// large GEMMs and the ResNet 1x1 convolutions were bound by (profiles/r1_resnet_gemm_analysis.txt).
+// Here each epilogue warp owns a 32-row x 64-byte staging tile in shared memory (+ one for the
+// residual): the thread still owns one row of the chunk, but it writes its 4 x 16 bytes to SHARED
+// memory (SWIZZLE_64B: chunk j of row t at j ^ ((t >> 1) & 3) -> a quarter-warp covers all 32 banks)
+// and one lane hands the 2 KB tile to the TMA engine (cp.async.bulk.tensor store).  The bf16 residual
+// tile arrives the same way (TMA load -> swizzled ld.shared), requested one chunk ahead -- the first
+// chunk of a tile while that tile's MMAs are still running.
+constexpr int EPI_WARP_BYTES = 32 * 64;                 // 32 rows x 32 bf16
+constexpr int EPI_SMEM_BYTES = 2 * 8 * EPI_WARP_BYTES;  // output + residual staging of 8 warps
+
+struct EpiWarp {
+  uint32_t st_out, st_res, res_bar;   // shared-window addresses of this warp's tiles / barrier
+  uint32_t res_phase;
+};
+
+__device__ __forceinline__ void epi_request_residual(const CUtensorMap* tmR, const EpiWarp& ew, int col0,
+                                                     int row0) {
+  mbar_arrive_expect_tx_u(ew.res_bar, EPI_WARP_BYTES);
+  tma_load_2d_u(ew.st_res, tmR, ew.res_bar, col0, row0);
+}
+
+// Whole-warp, warp-uniform control flow.  row0: first of the 32 rows this warp owns (all < M).
+template <int BN>
+__device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUtensorMap* tmC,
+                                                    const CUtensorMap* tmR, uint32_t tmem_acc, int half,
+                                                    int row0, int n0, EpiWarp& ew) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+  const uint32_t my_out = ew.st_out + static_cast<uint32_t>(lane) * 64u;
+  const uint32_t my_res = ew.st_res + static_cast<uint32_t>(lane) * 64u;
+  const bool has_res = g.tma_epi == 2;
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += 2) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= g.N) break;
+    float4 bv[8];
+    if (g.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);
+    }
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
+    uint4 rh[4];
+    if (has_res) {
+      mbar_wait_u(ew.res_bar, ew.res_phase);
+      ew.res_phase ^= 1u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a = my_res + ((static_cast<uint32_t>(j) ^ sw) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rh[j].x), "=r"(rh[j].y), "=r"(rh[j].z), "=r"(rh[j].w) : "r"(a));
+      }
+      // The refill below must not overtake the reads above: its coordinate is made to depend on
+      // the last ld.shared (a warp-wide instruction: once lane 0 has its data, every lane has).
+      uint32_t zero;
+      asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(rh[3].w));
+      __syncwarp();
+      const int cn = c + 2;
+      if (lane == 0 && cn < BN / 32 && n0 + cn * 32 < g.N)
+        epi_request_residual(tmR, ew, n0 + cn * 32 + static_cast<int>(zero), row0);
+    }
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (g.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+      }
+    }
+    if (g.alpha != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+    }
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+          v[8 * j + 2 * e] += __low2float(h2);
+          v[8 * j + 2 * e + 1] += __high2float(h2);
+        }
+      }
+    }
+    if (g.act == TT_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_bf16(v[j]);
+    } else if (g.act == TT_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    // the previous chunk's store must have finished reading the staging tile
+    if (lane == 0) bulk_wait_group_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = my_out + ((static_cast<uint32_t>(j) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                   "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                   "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                   : "memory");
+    }
+    fence_proxy_async();                  // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d_u(tmC, ew.st_out, col0, row0);
+      bulk_commit_group();
+    }
+  }
 }
 
 }  // namespace tt

@@ -79,6 +79,11 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
                       uint64_t ld_elems, uint32_t box_inner, uint32_t box_rows) {
+  return make_tmap_bf16_2d_sw(m, ptr, inner, rows, ld_elems, box_inner, box_rows, 128);
+}
+
+int make_tmap_bf16_2d_sw(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+                         uint64_t ld_elems, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -89,7 +94,8 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu rows=%llu ld=%llu box=%ux%u",

@@ -11,6 +11,9 @@ const unsigned long long* rng_step_ptr();
 // inner = contiguous extent (elements), ld_elems = row stride (elements, multiple of 8).
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
                       uint64_t ld_elems, uint32_t box_inner, uint32_t box_rows);
+// Same with the swizzle width chosen (64 or 128 bytes = the box's inner extent in bytes).
+int make_tmap_bf16_2d_sw(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+                         uint64_t ld_elems, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
 
 // Kernel launch helper; TT_PDL=1 turns on programmatic dependent launch (measured neutral under
 // CUDA-graph replay, so off by default).
