@@ -102,6 +102,50 @@ def test_registry_builds_reference_model_block():
         Decoder.from_params(bad)
 
 
+@pytest.mark.parametrize('name,model_cls,decoder_cls,n_ctx', [
+    ('9_transformer_objects', 'TransformerFacesObjectModel', 'DynamicConvFacesObjectsDecoder', 4),
+    ('8_transformer_faces', 'TransformerFacesModel', 'DynamicConvFacesParallelDecoder', 3),
+    ('5_transformer_roberta', 'TransformerFlattenedModel', 'DynamicConvFlattenedDecoder', 2),
+    ('4_no_image', 'TransformerFlattenedModel', 'DynamicConvDecoderNoImage', 1)])
+def test_registry_builds_the_real_model_blocks(name, model_cls, decoder_cls, n_ctx):
+    """The REAL `model:` blocks of expt/nytimes/*/config.yaml (tests/golden/model_blocks.yaml,
+    extracted verbatim by oracle/extract_model_blocks.py) construct through the registry unchanged;
+    the cfg-2 decoder has the reference's 200,461,312 parameters and strict-loads a
+    reference-keyed state dict.  The two frozen encoders are injected small (building
+    roberta.large on the CPU adds nothing to what this test checks)."""
+    import yaml
+    import tell_b200.models as M
+    from tell_b200 import synth
+    with open(os.path.join(ROOT, 'tests', 'golden', 'model_blocks.yaml')) as f:
+        blocks = yaml.safe_load(f)
+    resnet = M.ResNetFeatureExtractor((1, 1, 1, 1))
+    roberta = M.RobertaEncoder(n_layers=1, embed_dim=64, heads=4, ffn=64, vocab=100, max_pos=20)
+    model = M.Model.from_params(blocks[name], resnet=resnet, roberta=roberta)
+    assert type(model).__name__ == model_cls
+    assert type(model.decoder).__name__ == decoder_cls
+    assert len(model.decoder.layers) == 4
+    assert len(model.decoder.layers[0].context_attns) == n_ctx
+    assert [l.conv.kernel_size for l in model.decoder.layers] == [3, 7, 15, 31]
+    n_dec = sum(p.numel() for p in model.decoder.parameters())
+    if name == '9_transformer_objects':
+        assert n_dec == 200461312
+        assert model.weigh_bert and model.bert_weight.numel() == 2     # 1 injected layer + embeddings
+        sd = synth.decoder_state_dict(synth.CFG_FULL, 0)
+        missing, unexpected = model.decoder.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+    assert all(not p.requires_grad for p in model.resnet.parameters())
+    assert all(not p.requires_grad for p in model.roberta.parameters())
+
+
+def test_allennlp_bridge_is_shipped_and_explains_itself():
+    """INTEGRATION.md section 1 tells the maintainer to import tell_b200.allennlp_bridge; neither
+    allennlp nor the reference package exists in this image, so the import must fail with the
+    reason (not with a missing module)."""
+    import importlib
+    with pytest.raises(ImportError, match='allennlp'):
+        importlib.import_module('tell_b200.allennlp_bridge')
+
+
 def test_collator_host_packing_and_generations_writer(tmp_path):
     """Host half of the batch-dict producer (no GPU): ragged packing + offsets, and the
     generations.jsonl wire format of tell/commands/evaluate.py:196-215."""

@@ -19,6 +19,15 @@ class Registrable:
         return deco
 
     @classmethod
+    def registered_names(cls):
+        """{name: class} registered on this base (or on bases related to it)."""
+        out = {}
+        for base, table in Registrable._registry.items():
+            if issubclass(base, cls) or issubclass(cls, base):
+                out.update(table)
+        return out
+
+    @classmethod
     def by_name(cls, name):
         for base, table in Registrable._registry.items():
             if issubclass(base, cls) or issubclass(cls, base):
