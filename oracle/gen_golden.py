@@ -189,6 +189,28 @@ def op_goldens():
     g['mha_empty/q'], g['mha_empty/y'], g['mha_empty/w'] = q.numpy(), y.numpy(), w.numpy()
     ry, rw = restate.multi_head_attention(q, key, mask, sd, 'a.', H, True)
     assert (ry - y).abs().max() < 1e-5 and (rw - w).abs().max() < 1e-6
+    # LightweightConv1dTBC (lightweight.py:88-240): static taps [H,1,K] (+ optional channel bias)
+    from tell.modules import LightweightConv1dTBC
+    for (T, B, C, H, K, bias) in [(5, 2, 64, 4, 7, False), (12, 3, 64, 8, 3, False), (4, 2, 32, 2, 15, False)]:
+        m = LightweightConv1dTBC(C, K, padding_l=K - 1, num_heads=H, weight_softmax=True, bias=bias).eval()
+        w = torch.from_numpy(rs.standard_normal((H, 1, K)).astype(np.float32))
+        m.weight.data.copy_(w)
+        if bias:
+            m.bias.data.copy_(torch.from_numpy(rs.standard_normal(C).astype(np.float32)))
+        x = torch.from_numpy(rs.standard_normal((T, B, C)).astype(np.float32))
+        with torch.no_grad():
+            y = m(x)
+            state, steps = {}, []
+            for t in range(T):
+                steps.append(m(x[t:t + 1], incremental_state=state))
+            yi = torch.cat(steps, 0)
+        assert (yi - y).abs().max() < 1e-5
+        tag = 'lightconv_T%d_K%d/' % (T, K)
+        g[tag + 'x'], g[tag + 'w'], g[tag + 'y'] = x.numpy(), w.numpy(), y.numpy()
+        if bias:
+            g[tag + 'bias'] = m.bias.detach().numpy()
+        ry = restate.lightweight_conv(x, w, K, H, bias=m.bias.detach() if bias else None)
+        assert (ry - y).abs().max() < 1e-5
     np.savez_compressed(os.path.join(OUT, 'ops.npz'), **g)
     print('ops ok')
 
@@ -247,4 +269,6 @@ if __name__ == '__main__':
     forward_glue_goldens()
     decoder_goldens(synth.CFG_TINY, 'faces_objects', 'tiny_faces_objects', gain=4.0)
     decoder_goldens(synth.CFG_TINY_NO_IMAGE, 'no_image', 'tiny_no_image', gain=4.0)
+    decoder_goldens(synth.CFG_TINY_FLATTENED, 'flattened', 'tiny_flattened', gain=4.0)
+    decoder_goldens(synth.CFG_TINY_FACES, 'faces_parallel', 'tiny_faces_parallel', gain=4.0)
     facenet_goldens()

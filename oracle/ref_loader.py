@@ -131,6 +131,10 @@ def build_decoder(kind='faces_objects', vocab_size=50265, embed_dim=1024, heads=
         from tell.models.decoder_faces_objects import DynamicConvFacesObjectsDecoder as D
     elif kind == 'no_image':
         from tell.models.decoder_flattened_no_image import DynamicConvDecoderNoImage as D
+    elif kind == 'flattened':
+        from tell.models.decoder_flattened import DynamicConvDecoder as D
+    elif kind == 'faces_parallel':
+        from tell.models.decoder_faces_parallel import DynamicConvFacesParallelDecoder as D
     else:
         raise ValueError(kind)
     dec = D(None, emb, 512, dropout, True, embed_dim, embed_dim, True, 'dynamic', True,

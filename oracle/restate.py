@@ -99,6 +99,21 @@ def dynamic_conv(x, w_filter, K, H, weight_softmax=True):
     return torch.einsum('tbhrk,tbhk->tbhr', win, p).reshape(T, B, C)
 
 
+def lightweight_conv(x, w, K, H, weight_softmax=True, bias=None):
+    """convolutions/lightweight.py:88-240 in closed form: static taps w [H,1,K] shared by every
+    (t, b); the softmax runs over all K taps and the taps that fall before t = 0 are dropped without
+    renormalisation -- both in _forward_expanded (K > T: weight.narrow AFTER the softmax, :197-199)
+    and in the incremental path (:174-176)."""
+    T, B, C = x.shape
+    R = C // H
+    p = w.view(H, K)
+    p = F.softmax(p, dim=-1) if weight_softmax else p
+    xp = torch.cat([x.new_zeros(K - 1, B, C), x], dim=0)
+    win = xp.unfold(0, K, 1).view(T, B, H, R, K)
+    out = torch.einsum('tbhrk,hk->tbhr', win, p).reshape(T, B, C)
+    return out if bias is None else out + bias.view(1, 1, -1)
+
+
 # ------------------------------------------------------------------------------------- attention
 def multi_head_attention(query, key, key_padding_mask, sd, prefix, H, need_weights=False):
     """attention/multi_head.py:288-486, static_kv=True / incremental_state=None path."""

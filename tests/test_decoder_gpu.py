@@ -25,11 +25,15 @@ def T_(x):
 
 def _setup(tag, precision):
     from tell_b200 import config, synth
-    from tell_b200.models import DynamicConvDecoderNoImage, DynamicConvFacesObjectsDecoder
+    from tell_b200 import models as M
     from tell_b200.testing import build_decoder
     config.set_precision(precision)
-    cfg = synth.CFG_TINY if tag == 'tiny_faces_objects' else synth.CFG_TINY_NO_IMAGE
-    cls = DynamicConvFacesObjectsDecoder if tag == 'tiny_faces_objects' else DynamicConvDecoderNoImage
+    # decoder_faces_objects.py / decoder_flattened_no_image.py / decoder_flattened.py /
+    # decoder_faces_parallel.py: every registered decoder variant has a reference-made golden
+    cfg, cls = {'tiny_faces_objects': (synth.CFG_TINY, M.DynamicConvFacesObjectsDecoder),
+                'tiny_no_image': (synth.CFG_TINY_NO_IMAGE, M.DynamicConvDecoderNoImage),
+                'tiny_flattened': (synth.CFG_TINY_FLATTENED, M.DynamicConvFlattenedDecoder),
+                'tiny_faces_parallel': (synth.CFG_TINY_FACES, M.DynamicConvFacesParallelDecoder)}[tag]
     sd = synth.decoder_state_dict(cfg, seed=0, logit_gain=4.0)
     dec = build_decoder(cfg, cls, sd).cuda()
     cap, ctx = synth.decoder_inputs(cfg, **SHAPES, seed=1234)
@@ -37,7 +41,8 @@ def _setup(tag, precision):
     return cfg, sd, dec, cap, ctx, g
 
 
-@pytest.mark.parametrize('tag', ['tiny_faces_objects', 'tiny_no_image'])
+@pytest.mark.parametrize('tag', ['tiny_faces_objects', 'tiny_no_image', 'tiny_flattened',
+                                 'tiny_faces_parallel'])
 @pytest.mark.parametrize('precision,tol', [('bf16x3', 1e-3), ('bf16', 0.15)])
 def test_decoder_forward_loss_grads(tag, precision, tol):
     cfg, sd, dec, cap, ctx, g = _setup(tag, precision)

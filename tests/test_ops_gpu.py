@@ -595,3 +595,48 @@ def test_im2col_nchw_f32_exact(B, C, H, W, k, s, p):
     u = u.view(B, C, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, K)
     assert torch.equal(cols[:, :K].cpu(), u.bfloat16())
     assert (cols[:, K:] == 0).all()
+
+
+def test_operator_modules_vs_reference_goldens():
+    """tests/golden/ops.npz holds outputs of the reference's own DynamicConv1dTBC (dynamic.py),
+    LightweightConv1dTBC (lightweight.py:88-240, incl. kernel longer than the sequence) and
+    MultiHeadAttention over an empty context (multi_head.py:349-368): the operator surface of
+    tell/modules/__init__.py, called through the same constructor kwargs, full sequence AND one step
+    at a time with incremental state.  bf16x3 precision, 1e-3."""
+    import numpy as np
+    from tell_b200 import config
+    from tell_b200.modules import DynamicConv1dTBC, LightweightConv1dTBC, MultiHeadAttention
+    config.set_precision('bf16x3')
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ops.npz'))
+
+    def T_(k):
+        return torch.from_numpy(g[k]).cuda()
+    for (T, K, H) in [(5, 15, 4), (12, 7, 4)]:
+        tag = 'dynconv_T%d_K%d/' % (T, K)
+        x, w, y = T_(tag + 'x'), T_(tag + 'w'), T_(tag + 'y')
+        m = DynamicConv1dTBC(x.shape[2], K, padding_l=K - 1, num_heads=H, weight_softmax=True).cuda().eval()
+        m.weight_linear.weight.data.copy_(w)
+        with torch.no_grad():
+            assert (m(x) - y).abs().max().item() < 1e-3, tag
+            state = {}
+            steps = torch.cat([m(x[t:t + 1], incremental_state=state) for t in range(T)], 0)
+            assert (steps - y).abs().max().item() < 1e-3, tag
+    for (T, K, H) in [(5, 7, 4), (12, 3, 8), (4, 15, 2)]:
+        tag = 'lightconv_T%d_K%d/' % (T, K)
+        x, w, y = T_(tag + 'x'), T_(tag + 'w'), T_(tag + 'y')
+        m = LightweightConv1dTBC(x.shape[2], K, padding_l=K - 1, num_heads=H, weight_softmax=True).cuda().eval()
+        m.weight.data.copy_(w)
+        with torch.no_grad():
+            assert (m(x) - y).abs().max().item() < 1e-4, tag
+            state = {}
+            steps = torch.cat([m(x[t:t + 1], incremental_state=state) for t in range(T)], 0)
+            assert (steps - y).abs().max().item() < 1e-4, tag
+    m = MultiHeadAttention(64, 4, kdim=512, vdim=512).cuda().eval()
+    sd = {k[len('mha_empty/a.'):]: T_(k) for k in g.files if k.startswith('mha_empty/a.')}
+    m.load_state_dict(sd, strict=True)
+    key = torch.zeros(1, 2, 0, device='cuda')
+    with torch.no_grad():
+        y, w = m(T_('mha_empty/q'), key, key, key_padding_mask=torch.zeros(2, 1, dtype=torch.bool, device='cuda'),
+                 static_kv=True, need_weights=True)
+    assert (y - T_('mha_empty/y')).abs().max().item() < 1e-3
+    assert (w - T_('mha_empty/w')).abs().max().item() < 1e-3

@@ -37,6 +37,10 @@ def test_op_goldens():
         tag = 'dynconv_T%d_K%d/' % (T, K)
         y = restate.dynamic_conv(T_(g[tag + 'x']), T_(g[tag + 'w']), K, 4)
         assert (y - T_(g[tag + 'y'])).abs().max() < 1e-5
+    for (T, K, H) in [(5, 7, 4), (12, 3, 8), (4, 15, 2)]:       # lightweight.py:88-240, incl. K > T
+        tag = 'lightconv_T%d_K%d/' % (T, K)
+        y = restate.lightweight_conv(T_(g[tag + 'x']), T_(g[tag + 'w']), K, H)
+        assert (y - T_(g[tag + 'y'])).abs().max() < 1e-5
     sd = {k[len('mha_empty/'):]: T_(g[k]) for k in g.files if k.startswith('mha_empty/a.')}
     q = T_(g['mha_empty/q'])
     y, w = restate.multi_head_attention(q, torch.zeros(1, 2, 0), torch.zeros(2, 1, dtype=torch.bool),
@@ -58,7 +62,9 @@ def test_forward_glue_goldens():
 
 
 @pytest.mark.parametrize('tag,cfg', [('tiny_faces_objects', synth.CFG_TINY),
-                                     ('tiny_no_image', synth.CFG_TINY_NO_IMAGE)])
+                                     ('tiny_no_image', synth.CFG_TINY_NO_IMAGE),
+                                     ('tiny_flattened', synth.CFG_TINY_FLATTENED),
+                                     ('tiny_faces_parallel', synth.CFG_TINY_FACES)])
 def test_decoder_goldens(tag, cfg):
     g = np.load(os.path.join(GOLD, 'decoder_%s.npz' % tag))
     sd = synth.decoder_state_dict(cfg, seed=0, logit_gain=4.0)

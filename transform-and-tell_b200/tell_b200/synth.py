@@ -18,6 +18,8 @@ CFG_TINY = dict(vocab=2000, embed_dim=64, heads=4, ffn=128, kernels=(3, 7), cuto
                 max_pos=512,
                 contexts=(('image', 2048), ('article', 1024), ('faces', 512), ('obj', 2048)))
 CFG_TINY_NO_IMAGE = dict(CFG_TINY, contexts=(('article', 1024),))
+CFG_TINY_FLATTENED = dict(CFG_TINY, contexts=(('image', 2048), ('article', 1024)))
+CFG_TINY_FACES = dict(CFG_TINY, contexts=(('image', 2048), ('article', 1024), ('faces', 512)))
 
 
 def full_cutoffs(cfg):
