@@ -49,6 +49,16 @@ def _worker(rank, world, port, out):
     assert w.grad.data_ptr() != fg2.flat.data_ptr()
     fg2.pack()
     assert torch.allclose(fg2.flat, local)
+    # bf16 payload: pack() converts while it gathers; unpack() hands the mean back as fp32 .grad
+    fg3 = FlatGradients([w, b, tied, frozen], attach=False, dtype=torch.bfloat16)
+    assert fg3.flat.dtype == torch.bfloat16 and fg3.flat.numel() == 20
+    fg3.pack()
+    assert torch.allclose(fg3.flat.float(), local, rtol=1e-2, atol=1e-2)
+    fg3.allreduce_mean()
+    fg3.unpack()
+    assert w.grad.dtype == torch.float32
+    want = (sum(gathered) / world)[:15].view(5, 3)
+    assert torch.allclose(w.grad, want, rtol=2e-2, atol=2e-2)
     if rank == 0:
         out.put(fg.flat.clone())
     dist.destroy_process_group()
