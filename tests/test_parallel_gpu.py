@@ -56,7 +56,7 @@ def _worker(rank, world, port, q):
     ctx = {k: v.cuda() for k, v in ctx.items()}
     per = SHAPES['B'] // world
     res = {}
-    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1.5e-2)):
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 1.5e-2)):   # fp32: atomics order only
         fg = FlatGradients(dec.parameters(), attach=False, dtype=dtype)
         _grads_of_shard(dec, cap, ctx, rank * per, (rank + 1) * per)
         fg.pack()

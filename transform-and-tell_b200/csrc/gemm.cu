@@ -17,7 +17,7 @@ namespace tt {
 
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 
-template <int BN>
+template <int BN, bool STAGED = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
@@ -25,15 +25,20 @@ struct GemmCfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 512;   // staged-epilogue tiles (512 B aligned)
-  static constexpr int SMEM_BYTES = EPI_OFF + EPI_SMEM_BYTES + 1024;   // + barriers + align slack
+  // + barriers + align slack (+ the staged epilogue's tiles)
+  static constexpr int SMEM_BYTES = STAGED ? EPI_OFF + EPI_SMEM_BYTES + 1024 : STAGES * STAGE_BYTES + 256 + 1024;
 };
 
-template <int BN, bool TA, bool TB>
+// STAGED: the instantiation that carries the staged (TMA store) epilogue of gemm_common.cuh; the
+// plain one is compiled without it -- with both epilogues in one kernel the register allocation of
+// the row-per-thread path degraded (+1.4 us per launch, +3 us per tile on the fp32-output decoder
+// GEMMs, measured against the previous build on the same box: profiles/r2_gemm_small_ab.txt).
+template <int BN, bool TA, bool TB, bool STAGED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -45,8 +50,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
-  uint8_t* epi = smem + Cfg::EPI_OFF;
+  [[maybe_unused]] uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
+  [[maybe_unused]] uint8_t* epi = smem + Cfg::EPI_OFF;
 
   // shuffled so the compiler knows the role index is warp-uniform (uniform-datapath code)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -58,15 +63,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (g.tma_epi) tma_prefetch_desc(&tmC);
-    if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
+    if constexpr (STAGED) {
+      tma_prefetch_desc(&tmC);
+      if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    if constexpr (STAGED) {
+      for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], GEMM_THREADS - 128);
@@ -197,30 +206,38 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    EpiWarp ew;
-    ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
-    ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
-    ew.res_bar = smem_u32(&res_bar[warp - 4]);
-    ew.res_phase = 0;
+    [[maybe_unused]] EpiWarp ew;
+    if constexpr (STAGED) {
+      ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
+      ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
+      ew.res_bar = smem_u32(&res_bar[warp - 4]);
+      ew.res_phase = 0;
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ks = tile / num_mn, mn = tile - ks * num_mn;
       const int m_blk = mn % num_m, n_blk = mn / num_m;
       if (ks * kper >= min(num_k, (ks + 1) * kper)) continue;     // empty split
       const int row0 = m_blk * BM + q * 32;
       // staged (TMA) epilogue for warps whose 32 rows are all valid (never with split-K: the host
-      // only sets tma_epi for plain bf16-output problems)
-      const bool staged = g.tma_epi != 0 && row0 + 32 <= M;
-      if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
-        epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
+      // only picks the STAGED instantiation for plain bf16-output problems)
+      bool staged = false;
+      if constexpr (STAGED) {
+        staged = row0 + 32 <= M;
+        if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
+          epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       if (threadIdx.x == 128 && tile == blockIdx.x) trace_stamp(g, 5);
       const long long row = row0 + lane;
       const bool row_ok = row < M;
+      if constexpr (STAGED) {
+        if (staged)
+          epilogue_chunks_tma<BN>(g, &tmC, &tmR, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                                     static_cast<uint32_t>(acc * BN),
+                                  half, row0, n_blk * BN, ew);
+      }
       if (staged) {
-        epilogue_chunks_tma<BN>(g, &tmC, &tmR, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                                   static_cast<uint32_t>(acc * BN),
-                                half, row0, n_blk * BN, ew);
       } else if (splits > 1) {
         GemmArgs ge = g;                      // partial product: bias / residual enter once (split 0)
         ge.atomic = 1;
@@ -241,7 +258,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_phase ^= 1;
       }
     }
-    if (g.tma_epi != 0 && lane == 0) bulk_wait_group0();   // staged stores performed before exit
+    if constexpr (STAGED) {
+      if (lane == 0) bulk_wait_group0();   // staged stores performed before exit
+    }
   }
 
   tcgen05_fence_before();
@@ -253,13 +272,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, bool TA, bool TB>
+template <int BN, bool TA, bool TB, bool STAGED = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                          const CUtensorMap& tmR, const GemmArgs& g, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, TA, TB>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, TA, TB, STAGED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -269,8 +288,8 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     }
     attr_set = true;
   }
-  launch_k(gemm_bf16_tn_kernel<BN, TA, TB>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC,
-           tmR, g);
+  launch_k(gemm_bf16_tn_kernel<BN, TA, TB, STAGED>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA,
+           tmB, tmC, tmR, g);
   return check_launch("gemm_bf16_tn_kernel");
 }
 
@@ -288,6 +307,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (tb) {
       if constexpr (BN >= 64) return launch_gemm_t<BN, false, true>(tmA, tmB, tmC, tmR, g, grid, stream);
     } else {
+      if (g.tma_epi != 0) return launch_gemm_t<BN, false, false, true>(tmA, tmB, tmC, tmR, g, grid, stream);
       return launch_gemm_t<BN, false, false>(tmA, tmB, tmC, tmR, g, grid, stream);
     }
   }
@@ -396,8 +416,8 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
       const char* e = getenv("TT_GEMM_TMA_EPI");        // experiments: 0 = register epilogue everywhere
       g_staged = (e && e[0] == '0') ? 0 : 1;
     }
-    if (g_staged && p->C16 != nullptr && p->C == nullptr && p->residual == nullptr && !p->accumulate && vec &&
-        p->N % 32 == 0 && p->M >= 32) {
+    if (g_staged && !ta && !tb && p->C16 != nullptr && p->C == nullptr && p->residual == nullptr &&
+        !p->accumulate && vec && p->N % 32 == 0 && p->M >= 32) {
       rc = make_tmap_bf16_2d_sw(&tmC, p->C16, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldc16, 32, 32, 64);
       if (rc != TT_OK) return rc;
       g.tma_epi = 1;

@@ -22,7 +22,7 @@ namespace tt {
 
 constexpr int G2_THREADS = 384;
 
-template <int BN>
+template <int BN, bool STAGED>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of B
@@ -30,7 +30,7 @@ struct Gemm2Cfg {
   static constexpr int STAGES = (BN >= 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;               // double-buffered 128 x BN accumulator
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 512;   // staged-epilogue tiles (512 B aligned)
-  static constexpr int SMEM_BYTES = EPI_OFF + EPI_SMEM_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGED ? EPI_OFF + EPI_SMEM_BYTES + 1024 : STAGES * STAGE_BYTES + 256 + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -108,12 +108,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int BN>
+template <int BN, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const GemmArgs g) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -125,8 +125,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
-  uint8_t* epi = smem + Cfg::EPI_OFF;
+  [[maybe_unused]] uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // one per epilogue warp
+  [[maybe_unused]] uint8_t* epi = smem + Cfg::EPI_OFF;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -139,8 +139,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (g.tma_epi) tma_prefetch_desc(&tmC);
-    if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
+    if constexpr (STAGED) {
+      tma_prefetch_desc(&tmC);
+      if (g.tma_epi == 2) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -151,7 +153,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[s], 1);              // one multicast commit per tile
       mbar_init(&tmem_empty[s], 2 * 8);         // leader: 8 epilogue warps of each CTA
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    if constexpr (STAGED) {
+      for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -244,24 +248,31 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    EpiWarp ew;
-    ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
-    ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
-    ew.res_bar = smem_u32(&res_bar[warp - 4]);
-    ew.res_phase = 0;
+    [[maybe_unused]] EpiWarp ew;
+    if constexpr (STAGED) {
+      ew.st_out = smem_u32(epi) + static_cast<uint32_t>(warp - 4) * EPI_WARP_BYTES;
+      ew.st_res = ew.st_out + 8 * EPI_WARP_BYTES;
+      ew.res_bar = smem_u32(&res_bar[warp - 4]);
+      ew.res_phase = 0;
+    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       // staged (TMA) epilogue for warps whose 32 rows are all valid; the ragged last rows of a
       // row-limited problem keep the register path (rows beyond the limit stay untouched)
-      const bool staged = g.tma_epi != 0 && row0 + 32 <= M;
-      if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
-        epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
+      bool staged = false;
+      if constexpr (STAGED) {
+        staged = row0 + 32 <= M;
+        if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
+          epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if constexpr (STAGED) {
+        if (staged) epilogue_chunks_tma<BN>(g, &tmC, &tmR, tacc, half, row0, n_blk * BN, ew);
+      }
       if (staged) {
-        epilogue_chunks_tma<BN>(g, &tmC, &tmR, tacc, half, row0, n_blk * BN, ew);
       } else {
         const long long row = static_cast<long long>(row0) + lane;
         epilogue_chunks<BN>(g, tacc, half, row, row < M, n_blk * BN);
@@ -274,7 +285,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1;
       }
     }
-    if (g.tma_epi != 0 && lane == 0) bulk_wait_group0();   // staged stores performed before exit
+    if constexpr (STAGED) {
+      if (lane == 0) bulk_wait_group0();   // staged stores performed before exit
+    }
   }
 
   tcgen05_fence_before();
@@ -286,13 +299,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, bool STAGED>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                         const CUtensorMap& tmR, const GemmArgs& g, int pairs, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm2 BN=%d): %s", BN, cudaGetErrorString(e));
@@ -300,8 +313,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     }
     attr_set = true;
   }
-  launch_k(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR,
-           g);
+  launch_k(gemm2_bf16_kernel<BN, STAGED>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB,
+           tmC, tmR, g);
   return check_launch("gemm2_bf16_kernel");
 }
 
@@ -344,8 +357,12 @@ int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, 
   if (rc != TT_OK) return rc;
   const int tiles = ceil_div(p->M, 2 * BM) * ceil_div(p->N, bn);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  rc = (bn == 256) ? launch_gemm2<256>(tmA, tmB, tmC, tmR, g, pairs, stream)
-                   : launch_gemm2<128>(tmA, tmB, tmC, tmR, g, pairs, stream);
+  if (g.tma_epi != 0)
+    rc = (bn == 256) ? launch_gemm2<256, true>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                     : launch_gemm2<128, true>(tmA, tmB, tmC, tmR, g, pairs, stream);
+  else
+    rc = (bn == 256) ? launch_gemm2<256, false>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                     : launch_gemm2<128, false>(tmA, tmB, tmC, tmR, g, pairs, stream);
   return rc == TT_OK ? 1 : rc;
 }
 

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtt_b200.so')
+# TT_B200_LIB: load another build of the same ABI (A/B timing of two library versions); never a fallback
+LIB_PATH = os.environ.get('TT_B200_LIB') or os.path.join(_HERE, 'libtt_b200.so')
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
