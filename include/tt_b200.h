@@ -89,6 +89,11 @@ typedef struct {
    * indices k >= *k_limit (e.g. the rows of a gradient beyond a device-side row count), so the
    * kernel may stop its K loop there (rounded up to whole 64-wide k-blocks, at least one). */
   const int* k_limit;
+  /* Optional fp32 [2*N], zeroed by the caller: the kernel ADDS the per-column sum of the (bf16-rounded)
+   * outputs to col_stats[0..N) and the sum of their squares to col_stats[N..2N) -- the batch statistics
+   * a train-mode BatchNorm behind this convolution needs (tt_bn_apply_bf16), accumulated in the epilogue
+   * instead of by a separate pass over the output.  Needs the bf16 output (C16). */
+  float* col_stats;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
 /* Debug hook: when non-NULL, every CTA of the 1-CTA GEMM kernel writes 8 %globaltimer stamps (
@@ -449,6 +454,15 @@ int tt_maxpool_nhwc(const void* in, long long in_pitch, void* out, long long out
  * tt_bn_apply_bf16: in place x = relu?((x - mean) * rsqrt(var_biased + eps) * gamma + beta + residual?);
  *   when running_mean/var are given they move by `momentum` towards the batch mean / UNBIASED batch
  *   variance and *num_batches_tracked (may be NULL) is incremented, as F.batch_norm(training=True). */
+/* tt_im2col_nhwc_bn: tt_im2col_nhwc of relu((x - mean) * rsqrt(var + eps) * gamma + beta) where x is the
+ *   RAW output of the previous convolution and (mean, var) come from `stats` (its col_stats, over
+ *   n_stat rows): the train-mode BatchNorm + ReLU between a 1x1 and a 3x3 convolution applied while
+ *   gathering, so the normalised activation is never written.  Padding taps stay zero.  Running
+ *   statistics are updated exactly once, as in tt_bn_apply_bf16. */
+int tt_im2col_nhwc_bn(const void* in, void* out, int B, int H, int W, int C, int KH, int KW, int stride,
+                      int pad, int Kp, const float* stats, long long n_stat, const float* gamma,
+                      const float* beta, float eps, float* running_mean, float* running_var,
+                      float momentum, long long* num_batches_tracked, void* stream);
 int tt_bn_stats_bf16(const void* x, long long pitch, long long M, int C, float* stats, void* stream);
 int tt_bn_apply_bf16(void* x, long long pitch, long long M, int C, const float* stats, const float* gamma,
                      const float* beta, float eps, const void* residual, long long rpitch, int relu,

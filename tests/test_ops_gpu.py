@@ -640,3 +640,33 @@ def test_operator_modules_vs_reference_goldens():
                  static_kv=True, need_weights=True)
     assert (y - T_('mha_empty/y')).abs().max().item() < 1e-3
     assert (w - T_('mha_empty/w')).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize('B,H,W,C,stride', [(2, 14, 14, 256, 1), (2, 28, 28, 128, 2), (3, 7, 9, 64, 1), (1, 5, 5, 8, 2)])
+def test_im2col_with_fused_batchnorm_relu(B, H, W, C, stride):
+    """tt_im2col_nhwc_bn == tt_im2col_nhwc(relu(train-mode batchnorm(x))) (padding taps zero), and
+    the running statistics move as F.batch_norm(training=True) moves them."""
+    from tell_b200 import ops
+    torch.manual_seed(B * 100 + C)
+    x = (torch.randn(B, H, W, C, device='cuda') * 1.5 + 0.3).bfloat16()
+    gamma = 1 + 0.2 * torch.randn(C, device='cuda')
+    beta = 0.1 * torch.randn(C, device='cuda')
+    rm, rv = torch.randn(C, device='cuda') * 0.1, torch.rand(C, device='cuda') + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    nbt = torch.zeros((), dtype=torch.long, device='cuda')
+    x2 = x.view(-1, C)
+    st = torch.zeros(2 * C, device='cuda')
+    ops.bn_stats(x2, st)
+    cols, Ho, Wo = ops.im2col_nhwc_bn(x, 3, 3, stride, 1, st, x2.shape[0], gamma, beta, 1e-5, rm, rv, 0.1, nbt)
+    # reference: torch batch norm on the same bf16 values, then the plain im2col kernel
+    xf = x.float().permute(0, 3, 1, 2)
+    rm_r, rv_r = rm0.clone(), rv0.clone()
+    y = F.relu(F.batch_norm(xf, rm_r, rv_r, gamma, beta, True, 0.1, 1e-5))
+    y16 = y.permute(0, 2, 3, 1).contiguous().bfloat16()
+    ref, Ho2, Wo2 = ops.im2col_nhwc(y16, 3, 3, stride, 1)
+    assert (Ho, Wo) == (Ho2, Wo2) and cols.shape == ref.shape
+    assert (cols.float() - ref.float()).abs().max().item() <= 2e-2 * max(1.0, ref.float().abs().max().item())
+    # zero taps identical (padding stays exactly zero)
+    assert torch.equal(cols == 0, ref == 0) or ((cols == 0) != (ref == 0)).float().mean().item() < 1e-3
+    assert (rm - rm_r).abs().max().item() < 1e-4 and (rv - rv_r).abs().max().item() < 1e-3
+    assert int(nbt) == 1

@@ -92,6 +92,76 @@ __global__ void im2col_nhwc_rows_kernel(const __nv_bfloat16* __restrict__ in, __
     }
   }
 }
+// Same gather with the producer's train-mode BatchNorm + ReLU applied on the fly: `in` is the RAW
+// output of the previous (1x1) convolution, sc/sh = per-channel scale / shift derived from its column
+// sums (the GEMM epilogue's col_stats) once per CTA into shared memory.  Padding taps stay zero (the
+// reference pads the NORMALISED activation).  Block 0 moves the running statistics.
+__global__ void im2col_nhwc_bn_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                           int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
+                                           int stride, int pad, int Kp, int kw_inv,
+                                           const float* __restrict__ stats, long long n_stat,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           float eps, float* __restrict__ running_mean,
+                                           float* __restrict__ running_var, float momentum,
+                                           long long* __restrict__ nbt) {
+  pdl_prologue();
+  extern __shared__ float sc_sh[];          // [C] scale, [C] shift
+  float* sc = sc_sh;
+  float* sh = sc_sh + C;
+  const float inv_n = 1.f / static_cast<float>(n_stat);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = stats[c] * inv_n;
+    const float var = fmaxf(stats[C + c] * inv_n - mean * mean, 0.f);
+    const float a = gamma[c] * rsqrtf(var + eps);
+    sc[c] = a;
+    sh[c] = beta[c] - mean * a;
+    if (blockIdx.x == 0 && running_mean != nullptr) {
+      const float unbiased = var * (n_stat > 1 ? static_cast<float>(n_stat) / static_cast<float>(n_stat - 1) : 1.f);
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  const int cpr = Kp >> 3, C8 = C >> 3, taps = KH * KW;
+  const int rows = B * Ho * Wo;
+  for (int row = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+    const int wo = row % Wo, t = row / Wo;
+    const int ho = t % Ho, b = t / Ho;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const __nv_bfloat16* src = in + static_cast<long long>(b) * H * W * C;
+    uint4* dst = reinterpret_cast<uint4*>(out) + static_cast<long long>(row) * cpr;
+#pragma unroll 2
+    for (int ch = lane; ch < cpr; ch += 32) {
+      const int tap = ch / C8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (tap < taps) {
+        const int c8 = ch - tap * C8;
+        const int kh = (tap * kw_inv) >> 16, kw = tap - kh * KW;
+        const int hi = h0 + kh, wi = w0 + kw;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<long long>(hi) * W + wi) * C) + c8);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&v);
+          const float4 a0 = *reinterpret_cast<const float4*>(sc + c8 * 8), a1 = *reinterpret_cast<const float4*>(sc + c8 * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sh + c8 * 8), b1 = *reinterpret_cast<const float4*>(sh + c8 * 8 + 4);
+          float2 f;
+          f = __bfloat1622float2(h2[0]);
+          o2[0] = __floats2bfloat162_rn(fmaxf(fmaf(f.x, a0.x, b0.x), 0.f), fmaxf(fmaf(f.y, a0.y, b0.y), 0.f));
+          f = __bfloat1622float2(h2[1]);
+          o2[1] = __floats2bfloat162_rn(fmaxf(fmaf(f.x, a0.z, b0.z), 0.f), fmaxf(fmaf(f.y, a0.w, b0.w), 0.f));
+          f = __bfloat1622float2(h2[2]);
+          o2[2] = __floats2bfloat162_rn(fmaxf(fmaf(f.x, a1.x, b1.x), 0.f), fmaxf(fmaf(f.y, a1.y, b1.y), 0.f));
+          f = __bfloat1622float2(h2[3]);
+          o2[3] = __floats2bfloat162_rn(fmaxf(fmaf(f.x, a1.z, b1.z), 0.f), fmaxf(fmaf(f.y, a1.w, b1.w), 0.f));
+        }
+      }
+      dst[ch] = v;
+    }
+  }
+}
 // First layer: NCHW fp32 image (C = 3).  K index = (kh*KW + kw)*C + c.  One thread builds 8
 // consecutive k of one output pixel (a 16-byte store); the gathers hit the L1/L2-resident image.
 // CC / CKW > 0: compile-time channel count / kernel width (the 7x7, 3-channel ResNet stem), so the
@@ -624,6 +694,31 @@ extern "C" int tt_im2col_nhwc(const void* in, void* out, int B, int H, int W, in
         Ho, Wo, KH, KW, stride, pad, Kp);
   }
   return check_launch("im2col_nhwc_kernel");
+}
+
+extern "C" int tt_im2col_nhwc_bn(const void* in, void* out, int B, int H, int W, int C, int KH, int KW, int stride,
+                                 int pad, int Kp, const float* stats, long long n_stat, const float* gamma,
+                                 const float* beta, float eps, float* running_mean, float* running_var,
+                                 float momentum, long long* num_batches_tracked, void* stream) {
+  TT_REQUIRE(in && out && stats && gamma && beta, "tt_im2col_nhwc_bn: null pointer");
+  TT_REQUIRE(C % 8 == 0 && C <= 4096 && Kp % 8 == 0 && Kp >= KH * KW * C,
+             "tt_im2col_nhwc_bn: C (<= 4096), Kp must be multiples of 8");
+  TT_REQUIRE(n_stat > 0, "tt_im2col_nhwc_bn: n_stat must be positive");
+  TT_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
+             "tt_im2col_nhwc_bn: running_mean and running_var go together");
+  TT_REQUIRE(KH * KW < 65536 / KW, "tt_im2col_nhwc_bn: kernel too large");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long rows = static_cast<long long>(B) * Ho * Wo;
+  if (rows <= 0) return TT_OK;
+  TT_REQUIRE(rows * (Kp / 8) < (1ll << 31), "tt_im2col_nhwc_bn: problem too large");
+  long long ctas = ceil_div_ll(rows, 8);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (ctas > cap) ctas = cap;
+  launch_k(im2col_nhwc_bn_rows_kernel, dim3((int)ctas), dim3(256), static_cast<size_t>(2 * C) * sizeof(float),
+           (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B,
+           H, W, C, Ho, Wo, KH, KW, stride, pad, Kp, 65536 / KW + 1, stats, n_stat, gamma, beta, eps, running_mean,
+           running_var, momentum, num_batches_tracked);
+  return check_launch("im2col_nhwc_bn_rows_kernel");
 }
 
 extern "C" int tt_im2col_nchw_f32(const float* in, void* out, int B, int H, int W, int C, int KH,

@@ -246,9 +246,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     static_cast<uint32_t>(acc * BN),
                             half, row, row_ok, n_blk * BN);
       } else {
-        epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN),
-                            half, row, row_ok, n_blk * BN);
+        epilogue_chunks<BN, STAGED>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                           static_cast<uint32_t>(acc * BN),
+                                    half, row, row_ok, n_blk * BN);
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -395,6 +395,9 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.alpha = p->alpha; g.act = p->act; g.accumulate = p->accumulate;
   g.m_limit = p->m_limit;
   g.k_limit = p->k_limit;
+  g.col_stats = p->col_stats;
+  TT_REQUIRE(p->col_stats == nullptr || (p->C16 != nullptr && p->C == nullptr && !p->accumulate),
+             "tt_gemm_bf16_tn: col_stats needs a bf16-only output");
   bool vec = true;
   if (p->C) vec = vec && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0 && (p->ldc % 4 == 0);
   if (p->C16) vec = vec && (reinterpret_cast<uintptr_t>(p->C16) & 15) == 0 && (p->ldc16 % 8 == 0);
@@ -430,6 +433,10 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     }
   }
 
+  TT_REQUIRE(p->col_stats == nullptr || g.tma_epi != 0,
+             "tt_gemm_bf16_tn: col_stats needs a staged-epilogue problem (K-major operands, N %% 32 == 0, "
+             "16-byte aligned bf16 output rows, M >= 32)");
+
   {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
     const int r2 = gemm2_try(p, g, tmC, tmR, reinterpret_cast<cudaStream_t>(stream));
     if (r2 != 0) return r2 > 0 ? TT_OK : r2;
@@ -451,7 +458,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     // run-dependent, which the backward already tolerates (LayerNorm / column-sum / scatter
     // atomics) but greedy decoding must not -- its GEMMs never set a hint and stay bit-reproducible.
     if (sk && p->m_limit != nullptr && p->m_hint > 0 && p->C != nullptr && p->C16 == nullptr &&
-        p->act == TT_ACT_NONE && !p->accumulate && tiles * 2 <= sms && num_k >= 32) {
+        p->act == TT_ACT_NONE && !p->accumulate && tiles * 2 <= sms && num_k >= 32 && p->col_stats == nullptr) {
       int sp = sms / tiles;
       if (sp > num_k / 8) sp = num_k / 8;     // at least 8 k-blocks per split
       if (sp > 1) {

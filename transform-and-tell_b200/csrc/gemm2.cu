@@ -275,7 +275,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (staged) {
       } else {
         const long long row = static_cast<long long>(row0) + lane;
-        epilogue_chunks<BN>(g, tacc, half, row, row < M, n_blk * BN);
+        epilogue_chunks<BN, STAGED>(g, tacc, half, row, row < M, n_blk * BN);
       }
       tcgen05_fence_before();
       __syncwarp();

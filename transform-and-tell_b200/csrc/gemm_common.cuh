@@ -28,6 +28,7 @@ struct GemmArgs {
   int splits;           // split-K factor (1-CTA kernel): partial products are added atomically into C
   int atomic;           // epilogue adds into C with atomics (set per tile by the split-K kernel)
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
+  float* col_stats;   // optional [2N]: += column sums / sums of squares of the bf16-rounded outputs
   int tma_epi;  // staged epilogue (bf16-only output, N % 32 == 0): 1 = TMA store of C16, 2 = + TMA load of residual16
   long long* trace;  // debug: [grid, 8] globaltimer stamps (tt_gemm_set_trace), normally null
 };
@@ -47,11 +48,35 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Column statistics of one 32 x 32 chunk held row-per-thread (register epilogue: the ragged rows of
+// a problem, or problems the staged epilogue does not take).  Values are rounded to bf16 first, so
+// the statistics are those of the stored tensor.  64 warp reductions: rare path.
+static __device__ __noinline__ void chunk_col_stats_regs(const GemmArgs& g, const float (&v)[32], bool row_ok,
+                                                  int col0) {
+  const int lane = threadIdx.x & 31;
+  float s_mine = 0.f, q_mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float r = row_ok ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+    const float s = warp_sum(r), q = warp_sum(r * r);
+    if (lane == j) {
+      s_mine = s;
+      q_mine = q;
+    }
+  }
+  if (col0 + lane < g.N) {
+    atomicAdd(g.col_stats + col0 + lane, s_mine);
+    atomicAdd(g.col_stats + g.N + col0 + lane, q_mine);
+  }
+}
+
 // Epilogue of one 128 x BN accumulator (one thread = one row, 32 columns per tcgen05.ld).
 // tmem_acc: TMEM address of column 0 of the accumulator, already offset to this warp's lane quarter.
 // Two warps share a lane quarter: `half` selects the even / odd 32-column chunks.
 // Result = act(alpha * (acc + bias) + residual) -> fp32 and/or bf16, optional += into C.
-template <int BN>
+// STATS: compiled only into the staged instantiations (their ragged-row fallback); the plain kernels
+// never see col_stats (the host routes such problems to the staged kernels or rejects them).
+template <int BN, bool STATS = false>
 __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem_acc, int half,
                                                 long long row, bool row_ok, int n0) {
   const int lane = threadIdx.x & 31;
@@ -84,10 +109,22 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
         const uint32_t taddr = tmem_acc + static_cast<uint32_t>(c * 32);
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
-        if (!in_n || !row_ok) continue;
+        if (!in_n) continue;
+        if constexpr (!STATS) {
+          if (!row_ok) continue;
+        } else {
+          if (g.col_stats == nullptr && !row_ok) continue;    // (with statistics the warp stays together)
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if constexpr (STATS) {
+          if (g.col_stats != nullptr) {
+            // batch-statistics convolutions carry no bias / activation / residual: v is the output
+            chunk_col_stats_regs(g, v, row_ok, col0);
+            if (!row_ok) continue;
+          }
+        }
         if (full) {
           if (g.bias != nullptr) {
 #pragma unroll
@@ -229,8 +266,6 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
 #pragma unroll
       for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);
     }
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
     uint4 rh[4];
     if (has_res) {
       mbar_wait_u(ew.res_bar, ew.res_phase);
@@ -239,10 +274,10 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
       for (int j = 0; j < 4; ++j) {
         const uint32_t a = my_res + ((static_cast<uint32_t>(j) ^ sw) << 4);
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(rh[j].x), "=r"(rh[j].y), "=r"(rh[j].z), "=r"(rh[j].w) : "r"(a));
+                     : "=r"(rh[j].x), "=r"(rh[j].y), "=r"(rh[j].z), "=r"(rh[j].w) : "r"(a) : "memory");
       }
       // The refill below must not overtake the reads above: its coordinate is made to depend on
-      // the last ld.shared (a warp-wide instruction: once lane 0 has its data, every lane has).
+      // the last ld.shared (every lane executes the dependent instruction before the warp barrier).
       uint32_t zero;
       asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(rh[3].w));
       __syncwarp();
@@ -250,6 +285,11 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
       if (lane == 0 && cn < BN / 32 && n0 + cn * 32 < g.N)
         epi_request_residual(tmR, ew, n0 + cn * 32 + static_cast<int>(zero), row0);
     }
+    // tcgen05.ld writes its destination registers asynchronously until wait::ld: NOTHING may sit
+    // between the two (with other code in between the compiler is free to spill / move the
+    // not-yet-written registers -- observed as rare stale 16-byte pieces in the output).
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
     tmem_ld_wait();
     float v[32];
 #pragma unroll
@@ -299,6 +339,23 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
     if (lane == 0) {
       tma_store_2d_u(tmC, ew.st_out, col0, row0);
       bulk_commit_group();
+    }
+    if (g.col_stats != nullptr) {
+      // lane c sums column c of the staged bf16 tile (32 lanes read one 64-byte row per step: one
+      // wavefront), then one atomic per column per 32 rows
+      const uint32_t jc = static_cast<uint32_t>(lane >> 3), off = static_cast<uint32_t>(lane & 7) * 2u;
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const uint32_t a = ew.st_out + static_cast<uint32_t>(rr) * 64u + ((jc ^ static_cast<uint32_t>((rr >> 1) & 3)) << 4) + off;
+        unsigned short h;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a));
+        const float x = __uint_as_float(static_cast<uint32_t>(h) << 16);
+        s += x;
+        q = fmaf(x, x, q);
+      }
+      atomicAdd(g.col_stats + col0 + lane, s);
+      atomicAdd(g.col_stats + g.N + col0 + lane, q);
     }
   }
 }

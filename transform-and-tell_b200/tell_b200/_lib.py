@@ -30,7 +30,8 @@ class TtGemmParams(ctypes.Structure):
                 ('residual', c_void_p), ('ldr', c_ll),
                 ('residual16', c_void_p), ('ldr16', c_ll),
                 ('alpha', c_float), ('act', c_int), ('accumulate', c_int),
-                ('m_limit', c_void_p), ('trans_a', c_int), ('trans_b', c_int), ('m_hint', c_int), ('k_limit', c_void_p)]
+                ('m_limit', c_void_p), ('trans_a', c_int), ('trans_b', c_int), ('m_hint', c_int), ('k_limit', c_void_p),
+                ('col_stats', c_void_p)]
 
 
 _lib = None

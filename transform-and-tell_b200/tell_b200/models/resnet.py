@@ -10,9 +10,11 @@ BatchNorm follows nn.BatchNorm2d: `bn_mode`
              statistics and moving its running statistics every step; evaluate / demo run eval();
   'running'  always the running statistics, folded into the GEMM weights with bias, identity branch
              and ReLU in the GEMM epilogue;
-  'batch'    always batch statistics: GEMM writes the raw convolution, `tt_bn_stats_bf16` reduces
-             per-channel sums, `tt_bn_apply_bf16` normalises (+ identity, ReLU) in place and updates
-             running_mean / running_var / num_batches_tracked.
+  'batch'    always batch statistics: the GEMM writes the raw convolution and accumulates the
+             per-channel sums in its epilogue (`col_stats`); `tt_bn_apply_bf16` normalises (+ identity,
+             ReLU) in place -- except between conv1 and conv2 of a Bottleneck, where the 3x3 im2col
+             applies bn1 + ReLU while it gathers (`tt_im2col_nhwc_bn`) -- and the running statistics /
+             num_batches_tracked move as in nn.BatchNorm2d.  6 launches per Bottleneck instead of 10.
 State-dict keys are torchvision's (conv1.weight, bn1.*, layerL.i.convJ.weight, ...)."""
 import torch
 import torch.nn as nn
@@ -148,14 +150,24 @@ class ResNetFeatureExtractor(nn.Module):
             if not self.batch:
                 return ops.gemm_tn(cols, w, bias=b, residual16=residual,
                                    act=ops.ACT_RELU if relu else ops.ACT_NONE, want32=False, want16=True)
-            y = ops.gemm_tn(cols, w, want32=False, want16=True)
-            C = y.shape[1]
-            st = self.arena[self.off:self.off + 2 * C]
-            self.off = (self.off + 2 * C) % self.arena.numel()
-            ops.bn_stats(y, st)
+            y, st = self.conv_raw(cols, wb)
             return ops.bn_apply_(y, st, bn.weight, bn.bias, bn.eps, residual=residual, relu=relu,
                                  running_mean=bn.running_mean, running_var=bn.running_var,
                                  momentum=self.net.momentum, num_batches_tracked=bn.num_batches_tracked)
+
+        def conv_raw(self, cols, wb):
+            """Batch-statistics mode: the raw convolution [M,Cout] bf16 and its per-channel sums
+            [2*Cout], accumulated in the GEMM epilogue (col_stats) -- no pass over the output."""
+            w, _ = wb
+            C = w.shape[0]
+            st = self.arena[self.off:self.off + 2 * C]
+            self.off = (self.off + 2 * C) % self.arena.numel()
+            if cols.shape[0] >= 32:
+                y = ops.gemm_tn(cols, w, want32=False, want16=True, col_stats=st)
+            else:       # fewer rows than one epilogue warp owns: separate reduction
+                y = ops.gemm_tn(cols, w, want32=False, want16=True)
+                ops.bn_stats(y, st)
+            return y, st
 
     def _stem(self, ps, image):
         B = image.shape[0]
@@ -170,8 +182,17 @@ class ResNetFeatureExtractor(nn.Module):
         Bx, H, W, C = x.shape
         x2 = x.view(Bx * H * W, C)
         planes = c1[0].shape[0]
-        o = ps.conv_bn(x2, c1, blk.bn1)
-        cols, Ho, Wo = ops.im2col_nhwc(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1)
+        if ps.batch:
+            # bn1 + ReLU are applied by the 3x3 convolution's im2col while it gathers: the normalised
+            # activation between conv1 and conv2 is never written
+            o, st = ps.conv_raw(x2, c1)
+            bn = blk.bn1
+            cols, Ho, Wo = ops.im2col_nhwc_bn(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1, st,
+                                              o.shape[0], bn.weight, bn.bias, bn.eps, bn.running_mean,
+                                              bn.running_var, self.momentum, bn.num_batches_tracked)
+        else:
+            o = ps.conv_bn(x2, c1, blk.bn1)
+            cols, Ho, Wo = ops.im2col_nhwc(o.view(Bx, H, W, planes), 3, 3, blk.conv2.stride, 1)
         o = ps.conv_bn(cols, c2, blk.bn2)
         if ds is not None:
             if blk.conv2.stride != 1:

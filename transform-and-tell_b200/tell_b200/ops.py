@@ -71,7 +71,7 @@ def scalar_mul(a, b):
 
 def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act=ACT_NONE,
             accumulate=False, m_limit=None, want32=True, want16=False, residual16=None,
-            trans_a=False, trans_b=False, m_hint=0, k_limit=None):
+            trans_a=False, trans_b=False, m_hint=0, k_limit=None, col_stats=None):
     """C[M,N] = act(alpha * (a[M,K] @ b[N,K]^T + bias) + residual), bf16 operands, fp32 accumulate."""
     _check_cuda(a, b, out, out16, bias, residual)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -117,6 +117,9 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     if k_limit is not None:      # operands are zero for k >= *k_limit (device int32)
         assert k_limit.dtype == torch.int32
         p.k_limit = k_limit.data_ptr()
+    if col_stats is not None:    # fp32 [2N], zeroed by the caller: += column sums / sums of squares
+        assert col_stats.dtype == torch.float32 and col_stats.numel() == 2 * N and out is None
+        p.col_stats = col_stats.data_ptr()
     if _lib.PROFILE is not None:
         _lib.GEMM_FLOPS.append(0.0 if m_limit is not None else 2.0 * M * N * K)
     _lib.call('tt_gemm_bf16_tn', ctypes.byref(p), _stream())
@@ -517,6 +520,25 @@ def im2col_nhwc(x, KH, KW, stride, pad):
     out = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
     _lib.call('tt_im2col_nhwc', _ptr(x), _ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
               c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(Kp), _stream())
+    return out, Ho, Wo
+
+
+def im2col_nhwc_bn(x, KH, KW, stride, pad, stats, n_stat, gamma, beta, eps, running_mean=None,
+                   running_var=None, momentum=0.1, num_batches_tracked=None):
+    """im2col of relu(batchnorm_train(x)) for the RAW convolution output x [B,H,W,C] bf16 whose
+    per-channel sums over n_stat rows are in stats [2C]; -> ([B*Ho*Wo, Kp] bf16, Ho, Wo)."""
+    _check_cuda(x, stats, gamma, beta)
+    B, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and stats.numel() == 2 * C
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    Kp = (KH * KW * C + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_im2col_nhwc_bn', _ptr(x), _ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
+              c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(Kp), _ptr(stats), c_ll(n_stat),
+              _ptr(gamma), _ptr(beta), c_float(eps),
+              _ptr(running_mean) if running_mean is not None else None,
+              _ptr(running_var) if running_var is not None else None, c_float(momentum),
+              _ptr(num_batches_tracked) if num_batches_tracked is not None else None, _stream())
     return out, Ho, Wo
 
 
