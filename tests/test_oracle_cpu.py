@@ -1,5 +1,6 @@
 """CPU suite: pins the oracle (oracle/restate.py) to golden vectors produced by the reference's
 own modules (oracle/gen_golden.py) and to the reference's known-answer test."""
+import math
 import os
 import sys
 
@@ -254,3 +255,41 @@ def test_decoder_restatement_vs_reference_full_size_golden():
         assert (lp - T_(g['log_probs_last'])).abs().max().item() < 1e-4
     assert float(g['greedy_margin_min'][0]) > 2e-3      # the stored greedy path is decidable at 1e-3
     assert g['greedy_ids'].shape == (4, 101)
+
+
+def test_bert_adam_restatement_vs_torch_adam_trajectory():
+    """Independent cross-check of restate.bert_adam_step against torch's own optimizer arithmetic
+    over a 40-step trajectory (pytorch-pretrained-bert is absent, so its BertAdam cannot be run).
+    BertAdam is Adam WITHOUT bias correction: p -= lr_t * (m / (sqrt(v) + e) + wd * p).  torch's Adam
+    computes p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps) with bc1 = 1 - b1^t, bc2 = 1 - b2^t, so
+    feeding it lr = lr_t * bc1 / sqrt(bc2) and eps = e / sqrt(bc2) at every step reproduces the
+    uncorrected update exactly; the decoupled decay term and the per-tensor clip
+    (torch.nn.utils.clip_grad_norm_, what BertAdam itself calls) are applied around it."""
+    torch.manual_seed(0)
+    shapes = [(7, 5), (11,), (3, 4, 2)]
+    hyper = dict(lr=1e-3, warmup=0.1, t_total=40, b1=0.9, b2=0.999, e=1e-6, weight_decay=1e-2,
+                 max_grad_norm=0.1)
+    p_ref = [torch.randn(s) for s in shapes]
+    p_tch = [torch.nn.Parameter(p.clone()) for p in p_ref]
+    state = [dict() for _ in shapes]
+    opts = [torch.optim.Adam([p], lr=1.0, betas=(hyper['b1'], hyper['b2']), eps=1.0) for p in p_tch]
+    for step in range(40):
+        grads = [torch.randn(s) * (3.0 if step % 3 == 0 else 0.05) for s in shapes]   # clipped and unclipped steps
+        restate.bert_adam_step(p_ref, grads, state, **hyper)
+        lr_t = hyper['lr'] * restate.bert_adam_schedule(step, hyper['t_total'], hyper['warmup'])
+        t = step + 1
+        bc1, bc2 = 1 - hyper['b1'] ** t, 1 - hyper['b2'] ** t
+        for p, g, opt in zip(p_tch, grads, opts):
+            p.grad = g.clone()
+            torch.nn.utils.clip_grad_norm_([p], hyper['max_grad_norm'])
+            decay = lr_t * hyper['weight_decay'] * p.detach().clone()
+            for grp in opt.param_groups:
+                grp['lr'] = lr_t * bc1 / math.sqrt(bc2)
+                grp['eps'] = hyper['e'] / math.sqrt(bc2)
+            opt.step()
+            with torch.no_grad():
+                p.sub_(decay)
+        for a, b in zip(p_ref, p_tch):
+            assert (a - b.detach()).abs().max().item() < 2e-6, step
+    # the trajectory is not trivial: parameters moved
+    assert all((a - torch.zeros_like(a)).abs().max() > 0 for a in p_ref)

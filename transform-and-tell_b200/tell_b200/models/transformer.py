@@ -170,8 +170,9 @@ class _CaptionModelBase(Model):
         projected contexts are cached, and the host is consulted only every `sync_every` steps.
         Emits the same token_ids [B, 1+n] / log_probs [B, n] matrices as the reference's
         compacting loop."""
-        if self.sampling_topk != 1:
-            raise NotImplementedError('only greedy decoding (sampling_topk=1) is implemented')
+        topk = int(self.sampling_topk)
+        if topk < 1:
+            raise ValueError('sampling_topk must be >= 1')
         was_training = self.decoder.training
         self.decoder.eval()
         need_attn = [l.need_attn for l in self.decoder.layers]
@@ -180,7 +181,7 @@ class _CaptionModelBase(Model):
         eos, pad = 2, self.padding_idx
         B = caption_ids.shape[0]
         dev = caption_ids.device
-        if self.decode_graph and dev.type == 'cuda' and self.gen_len > 2 \
+        if self.decode_graph and dev.type == 'cuda' and self.gen_len > 2 and topk == 1 \
                 and not torch.cuda.is_current_stream_capturing():
             with torch.no_grad():
                 log_probs, token_ids = self._generate_graphed(caption_ids, contexts, early_exit,
@@ -199,7 +200,16 @@ class _CaptionModelBase(Model):
             with self.decoder.weight_scope(refresh=(i == 0)):
                 X, _ = self.decoder.forward_tbc({self.index: prev}, contexts,
                                                 incremental_state=state)
-                tok, lp = self.decoder.adaptive_softmax.greedy(X.view(B, -1))
+                if topk == 1:
+                    tok, lp = self.decoder.adaptive_softmax.greedy(X.view(B, -1))
+                else:
+                    # :450-464 -- top-k of the full-vocabulary log-probs, temperature, one multinomial
+                    # draw among the k candidates (torch's RNG stream, as in the reference)
+                    lprobs = self.decoder.adaptive_softmax.get_log_prob(X.view(B, 1, -1))[:, 0]
+                    top_lp, top_idx = lprobs.topk(topk)
+                    pick = torch.multinomial((top_lp / self.sampling_temp).exp(), num_samples=1)
+                    tok = top_idx.gather(-1, pick).view(B)
+                    lp = top_lp.gather(-1, pick).view(B)
             lp = lp / self.sampling_temp
             tok = torch.where(active, tok, torch.full_like(tok, pad))
             lp = torch.where(active, lp, torch.zeros_like(lp))
