@@ -33,11 +33,14 @@ struct GemmCfg {
 // plain one is compiled without it -- with both epilogues in one kernel the register allocation of
 // the row-per-thread path degraded (+1.4 us per launch, +3 us per tile on the fp32-output decoder
 // GEMMs, measured against the previous build on the same box: profiles/r2_gemm_small_ab.txt).
-template <int BN, bool TA, bool TB, bool STAGED>
+// MODE 0: plain (register epilogue), 1: staged epilogue, 2: staged epilogue + column statistics.
+template <int BN, bool TA, bool TB, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmArgs g) {
+  constexpr bool STAGED = MODE != 0;
+  constexpr bool STATS = MODE == 2;
   using Cfg = GemmCfg<BN, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -222,7 +225,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // only picks the STAGED instantiation for plain bf16-output problems)
       bool staged = false;
       if constexpr (STAGED) {
-        staged = row0 + 32 <= M;
+        staged = STATS ? row0 < M : row0 + 32 <= M;
         if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
           epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
       }
@@ -233,9 +236,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < M;
       if constexpr (STAGED) {
         if (staged)
-          epilogue_chunks_tma<BN>(g, &tmC, &tmR, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                                     static_cast<uint32_t>(acc * BN),
-                                  half, row0, n_blk * BN, ew);
+          epilogue_chunks_tma<BN, STATS>(g, &tmC, &tmR, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                                            static_cast<uint32_t>(acc * BN),
+                                         half, row0, n_blk * BN, ew, min(32, M - row0));
       }
       if (staged) {
       } else if (splits > 1) {
@@ -246,9 +249,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     static_cast<uint32_t>(acc * BN),
                             half, row, row_ok, n_blk * BN);
       } else {
-        epilogue_chunks<BN, STAGED>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                           static_cast<uint32_t>(acc * BN),
-                                    half, row, row_ok, n_blk * BN);
+        epilogue_chunks<BN>(g, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                          static_cast<uint32_t>(acc * BN),
+                                   half, row, row_ok, n_blk * BN);
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -272,13 +275,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, bool TA, bool TB, bool STAGED = false>
+template <int BN, bool TA, bool TB, int MODE = 0>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                          const CUtensorMap& tmR, const GemmArgs& g, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, STAGED>;
+  using Cfg = GemmCfg<BN, MODE != 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, TA, TB, STAGED>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, TA, TB, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -288,7 +291,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     }
     attr_set = true;
   }
-  launch_k(gemm_bf16_tn_kernel<BN, TA, TB, STAGED>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA,
+  launch_k(gemm_bf16_tn_kernel<BN, TA, TB, MODE>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA,
            tmB, tmC, tmR, g);
   return check_launch("gemm_bf16_tn_kernel");
 }
@@ -307,7 +310,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (tb) {
       if constexpr (BN >= 64) return launch_gemm_t<BN, false, true>(tmA, tmB, tmC, tmR, g, grid, stream);
     } else {
-      if (g.tma_epi != 0) return launch_gemm_t<BN, false, false, true>(tmA, tmB, tmC, tmR, g, grid, stream);
+      if (g.tma_epi != 0 && g.col_stats != nullptr)
+        return launch_gemm_t<BN, false, false, 2>(tmA, tmB, tmC, tmR, g, grid, stream);
+      if (g.tma_epi != 0) return launch_gemm_t<BN, false, false, 1>(tmA, tmB, tmC, tmR, g, grid, stream);
       return launch_gemm_t<BN, false, false>(tmA, tmB, tmC, tmR, g, grid, stream);
     }
   }
@@ -315,33 +320,68 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return TT_ERR_INVALID;
 }
 
-// Tile-width heuristic.  Operand re-reads from L2 scale with 1/BN (A is re-read N/BN times), so the
-// widest tile that still gives every SM a tile wins; when even BN=64 cannot fill the machine
-// (small-M decoder GEMMs) the per-SM L2 bandwidth is the limit and BN=64 keeps the most SMs busy
-// without the 2x A-traffic of BN=32.  TT_GEMM_BN overrides (experiments).
-static int pick_bn(int M, int N, int sms) {
-  static int forced = -1;
+// Tile configuration: a small cost model fitted to measurements (tools/gemm_tile_sweep.py,
+// profiles/r2_gemm_tile_sweep.txt: 30 signatures of the step x 6 configurations on a B200).
+//   cost = waves * (fixed + k-blocks * t_k(config) + columns * t_epilogue)        [microseconds]
+// waves = tiles / CTAs (148) or tiles / CTA pairs (74); t_k is what one k-block costs a CTA: the
+// larger of its share of the L2 -> shared-memory traffic and its MMAs (the CTA-pair kernel halves
+// the B traffic per SM, the 256-wide single-CTA tile is shared-memory-port bound).  It replaces
+// "widest tile that fills 87 % of the SMs", which left 5-45 % on the table for the short-K / many-
+// row convolution GEMMs (12544 x 128 x 1152: 14.3 -> 9.6 us) and the N = 2048 decoder GEMMs.
+struct TileChoice {
+  bool pair;
+  int bn;
+};
+static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sms) {
+  static int forced = -1, forced2 = -1, pair_enabled = -1;
   if (forced < 0) {
-    const char* e = getenv("TT_GEMM_BN");
+    const char* e = getenv("TT_GEMM_BN");          // experiments: force the single-CTA tile width
     forced = e ? atoi(e) : 0;
+    e = getenv("TT_GEMM2_BN");                     // ... or the CTA-pair kernel with this width
+    forced2 = e ? atoi(e) : 0;
+    e = getenv("TT_GEMM_2CTA");
+    pair_enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
-  const int num_m = ceil_div(M, BM);
-  if (N <= 32) return 32;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (N < bn && i < 2) continue;
-    const int tiles = num_m * ceil_div(N, bn);
-    if (tiles >= sms - sms / 8) return bn;   // >= ~87% of the SMs get a tile
+  if (pair_ok && pair_enabled && (forced2 == 128 || forced2 == 256) && N >= forced2) return {true, forced2};
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return {false, (tb && forced < 64) ? 64 : forced};
+  if (N <= 32 && !tb) return {false, 32};
+  if (pair_ok && pair_enabled && N >= 256) {
+    // At least two full waves of 256 x 256 pair tiles: the CTA-pair kernel at its widest tile is
+    // the most efficient configuration there is (half the B traffic per SM, 1.1-1.28 PFLOP/s), and
+    // unlike the single-CTA kernels it keeps that rate when the other encoder runs beside it.
+    // 128-wide pair tiles only when they save whole idle waves (15 % slower per FLOP, measured).
+    const long long t256 = static_cast<long long>(ceil_div(M, 2 * BM)) * ceil_div(N, 256);
+    if (t256 >= 2 * (sms / 2)) {
+      const long long t128 = static_cast<long long>(ceil_div(M, 2 * BM)) * ceil_div(N, 128);
+      const double c256 = static_cast<double>(ceil_div_ll(t256, sms / 2)) * 256.0;
+      const double c128 = static_cast<double>(ceil_div_ll(t128, sms / 2)) * 128.0 * 1.15;
+      return {true, c128 < c256 ? 128 : 256};
+    }
   }
-  // under-filled machine: BN=128 if it already yields >= half the SMs' worth of tiles, else 64
-  if (N >= 128 && num_m * ceil_div(N, 128) >= sms / 2) return 128;
-  return 64;
+  const int num_k = ceil_div(K, BK);
+  struct Cand { bool pair; int bn; double fixed, tk; };
+  const Cand cands[5] = {{false, 64, 0.6, 0.17}, {false, 128, 0.6, 0.22}, {false, 256, 0.6, 0.55},
+                         {true, 128, 1.0, 0.2125}, {true, 256, 1.0, 0.418}};
+  TileChoice best = {false, 64};
+  double best_cost = 1e30;
+  for (const Cand& c : cands) {
+    if (c.pair && !(pair_ok && pair_enabled)) continue;
+    if (N < c.bn && c.bn > 64) continue;
+    const long long tiles = static_cast<long long>(ceil_div(M, c.pair ? 2 * BM : BM)) * ceil_div(N, c.bn);
+    const long long slots = c.pair ? sms / 2 : sms;
+    const double waves = static_cast<double>(ceil_div_ll(tiles, slots));
+    double cost = waves * (c.fixed + num_k * c.tk + 0.02 * (N < c.bn ? N : c.bn));
+    if (!c.pair && c.bn >= 128 && pair_ok && pair_enabled) cost *= 1.05;   // ties go to the pair kernel
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = {c.pair, c.bn};
+    }
+  }
+  return best;
 }
 
-int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR,
-              cudaStream_t stream);  // gemm2.cu
+int gemm2_launch(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR, int bn,
+                 cudaStream_t stream);  // gemm2.cu
 
 static int g_staged = -1;    // staged (TMA) epilogue switch: -1 = read TT_GEMM_TMA_EPI on first use
 static long long* g_trace = nullptr;
@@ -372,8 +412,10 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   TT_REQUIRE(!(p->accumulate && !p->C), "tt_gemm_bf16_tn: accumulate needs the fp32 output");
 
   const int sms = num_sms();
-  int bn = pick_bn(p->M, p->N, sms);
-  if (tb && bn < 64) bn = 64;   // an MN-major B tile is built from 64-column TMA boxes
+  // rows the kernel will really compute (a host-side hint for device-limited problems)
+  const int m_eff = (p->m_limit != nullptr && p->m_hint > 0 && p->m_hint < p->M) ? p->m_hint : p->M;
+  const TileChoice choice = choose_tile(m_eff, p->N, p->K, !ta && !tb, tb, sms);
+  int bn = choice.bn;           // (an MN-major B tile is built from 64-column TMA boxes: bn >= 64)
 
   CUtensorMap tmA, tmB;
   // K-major operand: rows = M (or N), inner = K, box 64(k) x rows.  MN-major operand (stored
@@ -396,8 +438,9 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.m_limit = p->m_limit;
   g.k_limit = p->k_limit;
   g.col_stats = p->col_stats;
-  TT_REQUIRE(p->col_stats == nullptr || (p->C16 != nullptr && p->C == nullptr && !p->accumulate),
-             "tt_gemm_bf16_tn: col_stats needs a bf16-only output");
+  TT_REQUIRE(p->col_stats == nullptr || (p->C16 != nullptr && p->C == nullptr && !p->accumulate &&
+                                         p->m_limit == nullptr && p->bias == nullptr && p->residual16 == nullptr),
+             "tt_gemm_bf16_tn: col_stats needs a plain bf16-only output (no bias / residual / row limit)");
   bool vec = true;
   if (p->C) vec = vec && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0 && (p->ldc % 4 == 0);
   if (p->C16) vec = vec && (reinterpret_cast<uintptr_t>(p->C16) & 15) == 0 && (p->ldc16 % 8 == 0);
@@ -437,10 +480,8 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
              "tt_gemm_bf16_tn: col_stats needs a staged-epilogue problem (K-major operands, N %% 32 == 0, "
              "16-byte aligned bf16 output rows, M >= 32)");
 
-  {  // large K-major problems go to the CTA-pair kernel (gemm2.cu)
-    const int r2 = gemm2_try(p, g, tmC, tmR, reinterpret_cast<cudaStream_t>(stream));
-    if (r2 != 0) return r2 > 0 ? TT_OK : r2;
-  }
+  if (choice.pair)   // CTA-pair kernel (gemm2.cu)
+    return gemm2_launch(p, g, tmC, tmR, choice.bn, reinterpret_cast<cudaStream_t>(stream));
 
   int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

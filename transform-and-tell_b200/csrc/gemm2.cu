@@ -108,11 +108,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int BN, bool STAGED>
+template <int BN, int MODE>     // MODE as in gemm.cu: 0 plain, 1 staged epilogue, 2 staged + column statistics
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const GemmArgs g) {
+  constexpr bool STAGED = MODE != 0;
+  constexpr bool STATS = MODE == 2;
   using Cfg = Gemm2Cfg<BN, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -262,7 +264,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // row-limited problem keep the register path (rows beyond the limit stay untouched)
       bool staged = false;
       if constexpr (STAGED) {
-        staged = row0 + 32 <= M;
+        staged = STATS ? row0 < M : row0 + 32 <= M;
         if (staged && g.tma_epi == 2 && lane == 0 && n_blk * BN + half * 32 < g.N)
           epi_request_residual(&tmR, ew, n_blk * BN + half * 32, row0);   // lands under this tile's MMAs
       }
@@ -270,12 +272,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
       if constexpr (STAGED) {
-        if (staged) epilogue_chunks_tma<BN>(g, &tmC, &tmR, tacc, half, row0, n_blk * BN, ew);
+        if (staged) epilogue_chunks_tma<BN, STATS>(g, &tmC, &tmR, tacc, half, row0, n_blk * BN, ew, min(32, M - row0));
       }
       if (staged) {
       } else {
         const long long row = static_cast<long long>(row0) + lane;
-        epilogue_chunks<BN, STAGED>(g, tacc, half, row, row < M, n_blk * BN);
+        epilogue_chunks<BN>(g, tacc, half, row, row < M, n_blk * BN);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -299,13 +301,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, bool STAGED>
+template <int BN, int MODE>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                         const CUtensorMap& tmR, const GemmArgs& g, int pairs, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN, STAGED>;
+  using Cfg = Gemm2Cfg<BN, MODE != 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGED>,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm2 BN=%d): %s", BN, cudaGetErrorString(e));
@@ -313,43 +315,16 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     }
     attr_set = true;
   }
-  launch_k(gemm2_bf16_kernel<BN, STAGED>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB,
+  launch_k(gemm2_bf16_kernel<BN, MODE>, dim3(2 * pairs), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB,
            tmC, tmR, g);
   return check_launch("gemm2_bf16_kernel");
 }
 
-// Called by tt_gemm_bf16_tn for large K-major problems.  Returns 1 if it took the problem, 0 if
-// the caller should use the 1-CTA kernel, <0 on error.
-int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR,
-              cudaStream_t stream) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("TT_GEMM_2CTA");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled || p->trans_a || p->trans_b) return 0;
-  const int sms = num_sms();
-  const int pairs_max = sms / 2;
-  int bn = 0;
-  if (p->N >= 256 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 256) >= pairs_max) bn = 256;
-  else if (p->N >= 128 && ceil_div(p->M, 2 * BM) * ceil_div(p->N, 128) >= pairs_max) bn = 128;
-  if (bn == 0) return 0;
-  if (bn == 256 && p->m_limit != nullptr && p->m_hint > 0 && p->m_hint < p->M) {
-    // Row-limited problem (packed RoBERTa batch): the host's estimate of the row count tells how
-    // the tiles quantise into waves of 74 CTA pairs.  128-wide tiles run ~15 % below 256-wide ones
-    // per FLOP (measured), so they are chosen only when they save more than that in idle waves:
-    // 5957 x 1024 is 96 wide tiles = 2 waves (second one 30 % full) but 192 narrow tiles = 3 waves.
-    const int mt = ceil_div(p->m_hint, 2 * BM);
-    const double cost256 = static_cast<double>(ceil_div(mt * ceil_div(p->N, 256), pairs_max)) * 256.0;
-    const double cost128 = static_cast<double>(ceil_div(mt * ceil_div(p->N, 128), pairs_max)) * 128.0 * 1.15;
-    if (cost128 < cost256) bn = 128;
-  }
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("TT_GEMM2_BN");     // experiments: force the pair kernel's tile width
-    forced = e ? atoi(e) : 0;
-  }
-  if ((forced == 128 || forced == 256) && p->N >= forced) bn = forced;
+// Called by tt_gemm_bf16_tn when its tile model (gemm.cu: choose_tile) picks the CTA-pair kernel
+// with tile width bn (128 or 256) for a K-major problem.
+int gemm2_launch(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR, int bn,
+                 cudaStream_t stream) {
+  const int pairs_max = num_sms() / 2;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
   if (rc != TT_OK) return rc;
@@ -357,13 +332,16 @@ int gemm2_try(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, 
   if (rc != TT_OK) return rc;
   const int tiles = ceil_div(p->M, 2 * BM) * ceil_div(p->N, bn);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  if (g.tma_epi != 0)
-    rc = (bn == 256) ? launch_gemm2<256, true>(tmA, tmB, tmC, tmR, g, pairs, stream)
-                     : launch_gemm2<128, true>(tmA, tmB, tmC, tmR, g, pairs, stream);
+  if (g.tma_epi != 0 && g.col_stats != nullptr)
+    rc = (bn == 256) ? launch_gemm2<256, 2>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                     : launch_gemm2<128, 2>(tmA, tmB, tmC, tmR, g, pairs, stream);
+  else if (g.tma_epi != 0)
+    rc = (bn == 256) ? launch_gemm2<256, 1>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                     : launch_gemm2<128, 1>(tmA, tmB, tmC, tmR, g, pairs, stream);
   else
-    rc = (bn == 256) ? launch_gemm2<256, false>(tmA, tmB, tmC, tmR, g, pairs, stream)
-                     : launch_gemm2<128, false>(tmA, tmB, tmC, tmR, g, pairs, stream);
-  return rc == TT_OK ? 1 : rc;
+    rc = (bn == 256) ? launch_gemm2<256, 0>(tmA, tmB, tmC, tmR, g, pairs, stream)
+                     : launch_gemm2<128, 0>(tmA, tmB, tmC, tmR, g, pairs, stream);
+  return rc;
 }
 
 }  // namespace tt

@@ -48,35 +48,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Column statistics of one 32 x 32 chunk held row-per-thread (register epilogue: the ragged rows of
-// a problem, or problems the staged epilogue does not take).  Values are rounded to bf16 first, so
-// the statistics are those of the stored tensor.  64 warp reductions: rare path.
-static __device__ __noinline__ void chunk_col_stats_regs(const GemmArgs& g, const float (&v)[32], bool row_ok,
-                                                  int col0) {
-  const int lane = threadIdx.x & 31;
-  float s_mine = 0.f, q_mine = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float r = row_ok ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
-    const float s = warp_sum(r), q = warp_sum(r * r);
-    if (lane == j) {
-      s_mine = s;
-      q_mine = q;
-    }
-  }
-  if (col0 + lane < g.N) {
-    atomicAdd(g.col_stats + col0 + lane, s_mine);
-    atomicAdd(g.col_stats + g.N + col0 + lane, q_mine);
-  }
-}
-
 // Epilogue of one 128 x BN accumulator (one thread = one row, 32 columns per tcgen05.ld).
 // tmem_acc: TMEM address of column 0 of the accumulator, already offset to this warp's lane quarter.
 // Two warps share a lane quarter: `half` selects the even / odd 32-column chunks.
 // Result = act(alpha * (acc + bias) + residual) -> fp32 and/or bf16, optional += into C.
-// STATS: compiled only into the staged instantiations (their ragged-row fallback); the plain kernels
-// never see col_stats (the host routes such problems to the staged kernels or rejects them).
-template <int BN, bool STATS = false>
+template <int BN>
 __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem_acc, int half,
                                                 long long row, bool row_ok, int n0) {
   const int lane = threadIdx.x & 31;
@@ -109,22 +85,10 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tmem
         const uint32_t taddr = tmem_acc + static_cast<uint32_t>(c * 32);
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
-        if (!in_n) continue;
-        if constexpr (!STATS) {
-          if (!row_ok) continue;
-        } else {
-          if (g.col_stats == nullptr && !row_ok) continue;    // (with statistics the warp stays together)
-        }
+        if (!in_n || !row_ok) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if constexpr (STATS) {
-          if (g.col_stats != nullptr) {
-            // batch-statistics convolutions carry no bias / activation / residual: v is the output
-            chunk_col_stats_regs(g, v, row_ok, col0);
-            if (!row_ok) continue;
-          }
-        }
         if (full) {
           if (g.bias != nullptr) {
 #pragma unroll
@@ -248,10 +212,15 @@ __device__ __forceinline__ void epi_request_residual(const CUtensorMap* tmR, con
 }
 
 // Whole-warp, warp-uniform control flow.  row0: first of the 32 rows this warp owns (all < M).
-template <int BN>
+// STATS: compiled only into the instantiations that serve col_stats problems (the extra loop costs
+// the plain staged epilogue registers: +150 B of spills, 10-35 % on the epilogue-bound N = 64 shapes).
+// rows_valid: how many of the warp's 32 rows exist (< 32 only in STATS mode, where the ragged last
+// rows of the problem also take this path: they enter the tile and the sums as zeros and the TMA
+// store clips them -- statistics problems carry no device-side row limit).
+template <int BN, bool STATS>
 __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUtensorMap* tmC,
                                                     const CUtensorMap* tmR, uint32_t tmem_acc, int half,
-                                                    int row0, int n0, EpiWarp& ew) {
+                                                    int row0, int n0, EpiWarp& ew, int rows_valid = 32) {
   const int lane = threadIdx.x & 31;
   const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
   const uint32_t my_out = ew.st_out + static_cast<uint32_t>(lane) * 64u;
@@ -294,6 +263,12 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if constexpr (STATS) {
+      if (lane >= rows_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+    }
     if (g.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -340,7 +315,7 @@ __device__ __forceinline__ void epilogue_chunks_tma(const GemmArgs& g, const CUt
       tma_store_2d_u(tmC, ew.st_out, col0, row0);
       bulk_commit_group();
     }
-    if (g.col_stats != nullptr) {
+    if constexpr (STATS) {
       // lane c sums column c of the staged bf16 tile (32 lanes read one 64-byte row per step: one
       // wavefront), then one atomic per column per 32 rows
       const uint32_t jc = static_cast<uint32_t>(lane >> 3), off = static_cast<uint32_t>(lane & 7) * 2u;
