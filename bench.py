@@ -219,6 +219,13 @@ def run_b200(args):
             os.environ['NCCL_DEBUG'] = 'WARN'     # level VERSION printf()s its banner to stdout
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
+    extras = None
+    if world == 1 and not args.skip_extras:
+        # BASELINE.json configs[3] (greedy decode latency, batch 256, 50 steps) and configs[4] (long
+        # article, one GPU's share), each in its own process, BEFORE this process creates its CUDA
+        # context: measured after the main benchmark (this process idle but holding its graphs and
+        # ~30 GB) the same tools ran 2-3.5x slower and erratically (392 / 242 ms vs 110 ms alone).
+        extras = {'decode': run_extra('bench_decode.py', '--reps', '3'), 'cfg5': run_extra('bench_cfg5.py')}
     config.set_precision('bf16')
     config.manual_seed(1234 + rank)
     config.enable_device_step(dev)
@@ -617,12 +624,8 @@ def run_b200(args):
                                  'gaps included -- read as shares of the step, not as device time',
         'clocks': sampler.summary() if sampler else None,
     }
-    if world == 1 and not args.skip_extras:
-        # BASELINE.json configs[3] (greedy decode latency, batch 256, 50 steps) and configs[4] (long
-        # article, one GPU's share), each in its own process (a few GB beside this one's)
-        torch.cuda.empty_cache()
-        line['decode'] = run_extra('bench_decode.py', '--reps', '2')
-        line['cfg5'] = run_extra('bench_cfg5.py')
+    if extras is not None:
+        line.update(extras)
     if not args.skip_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(budget_s=25.0, bn_mode=args.bn_mode)
     print(json.dumps(line), flush=True)

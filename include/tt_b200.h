@@ -253,6 +253,36 @@ int tt_attn_bwd_tc_kv16(const float* dout, const float* q, const void* k16, cons
                         float* dq, void* dk16, void* dv16, float* dbias_k, float* dbias_v, int T,
                         int B, int S, int H, int D, long long ldq, long long ldkv, long long ldo,
                         int zero_row, float p_drop, unsigned long long seed, void* stream);
+/* One decoder layer's cross-attention over up to 4 contexts (image / article / faces / objects,
+ * decoder_faces_objects.py:272-352; multi_head.py:355-466 per context) as ONE launch per kernel type:
+ * blockIdx.z walks the contexts.  Same math as tt_attn_fwd_tc / tt_attn_bwd_tc(_kv16) per context; T, B,
+ * H, D, zero_row, p_drop are shared, everything else is per context.  kv16: k / v / dk / dv are bf16.
+ * tt_attn_decode_hm_multi: the T = 1 incremental step over head-major caches (k, v = [B,H,S,64] bf16;
+ * S = 0 with null k / v is an empty context: only bias_k / the zero row). */
+typedef struct {
+  const float* q;              /* [T*B, ldq] already scaled */
+  const void* k;               /* fp32 or bf16 (kv16) [S*B, ldkv] */
+  const void* v;
+  const float* bias_k;         /* [E] or NULL */
+  const float* bias_v;
+  const unsigned char* mask;   /* [B,S] 1 = padding, or NULL */
+  float* out;                  /* [T*B, ldo] */
+  float* lse;                  /* [B,H,T] */
+  int S;
+  long long ldq, ldkv, ldo;
+  unsigned long long seed;     /* dropout stream of this context */
+  const float* dout;           /* backward only */
+  float* dq;
+  void* dk;
+  void* dv;
+  float* dbias_k;
+  float* dbias_v;
+} TtAttnCtx;
+int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
+                         int kv16, void* stream);
+int tt_attn_bwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
+                         int kv16, void* stream);
+int tt_attn_decode_hm_multi(const TtAttnCtx* ctx, int n, int B, int H, int D, int zero_row, void* stream);
 /* Incremental decoding (transformer_faces_objects.py:399-494 recomputes every K|V projection per
  * step; here they are projected once and cached).  tt_kv_repack_heads turns the token-major bf16
  * projection ([S*B, ldkv] rows, key j of batch b at row j*B+b) into head-major K, V [B,H,S,64];

@@ -194,3 +194,56 @@ def test_long_article_stress_shapes_match_oracle():
     config.set_precision('bf16x3')
     del dec
     torch.cuda.empty_cache()
+
+
+def test_one_attention_launch_per_layer_equals_per_context_launches():
+    """The four cross-attentions of a layer as ONE launch per kernel type (blockIdx.z walks the
+    contexts: tt_attn_fwd_tc_multi / tt_attn_bwd_tc_multi / tt_attn_decode_hm_multi) must give what
+    the per-context launches give -- output, loss, every gradient, and the greedy tokens of the
+    captured decode step -- and must really launch fewer kernels."""
+    from tell_b200 import _lib, config, synth
+    from tell_b200.models import DynamicConvFacesObjectsDecoder, TransformerFacesObjectModel
+    from tell_b200.modules import AdaptiveLoss
+    from tell_b200.testing import build_decoder
+    config.set_precision('bf16')
+    cfg = dict(synth.CFG_TINY, embed_dim=256, heads=4, ffn=256)        # head_dim 64: tensor-core kernels
+    sd = synth.decoder_state_dict(cfg, seed=3, logit_gain=3.0)
+    cap, ctx = synth.decoder_inputs(cfg, B=3, T=9, S=70, F=3, O=4, P=5, seed=21)
+    ctx['faces'] = ctx['faces'][:0]                                     # an EMPTY context rides along
+    ctx['faces_mask'] = ctx['faces_mask'][:, :0]
+    inp, tgt = cap[:, :-1].contiguous().cuda(), cap[:, 1:].contiguous().cuda()
+    res = {}
+    try:
+        for multi in (False, True):
+            config.attn_multi = multi
+            dec = build_decoder(cfg, DynamicConvFacesObjectsDecoder, sd).cuda().eval()
+            for l in dec.layers:
+                l.need_attn = False
+            cctx = {k: v.cuda() for k, v in ctx.items()}
+            cctx['article'].requires_grad_(True)
+            _lib.reset_launch_count()
+            out, _ = dec({'roberta': inp}, cctx)
+            loss, _ = dec.adaptive_softmax.fused_loss(out, tgt)
+            loss.backward()
+            torch.cuda.synchronize()
+            n_launch = _lib.launch_count()
+            grads = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+            model = TransformerFacesObjectModel(None, dec, AdaptiveLoss(1), weigh_bert=True,
+                                                resnet=torch.nn.Identity(), roberta=type('R', (torch.nn.Module,), {'n_layers': 24})(),
+                                                padding_value=1, vocab_size=cfg['vocab']).cuda().eval()
+            model.gen_len = 14
+            with torch.no_grad():
+                lp, ids, _ = model._generate(cap[:, 0:1].cuda(), {k: v.detach() for k, v in cctx.items()},
+                                             early_exit=False)
+            res[multi] = (out.detach().clone(), loss.item(), grads, cctx['article'].grad.clone(), ids.clone(),
+                          lp.clone(), n_launch)
+    finally:
+        config.attn_multi = True
+    a, b = res[False], res[True]
+    assert torch.equal(a[0], b[0]) and a[1] == b[1]
+    assert torch.equal(a[3], b[3])
+    for n in a[2]:
+        assert (a[2][n] - b[2][n]).abs().max().item() <= 1e-6 * max(1e-6, a[2][n].abs().max().item()), n
+    assert torch.equal(a[4], b[4]) and torch.equal(a[5], b[5])
+    n_layers = len(cfg['kernels'])
+    assert a[6] - b[6] == n_layers * 3 * 3, (a[6], b[6])     # (4 - 1) launches x {fwd, dq, dkv} per layer

@@ -32,6 +32,15 @@ struct AttnArgs {
   // decode kernel only: element strides of k/v between keys, batch rows and heads
   // (token-major projection buffer: B*ldkv, ldkv, 64; head-major decode cache: 64, H*S*64, S*64)
   long long kv_j_stride, kv_b_stride, kv_h_stride;
+  int Lp;               // decode kernel: padded key count of THIS context (scores row pitch in smem)
+};
+
+// Up to four contexts per launch (image / article / faces / objects of one decoder layer,
+// decoder_faces_objects.py:272-352): blockIdx.z selects the context, so a layer's cross-attention
+// is ONE launch per kernel type instead of one per context.
+constexpr int ATTN_MAX_CTX = 4;
+struct AttnArgsN {
+  AttnArgs a[ATTN_MAX_CTX];
 };
 
 }  // namespace tt

@@ -199,8 +199,9 @@ __device__ __forceinline__ float quad_sum(float v) {
 // ------------------------------------------------------------------------------------------ forward
 template <bool KV16>
 __global__ void __launch_bounds__(128)
-attn_fwd_tc_kernel(AttnArgs a) {
+attn_fwd_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
+  AttnArgs a = args.a[blockIdx.z];
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[64][TC_LD];
@@ -326,8 +327,9 @@ __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h,
 // ------------------------------------------------------------------------------------------ dQ
 template <bool KV16>
 __global__ void __launch_bounds__(128)
-attn_bwd_dq_tc_kernel(AttnArgs a) {
+attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
+  AttnArgs a = args.a[blockIdx.z];
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
@@ -407,8 +409,9 @@ attn_bwd_dq_tc_kernel(AttnArgs a) {
 // ------------------------------------------------------------------------------------------ dK, dV
 template <bool KV16>
 __global__ void __launch_bounds__(128)
-attn_bwd_dkv_tc_kernel(AttnArgs a) {
+attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
+  AttnArgs a = args.a[blockIdx.z];
   a.seed = mix_seed(a.seed, a.step_ptr);
   __shared__ __align__(16) __nv_bfloat16 sQ[64][TC_LD];
   __shared__ __align__(16) __nv_bfloat16 sdO[64][TC_LD];
@@ -417,6 +420,7 @@ attn_bwd_dkv_tc_kernel(AttnArgs a) {
   __shared__ float sMask[64], sD[64], sLse[64];
   const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
   const int j0 = blockIdx.y * TC_BN;
+  if (j0 >= a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0)) return;   // grid.y covers the longest context
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const bool has_bias = a.bias_k != nullptr;
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
@@ -528,8 +532,10 @@ __device__ __forceinline__ float dot4(float acc, float x0, float x1, float x2, f
 constexpr int DEC_HG = 8;      // heads (warps) per CTA
 template <bool KV16>
 __global__ void __launch_bounds__(DEC_HG * 32)
-attn_decode_kernel(AttnArgs a, int Lp) {
+attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
+  const AttnArgs& a = args.a[blockIdx.z];
+  const int Lp = a.Lp;
   extern __shared__ float dsm[];        // [DEC_HG][Lp] scores -> probabilities
   __shared__ float sq_all[DEC_HG][TC_D];
   const int b = blockIdx.x;
@@ -702,14 +708,19 @@ static int attn_fwd_tc_impl(const float* q, const void* k, const void* v, const 
     const size_t smem = static_cast<size_t>(DEC_HG) * Lp * sizeof(float);
     if (smem <= 40 * 1024) {
       const dim3 grid(B, ceil_div(H, DEC_HG));
-      if (kv16) launch_k(attn_decode_kernel<true>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, a, Lp);
-      else launch_k(attn_decode_kernel<false>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, a, Lp);
+      a.Lp = Lp;
+      AttnArgsN an{};
+      an.a[0] = a;
+      if (kv16) launch_k(attn_decode_kernel<true>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, an);
+      else launch_k(attn_decode_kernel<false>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, an);
       return check_launch("attn_decode_kernel");
     }
   }
   dim3 grid(B * H, ceil_div(T, TC_BM));
-  if (kv16) launch_k(attn_fwd_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
-  else launch_k(attn_fwd_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  AttnArgsN an{};
+  an.a[0] = a;
+  if (kv16) launch_k(attn_fwd_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_fwd_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, an);
   return check_launch("attn_fwd_tc_kernel");
 }
 
@@ -735,13 +746,15 @@ static int attn_bwd_tc_impl(const float* dout, const float* q, const void* k, co
   if (rc != TT_OK) return rc;
   const int L = S + (bias_k ? 1 : 0) + (zero_row ? 1 : 0);
   dim3 grid(B * H, ceil_div(T, TC_BM));
-  if (kv16) launch_k(attn_bwd_dq_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
-  else launch_k(attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a);
+  AttnArgsN an{};
+  an.a[0] = a;
+  if (kv16) launch_k(attn_bwd_dq_tc_kernel<true>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, an);
   rc = check_launch("attn_bwd_dq_tc_kernel");
   if (rc != TT_OK) return rc;
   dim3 grid2(B * H, ceil_div(L, TC_BN));
-  if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
-  else launch_k(attn_bwd_dkv_tc_kernel<false>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, a);
+  if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_bwd_dkv_tc_kernel<false>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, an);
   return check_launch("attn_bwd_dkv_tc_kernel");
 }
 
@@ -825,7 +838,117 @@ extern "C" int tt_attn_decode_hm(const float* q, const void* k_hm, const void* v
   const int Lp = (L + 3) & ~3;
   const size_t smem = static_cast<size_t>(DEC_HG) * Lp * sizeof(float);
   TT_REQUIRE(smem <= 40 * 1024, "tt_attn_decode_hm: key set too long for the decode kernel (L=%d)", L);
+  a.Lp = Lp;
+  AttnArgsN an{};
+  an.a[0] = a;
   launch_k(attn_decode_kernel<true>, dim3(B, ceil_div(H, DEC_HG)), dim3(DEC_HG * 32), smem,
-           (cudaStream_t)stream, a, Lp);
+           (cudaStream_t)stream, an);
+  return check_launch("attn_decode_kernel");
+}
+
+
+// ---------------------------------------------------------------------------- multi-context launches
+namespace tt {
+static int fill_ctx(AttnArgs& a, const TtAttnCtx& c, int T, int B, int H, int D, int zero_row, float p_drop,
+                    bool kv16, bool backward, const char* who) {
+  TT_REQUIRE(c.q && c.out && c.lse, "%s: null q/out/lse", who);
+  TT_REQUIRE(c.S >= 0 && (c.S == 0 || (c.k && c.v)), "%s: null k/v with S > 0", who);
+  TT_REQUIRE((c.bias_k == nullptr) == (c.bias_v == nullptr), "%s: bias_k/bias_v mismatch", who);
+  TT_REQUIRE(c.S + (c.bias_k ? 1 : 0) + (zero_row ? 1 : 0) > 0, "%s: empty key set", who);
+  a = AttnArgs{};
+  a.q = c.q; a.k = reinterpret_cast<const float*>(c.k); a.v = reinterpret_cast<const float*>(c.v);
+  a.bias_k = c.bias_k; a.bias_v = c.bias_v; a.mask = c.mask;
+  a.out = c.out; a.lse = c.lse; a.T = T; a.B = B; a.S = c.S; a.H = H; a.zero_row = zero_row;
+  a.ldq = c.ldq; a.ldkv = c.ldkv; a.ldo = c.ldo;
+  a.p_drop = p_drop; a.seed = c.seed; a.step_ptr = rng_step_ptr();
+  a.kv_j_stride = static_cast<long long>(B) * c.ldkv; a.kv_b_stride = c.ldkv; a.kv_h_stride = TC_D;
+  if (backward) {
+    TT_REQUIRE(c.dout && c.dq && (c.S == 0 || (c.dk && c.dv)), "%s: null dout/dq/dk/dv", who);
+    a.dout = c.dout; a.dq = c.dq; a.dk = reinterpret_cast<float*>(c.dk); a.dv = reinterpret_cast<float*>(c.dv);
+    a.dbias_k = c.dbias_k; a.dbias_v = c.dbias_v;
+  }
+  return tc_check(a, D, kv16 && c.S > 0);
+}
+}  // namespace tt
+
+extern "C" int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row,
+                                    float p_drop, int kv16, void* stream) {
+  TT_REQUIRE(ctx && n >= 1 && n <= ATTN_MAX_CTX, "tt_attn_fwd_tc_multi: 1..%d contexts", ATTN_MAX_CTX);
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgsN an{};
+  for (int i = 0; i < n; ++i) {
+    const int rc = fill_ctx(an.a[i], ctx[i], T, B, H, D, zero_row, p_drop, kv16 != 0, false, "tt_attn_fwd_tc_multi");
+    if (rc != TT_OK) return rc;
+  }
+  if (T == 1 && p_drop == 0.f) {      // incremental decoding: one query row per (b, h), as tt_attn_fwd_tc
+    size_t smem = 0;
+    for (int i = 0; i < n; ++i) {
+      const int L = ctx[i].S + (ctx[i].bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+      an.a[i].Lp = (L + 3) & ~3;
+      const size_t need = static_cast<size_t>(DEC_HG) * an.a[i].Lp * sizeof(float);
+      smem = need > smem ? need : smem;
+    }
+    if (smem <= 40 * 1024) {
+      const dim3 grid(B, ceil_div(H, DEC_HG), n);
+      if (kv16) launch_k(attn_decode_kernel<true>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, an);
+      else launch_k(attn_decode_kernel<false>, grid, dim3(DEC_HG * 32), smem, (cudaStream_t)stream, an);
+      return check_launch("attn_decode_kernel");
+    }
+  }
+  const dim3 grid(B * H, ceil_div(T, TC_BM), n);
+  if (kv16) launch_k(attn_fwd_tc_kernel<true>, grid, dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_fwd_tc_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, an);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+extern "C" int tt_attn_bwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row,
+                                    float p_drop, int kv16, void* stream) {
+  TT_REQUIRE(ctx && n >= 1 && n <= ATTN_MAX_CTX, "tt_attn_bwd_tc_multi: 1..%d contexts", ATTN_MAX_CTX);
+  if (T <= 0 || B <= 0) return TT_OK;
+  AttnArgsN an{};
+  int Lmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const int rc = fill_ctx(an.a[i], ctx[i], T, B, H, D, zero_row, p_drop, kv16 != 0, true, "tt_attn_bwd_tc_multi");
+    if (rc != TT_OK) return rc;
+    const int L = ctx[i].S + (ctx[i].bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+    Lmax = L > Lmax ? L : Lmax;
+  }
+  const dim3 grid(B * H, ceil_div(T, TC_BM), n);
+  if (kv16) launch_k(attn_bwd_dq_tc_kernel<true>, grid, dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_bwd_dq_tc_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, an);
+  int rc = check_launch("attn_bwd_dq_tc_kernel");
+  if (rc != TT_OK) return rc;
+  const dim3 grid2(B * H, ceil_div(Lmax, TC_BN), n);
+  if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, grid2, dim3(128), 0, (cudaStream_t)stream, an);
+  else launch_k(attn_bwd_dkv_tc_kernel<false>, grid2, dim3(128), 0, (cudaStream_t)stream, an);
+  return check_launch("attn_bwd_dkv_tc_kernel");
+}
+
+extern "C" int tt_attn_decode_hm_multi(const TtAttnCtx* ctx, int n, int B, int H, int D, int zero_row, void* stream) {
+  TT_REQUIRE(ctx && n >= 1 && n <= ATTN_MAX_CTX, "tt_attn_decode_hm_multi: 1..%d contexts", ATTN_MAX_CTX);
+  TT_REQUIRE(D == TC_D, "tt_attn_decode_hm_multi: head_dim must be %d (got %d)", TC_D, D);
+  if (B <= 0) return TT_OK;
+  AttnArgsN an{};
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const TtAttnCtx& c = ctx[i];
+    TT_REQUIRE(c.q && c.out && (c.S == 0 || (c.k && c.v)), "tt_attn_decode_hm_multi: null pointer");
+    TT_REQUIRE((c.bias_k == nullptr) == (c.bias_v == nullptr), "tt_attn_decode_hm_multi: bias_k/bias_v mismatch");
+    TT_REQUIRE(c.ldq % 2 == 0 && c.ldo % 4 == 0, "tt_attn_decode_hm_multi: ldq must be even, ldo a multiple of 4");
+    AttnArgs& a = an.a[i];
+    a.q = c.q; a.k = reinterpret_cast<const float*>(c.k); a.v = reinterpret_cast<const float*>(c.v);
+    a.bias_k = c.bias_k; a.bias_v = c.bias_v; a.mask = c.mask;
+    a.out = c.out; a.lse = c.lse; a.T = 1; a.B = B; a.S = c.S; a.H = H; a.zero_row = zero_row;
+    a.ldq = c.ldq; a.ldo = c.ldo; a.ldkv = 0;
+    a.kv_j_stride = TC_D; a.kv_b_stride = static_cast<long long>(H) * c.S * TC_D;
+    a.kv_h_stride = static_cast<long long>(c.S) * TC_D;
+    const int L = c.S + (c.bias_k ? 1 : 0) + (zero_row ? 1 : 0);
+    TT_REQUIRE(L > 0, "tt_attn_decode_hm_multi: empty key set");
+    a.Lp = (L + 3) & ~3;
+    const size_t need = static_cast<size_t>(DEC_HG) * a.Lp * sizeof(float);
+    smem = need > smem ? need : smem;
+  }
+  TT_REQUIRE(smem <= 40 * 1024, "tt_attn_decode_hm_multi: key set too long for the decode kernel");
+  launch_k(attn_decode_kernel<true>, dim3(B, ceil_div(H, DEC_HG), n), dim3(DEC_HG * 32), smem, (cudaStream_t)stream, an);
   return check_launch("attn_decode_kernel");
 }

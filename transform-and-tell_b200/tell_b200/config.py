@@ -20,6 +20,8 @@ kv_bf16 = True
 flash_tc5 = os.environ.get('TT_FLASH_TC5', '1') == '1'
 # run the ResNet encoder as a parallel stream branch beside RoBERTa in Model.encode()
 encoder_overlap = True
+# the cross-attentions of one decoder layer (up to 4 contexts) as ONE launch per kernel type
+attn_multi = os.environ.get('TT_ATTN_MULTI', '1') == '1'
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks
 
 _seed_base = 0x5EED

@@ -615,6 +615,8 @@ class MultiCtxAttentionFn(Function):
         tc = config.precision == 'bf16' and D == 64
         out_all = torch.empty_like(q_all)
         lses, weights, Ss = [], [], []
+        multi = tc and n <= 4 and config.attn_multi      # one launch for all contexts of the layer
+        items = []
         for c in range(n):
             kv = kvs[c]
             S = kv.shape[0] // B if kv is not None else 0
@@ -622,22 +624,35 @@ class MultiCtxAttentionFn(Function):
             q = q_all[:, c * E:(c + 1) * E]
             bk = bks[c].view(-1) if bks[c] is not None else None
             bv = bvs[c].view(-1) if bvs[c] is not None else None
-            _, lse = ops.attn_fwd(q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None, bk, bv,
-                                  masks[c] if S > 0 else None, T, B, S, H, D, zero_row, p, seeds[c],
-                                  tc=tc, out=out_all[:, c * E:(c + 1) * E])
+            if multi:
+                lse = torch.empty((B, H, T), dtype=torch.float32, device=q_all.device)
+                items.append(dict(q=q, k=kv[:, :E] if S > 0 else None, v=kv[:, E:] if S > 0 else None,
+                                  bias_k=bk, bias_v=bv, mask=masks[c], out=out_all[:, c * E:(c + 1) * E],
+                                  lse=lse, S=S, seed=seeds[c]))
+            else:
+                _, lse = ops.attn_fwd(q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None, bk, bv,
+                                      masks[c] if S > 0 else None, T, B, S, H, D, zero_row, p, seeds[c],
+                                      tc=tc, out=out_all[:, c * E:(c + 1) * E])
             lses.append(lse)
+        if multi:
+            ops.attn_fwd_tc_multi(items, T, B, H, D, zero_row, p)
+        for c in range(n):
+            kv, S = kvs[c], Ss[c]
+            q = q_all[:, c * E:(c + 1) * E]
+            bk = bks[c].view(-1) if bks[c] is not None else None
+            lse = lses[c]
             if need_weights:
                 weights.append(ops.attn_avg_weights(q, kv[:, :E] if S > 0 else None, bk,
                                                     masks[c] if S > 0 else None, lse, T, B, S, H, D,
                                                     zero_row))
-        ctx.cfg = (T, B, H, D, zero_row, p, seeds, n, tuple(Ss), tc)
+        ctx.cfg = (T, B, H, D, zero_row, p, seeds, n, tuple(Ss), tc, multi)
         ctx.save_for_backward(q_all, out_all, *kvs, *bks, *bvs, *masks, *lses)
         ctx.mark_non_differentiable(*weights)
         return (out_all,) + tuple(weights)
 
     @staticmethod
     def backward(ctx, dout_all, *_dw):
-        T, B, H, D, zero_row, p, seeds, n, Ss, tc = ctx.cfg
+        T, B, H, D, zero_row, p, seeds, n, Ss, tc, multi = ctx.cfg
         sv = ctx.saved_tensors
         q_all, out_all = sv[0], sv[1]
         kvs, bks, bvs = sv[2:2 + n], sv[2 + n:2 + 2 * n], sv[2 + 2 * n:2 + 3 * n]
@@ -646,6 +661,7 @@ class MultiCtxAttentionFn(Function):
         dout_all = _c(dout_all)
         dq_all = torch.empty_like(q_all)
         dkvs, dbks, dbvs = [], [], []
+        items = []
         for c in range(n):
             S, kv = Ss[c], kvs[c]
             if S > 0 and ctx.slabs[c] is not None:
@@ -655,16 +671,27 @@ class MultiCtxAttentionFn(Function):
             dbk = ops.zeros_f32(bks[c].shape, bks[c]) if bks[c] is not None else None
             dbv = ops.zeros_f32(bvs[c].shape, bvs[c]) if bvs[c] is not None else None
             sl = slice(c * E, (c + 1) * E)
-            ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
-                         kv[:, E:] if S > 0 else None,
-                         bks[c].view(-1) if bks[c] is not None else None,
-                         bvs[c].view(-1) if bvs[c] is not None else None,
-                         masks[c] if S > 0 else None, out_all[:, sl], lses[c], dq_all[:, sl],
-                         dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None, dbk, dbv,
-                         T, B, S, H, D, zero_row, p, seeds[c], tc=tc)
+            if multi:
+                items.append(dict(q=q_all[:, sl], k=kv[:, :E] if S > 0 else None, v=kv[:, E:] if S > 0 else None,
+                                  bias_k=bks[c].view(-1) if bks[c] is not None else None,
+                                  bias_v=bvs[c].view(-1) if bvs[c] is not None else None,
+                                  mask=masks[c], out=out_all[:, sl], lse=lses[c], S=S, seed=seeds[c],
+                                  dout=dout_all[:, sl], dq=dq_all[:, sl],
+                                  dk=dkv[:, :E] if S > 0 else None, dv=dkv[:, E:] if S > 0 else None,
+                                  dbias_k=dbk, dbias_v=dbv))
+            else:
+                ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
+                             kv[:, E:] if S > 0 else None,
+                             bks[c].view(-1) if bks[c] is not None else None,
+                             bvs[c].view(-1) if bvs[c] is not None else None,
+                             masks[c] if S > 0 else None, out_all[:, sl], lses[c], dq_all[:, sl],
+                             dkv[:, :E] if S > 0 else None, dkv[:, E:] if S > 0 else None, dbk, dbv,
+                             T, B, S, H, D, zero_row, p, seeds[c], tc=tc)
             dkvs.append(dkv)
             dbks.append(dbk)
             dbvs.append(dbv)
+        if multi:
+            ops.attn_bwd_tc_multi(items, T, B, H, D, zero_row, p)
         return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n \
             + (None,) * (1 if len(ctx.needs_input_grad) > 9 + 4 * n else 0)
 

@@ -134,16 +134,29 @@ class DynamicConvDecoderLayer(DecoderLayer):
                 all(h_ is not None or kv is None for h_, kv in zip(hm, kvs)) and any(h_ is not None for h_ in hm):
             # incremental decoding over the head-major K|V cache (built once by the generate loop)
             A_all = torch.empty_like(Q_all)
-            for c, (mha, kv) in enumerate(zip(mhas, kvs)):
-                sl = slice(c * E_, (c + 1) * E_)
-                bk = mha.bias_k.view(-1) if mha.bias_k is not None else None
-                bv = mha.bias_v.view(-1) if mha.bias_v is not None else None
-                if kv is None:        # empty context: only the bias / zero rows
-                    ops.attn_fwd(Q_all[:, sl], None, None, bk, bv, None, 1, B, 0, mha.num_heads,
-                                 mha.head_dim, mha.add_zero_attn, tc=True, out=A_all[:, sl])
-                else:
-                    ops.attn_decode_hm(Q_all[:, sl], hm[c][0], hm[c][1], bk, bv, masks[c], A_all[:, sl],
-                                       mha.add_zero_attn)
+            if config.attn_multi and n <= 4 and mhas[0].head_dim == 64:
+                # all contexts of the layer in ONE launch (blockIdx.z walks them)
+                items = []
+                for c, (mha, kv) in enumerate(zip(mhas, kvs)):
+                    sl = slice(c * E_, (c + 1) * E_)
+                    S_c = hm[c][0].shape[2] if kv is not None else 0
+                    items.append(dict(q=Q_all[:, sl], k=hm[c][0] if kv is not None else None,
+                                      v=hm[c][1] if kv is not None else None,
+                                      bias_k=mha.bias_k.view(-1) if mha.bias_k is not None else None,
+                                      bias_v=mha.bias_v.view(-1) if mha.bias_v is not None else None,
+                                      mask=masks[c], out=A_all[:, sl], lse=None, S=S_c))
+                ops.attn_decode_hm_multi(items, B, mhas[0].num_heads, mhas[0].head_dim, mhas[0].add_zero_attn)
+            else:
+                for c, (mha, kv) in enumerate(zip(mhas, kvs)):
+                    sl = slice(c * E_, (c + 1) * E_)
+                    bk = mha.bias_k.view(-1) if mha.bias_k is not None else None
+                    bv = mha.bias_v.view(-1) if mha.bias_v is not None else None
+                    if kv is None:        # empty context: only the bias / zero rows
+                        ops.attn_fwd(Q_all[:, sl], None, None, bk, bv, None, 1, B, 0, mha.num_heads,
+                                     mha.head_dim, mha.add_zero_attn, tc=True, out=A_all[:, sl])
+                    else:
+                        ops.attn_decode_hm(Q_all[:, sl], hm[c][0], hm[c][1], bk, bv, masks[c], A_all[:, sl],
+                                           mha.add_zero_attn)
             attns = {}
         else:
             res = Fn.MultiCtxAttentionFn.apply(Q_all, T, B, mhas[0].num_heads, mhas[0].add_zero_attn,

@@ -348,6 +348,64 @@ def attn_bwd(dout, q, k, v, bias_k, bias_v, mask, out, lse, dq, dk, dv, dbias_k,
               c_int(1 if zero_row else 0), c_float(p), _ull(seed), _stream())
 
 
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _attn_ctx_array(items, E):
+    """items: dicts with q, k, v, bias_k, bias_v, mask, out, lse, S, seed (+ dout, dq, dk, dv, dbias_k,
+    dbias_v for the backward) -> ctypes array of TtAttnCtx."""
+    arr = (_lib.TtAttnCtx * len(items))()
+    for c, it in zip(arr, items):
+        S = it['S']
+        c.q, c.out, c.lse = _dp(it['q']), _dp(it['out']), _dp(it.get('lse'))
+        c.k, c.v = (_dp(it['k']), _dp(it['v'])) if S > 0 else (None, None)
+        c.bias_k, c.bias_v = _dp(it.get('bias_k')), _dp(it.get('bias_v'))
+        c.mask = _dp(it.get('mask')) if S > 0 else None
+        c.S = S
+        c.ldq, c.ldo = it['q'].stride(0), it['out'].stride(0)
+        c.ldkv = it['k'].stride(0) if (S > 0 and it['k'].dim() == 2) else E
+        c.seed = int(it.get('seed', 0)) & 0xFFFFFFFFFFFFFFFF
+        if it.get('dout') is not None:
+            c.dout, c.dq = _dp(it['dout']), _dp(it['dq'])
+            c.dk, c.dv = (_dp(it['dk']), _dp(it['dv'])) if S > 0 else (None, None)
+            c.dbias_k, c.dbias_v = _dp(it.get('dbias_k')), _dp(it.get('dbias_v'))
+    return arr
+
+
+def _attn_kv16(items):
+    kinds = {it['k'].dtype for it in items if it['S'] > 0}
+    assert len(kinds) <= 1, 'contexts of one launch must store k/v in one dtype'
+    return bool(kinds) and kinds.pop() == torch.bfloat16
+
+
+def attn_fwd_tc_multi(items, T, B, H, D, zero_row=True, p=0.0):
+    """One launch for the cross-attention of up to 4 contexts (tensor-core kernels); `items` as in
+    _attn_ctx_array; out / lse are caller-allocated (out may be a column block of a wider buffer)."""
+    arr = _attn_ctx_array(items, H * D)
+    _lib.call('tt_attn_fwd_tc_multi', arr, c_int(len(items)), c_int(T), c_int(B), c_int(H), c_int(D),
+              c_int(1 if zero_row else 0), c_float(p), c_int(1 if _attn_kv16(items) else 0), _stream())
+
+
+def attn_bwd_tc_multi(items, T, B, H, D, zero_row=True, p=0.0):
+    for it in items:
+        assert it['dout'].stride(0) == it['out'].stride(0) and it['dq'].stride(0) == it['q'].stride(0)
+        if it['S'] > 0:
+            assert it['dk'].stride(0) == it['k'].stride(0) and it['dv'].stride(0) == it['k'].stride(0)
+            assert it['dk'].dtype == it['k'].dtype
+    arr = _attn_ctx_array(items, H * D)
+    _lib.call('tt_attn_bwd_tc_multi', arr, c_int(len(items)), c_int(T), c_int(B), c_int(H), c_int(D),
+              c_int(1 if zero_row else 0), c_float(p), c_int(1 if _attn_kv16(items) else 0), _stream())
+
+
+def attn_decode_hm_multi(items, B, H, D, zero_row=True):
+    """T = 1 step over head-major bf16 caches (k, v = [B,H,S,64]) for up to 4 contexts in one launch;
+    a context with S = 0 attends to its bias / zero rows only."""
+    arr = _attn_ctx_array(items, H * D)
+    _lib.call('tt_attn_decode_hm_multi', arr, c_int(len(items)), c_int(B), c_int(H), c_int(D),
+              c_int(1 if zero_row else 0), _stream())
+
+
 def kv_repack_heads(k, v, S, B, H, D):
     """Token-major bf16 k, v views ([S*B, H*D], shared row stride) -> head-major K, V [B,H,S,D]."""
     _check_cuda(k, v)
