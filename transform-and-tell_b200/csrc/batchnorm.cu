@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 }
 
 // In place on x.  residual (bf16, may be null) is added after the affine transform, before the ReLU.
+// The per-channel scale / shift are computed once per CTA into shared memory (a thread then reads the
+// 8 it owns), two rows are in flight per thread.
 __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict__ x, long long pitch, long long M,
                                                        int C, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
@@ -84,36 +86,38 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
                                                        float* __restrict__ running_var, float momentum,
                                                        long long* __restrict__ num_batches_tracked) {
   pdl_prologue();
-  const int ncg = C >> 3;
-  const int rows_per_pass = blockDim.x / ncg;
-  const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
+  extern __shared__ float sh[];            // [C] scale, [C] shift
   const float inv_m = 1.f / static_cast<float>(M);
-  float sc[8], sf[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = cg * 8 + i;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float mean = stats[c] * inv_m;
     const float var = fmaxf(stats[C + c] * inv_m - mean * mean, 0.f);
-    sc[i] = gamma[c] * rsqrtf(var + eps);
-    sf[i] = beta[c] - mean * sc[i];
-    if (blockIdx.x == 0 && rl == 0 && running_mean != nullptr) {
+    const float a = gamma[c] * rsqrtf(var + eps);
+    sh[c] = a;
+    sh[C + c] = beta[c] - mean * a;
+    if (blockIdx.x == 0 && running_mean != nullptr) {
       const float unbiased = var * (M > 1 ? static_cast<float>(M) / static_cast<float>(M - 1) : 1.f);
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  __syncthreads();
+  const int ncg = C >> 3;
+  const int rows_per_pass = blockDim.x / ncg;
+  const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
   if (rl >= rows_per_pass) return;
-  const long long step = static_cast<long long>(gridDim.x) * rows_per_pass;
-  for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl; r < M; r += step) {
-    uint4* px = reinterpret_cast<uint4*>(x + r * pitch) + cg;
-    const uint4 v = *px;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = sh[cg * 8 + i];
+    sf[i] = sh[C + cg * 8 + i];
+  }
+  auto apply = [&](uint4 v, uint4 rv, bool has_res) -> uint4 {
     float f[8];
     unpack8(v, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = f[i] * sc[i] + sf[i];
-    if (residual != nullptr) {
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + r * rpitch) + cg);
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
+    if (has_res) {
       float g[8];
       unpack8(rv, g);
 #pragma unroll
@@ -127,14 +131,36 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
     __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    *px = o;
+    return o;
+  };
+  const bool has_res = residual != nullptr;
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_pass;
+  long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl;
+  for (; r + step < M; r += 2 * step) {
+    uint4* p0 = reinterpret_cast<uint4*>(x + r * pitch) + cg;
+    uint4* p1 = reinterpret_cast<uint4*>(x + (r + step) * pitch) + cg;
+    const uint4 v0 = *p0, v1 = *p1;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (has_res) {
+      r0 = __ldg(reinterpret_cast<const uint4*>(residual + r * rpitch) + cg);
+      r1 = __ldg(reinterpret_cast<const uint4*>(residual + (r + step) * rpitch) + cg);
+    }
+    *p0 = apply(v0, r0, has_res);
+    *p1 = apply(v1, r1, has_res);
+  }
+  if (r < M) {
+    uint4* p0 = reinterpret_cast<uint4*>(x + r * pitch) + cg;
+    const uint4 v0 = *p0;
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    if (has_res) r0 = __ldg(reinterpret_cast<const uint4*>(residual + r * rpitch) + cg);
+    *p0 = apply(v0, r0, has_res);
   }
 }
 
 static inline int bn_grid(long long M, int C) {
   const int rows_per_pass = 256 / (C / 8);
-  long long g = ceil_div_ll(M, static_cast<long long>(rows_per_pass) * 4);   // >= 4 rows per thread
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+  long long g = ceil_div_ll(M, static_cast<long long>(rows_per_pass) * 8);   // >= 8 rows per thread
+  const long long cap = static_cast<long long>(num_sms()) * 4;
   if (g > cap) g = cap;
   return static_cast<int>(g > 0 ? g : 1);
 }
@@ -164,7 +190,8 @@ extern "C" int tt_bn_apply_bf16(void* x, long long pitch, long long M, int C, co
   TT_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
              "tt_bn_apply_bf16: running_mean and running_var go together");
   if (M <= 0) return TT_OK;
-  launch_k(bn_apply_kernel, dim3(bn_grid(M, C)), dim3(256), 0, (cudaStream_t)stream,
+  launch_k(bn_apply_kernel, dim3(bn_grid(M, C)), dim3(256), static_cast<size_t>(2 * C) * sizeof(float),
+           (cudaStream_t)stream,
            reinterpret_cast<__nv_bfloat16*>(x), pitch, M, C, stats, gamma, beta, eps,
            reinterpret_cast<const __nv_bfloat16*>(residual), rpitch, relu, running_mean, running_var, momentum,
            num_batches_tracked);

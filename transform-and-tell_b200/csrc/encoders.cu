@@ -96,9 +96,10 @@ __global__ void im2col_nhwc_rows_kernel(const __nv_bfloat16* __restrict__ in, __
 // output of the previous (1x1) convolution, sc/sh = per-channel scale / shift derived from its column
 // sums (the GEMM epilogue's col_stats) once per CTA into shared memory.  Padding taps stay zero (the
 // reference pads the NORMALISED activation).  Block 0 moves the running statistics.
+template <bool POW2>
 __global__ void im2col_nhwc_bn_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                            int B, int H, int W, int C, int Ho, int Wo, int KH, int KW,
-                                           int stride, int pad, int Kp, int kw_inv,
+                                           int stride, int pad, int Kp, int c8_shift, int kw_inv,
                                            const float* __restrict__ stats, long long n_stat,
                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                            float eps, float* __restrict__ running_mean,
@@ -133,9 +134,9 @@ __global__ void im2col_nhwc_bn_rows_kernel(const __nv_bfloat16* __restrict__ in,
     const int h0 = ho * stride - pad, w0 = wo * stride - pad;
     const __nv_bfloat16* src = in + static_cast<long long>(b) * H * W * C;
     uint4* dst = reinterpret_cast<uint4*>(out) + static_cast<long long>(row) * cpr;
-#pragma unroll 2
+#pragma unroll 4
     for (int ch = lane; ch < cpr; ch += 32) {
-      const int tap = ch / C8;
+      const int tap = POW2 ? (ch >> c8_shift) : (ch / C8);
       uint4 v = make_uint4(0, 0, 0, 0);
       if (tap < taps) {
         const int c8 = ch - tap * C8;
@@ -714,10 +715,20 @@ extern "C" int tt_im2col_nhwc_bn(const void* in, void* out, int B, int H, int W,
   long long ctas = ceil_div_ll(rows, 8);
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (ctas > cap) ctas = cap;
-  launch_k(im2col_nhwc_bn_rows_kernel, dim3((int)ctas), dim3(256), static_cast<size_t>(2 * C) * sizeof(float),
-           (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B,
-           H, W, C, Ho, Wo, KH, KW, stride, pad, Kp, 65536 / KW + 1, stats, n_stat, gamma, beta, eps, running_mean,
-           running_var, momentum, num_batches_tracked);
+  const int C8 = C / 8;
+  const bool pow2 = (C8 & (C8 - 1)) == 0;
+  int sh = 0;
+  while ((1 << sh) < C8) ++sh;
+  if (pow2)
+    launch_k(im2col_nhwc_bn_rows_kernel<true>, dim3((int)ctas), dim3(256), static_cast<size_t>(2 * C) * sizeof(float),
+             (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B,
+             H, W, C, Ho, Wo, KH, KW, stride, pad, Kp, sh, 65536 / KW + 1, stats, n_stat, gamma, beta, eps,
+             running_mean, running_var, momentum, num_batches_tracked);
+  else
+    launch_k(im2col_nhwc_bn_rows_kernel<false>, dim3((int)ctas), dim3(256), static_cast<size_t>(2 * C) * sizeof(float),
+             (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B,
+             H, W, C, Ho, Wo, KH, KW, stride, pad, Kp, sh, 65536 / KW + 1, stats, n_stat, gamma, beta, eps,
+             running_mean, running_var, momentum, num_batches_tracked);
   return check_launch("im2col_nhwc_bn_rows_kernel");
 }
 
