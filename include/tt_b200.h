@@ -94,6 +94,16 @@ typedef struct {
    * a train-mode BatchNorm behind this convolution needs (tt_bn_apply_bf16), accumulated in the epilogue
    * instead of by a separate pass over the output.  Needs the bf16 output (C16). */
   float* col_stats;
+  /* Batched launch: nbatch (<= 16; 0 / 1 = a single problem) same-shape problems in ONE launch -- the
+   * four out-projections of a decoder layer's cross-attentions (multi_head.py:476), their dX and
+   * their dW GEMMs.  Operands are blocks of shared buffers: batch z reads A at TMA coordinate
+   * (c0 + z*a_off0, c1 + z*a_off1) [c0 = the contiguous axis of the STORED matrix, c1 = its rows],
+   * likewise B; writes C / C16 at + z*c_off elements and reads bias at + z*bias_off.  lda / ldb / ldc
+   * are the pitches of the shared buffers.  Plain problems only (bias / activation; no residual, row
+   * limit, accumulate, col_stats); K-major operands batched along K need K % 64 == 0. */
+  int nbatch;
+  int a_off0, a_off1, b_off0, b_off1, bias_off;
+  long long c_off;
 } TtGemmParams;
 int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream);
 /* Debug hook: when non-NULL, every CTA of the 1-CTA GEMM kernel writes 8 %globaltimer stamps (

@@ -262,3 +262,35 @@ def test_gemm_column_statistics_in_the_epilogue(M, N, K):
     # accumulates: a second launch doubles the sums
     ops.gemm_tn(a, b, want32=False, want16=True, col_stats=st)
     assert ((st[N:].double() - 2 * q_ref).abs() / q_ref.clamp_min(1e-6)).max().item() < 1e-4
+
+
+@pytest.mark.parametrize('nb,M,E', [(4, 800, 1024), (4, 256, 1024), (3, 77, 64), (2, 130, 256)])
+def test_gemm_batched_launch_equals_separate_launches(nb, M, E):
+    """nbatch same-shape problems in ONE launch (the four out-projections of a decoder layer, their
+    dX and dW GEMMs): forward layout (A column blocks, stacked weights), dX (trans_b) and dW
+    (trans_a, trans_b) each bit-identical to nb separate launches."""
+    from tell_b200 import ops
+    torch.manual_seed(nb * 1000 + M)
+    a = (torch.randn(M, nb * E, device='cuda') / 8).bfloat16()
+    w = (torch.randn(nb * E, E, device='cuda') / 8).bfloat16()
+    bias = torch.randn(nb * E, device='cuda')
+    d = (torch.randn(M, nb * E, device='cuda') / 8).bfloat16()
+    # forward: out[z] = a[:, zE:(z+1)E] @ w[zE:(z+1)E]^T + bias[zE:(z+1)E]
+    out = torch.empty(nb, M, E, device='cuda')
+    ops.gemm_tn_batched(a, w, nb, M, E, E, out.view(nb * M, E), M * E, a_off=(E, 0), b_off=(0, E), bias=bias,
+                        bias_off=E)
+    for z in range(nb):
+        ref = ops.gemm_tn(a[:, z * E:(z + 1) * E], w[z * E:(z + 1) * E], bias=bias[z * E:(z + 1) * E].contiguous())
+        assert torch.equal(out[z], ref), ('fwd', z)
+    # dX: dx[:, zE:(z+1)E] = d[:, zE:(z+1)E] @ w[zE:(z+1)E]      (B stored [K, N])
+    dx = torch.empty(M, nb * E, device='cuda')
+    ops.gemm_tn_batched(d, w, nb, M, E, E, dx, E, a_off=(E, 0), b_off=(0, E), trans_b=True)
+    for z in range(nb):
+        ref = ops.gemm_tn(d[:, z * E:(z + 1) * E], w[z * E:(z + 1) * E], trans_b=True)
+        assert torch.equal(dx[:, z * E:(z + 1) * E], ref), ('dx', z)
+    # dW: dw[zE:(z+1)E] = d[:, zE:(z+1)E]^T @ a[:, zE:(z+1)E]      (both stored [K = rows, .])
+    dw = torch.empty(nb * E, E, device='cuda')
+    ops.gemm_tn_batched(d, a, nb, E, E, M, dw, E * E, a_off=(E, 0), b_off=(E, 0), trans_a=True, trans_b=True)
+    for z in range(nb):
+        ref = ops.gemm_tn(d[:, z * E:(z + 1) * E], a[:, z * E:(z + 1) * E], trans_a=True, trans_b=True)
+        assert torch.equal(dw[z * E:(z + 1) * E], ref), ('dw', z)

@@ -110,7 +110,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // blocks x 473 k-blocks on 16 SMs) spread over the machine; partials meet in C through atomics.
   const int splits = g.splits > 1 ? g.splits : 1;
   const int kper = (num_k + splits - 1) / splits;
-  const int num_tiles = num_mn * splits;
+  const int nbatch = g.nbatch > 1 ? g.nbatch : 1;      // batched launches never split K
+  const int num_tiles = num_mn * splits * nbatch;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -122,27 +123,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), full_u = smem_u32(full_bar);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ks = tile / num_mn, mn = tile - ks * num_mn;
+      const int kz = tile / num_mn, mn = tile - kz * num_mn;
+      const int ks = nbatch > 1 ? 0 : kz, z = nbatch > 1 ? kz : 0;
       const int m_blk = mn % num_m, n_blk = mn / num_m;
       const int kb_end = min(num_k, (ks + 1) * kper);
+      const int a0 = z * g.a_off0, a1 = z * g.a_off1, b0 = z * g.b_off0, b1 = z * g.b_off1;
       for (int kb = ks * kper; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           const uint32_t bar = full_u + stage * 8;
           mbar_arrive_expect_tx_u(bar, Cfg::STAGE_BYTES);
           if (!TA) {
-            tma_load_2d_u(sA_u + stage * Cfg::A_BYTES, &tmA, bar, kb * BK, m_blk * BM);
+            tma_load_2d_u(sA_u + stage * Cfg::A_BYTES, &tmA, bar, kb * BK + a0, m_blk * BM + a1);
           } else {  // MN-major: one 64(m) x 64(k) box per 64-row chunk of the tile
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d_u(sA_u + stage * Cfg::A_BYTES + c * 8192, &tmA, bar, m_blk * BM + c * 64, kb * BK);
+              tma_load_2d_u(sA_u + stage * Cfg::A_BYTES + c * 8192, &tmA, bar, m_blk * BM + c * 64 + a0, kb * BK + a1);
           }
           if (!TB) {
-            tma_load_2d_u(sB_u + stage * Cfg::B_BYTES, &tmB, bar, kb * BK, n_blk * BN);
+            tma_load_2d_u(sB_u + stage * Cfg::B_BYTES, &tmB, bar, kb * BK + b0, n_blk * BN + b1);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d_u(sB_u + stage * Cfg::B_BYTES + c * 8192, &tmB, bar, n_blk * BN + c * 64, kb * BK);
+              tma_load_2d_u(sB_u + stage * Cfg::B_BYTES + c * 8192, &tmB, bar, n_blk * BN + c * 64 + b0, kb * BK + b1);
           }
           if (kb == ks * kper && tile == blockIdx.x) trace_stamp(g, 2);
         }
@@ -166,7 +169,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ks = tile / num_mn;
+      const int ks = nbatch > 1 ? 0 : tile / num_mn;
       const int kb0 = ks * kper, kb_end = min(num_k, (ks + 1) * kper);
       if (kb0 >= kb_end) continue;            // empty split (num_k not a multiple): no accumulator
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -217,7 +220,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ew.res_phase = 0;
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ks = tile / num_mn, mn = tile - ks * num_mn;
+      const int kz = tile / num_mn, mn = tile - kz * num_mn;
+      const int ks = nbatch > 1 ? 0 : kz, z = nbatch > 1 ? kz : 0;
       const int m_blk = mn % num_m, n_blk = mn / num_m;
       if (ks * kper >= min(num_k, (ks + 1) * kper)) continue;     // empty split
       const int row0 = m_blk * BM + q * 32;
@@ -241,10 +245,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                          half, row0, n_blk * BN, ew, min(32, M - row0));
       }
       if (staged) {
-      } else if (splits > 1) {
-        GemmArgs ge = g;                      // partial product: bias / residual enter once (split 0)
-        ge.atomic = 1;
-        if (ks > 0) { ge.bias = nullptr; ge.residual = nullptr; ge.residual16 = nullptr; }
+      } else if (splits > 1 || nbatch > 1) {
+        GemmArgs ge = g;
+        if (splits > 1) {                     // partial product: bias / residual enter once (split 0)
+          ge.atomic = 1;
+          if (ks > 0) { ge.bias = nullptr; ge.residual = nullptr; ge.residual16 = nullptr; }
+        } else {                              // batch z: its block of the shared output / bias buffers
+          if (ge.C != nullptr) ge.C += z * g.c_off;
+          if (ge.C16 != nullptr) ge.C16 += z * g.c_off;
+          if (ge.bias != nullptr) ge.bias += z * g.bias_off;
+        }
         epilogue_chunks<BN>(ge, tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                     static_cast<uint32_t>(acc * BN),
                             half, row, row_ok, n_blk * BN);
@@ -332,7 +342,7 @@ struct TileChoice {
   bool pair;
   int bn;
 };
-static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sms) {
+static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sms, int nbatch = 1) {
   static int forced = -1, forced2 = -1, pair_enabled = -1;
   if (forced < 0) {
     const char* e = getenv("TT_GEMM_BN");          // experiments: force the single-CTA tile width
@@ -367,7 +377,7 @@ static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sm
   for (const Cand& c : cands) {
     if (c.pair && !(pair_ok && pair_enabled)) continue;
     if (N < c.bn && c.bn > 64) continue;
-    const long long tiles = static_cast<long long>(ceil_div(M, c.pair ? 2 * BM : BM)) * ceil_div(N, c.bn);
+    const long long tiles = static_cast<long long>(ceil_div(M, c.pair ? 2 * BM : BM)) * ceil_div(N, c.bn) * nbatch;
     const long long slots = c.pair ? sms / 2 : sms;
     const double waves = static_cast<double>(ceil_div_ll(tiles, slots));
     double cost = waves * (c.fixed + num_k * c.tk + 0.02 * (N < c.bn ? N : c.bn));
@@ -401,6 +411,9 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   TT_REQUIRE(p->A && p->B, "tt_gemm_bf16_tn: null operand");
   TT_REQUIRE(p->C || p->C16, "tt_gemm_bf16_tn: no output buffer");
   const bool ta = p->trans_a != 0, tb = p->trans_b != 0;
+  TT_REQUIRE(p->nbatch <= 1 || (p->nbatch <= 16 && p->a_off0 >= 0 && p->a_off1 >= 0 && p->b_off0 >= 0 &&
+                                p->b_off1 >= 0 && p->c_off >= 0 && p->bias_off >= 0),
+             "tt_gemm_bf16_tn: bad batch description");
   TT_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->lda >= (ta ? p->M : p->K) &&
                  p->ldb >= (tb ? p->N : p->K),
              "tt_gemm_bf16_tn: lda/ldb must be multiples of 8 and cover a stored row "
@@ -414,17 +427,21 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   const int sms = num_sms();
   // rows the kernel will really compute (a host-side hint for device-limited problems)
   const int m_eff = (p->m_limit != nullptr && p->m_hint > 0 && p->m_hint < p->M) ? p->m_hint : p->M;
-  const TileChoice choice = choose_tile(m_eff, p->N, p->K, !ta && !tb, tb, sms);
+  const int nb = p->nbatch > 1 ? p->nbatch : 1;
+  const TileChoice choice = choose_tile(m_eff, p->N, p->K, !ta && !tb && nb == 1, tb, sms, nb);
   int bn = choice.bn;           // (an MN-major B tile is built from 64-column TMA boxes: bn >= 64)
 
   CUtensorMap tmA, tmB;
   // K-major operand: rows = M (or N), inner = K, box 64(k) x rows.  MN-major operand (stored
   // [K, M] or [K, N]): rows = K, inner = M (or N), box 64(mn) x 64(k).
-  int rc = ta ? make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->M, (uint64_t)p->K, (uint64_t)p->lda, 64, BK)
-              : make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
+  // (a batched launch addresses batch z at coordinate + z * off: the maps span all batches)
+  const uint64_t ax0 = static_cast<uint64_t>(nb - 1) * p->a_off0, ax1 = static_cast<uint64_t>(nb - 1) * p->a_off1;
+  const uint64_t bx0 = static_cast<uint64_t>(nb - 1) * p->b_off0, bx1 = static_cast<uint64_t>(nb - 1) * p->b_off1;
+  int rc = ta ? make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->M + ax0, (uint64_t)p->K + ax1, (uint64_t)p->lda, 64, BK)
+              : make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K + ax0, (uint64_t)p->M + ax1, (uint64_t)p->lda, BK, BM);
   if (rc != TT_OK) return rc;
-  rc = tb ? make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->N, (uint64_t)p->K, (uint64_t)p->ldb, 64, BK)
-          : make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->ldb, BK, bn);
+  rc = tb ? make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->N + bx0, (uint64_t)p->K + bx1, (uint64_t)p->ldb, 64, BK)
+          : make_tmap_bf16_2d(&tmB, p->B, (uint64_t)p->K + bx0, (uint64_t)p->N + bx1, (uint64_t)p->ldb, BK, bn);
   if (rc != TT_OK) return rc;
 
   GemmArgs g;
@@ -453,6 +470,20 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   g.trace = gemm_trace_ptr();
   g.splits = 1;
   g.atomic = 0;
+  g.nbatch = p->nbatch > 1 ? p->nbatch : 1;
+  g.a_off0 = p->a_off0; g.a_off1 = p->a_off1; g.b_off0 = p->b_off0; g.b_off1 = p->b_off1;
+  g.bias_off = p->bias_off; g.c_off = p->c_off;
+  if (g.nbatch > 1) {
+    TT_REQUIRE(p->residual == nullptr && p->residual16 == nullptr && p->m_limit == nullptr &&
+                   p->k_limit == nullptr && !p->accumulate && p->col_stats == nullptr,
+               "tt_gemm_bf16_tn: a batched launch takes plain problems (bias / activation only)");
+    TT_REQUIRE((ta || p->a_off0 == 0 || p->K % BK == 0) && (tb || p->b_off0 == 0 || p->K % BK == 0),
+               "tt_gemm_bf16_tn: batches laid side by side along K need K %% 64 == 0");
+    if (p->bias) vec = vec && (p->bias_off % 4 == 0);
+    if (p->C) vec = vec && (p->c_off % 4 == 0);
+    if (p->C16) vec = vec && (p->c_off % 8 == 0);
+    g.vec_ok = vec ? 1 : 0;
+  }
 
   // Staged epilogue (gemm_common.cuh): bf16-only output whose rows the TMA engine can address.
   CUtensorMap tmC = tmA, tmR = tmA;
@@ -462,7 +493,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
       const char* e = getenv("TT_GEMM_TMA_EPI");        // experiments: 0 = register epilogue everywhere
       g_staged = (e && e[0] == '0') ? 0 : 1;
     }
-    if (g_staged && !ta && !tb && p->C16 != nullptr && p->C == nullptr && p->residual == nullptr &&
+    if (g_staged && nb == 1 && !ta && !tb && p->C16 != nullptr && p->C == nullptr && p->residual == nullptr &&
         !p->accumulate && vec && p->N % 32 == 0 && p->M >= 32) {
       rc = make_tmap_bf16_2d_sw(&tmC, p->C16, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldc16, 32, 32, 64);
       if (rc != TT_OK) return rc;
@@ -483,7 +514,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   if (choice.pair)   // CTA-pair kernel (gemm2.cu)
     return gemm2_launch(p, g, tmC, tmR, choice.bn, reinterpret_cast<cudaStream_t>(stream));
 
-  int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
+  int tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * nb;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {
     // split-K for few-tile, long-K problems with a plain fp32 epilogue
@@ -498,7 +529,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     // Opt-in through m_hint (row-limited training GEMMs): atomics make the fp32 summation order
     // run-dependent, which the backward already tolerates (LayerNorm / column-sum / scatter
     // atomics) but greedy decoding must not -- its GEMMs never set a hint and stay bit-reproducible.
-    if (sk && p->m_limit != nullptr && p->m_hint > 0 && p->C != nullptr && p->C16 == nullptr &&
+    if (sk && nb == 1 && p->m_limit != nullptr && p->m_hint > 0 && p->C != nullptr && p->C16 == nullptr &&
         p->act == TT_ACT_NONE && !p->accumulate && tiles * 2 <= sms && num_k >= 32 && p->col_stats == nullptr) {
       int sp = sms / tiles;
       if (sp > num_k / 8) sp = num_k / 8;     // at least 8 k-blocks per split
@@ -509,7 +540,7 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
         tiles *= sp;
       }
     }
-    if (g.splits == 1) tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn);
+    if (g.splits == 1) tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * nb;
     else tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * g.splits;
   }
   const int grid = tiles < sms ? tiles : sms;

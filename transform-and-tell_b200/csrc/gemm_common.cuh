@@ -27,6 +27,12 @@ struct GemmArgs {
   const int* k_limit;   // device int, optional: operand rows/cols k >= *k_limit are known to be zero
   int splits;           // split-K factor (1-CTA kernel): partial products are added atomically into C
   int atomic;           // epilogue adds into C with atomics (set per tile by the split-K kernel)
+  // Batched launch (single-CTA kernel, register epilogue): nbatch same-shape problems whose operands
+  // are blocks of shared buffers; batch z adds z * off to the TMA coordinates of A / B, z * c_off
+  // elements to the output pointers and z * bias_off to the bias pointer.
+  int nbatch;
+  int a_off0, a_off1, b_off0, b_off1, bias_off;
+  long long c_off;
   int vec_ok;  // all fp32/bf16 row pointers 16-byte aligned for 32-column chunks
   float* col_stats;   // optional [2N]: += column sums / sums of squares of the bf16-rounded outputs
   int tma_epi;  // staged epilogue (bf16-only output, N % 32 == 0): 1 = TMA store of C16, 2 = + TMA load of residual16

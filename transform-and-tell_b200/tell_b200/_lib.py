@@ -31,7 +31,8 @@ class TtGemmParams(ctypes.Structure):
                 ('residual16', c_void_p), ('ldr16', c_ll),
                 ('alpha', c_float), ('act', c_int), ('accumulate', c_int),
                 ('m_limit', c_void_p), ('trans_a', c_int), ('trans_b', c_int), ('m_hint', c_int), ('k_limit', c_void_p),
-                ('col_stats', c_void_p)]
+                ('col_stats', c_void_p), ('nbatch', c_int), ('a_off0', c_int), ('a_off1', c_int),
+                ('b_off0', c_int), ('b_off1', c_int), ('bias_off', c_int), ('c_off', c_ll)]
 
 
 class TtAttnCtx(ctypes.Structure):

@@ -698,12 +698,30 @@ class MultiCtxAttentionFn(Function):
 
 class FusedOutProjFn(Function):
     """h_c = a_c @ Wo_c^T + bo_c for the n attention outputs living side by side in a_all [N, n*E]
-    (multi_head.py:476 out_proj): one operand cast, n GEMMs reading column blocks by stride."""
+    (multi_head.py:476 out_proj).  Throughput mode: ONE batched launch for the n same-shape GEMMs
+    (tt_gemm_bf16_tn nbatch: batch c reads column block c of the shared bf16 operand and row block c
+    of the stacked weights), and likewise ONE launch for the n dX and ONE for the n dW GEMMs of the
+    backward -- 3 launches per layer instead of 12.  Parity mode: n GEMMs on re-cast operands."""
 
     @staticmethod
     def forward(ctx, a_all, n, *args):
         ws, bs = args[:n], args[n:2 * n]
         E = a_all.shape[1] // n
+        N = a_all.shape[0]
+        fast = _fast()
+        batched = fast and config.gemm_batched and n > 1 and E % 64 == 0 and n <= 16 \
+            and all(w.shape == (E, E) for w in ws)
+        has_bias = bs[0] is not None
+        if batched:
+            a16 = operand(a_all, 'a')
+            w16 = concat_rows_operand(list(ws), 'b', a_all.device)          # [n*E, E], one prep launch
+            bias = torch.cat([b.reshape(-1) for b in bs]) if has_bias else None
+            out = torch.empty((n, N, E), dtype=torch.float32, device=a_all.device)
+            ops.gemm_tn_batched(a16, w16, n, N, E, E, out.view(n * N, E), N * E, a_off=(E, 0), b_off=(0, E),
+                                bias=bias, bias_off=E)
+            ctx.cfg = (n, E, fast, has_bias, True)
+            ctx.save_for_backward(a16, w16)
+            return tuple(out[c] for c in range(n))
         a16 = operand(a_all, 'a')
         rep = _rep()
         w16s, hs = [], []
@@ -715,8 +733,8 @@ class FusedOutProjFn(Function):
             else:   # split layout is per full row: cast the block on its own
                 a_c = operand(a_all[:, c * E:(c + 1) * E], 'a')
             hs.append(ops.gemm_tn(a_c, w16, bias=bs[c]))
-        ctx.cfg = (n, E, _fast(), bs[0] is not None)
-        if ctx.cfg[2]:
+        ctx.cfg = (n, E, fast, has_bias, False)
+        if fast:
             ctx.save_for_backward(a16, *w16s)
         else:
             ctx.save_for_backward(a_all, *ws)
@@ -724,11 +742,28 @@ class FusedOutProjFn(Function):
 
     @staticmethod
     def backward(ctx, *dhs):
-        n, E, fast, has_bias = ctx.cfg
+        n, E, fast, has_bias, batched = ctx.cfg
         sv = ctx.saved_tensors
         a, ws = sv[0], sv[1:]
         N = a.shape[0]
         da_all = torch.empty((N, n * E), dtype=torch.float32, device=a.device)
+        if batched:
+            w16 = ws[0]                                                   # stacked [n*E, E]
+            d16 = torch.empty((N, n * E), dtype=torch.bfloat16, device=a.device)
+            for c in range(n):
+                ops.cast_bf16(_c(dhs[c]), out=d16[:, c * E:(c + 1) * E])
+            # dX_c = dh_c . W_c      (B stored [K = E_out, N = E_in]: row block c of the stack)
+            ops.gemm_tn_batched(d16, w16, n, N, E, E, da_all, E, a_off=(E, 0), b_off=(0, E), trans_b=True)
+            # dW_c = dh_c^T . a_c    (both operands stored [K = rows, .]: column blocks c)
+            dW = torch.empty((n * E, E), dtype=torch.float32, device=a.device)
+            ops.gemm_tn_batched(d16, a, n, E, E, N, dW, E * E, a_off=(E, 0), b_off=(E, 0), trans_a=True,
+                                trans_b=True)
+            dws = tuple(dW[c * E:(c + 1) * E] for c in range(n))
+            dbs = (None,) * n
+            if has_bias:
+                db = ops.colsum(d16)                                      # one pass over the bf16 operand
+                dbs = tuple(db[c * E:(c + 1) * E] for c in range(n))
+            return (da_all, None) + dws + dbs
         dws, dbs = [], []
         for c in range(n):
             dh = _c(dhs[c])

@@ -128,6 +128,39 @@ def gemm_tn(a, b, out=None, out16=None, bias=None, residual=None, alpha=1.0, act
     return out if out is not None else out16
 
 
+def gemm_tn_batched(a, b, nbatch, M, N, K, out, ldc_off, a_off=(0, 0), b_off=(0, 0), bias=None,
+                    bias_off=0, alpha=1.0, act=ACT_NONE, trans_a=False, trans_b=False):
+    """nbatch same-shape problems C_z = act(alpha * (A_z . B_z^T + bias_z)) in ONE launch.  a / b are
+    the SHARED bf16 buffers the per-batch operands are blocks of (batch z starts a_off[0] * z
+    elements along the contiguous axis and a_off[1] * z rows further; same for b); out is the shared
+    fp32 or bf16 output buffer, batch z written at + z * ldc_off elements with row pitch
+    out.stride(0); bias a shared fp32 vector read at + z * bias_off."""
+    _check_cuda(a, b, out, bias)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    p = TtGemmParams()
+    p.M, p.N, p.K = M, N, K
+    p.A, p.lda = a.data_ptr(), a.stride(0)
+    p.B, p.ldb = b.data_ptr(), b.stride(0)
+    if out.dtype == torch.float32:
+        p.C, p.ldc = out.data_ptr(), out.stride(0)
+    else:
+        assert out.dtype == torch.bfloat16
+        p.C16, p.ldc16 = out.data_ptr(), out.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        p.bias = bias.data_ptr()
+    p.alpha, p.act = alpha, act
+    p.trans_a, p.trans_b = (1 if trans_a else 0), (1 if trans_b else 0)
+    p.nbatch = nbatch
+    p.a_off0, p.a_off1 = a_off
+    p.b_off0, p.b_off1 = b_off
+    p.bias_off, p.c_off = bias_off, ldc_off
+    if _lib.PROFILE is not None:
+        _lib.GEMM_FLOPS.append(2.0 * nbatch * M * N * K)
+    _lib.call('tt_gemm_bf16_tn', ctypes.byref(p), _stream())
+    return out
+
+
 # --------------------------------------------------------------------------- row-wise kernels
 def _ull(x):
     return ctypes.c_ulonglong(int(x) & 0xFFFFFFFFFFFFFFFF)
