@@ -225,7 +225,7 @@ def run_b200(args):
         # article, one GPU's share), each in its own process, BEFORE this process creates its CUDA
         # context: measured after the main benchmark (this process idle but holding its graphs and
         # ~30 GB) the same tools ran 2-3.5x slower and erratically (392 / 242 ms vs 110 ms alone).
-        extras = {'decode': run_extra('bench_decode.py', '--reps', '3'), 'cfg5': run_extra('bench_cfg5.py')}
+        extras = {'decode': run_extra('bench_decode.py', '--reps', '5'), 'cfg5': run_extra('bench_cfg5.py')}
     config.set_precision('bf16')
     config.manual_seed(1234 + rank)
     config.enable_device_step(dev)
