@@ -170,3 +170,13 @@ def test_collator_host_packing_and_generations_writer(tmp_path):
     assert rows[0] == {'caption': 'a cap', 'raw_caption': 'A Cap', 'generation': 'a gen', 'copied_texts': 'cp',
                        'web_url': 'http://x', 'image_path': '/i.jpg', 'context': 'ctx', 'copied_text': 'cp'}
     assert rows[1]['generated_names'] == ['A GEN'] and rows[1]['context_names'] == ['CTX']
+    # Model.forward(evaluate_mode) emits gen_ids, not generations: the writer builds them with the
+    # caller's BPE decoder from x[x > 1] (transformer_faces_objects.py:95-96); without one it says so
+    model_out = {'captions': ['a cap', 'b cap'], 'metadata': [{'caption': 'A'}, None],
+                 'gen_ids': np.array([[0, 17, 23, 2, 1, 1], [0, 9, 2, 1, 1, 1]])}
+    with pytest.raises(KeyError, match='decode'):
+        write_generations_jsonl(path, model_out)
+    assert write_generations_jsonl(path, model_out, decode=lambda ids: ' '.join(str(int(i)) for i in ids)) == 2
+    rows = [json.loads(l) for l in open(path)]
+    assert rows[-2]['generation'] == '17 23 2' and rows[-1]['generation'] == '9 2'
+    assert rows[-1]['raw_caption'] == 'b cap' and rows[-1]['web_url'] is None

@@ -313,3 +313,31 @@ def test_dynconv_decode_step_matches_full_convolution():
             if K > 1:
                 assert buf[0].shape == (K - 1, B, C)
                 assert torch.equal(buf[0], x[T - K + 1:])
+
+
+def test_load_state_dict_after_a_forward_invalidates_the_derived_operands():
+    """The frozen encoders cache bf16 / BatchNorm-folded operands made from their weights;
+    load_state_dict() copies in place, so loading a checkpoint AFTER a warm-up forward must drop
+    those caches (a stale cache would silently keep the random-init weights)."""
+    from tell_b200 import synth
+    from tell_b200.models import ResNetFeatureExtractor, RobertaEncoder
+    L, E, H, ffn, V, P = 1, 256, 4, 256, 300, 64
+    ids = synth.article_batch(2, 20, V, np.random.RandomState(0), min_len=10).cuda()
+    enc = RobertaEncoder(L, E, H, ffn, V, P).cuda().eval()
+    enc.extract_features(ids)                                       # warm-up with random-init weights
+    sd = synth.roberta_state_dict(L, E, ffn, V, P, seed=9)
+    enc.load_state_dict(sd, strict=True)
+    fresh = RobertaEncoder(L, E, H, ffn, V, P)
+    fresh.load_state_dict(sd, strict=True)
+    fresh = fresh.cuda().eval()
+    assert torch.equal(enc.extract_features(ids), fresh.extract_features(ids))
+    layers = (1, 1, 1, 1)
+    img = torch.randn(1, 3, 64, 64, device='cuda')
+    net = ResNetFeatureExtractor(layers).cuda().eval()
+    net(img)
+    rsd = synth.resnet_state_dict(layers, seed=4)
+    net.load_state_dict(rsd, strict=True)
+    fresh = ResNetFeatureExtractor(layers)
+    fresh.load_state_dict(rsd, strict=True)
+    fresh = fresh.cuda().eval()
+    assert torch.equal(net(img), fresh(img))

@@ -153,25 +153,37 @@ class Collator:
         return batch
 
 
-def write_generations_jsonl(path, output_dict, nlp=None, extra=None):
+def write_generations_jsonl(path, output_dict, nlp=None, extra=None, decode=None):
     """Append one JSON line per sample, keys as tell/commands/evaluate.py:196-215.  `nlp`: optional
     callable text -> dict of the spaCy-derived keys for that text (names / entities / readability);
-    without it those keys are omitted."""
-    if 'captions' not in output_dict:
+    without it those keys are omitted.  `decode`: callable ids (1-D int array with <s> and <pad>
+    removed, i.e. x[x > 1] as in transformer_faces_objects.py:96) -> text, used when output_dict
+    carries `gen_ids` (what Model.forward emits in evaluate_mode) but no `generations`: the reference
+    decodes them with the RoBERTa BPE inside forward, host-side string work this package leaves to
+    the caller."""
+    if 'captions' not in output_dict or output_dict['captions'] is None:
         return 0
-    captions, generations = output_dict['captions'], output_dict['generations']
+    captions = output_dict['captions']
+    generations = output_dict.get('generations')
+    if generations is None:
+        if decode is None or 'gen_ids' not in output_dict:
+            raise KeyError("output_dict has no 'generations': pass decode= (ids -> text) to build them "
+                           "from 'gen_ids'")
+        generations = []
+        for row in np.asarray(output_dict['gen_ids']):
+            generations.append(decode(row[row > 1]))        # "We ignore <s> and <pad>" (:95-96)
     metadatas = output_dict['metadata']
     copied = output_dict.get('copied_texts', ['' for _ in captions])
     n = 0
     with open(path, 'a') as f:
         for i, caption in enumerate(captions):
-            m = metadatas[i]
-            obj = {'caption': caption, 'raw_caption': m['caption'], 'generation': generations[i],
-                   'copied_texts': copied[i], 'web_url': m['web_url'], 'image_path': m['image_path'],
-                   'context': m['context']}
+            m = metadatas[i] or {}
+            obj = {'caption': caption, 'raw_caption': m.get('caption', caption), 'generation': generations[i],
+                   'copied_texts': copied[i], 'web_url': m.get('web_url'), 'image_path': m.get('image_path'),
+                   'context': m.get('context')}
             if nlp is not None:
-                for prefix, text in (('caption', m['caption']), ('generated', generations[i]),
-                                     ('context', m['context'])):
+                for prefix, text in (('caption', m.get('caption', caption)), ('generated', generations[i]),
+                                     ('context', m.get('context') or '')):
                     for k, v in nlp(text).items():
                         obj['%s_%s' % (prefix, k)] = v
             if 'copied_texts' in output_dict:

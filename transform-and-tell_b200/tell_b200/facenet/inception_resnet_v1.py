@@ -221,12 +221,20 @@ class InceptionResnetV1(nn.Module):
         self.logits = nn.Linear(512, num_classes)
         self._f = None
 
-    def _apply(self, fn, *a, **k):
+    def _invalidate(self):
         self._f = None
         for m in self.modules():
             if isinstance(m, (_ResidualBlock, _Reduction)):
                 m._f = None
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
         return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)      # in-place copies: folded operands are stale
+        self._invalidate()
+        return r
 
     def prepare(self):
         stem = [self.conv2d_1a, self.conv2d_2a, self.conv2d_2b, self.conv2d_3b, self.conv2d_4a,

@@ -49,6 +49,11 @@ class _Net(nn.Module):
         self._f = None
         return super()._apply(fn, *a, **k)
 
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)      # in-place copies: folded operands are stale
+        self._f = None
+        return r
+
     def _conv(self, x, folded, slope, k):
         """x [B,H,W,Cp] bf16 -> PReLU(conv_kxk(x)) [B,H-k+1,W-k+1,Coutp] bf16."""
         w, b = folded

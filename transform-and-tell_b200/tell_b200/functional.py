@@ -827,6 +827,9 @@ class EmbedFn(Function):
 
     @staticmethod
     def forward(ctx, ids, pos_table, start_pos, pad, scale, cutoffs, n, *args):
+        # n may be (n_bands, padding_idx of the adaptive embedder): nn.Embedding(padding_idx) keeps
+        # that local row of every band out of the gradient (adaptive.py:35-40)
+        n, ctx.emb_pad = n if isinstance(n, tuple) else (n, 0)
         tables, projs = args[:n], args[n:2 * n]
         B, T = ids.shape
         E = projs[0].shape[0]
@@ -879,7 +882,7 @@ class EmbedFn(Function):
                 dtables.append(g)
                 ret.append(g)
         _TIED_GRADS.clear()
-        ops.embed_scatter_grad(ids, cutoffs, dtables, E, dA, padding_idx=0, tbc=True)
+        ops.embed_scatter_grad(ids, cutoffs, dtables, E, dA, padding_idx=ctx.emb_pad, tbc=True)
         return (None,) * 7 + tuple(ret) + tuple(dprojs)
 
 

@@ -76,6 +76,11 @@ class RobertaEncoder(nn.Module):
         object.__setattr__(self, '_qkv_key', None)
         return super()._apply(fn, *a, **k)
 
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)      # in-place copies: the derived bf16 operands are stale
+        self._prep = None
+        return r
+
     def prepare(self):
         """bf16 GEMM operands, with the query scaling d^-0.5 folded into Wq / bq (frozen weights)."""
         E, d = self.embed_dim, self.embed_dim // self.heads

@@ -142,7 +142,7 @@ def embed_tokens(ids, adaptive, positional, start_pos):
         pos_table = torch.zeros((ids.shape[1] + 2, adaptive.embed_size), device=ids.device)
         pad, start_pos = 0, 0
     return Fn.EmbedFn.apply(ids, pos_table, start_pos, pad, float(adaptive.embed_scale),
-                            tuple(adaptive.cutoff), len(tables), *tables, *projs)
+                            tuple(adaptive.cutoff), (len(tables), int(adaptive.padding_idx)), *tables, *projs)
 
 
 @TextFieldEmbedder.register('sum')
