@@ -217,7 +217,10 @@ def run_b200(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/nccl_bench_%h_%p.log')
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
             os.environ['NCCL_DEBUG'] = 'WARN'     # level VERSION printf()s its banner to stdout
-        dist.init_process_group('nccl', device_id=dev)
+        # a rank that dies or hangs must take the job down instead of leaving the others in a collective
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '1')
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(minutes=10))
     _lib.lib()
     extras = None
     if world == 1 and not args.skip_extras:

@@ -26,6 +26,28 @@ attn_multi = os.environ.get('TT_ATTN_MULTI', '1') == '1'
 gemm_batched = os.environ.get('TT_GEMM_BATCHED', '1') == '1'
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks
 
+# NVTX ranges around the phases of Model.forward / generate (encoders, decoder, loss, decode steps):
+# visible in Nsight Systems / ncu --nvtx; off by default (a push/pop pair per phase costs ~1 us of host time)
+nvtx = os.environ.get('TT_NVTX', '0') == '1'
+
+
+class nvtx_range:
+    """`with config.nvtx_range('name'):` -- a torch.cuda.nvtx range when config.nvtx is on."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.on = nvtx
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 _seed_base = 0x5EED
 _counter = itertools.count(1)
 _step = None  # device-resident step counter mixed into every dropout seed

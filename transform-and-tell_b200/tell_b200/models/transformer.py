@@ -94,8 +94,9 @@ class _CaptionModelBase(Model):
             hid, _ = self.roberta.all_hiddens(context[self.index], n_real_tokens)
             cur.wait_stream(side)
             return feats, hid
-        feats = self.resnet.features_nhwc(image) if self.USES_IMAGE else None
-        hid, _ = self.roberta.all_hiddens(context[self.index], n_real_tokens)
+        with config.nvtx_range('tt/encode'):
+            feats = self.resnet.features_nhwc(image) if self.USES_IMAGE else None
+            hid, _ = self.roberta.all_hiddens(context[self.index], n_real_tokens)
         return feats, hid
 
     # ------------------------------------------------------------------ _forward (:311-397)
@@ -141,18 +142,22 @@ class _CaptionModelBase(Model):
                 names=None, attn_idx=None, encoded=None):
         if config.zero_arena is not None and torch.is_grad_enabled():
             config.zero_arena.reset()          # one memset for every small gradient of this step
-        caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
-                                                          obj_embeds, encoded)
+        with config.nvtx_range('tt/_forward'):
+            caption_ids, target_ids, contexts = self._forward(context, image, caption, face_embeds,
+                                                              obj_embeds, encoded)
         with self.decoder.weight_scope():      # one launch prepares every decoder weight operand
-            X, _ = self.decoder.forward_tbc(caption, contexts)       # [T,B,E], no transpose needed
+            with config.nvtx_range('tt/decoder'):
+                X, _ = self.decoder.forward_tbc(caption, contexts)       # [T,B,E], no transpose needed
             T, B, E = X.shape
             # the loss is a sum over tokens, so (t,b) order with the target transposed alike is exact
             tgt_tb = target_ids.t().contiguous()
-            loss, ntokens = self.criterion.fused(self.decoder.adaptive_softmax,
-                                                 (X.view(T * B, E), None), tgt_tb)
+            with config.nvtx_range('tt/adaptive_loss'):
+                loss, ntokens = self.criterion.fused(self.decoder.adaptive_softmax,
+                                                     (X.view(T * B, E), None), tgt_tb)
         output_dict = {'loss': loss.view(()), 'sample_size': ntokens}
         if not self.training and self.evaluate_mode:
-            _, gen_ids, attns = self._generate(caption_ids, contexts, attn_idx)
+            with config.nvtx_range('tt/_generate'):
+                _, gen_ids, attns = self._generate(caption_ids, contexts, attn_idx)
             output_dict['captions'] = [m['caption'] for m in metadata] if metadata else None
             output_dict['metadata'] = metadata
             output_dict['attns'] = attns
