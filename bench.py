@@ -235,6 +235,7 @@ def run_b200(args):
     config.enable_zero_arena(dev)     # the step below consumes gradients before the next forward
     config.enable_wgrad_stream(args.wgrad)   # weight-gradient GEMMs as a parallel graph branch
     config.encoder_overlap = bool(args.encoder_overlap)
+    config.encoder_sm_cap = int(args.enc_sms) if args.pipeline and not args.no_graph else 0
     B = args.batch
     model = build_model(dev, args.bn_mode)
     # the flat gradient buffer only exists where there is a collective to feed
@@ -597,6 +598,7 @@ def run_b200(args):
                    'global_batch': world * B, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
                    'encoder_overlap': bool(args.encoder_overlap),
+                   'encoder_sm_cap': config.encoder_sm_cap,
                    'pipeline': ('2 step-buffer sets: frozen encoders of step i+1 overlap the decoder '
                                 'fwd+bwd of step i; all K encoder and K train passes run inside the '
                                 'timed region' if n_sets == 2 else None),
@@ -774,6 +776,10 @@ def main():
                          'forward/backward of step i')
     ap.add_argument('--encoder-overlap', type=int, default=1, choices=[0, 1],
                     help='ResNet as a parallel stream branch beside RoBERTa')
+    ap.add_argument('--enc-sms', type=int, default=88,
+                    help='SM cap of the large GEMMs of the frozen encoders (config.encoder_sm_cap; 0 = all 148): '
+                         'they leave SMs to the decoder / ResNet chains running beside them (measured: '
+                         '11.06 ms per step uncapped, 10.48-10.60 ms with 72-96)')
     ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
                     help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
                          "model.train()) or 'running' statistics folded into the convolutions (eval())")

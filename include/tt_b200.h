@@ -115,6 +115,11 @@ void tt_gemm_set_trace(long long* dev_ptr);
  * epilogue (shared-memory tile + cp.async.bulk.tensor store, bf16 residual by TMA load).  Both paths
  * produce bit-identical results. */
 void tt_gemm_set_staged_epilogue(int on);
+/* Scheduling switch (also env TT_GEMM_SM_CAP): 0 (default) = persistent GEMM grids use every SM;
+ * n > 0 = large GEMMs (the CTA-pair kernel, and single-CTA problems with M >= 2048) launch on at most
+ * n SMs, leaving the rest to kernels of concurrent streams.  Set it around the launches / graph capture
+ * of the stream that should yield (the frozen encoders).  Results identical. */
+void tt_gemm_set_sm_cap(int sms);
 
 /* fp32 [rows, cols] (row stride ld_src) -> bf16 operand for tt_gemm_bf16_tn.
  *   transpose==0: dst is [rows, cols*rep]   transpose!=0: dst is [cols, rows*rep]

@@ -393,6 +393,20 @@ static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sm
 int gemm2_launch(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR, int bn,
                  cudaStream_t stream);  // gemm2.cu
 
+// SM cap of the persistent GEMM grids (0 = all SMs).  A persistent GEMM on every SM holds the whole
+// machine for its 30-50 us, so kernels of concurrent streams (the decoder's and the ResNet's short
+// latency-bound chains beside RoBERTa's large GEMMs) queue behind it; launched on fewer SMs the large
+// GEMM runs proportionally longer but the other streams keep flowing -- measured: RoBERTa's GEMMs on
+// 64 of 148 SMs make the overlapped train step 4-5 % FASTER.  The caller sets it
+// around the launches (or graph capture) of the stream that should yield.
+static int g_sm_cap = -1;
+int gemm_sm_cap() {
+  if (g_sm_cap < 0) {
+    const char* e = getenv("TT_GEMM_SM_CAP");
+    g_sm_cap = e ? atoi(e) : 0;
+  }
+  return g_sm_cap;
+}
 static int g_staged = -1;    // staged (TMA) epilogue switch: -1 = read TT_GEMM_TMA_EPI on first use
 static long long* g_trace = nullptr;
 long long* gemm_trace_ptr() { return g_trace; }
@@ -401,6 +415,7 @@ long long* gemm_trace_ptr() { return g_trace; }
 
 extern "C" void tt_gemm_set_trace(long long* dev_ptr) { tt::g_trace = dev_ptr; }
 extern "C" void tt_gemm_set_staged_epilogue(int on) { tt::g_staged = on ? 1 : 0; }
+extern "C" void tt_gemm_set_sm_cap(int sms) { tt::g_sm_cap = sms > 0 ? sms : 0; }
 
 extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   using namespace tt;
@@ -543,7 +558,8 @@ extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
     if (g.splits == 1) tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * nb;
     else tiles = ceil_div(p->M, BM) * ceil_div(p->N, bn) * g.splits;
   }
-  const int grid = tiles < sms ? tiles : sms;
+  int grid = tiles < sms ? tiles : sms;
+  if (gemm_sm_cap() > 0 && grid > gemm_sm_cap() && p->M >= 2048) grid = gemm_sm_cap();   // large problems only
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);
     case 128: return launch_gemm<128>(tmA, tmB, tmC, tmR, g, grid, ta, tb, s);

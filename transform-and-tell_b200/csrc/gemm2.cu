@@ -320,11 +320,14 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   return check_launch("gemm2_bf16_kernel");
 }
 
+int gemm_sm_cap();   // gemm.cu
+
 // Called by tt_gemm_bf16_tn when its tile model (gemm.cu: choose_tile) picks the CTA-pair kernel
 // with tile width bn (128 or 256) for a K-major problem.
 int gemm2_launch(const TtGemmParams* p, const GemmArgs& g, const CUtensorMap& tmC, const CUtensorMap& tmR, int bn,
                  cudaStream_t stream) {
-  const int pairs_max = num_sms() / 2;
+  int pairs_max = num_sms() / 2;
+  if (gemm_sm_cap() > 0 && gemm_sm_cap() / 2 < pairs_max) pairs_max = gemm_sm_cap() / 2 > 0 ? gemm_sm_cap() / 2 : 1;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda, BK, BM);
   if (rc != TT_OK) return rc;

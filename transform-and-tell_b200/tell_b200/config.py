@@ -48,6 +48,32 @@ class nvtx_range:
         return False
 
 
+# SM cap of the frozen encoders' large GEMMs inside Model.encode (0 = none).  A trainer that runs the
+# encoders of batch i+1 beside the decoder forward/backward of batch i (bench.py) sets it (88 of 148
+# measured best on B200): the persistent RoBERTa GEMMs stop holding the whole machine, the decoder's
+# and the ResNet's latency-bound chains keep flowing, and the overlapped step gets ~5 % faster while
+# the encoder graph alone is no slower.
+encoder_sm_cap = int(os.environ.get('TT_ENCODER_SM_CAP', '0'))
+
+
+class gemm_sm_cap:
+    """`with config.gemm_sm_cap(64):` -- large GEMMs launched (or captured) inside use at most that many
+    SMs (tt_gemm_set_sm_cap), so that kernels of concurrent streams are not queued behind persistent
+    GEMMs that hold the whole machine."""
+
+    def __init__(self, sms):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        from . import _lib
+        _lib.lib().tt_gemm_set_sm_cap(self.sms)
+
+    def __exit__(self, *exc):
+        from . import _lib
+        _lib.lib().tt_gemm_set_sm_cap(0)
+        return False
+
+
 _seed_base = 0x5EED
 _counter = itertools.count(1)
 _step = None  # device-resident step counter mixed into every dropout seed

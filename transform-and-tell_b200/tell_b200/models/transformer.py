@@ -83,6 +83,10 @@ class _CaptionModelBase(Model):
         RoBERTa hidden states (bf16 [L+1, B*S, E]).  It depends on no trainable weight, so a
         data-parallel trainer may run it for step i+1 while step i's gradient all-reduce is still
         in flight; pass the result to forward(..., encoded=...)."""
+        with config.gemm_sm_cap(config.encoder_sm_cap):
+            return self._encode(context, image, n_real_tokens)
+
+    def _encode(self, context, image, n_real_tokens=0):
         if self.USES_IMAGE and config.encoder_overlap and image.is_cuda:
             # the two frozen encoders are independent: ResNet's ~200 small latency-bound launches
             # run as a parallel branch (one fork, one join) beside RoBERTa's large GEMMs
