@@ -33,6 +33,7 @@ struct AttnArgs {
   // (token-major projection buffer: B*ldkv, ldkv, 64; head-major decode cache: 64, H*S*64, S*64)
   long long kv_j_stride, kv_b_stride, kv_h_stride;
   int Lp;               // decode kernel: padded key count of THIS context (scores row pitch in smem)
+  const int* kv_len;    // decode kernel, optional [B]: keys j >= kv_len[b] are all padding (not loaded)
 };
 
 // Up to four contexts per launch (image / article / faces / objects of one decoder layer,

@@ -544,6 +544,9 @@ attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
   if (h >= a.H) return;                 // warp-uniform; no block barrier below
   const bool has_bias = a.bias_k != nullptr;
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
+  // trailing padding of this sample's context (an article shorter than the batch maximum): those keys
+  // are masked, their probability is exactly 0 -- their K and V rows are never read
+  const int Sv = a.kv_len != nullptr ? min(a.S, __ldg(a.kv_len + b)) : a.S;
   float* sp = dsm + warp * Lp;
   float* sq = sq_all[warp];
   {
@@ -556,7 +559,9 @@ attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
   float m = -INFINITY;
   for (int j = lane; j < L; j += 32) {
     float sc;
-    if (j < a.S) {
+    if (j < a.S && j >= Sv) {
+      sc = -INFINITY;
+    } else if (j < a.S) {
       const long long off = j * a.kv_j_stride + b * a.kv_b_stride + h * a.kv_h_stride;
       float acc = 0.f;
       if (KV16) {
@@ -613,7 +618,7 @@ attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
   if (KV16) {
     const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + vbase;
 #pragma unroll 4
-    for (int j = kq; j < a.S; j += 4) {
+    for (int j = kq; j < Sv; j += 4) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(vp + j * vstep));
       const float pj = sp[j];
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -626,7 +631,7 @@ attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
   } else {
     const float* vp = a.v + vbase;
 #pragma unroll 4
-    for (int j = kq; j < a.S; j += 4) {
+    for (int j = kq; j < Sv; j += 4) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(vp + j * vstep));
       const float4 y = __ldg(reinterpret_cast<const float4*>(vp + j * vstep) + 1);
       const float pj = sp[j];
@@ -942,6 +947,7 @@ extern "C" int tt_attn_decode_hm_multi(const TtAttnCtx* ctx, int n, int B, int H
     a.ldq = c.ldq; a.ldo = c.ldo; a.ldkv = 0;
     a.kv_j_stride = TC_D; a.kv_b_stride = static_cast<long long>(H) * c.S * TC_D;
     a.kv_h_stride = static_cast<long long>(c.S) * TC_D;
+    a.kv_len = c.kv_len;
     const int L = c.S + (c.bias_k ? 1 : 0) + (zero_row ? 1 : 0);
     TT_REQUIRE(L > 0, "tt_attn_decode_hm_multi: empty key set");
     a.Lp = (L + 3) & ~3;

@@ -138,6 +138,51 @@ dynconv_step_kernel(float* __restrict__ window, const float* __restrict__ x_new,
   out[idx] = acc;
 }
 
+// Same step for heads of 64 channels (every shipped decoder: C 1024 / 16 heads): ONE WARP per (b, h).
+// Lane k owns tap k for the softmax (one expf per tap per head instead of one per tap per CHANNEL:
+// the thread-per-channel form above spends 64x the exponentials and was compute-bound at K = 31),
+// then every lane owns two adjacent channels of the head (float2: 256 contiguous bytes per warp row)
+// and the tap weights are broadcast by shuffle while the window is read, shifted and appended.
+__global__ void __launch_bounds__(256)
+dynconv_step_warp_kernel(float* __restrict__ window, const float* __restrict__ x_new,
+                         const float* __restrict__ z, long long z_b_stride, float* __restrict__ out, int B,
+                         int C, int H, int K, int softmax) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (wid >= static_cast<long long>(B) * H) return;          // warp-uniform
+  const int b = static_cast<int>(wid / H), h = static_cast<int>(wid - static_cast<long long>(b) * H);
+  const long long BC = static_cast<long long>(B) * C;
+  float w = lane < K ? __ldg(z + b * z_b_stride + h * K + lane) : -INFINITY;
+  if (softmax) {
+    const float m = warp_max(w);
+    const float e = lane < K ? expf(w - m) : 0.f;
+    const float sum = warp_sum(e);
+    w = e / sum;
+  } else if (lane >= K) {
+    w = 0.f;
+  }
+  const long long idx = static_cast<long long>(b) * C + h * 64 + 2 * lane;
+  float2 acc = make_float2(0.f, 0.f);
+  float2 cur = K > 1 ? *reinterpret_cast<const float2*>(window + idx) : make_float2(0.f, 0.f);
+  for (int k = 0; k < K - 1; ++k) {
+    const float wk = __shfl_sync(0xffffffffu, w, k);
+    // prefetch the next row before this one is written back one slot earlier
+    float2 nxt = make_float2(0.f, 0.f);
+    if (k + 1 < K - 1) nxt = *reinterpret_cast<const float2*>(window + (k + 1) * BC + idx);
+    acc.x = fmaf(wk, cur.x, acc.x);
+    acc.y = fmaf(wk, cur.y, acc.y);
+    if (k > 0) *reinterpret_cast<float2*>(window + (k - 1) * BC + idx) = cur;     // shift: row k -> k-1
+    cur = nxt;
+  }
+  const float2 xn = __ldg(reinterpret_cast<const float2*>(x_new + idx));
+  const float wl = __shfl_sync(0xffffffffu, w, K - 1);
+  acc.x = fmaf(wl, xn.x, acc.x);
+  acc.y = fmaf(wl, xn.y, acc.y);
+  if (K > 1) *reinterpret_cast<float2*>(window + (K - 2) * BC + idx) = xn;
+  *reinterpret_cast<float2*>(out + idx) = acc;
+}
+
 struct DynConvBwdArgs {
   const float* dout;  // [T,B,C]
   const float* x;     // [T,B,C]
@@ -269,6 +314,13 @@ extern "C" int tt_dynconv_step(float* window, const float* x_new, const float* z
   if (rc != TT_OK) return rc;
   const long long BC = static_cast<long long>(B) * C;
   if (BC == 0) return TT_OK;
+  if (C == H * 64 && K <= 32 && (reinterpret_cast<uintptr_t>(x_new) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (reinterpret_cast<uintptr_t>(window) & 7) == 0) {
+    const long long warps = static_cast<long long>(B) * H;
+    launch_k(dynconv_step_warp_kernel, dim3(static_cast<unsigned>(ceil_div_ll(warps, 8))), dim3(256), 0,
+             (cudaStream_t)stream, window, x_new, z, z_b_stride, out, B, C, H, K, softmax);
+    return check_launch("dynconv_step_warp_kernel");
+  }
   launch_k(dynconv_step_kernel, dim3(static_cast<unsigned>(ceil_div_ll(BC, 256))), dim3(256), 0,
            (cudaStream_t)stream, window, x_new, z, z_b_stride, out, B, C, H, K, softmax);
   return check_launch("dynconv_step_kernel");

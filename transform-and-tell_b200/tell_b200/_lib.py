@@ -40,7 +40,7 @@ class TtAttnCtx(ctypes.Structure):
                 ('bias_v', c_void_p), ('mask', c_void_p), ('out', c_void_p), ('lse', c_void_p),
                 ('S', c_int), ('ldq', c_ll), ('ldkv', c_ll), ('ldo', c_ll),
                 ('seed', ctypes.c_ulonglong), ('dout', c_void_p), ('dq', c_void_p), ('dk', c_void_p),
-                ('dv', c_void_p), ('dbias_k', c_void_p), ('dbias_v', c_void_p)]
+                ('dv', c_void_p), ('dbias_k', c_void_p), ('dbias_v', c_void_p), ('kv_len', c_void_p)]
 
 
 _lib = None

@@ -144,7 +144,8 @@ class DynamicConvDecoderLayer(DecoderLayer):
                                       v=hm[c][1] if kv is not None else None,
                                       bias_k=mha.bias_k.view(-1) if mha.bias_k is not None else None,
                                       bias_v=mha.bias_v.view(-1) if mha.bias_v is not None else None,
-                                      mask=masks[c], out=A_all[:, sl], lse=None, S=S_c))
+                                      mask=masks[c], out=A_all[:, sl], lse=None, S=S_c,
+                                      kv_len=kv_cache.get(names[c] + '/len')))
                 ops.attn_decode_hm_multi(items, B, mhas[0].num_heads, mhas[0].head_dim, mhas[0].add_zero_attn)
             else:
                 for c, (mha, kv) in enumerate(zip(mhas, kvs)):
@@ -310,7 +311,7 @@ class _DynamicConvDecoderBase(Decoder):
                 if slab is not None:
                     caches[l][nm + '/slab'] = (slab, l)
 
-    def build_decode_cache(self, incremental_state):
+    def build_decode_cache(self, incremental_state, contexts=None):
         """After the first incremental step: repack every projected context of every layer from the
         token-major [S*B, 2E] bf16 views into head-major K, V [B,H,S,64] (tt_kv_repack_heads).  Returns
         the number of caches built (0 when keys|values are not bf16 / head_dim is not 64)."""
@@ -318,6 +319,15 @@ class _DynamicConvDecoderBase(Decoder):
         if not caches:
             return 0
         built = 0
+        # per context: how many leading keys of each sample can be unmasked at all (padding is
+        # trailing): the decode kernel never reads the cache rows beyond
+        lens = {}
+        if contexts is not None:
+            for nm in self.layers[0].context_names:
+                m = contexts.get(nm + '_mask')
+                if m is not None and m.dim() == 2 and m.shape[1] > 0:
+                    pos = torch.arange(1, m.shape[1] + 1, device=m.device, dtype=torch.int32)
+                    lens[nm] = ((~m.bool()).to(torch.int32) * pos).amax(dim=1).to(torch.int32).contiguous()
         for layer, cache in zip(self.layers, caches):
             for nm in layer.context_names:
                 kv = cache.get(nm)
@@ -330,6 +340,8 @@ class _DynamicConvDecoderBase(Decoder):
                 if (S + 2) * 8 * 4 > 40 * 1024:          # key set beyond the decode kernel's budget
                     continue
                 cache[nm + '/hm'] = ops.kv_repack_heads(kv[:, :E], kv[:, E:], S, B, mha.num_heads, 64)
+                if nm in lens and lens[nm].shape[0] == B:
+                    cache[nm + '/len'] = lens[nm]
                 built += 1
         return built
 

@@ -288,7 +288,7 @@ class _CaptionModelBase(Model):
 
         with dec.weight_scope(refresh=True):
             one_step()                                               # step 0, eager
-        dec.build_decode_cache(state)        # head-major K|V for the T = 1 attention kernel
+        dec.build_decode_cache(state, contexts)   # head-major K|V (+ valid key counts) for the T = 1 attention kernel
         # Step 1 runs eagerly on the capture stream (warms every lazy path), then the same stream
         # records the step.  capture_begin/capture_end directly: torch.cuda.graph() would also
         # synchronise the device, run the Python GC and empty the allocator cache on every call.

@@ -399,6 +399,7 @@ def _attn_ctx_array(items, E):
         c.ldq, c.ldo = it['q'].stride(0), it['out'].stride(0)
         c.ldkv = it['k'].stride(0) if (S > 0 and it['k'].dim() == 2) else E
         c.seed = int(it.get('seed', 0)) & 0xFFFFFFFFFFFFFFFF
+        c.kv_len = _dp(it.get('kv_len')) if S > 0 else None
         if it.get('dout') is not None:
             c.dout, c.dq = _dp(it['dout']), _dp(it['dq'])
             c.dk, c.dv = (_dp(it['dk']), _dp(it['dv'])) if S > 0 else (None, None)
