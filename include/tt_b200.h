@@ -292,8 +292,8 @@ typedef struct {
   void* dv;
   float* dbias_k;
   float* dbias_v;
-  const int* kv_len;           /* tt_attn_decode_hm_multi only, optional [B]: keys j >= kv_len[b] of sample b
-                                * are all padding (mask = 1): their cache rows are not read */
+  const int* kv_len;           /* optional [B]: keys j >= kv_len[b] of sample b are all padding (mask = 1): the
+                                * kernels skip those rows / whole key tiles (results identical) */
 } TtAttnCtx;
 int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
                          int kv16, void* stream);

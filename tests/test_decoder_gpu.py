@@ -253,3 +253,45 @@ def test_one_attention_launch_per_layer_equals_per_context_launches():
     # per layer: attention (4 - 1) x {fwd, dq, dkv}; out-projection (4 - 1) x {fwd, dX, dW} and 4 -> 1
     # bias column sums, minus nothing else
     assert a[6] - b[6] >= n_layers * (9 + 9), (a[6], b[6])
+
+
+def test_attention_skips_trailing_padding_tiles_without_changing_anything():
+    """Long article context with ragged lengths (trailing padding): the tensor-core attention walks
+    only the key tiles that hold a valid key plus the bias / zero-row tile (per-sample valid key
+    count), dK|dV of the skipped tiles are written as zeros.  Output, loss and every gradient must
+    equal the full walk bit for bit (a masked key's probability is exactly 0 either way)."""
+    from tell_b200 import config, synth
+    from tell_b200.models import DynamicConvFacesObjectsDecoder
+    from tell_b200.testing import build_decoder
+    config.set_precision('bf16')
+    cfg = dict(synth.CFG_TINY, embed_dim=256, heads=4, ffn=256)
+    sd = synth.decoder_state_dict(cfg, seed=3, logit_gain=3.0)
+    cap, ctx = synth.decoder_inputs(cfg, B=4, T=9, S=300, F=3, O=4, P=5, seed=33)
+    lens = [300, 40, 129, 191]                       # full, < 1 tile, just over 2 tiles, 3 tiles
+    mask = torch.zeros(4, 300, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        mask[b, n:] = True
+    ctx['article_mask'] = mask
+    inp, tgt = cap[:, :-1].contiguous().cuda(), cap[:, 1:].contiguous().cuda()
+    res = {}
+    try:
+        for skip in (False, True):
+            config.attn_skip_padding = skip
+            dec = build_decoder(cfg, DynamicConvFacesObjectsDecoder, sd).cuda().eval()
+            for l in dec.layers:
+                l.need_attn = False
+            cctx = {k: v.cuda() for k, v in ctx.items()}
+            cctx['article'].requires_grad_(True)
+            out, _ = dec({'roberta': inp}, cctx)
+            loss, _ = dec.adaptive_softmax.fused_loss(out, tgt)
+            loss.backward()
+            res[skip] = (out.detach().clone(), loss.item(), cctx['article'].grad.clone(),
+                         {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None})
+    finally:
+        config.attn_skip_padding = True
+    a, b = res[False], res[True]
+    assert torch.equal(a[0], b[0]) and a[1] == b[1]
+    assert torch.equal(a[2], b[2])
+    assert (b[2][200:, 1] == 0).all()                # padded article rows get no gradient
+    for n in a[3]:
+        assert (a[3][n] - b[3][n]).abs().max().item() <= 1e-6 * max(1e-6, a[3][n].abs().max().item()), n

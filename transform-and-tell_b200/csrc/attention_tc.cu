@@ -196,6 +196,23 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// Key tiles that consist of trailing padding only (an article shorter than the batch maximum: keys
+// [kv_len[b], S) are masked, their probabilities exactly 0) are skipped: the tile walk jumps from the
+// last tile holding a valid key to the tile holding key S (the bias / zero rows).
+struct TileWalk {
+  int skip_from, skip_to;       // tile starts in [skip_from, skip_to) are all padding
+  __device__ __forceinline__ TileWalk(const AttnArgs& a, int b) {
+    const int Sv = a.kv_len != nullptr ? min(a.S, __ldg(a.kv_len + b)) : a.S;
+    skip_from = max((Sv + TC_BN - 1) / TC_BN * TC_BN, TC_BN);      // tile 0 is always walked
+    skip_to = a.S / TC_BN * TC_BN;
+  }
+  __device__ __forceinline__ int next(int j0) const {
+    const int n = j0 + TC_BN;
+    return (n >= skip_from && n < skip_to) ? skip_to : n;
+  }
+  __device__ __forceinline__ bool skipped(int j0) const { return j0 >= skip_from && j0 < skip_to; }
+};
+
 // ------------------------------------------------------------------------------------------ forward
 template <bool KV16>
 __global__ void __launch_bounds__(128)
@@ -229,13 +246,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnArgsN args) {
   const int t0 = q0 + warp * 16 + g, t1 = t0 + 8;
   const unsigned long long base0 = (static_cast<unsigned long long>(bh) * a.T + t0) * L;
   const unsigned long long base1 = (static_cast<unsigned long long>(bh) * a.T + t1) * L;
-  for (int j0 = 0; j0 < L; j0 += TC_BN) {
+  const TileWalk walk(a, b);
+  for (int j0 = 0; j0 < L; j0 = walk.next(j0)) {
     if (j0 > 0) {
       __syncthreads();                        // everyone is done with the previous tile
       store_kv(nxt, sK, sV, sMask);
       __syncthreads();
     }
-    if (j0 + TC_BN < L) load_kv(a, b, h, j0 + TC_BN, L, nxt);   // prefetch under the MMAs below
+    if (walk.next(j0) < L) load_kv(a, b, h, walk.next(j0), L, nxt);   // prefetch under the MMAs below
     float s[8][4];
     zero_acc(s);
     mma_a_bt(s, qf, sK, lane);
@@ -362,13 +380,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
   const unsigned long long base1 = (static_cast<unsigned long long>(bh) * a.T + q0 + r1) * L;
   float dq[8][4];
   zero_acc(dq);
-  for (int j0 = 0; j0 < L; j0 += TC_BN) {
+  const TileWalk walk(a, b);
+  for (int j0 = 0; j0 < L; j0 = walk.next(j0)) {
     if (j0 > 0) {
       __syncthreads();
       store_kv(nxt, sK, sV, sMask);
       __syncthreads();
     }
-    if (j0 + TC_BN < L) load_kv(a, b, h, j0 + TC_BN, L, nxt);   // prefetch under the MMAs below
+    if (walk.next(j0) < L) load_kv(a, b, h, walk.next(j0), L, nxt);   // prefetch under the MMAs below
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
@@ -425,6 +444,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnArgsN args) {
   const bool has_bias = a.bias_k != nullptr;
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  if (TileWalk(a, b).skipped(j0)) {
+    // a tile of trailing padding: every probability is 0, so dK = dV = 0 (the rows are still written:
+    // the projection's dW GEMM reads the whole slab)
+    for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+      const int r = i >> 3, c8 = i & 7;
+      const long long off = (static_cast<long long>(j0 + r) * a.B + b) * a.ldkv + h * TC_D + c8 * 8;
+      if (KV16) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = make_uint4(0, 0, 0, 0);
+      } else {
+        *reinterpret_cast<float4*>(a.dk + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.dk + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.dv + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.dv + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
   {
     KvRegs<KV16> kv;
     float4 qreg[TC_ST], doreg[TC_ST];
@@ -867,6 +904,7 @@ static int fill_ctx(AttnArgs& a, const TtAttnCtx& c, int T, int B, int H, int D,
   a.ldq = c.ldq; a.ldkv = c.ldkv; a.ldo = c.ldo;
   a.p_drop = p_drop; a.seed = c.seed; a.step_ptr = rng_step_ptr();
   a.kv_j_stride = static_cast<long long>(B) * c.ldkv; a.kv_b_stride = c.ldkv; a.kv_h_stride = TC_D;
+  a.kv_len = c.kv_len;
   if (backward) {
     TT_REQUIRE(c.dout && c.dq && (c.S == 0 || (c.dk && c.dv)), "%s: null dout/dq/dk/dv", who);
     a.dout = c.dout; a.dq = c.dq; a.dk = reinterpret_cast<float*>(c.dk); a.dv = reinterpret_cast<float*>(c.dv);

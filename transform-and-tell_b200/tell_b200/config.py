@@ -22,6 +22,8 @@ flash_tc5 = os.environ.get('TT_FLASH_TC5', '1') == '1'
 encoder_overlap = True
 # the cross-attentions of one decoder layer (up to 4 contexts) as ONE launch per kernel type
 attn_multi = os.environ.get('TT_ATTN_MULTI', '1') == '1'
+# cross-attention over long contexts skips the key tiles of trailing padding (per-sample valid key count)
+attn_skip_padding = os.environ.get('TT_ATTN_SKIP_PADDING', '1') == '1'
 # same-shape GEMMs of one layer (the four out-projections, their dX and dW) as ONE batched launch
 gemm_batched = os.environ.get('TT_GEMM_BATCHED', '1') == '1'
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks

@@ -610,6 +610,8 @@ class MultiCtxAttentionFn(Function):
         kvs, bks, bvs, masks = args[:n], args[n:2 * n], args[2 * n:3 * n], args[3 * n:4 * n]
         # optional (GradSlab, layer) per context: where the backward writes dL/dkv
         ctx.slabs = args[4 * n] if len(args) > 4 * n else (None,) * n
+        # optional per-context valid key counts (int32 [B]): trailing padding is skipped
+        ctx.kv_lens = args[4 * n + 1] if len(args) > 4 * n + 1 else (None,) * n
         E = q_all.shape[1] // n
         D = E // H
         tc = config.precision == 'bf16' and D == 64
@@ -628,7 +630,7 @@ class MultiCtxAttentionFn(Function):
                 lse = torch.empty((B, H, T), dtype=torch.float32, device=q_all.device)
                 items.append(dict(q=q, k=kv[:, :E] if S > 0 else None, v=kv[:, E:] if S > 0 else None,
                                   bias_k=bk, bias_v=bv, mask=masks[c], out=out_all[:, c * E:(c + 1) * E],
-                                  lse=lse, S=S, seed=seeds[c]))
+                                  lse=lse, S=S, seed=seeds[c], kv_len=ctx.kv_lens[c]))
             else:
                 _, lse = ops.attn_fwd(q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None, bk, bv,
                                       masks[c] if S > 0 else None, T, B, S, H, D, zero_row, p, seeds[c],
@@ -678,7 +680,7 @@ class MultiCtxAttentionFn(Function):
                                   mask=masks[c], out=out_all[:, sl], lse=lses[c], S=S, seed=seeds[c],
                                   dout=dout_all[:, sl], dq=dq_all[:, sl],
                                   dk=dkv[:, :E] if S > 0 else None, dv=dkv[:, E:] if S > 0 else None,
-                                  dbias_k=dbk, dbias_v=dbv))
+                                  dbias_k=dbk, dbias_v=dbv, kv_len=ctx.kv_lens[c]))
             else:
                 ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
                              kv[:, E:] if S > 0 else None,
@@ -693,7 +695,7 @@ class MultiCtxAttentionFn(Function):
         if multi:
             ops.attn_bwd_tc_multi(items, T, B, H, D, zero_row, p)
         return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n \
-            + (None,) * (1 if len(ctx.needs_input_grad) > 9 + 4 * n else 0)
+            + (None,) * max(0, len(ctx.needs_input_grad) - (9 + 4 * n))
 
 
 class FusedOutProjFn(Function):

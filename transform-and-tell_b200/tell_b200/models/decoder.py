@@ -128,7 +128,8 @@ class DynamicConvDecoderLayer(DecoderLayer):
         p_att = self._p(mhas[0].dropout)
         seeds_a = tuple(self._seed(p_att) for _ in range(n))
         slabs = tuple(kv_cache.get(nm + '/slab') if kv_cache is not None else None for nm in names)
-        extra = (slabs,) if any(s_ is not None for s_ in slabs) else ()
+        lens = tuple(contexts.get(nm + '_mask/len') for nm in names)     # valid key counts (long contexts)
+        extra = (slabs, lens) if any(s_ is not None for s_ in slabs + lens) else ()
         hm = [kv_cache.get(nm + '/hm') if kv_cache is not None else None for nm in names]
         if T == 1 and not need_w and not torch.is_grad_enabled() and \
                 all(h_ is not None or kv is None for h_, kv in zip(hm, kvs)) and any(h_ is not None for h_ in hm):
@@ -367,6 +368,14 @@ class _DynamicConvDecoderBase(Decoder):
             m = contexts.get(nm + '_mask')
             if m is not None and nm + '_mask/u8' not in contexts:
                 contexts[nm + '_mask/u8'] = m.to(torch.uint8).contiguous()
+            # long contexts (the article): per-sample count of leading keys that can be unmasked, so
+            # that the attention kernels skip the key tiles of trailing padding (full forward only;
+            # the incremental step takes it from the decode cache)
+            if config.attn_skip_padding and m is not None and m.dim() == 2 and m.shape[1] >= 128 \
+                    and X.shape[0] > 1 and nm + '_mask/len' not in contexts:
+                pos = torch.arange(1, m.shape[1] + 1, device=m.device, dtype=torch.int32)
+                contexts[nm + '_mask/len'] = ((~m.bool()).to(torch.int32) * pos).amax(dim=1) \
+                    .to(torch.int32).contiguous()
         if self.batch_kv_layers and not use_layers:
             self._project_contexts_all_layers(contexts, caches)
         for i, layer in enumerate(self.layers):
