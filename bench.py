@@ -236,6 +236,8 @@ def run_b200(args):
     config.enable_wgrad_stream(args.wgrad)   # weight-gradient GEMMs as a parallel graph branch
     config.encoder_overlap = bool(args.encoder_overlap)
     config.encoder_sm_cap = int(args.enc_sms) if args.pipeline and not args.no_graph else 0
+    occ_w = float(args.occ_weight) if args.pipeline and not args.no_graph else 0.0
+    config.set_gemm_occupancy_weight(occ_w)
     B = args.batch
     model = build_model(dev, args.bn_mode)
     # the flat gradient buffer only exists where there is a collective to feed
@@ -598,7 +600,7 @@ def run_b200(args):
                    'global_batch': world * B, 'parallelism': 'dp%d' % world,
                    'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
                    'encoder_overlap': bool(args.encoder_overlap),
-                   'encoder_sm_cap': config.encoder_sm_cap,
+                   'encoder_sm_cap': config.encoder_sm_cap, 'gemm_occupancy_weight': occ_w,
                    'pipeline': ('2 step-buffer sets: frozen encoders of step i+1 overlap the decoder '
                                 'fwd+bwd of step i; all K encoder and K train passes run inside the '
                                 'timed region' if n_sets == 2 else None),
@@ -780,6 +782,9 @@ def main():
                     help='SM cap of the large GEMMs of the frozen encoders (config.encoder_sm_cap; 0 = all 148): '
                          'they leave SMs to the decoder / ResNet chains running beside them (measured: '
                          '11.06 ms per step uncapped, 10.48-10.60 ms with 72-96)')
+    ap.add_argument('--occ-weight', type=float, default=1.0,
+                    help='GEMM tile objective cost * (SM fraction)^w: 1 = SMs x time (the pipelined step is '
+                         'bound by SM occupancy: 10.69 ms at w = 0, 10.33 ms at w = 1), 0 = shortest launch')
     ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
                     help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
                          "model.train()) or 'running' statistics folded into the convolutions (eval())")

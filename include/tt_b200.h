@@ -120,6 +120,10 @@ void tt_gemm_set_staged_epilogue(int on);
  * n SMs, leaving the rest to kernels of concurrent streams.  Set it around the launches / graph capture
  * of the stream that should yield (the frozen encoders).  Results identical. */
 void tt_gemm_set_sm_cap(int sms);
+/* Tile-choice objective (also env TT_GEMM_OCC_WEIGHT): 0 (default) = the configuration with the shortest
+ * launch; w > 0 = cost * (fraction of SMs held)^w, w = 1 being SMs x time -- for steps whose streams
+ * share the machine (throughput bound by SM occupancy, not by one chain's latency).  Results identical. */
+void tt_gemm_set_occupancy_weight(float w);
 
 /* fp32 [rows, cols] (row stride ld_src) -> bf16 operand for tt_gemm_bf16_tn.
  *   transpose==0: dst is [rows, cols*rep]   transpose!=0: dst is [cols, rows*rep]

@@ -7,6 +7,7 @@
 //   warps 4-11  epilogue       : tcgen05.ld accumulator -> registers -> alpha/bias/act/residual -> HBM
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, the
 // accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -338,6 +339,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 // the B traffic per SM, the 256-wide single-CTA tile is shared-memory-port bound).  It replaces
 // "widest tile that fills 87 % of the SMs", which left 5-45 % on the table for the short-K / many-
 // row convolution GEMMs (12544 x 128 x 1152: 14.3 -> 9.6 us) and the N = 2048 decoder GEMMs.
+// Occupancy weight w of the tile model's objective: cost * (fraction of the SMs a launch holds)^w.
+// w = 0 minimises the launch's own duration (a latency-bound chain running alone: greedy decoding);
+// w = 1 minimises SMs x time -- what counts when several streams share the machine: the overlapped
+// train step is bound by SM occupancy (sum over all kernels of SMs held x duration / 148 = 10.3 ms of
+// the 10.6 ms step), and an M = 800 GEMM on 112 CTAs of 64 columns holds 870 SM.us where 56 CTAs of
+// 128 columns hold 529 for 22 % more latency.
+static double g_occ_weight = -1.0;
 struct TileChoice {
   bool pair;
   int bn;
@@ -368,6 +376,11 @@ static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sm
       return {true, c128 < c256 ? 128 : 256};
     }
   }
+  if (g_occ_weight < 0.0) {
+    const char* e = getenv("TT_GEMM_OCC_WEIGHT");
+    g_occ_weight = e ? atof(e) : 0.0;
+  }
+  const double occ_weight = g_occ_weight;
   const int num_k = ceil_div(K, BK);
   struct Cand { bool pair; int bn; double fixed, tk; };
   const Cand cands[5] = {{false, 64, 0.6, 0.17}, {false, 128, 0.6, 0.22}, {false, 256, 0.6, 0.55},
@@ -382,6 +395,11 @@ static TileChoice choose_tile(int M, int N, int K, bool pair_ok, bool tb, int sm
     const double waves = static_cast<double>(ceil_div_ll(tiles, slots));
     double cost = waves * (c.fixed + num_k * c.tk + 0.02 * (N < c.bn ? N : c.bn));
     if (!c.pair && c.bn >= 128 && pair_ok && pair_enabled) cost *= 1.05;   // ties go to the pair kernel
+    if (occ_weight > 0.0) {
+      // occupancy-aware objective: SMs held x time (w = 1) instead of time alone (w = 0)
+      const double used = static_cast<double>(tiles < slots ? tiles : slots) * (c.pair ? 2 : 1) / sms;
+      cost *= pow(used, occ_weight);
+    }
     if (cost < best_cost) {
       best_cost = cost;
       best = {c.pair, c.bn};
@@ -416,6 +434,7 @@ long long* gemm_trace_ptr() { return g_trace; }
 extern "C" void tt_gemm_set_trace(long long* dev_ptr) { tt::g_trace = dev_ptr; }
 extern "C" void tt_gemm_set_staged_epilogue(int on) { tt::g_staged = on ? 1 : 0; }
 extern "C" void tt_gemm_set_sm_cap(int sms) { tt::g_sm_cap = sms > 0 ? sms : 0; }
+extern "C" void tt_gemm_set_occupancy_weight(float w) { tt::g_occ_weight = w > 0.f ? w : 0.0; }
 
 extern "C" int tt_gemm_bf16_tn(const TtGemmParams* p, void* stream) {
   using namespace tt;

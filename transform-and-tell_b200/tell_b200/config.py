@@ -58,6 +58,15 @@ class nvtx_range:
 encoder_sm_cap = int(os.environ.get('TT_ENCODER_SM_CAP', '0'))
 
 
+def set_gemm_occupancy_weight(w):
+    """Tile-choice objective of the GEMM dispatcher (tt_gemm_set_occupancy_weight): 0 = shortest launch
+    (a chain running alone, e.g. greedy decoding), 1 = fewest SMs x time (several streams sharing the
+    machine, e.g. the pipelined train step of bench.py)."""
+    from . import _lib
+    import ctypes
+    _lib.lib().tt_gemm_set_occupancy_weight(ctypes.c_float(float(w)))
+
+
 class gemm_sm_cap:
     """`with config.gemm_sm_cap(64):` -- large GEMMs launched (or captured) inside use at most that many
     SMs (tt_gemm_set_sm_cap), so that kernels of concurrent streams are not queued behind persistent
