@@ -203,6 +203,62 @@ int tt_wnorm_bwd(const float* dw, const float* v, const float* g, const float* n
 int tt_nan_rows(float* x, uint8_t* mask, int R, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * "Twin" producers (twin.cu): the kernels above that also write their result as the bf16 operand
+ * of the tcgen05 GEMM that consumes it (nn.Linear / GehringLinear of decoder_faces_objects.py:255-365
+ * and their backward), so no standalone fp32 -> bf16 cast pass runs between a row kernel and a GEMM.
+ * fp32 outputs are bit-identical to the single-output entries; *16 outputs are bf16 (round to
+ * nearest even), contiguous unless a pitch is given, and optional (NULL = not written).
+ */
+int tt_dropout_tw(const float* x, float* y, void* y16, long long n, float p, unsigned long long seed,
+                  void* stream);                                   /* n % 4 == 0; y or y16 may be NULL */
+int tt_relu_bwd_tw(const float* dy, const float* y, float* dx, void* dx16, long long n, void* stream);
+int tt_glu_fwd_tw(const float* h, float* out, void* out16, long long N, int C, void* stream);
+int tt_glu_bwd_tw(const float* dout, const float* h, float* dh, void* dh16, long long N, int C,
+                  void* stream);
+/* n <= 4 LayerNorms sharing their residual in ONE launch: the parallel context branches of a decoder
+ * layer (decoder_faces_objects.py:272-352: x_c = LN_c(X + dropout(attn_c)) for image / article / faces
+ * / objects, then torch.cat :354) -- context c reads h[c] [N,E] (overwritten with the pre-norm sum),
+ * writes Y[:, c*E:(c+1)*E] as fp32 (y, ldy) and/or bf16 (y16, ldy16) and mean[c] / rstd[c] [N].
+ * n = 1 is tt_ln_fwd with an operand twin.  E % 4 == 0, E <= 1024. */
+typedef struct {
+  float* h[4];
+  const float* gamma[4];
+  const float* beta[4];
+  float* mean[4];
+  float* rstd[4];
+  unsigned long long seed[4];
+  const float* res;            /* shared residual [N,E] or NULL */
+  float* y;                    /* [N, >= n*E] fp32 or NULL */
+  long long ldy;
+  void* y16;                   /* [N, >= n*E] bf16 or NULL */
+  long long ldy16;
+  int n, N, E;
+  float eps, p_drop;
+} TtLnFwdMulti;
+int tt_ln_fwd_multi(const TtLnFwdMulti* p, void* stream);
+/* Backward of tt_ln_fwd_multi in ONE launch: dy [N, n*E] (lddy); per context dh[c] (fp32 [N,E],
+ * optional) and dh16[:, c*E:(c+1)*E] (bf16, optional) = dx_c * dropmask_c/(1-p); dx [N,E] = sum_c dx_c
+ * (the gradient of the shared residual, optional); dgamma[c] / dbeta[c] ACCUMULATED (zero them). */
+typedef struct {
+  const float* x[4];           /* pre-norm sums saved by the forward (its h[c]) */
+  const float* mean[4];
+  const float* rstd[4];
+  const float* gamma[4];
+  float* dgamma[4];
+  float* dbeta[4];
+  float* dh[4];
+  unsigned long long seed[4];
+  const float* dy;
+  long long lddy;
+  float* dx;
+  void* dh16;
+  long long lddh16;
+  int n, N, E;
+  float p_drop;
+} TtLnBwdMulti;
+int tt_ln_bwd_multi(const TtLnBwdMulti* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DynamicConv1dTBC core, tell/modules/convolutions/dynamic.py:285-336 (_forward_expanded).
  * x/out [T,B,C]; z = filter logits [T,B,H,K] (z_tb_stride = H*K) or [H,K] broadcast
  * (z_tb_stride = 0: LightweightConv1dTBC, lightweight.py:88-240); K <= 32, C/H <= 64.
@@ -220,6 +276,16 @@ int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float*
  * (z_b_stride = H*K, or 0 for taps shared by the batch), out [B,C]. */
 int tt_dynconv_step(float* window, const float* x_new, const float* z, long long z_b_stride,
                     float* out, int B, int C, int H, int K, int softmax, void* stream);
+/* The same three with bf16 twins: out16 mirrors out (operand of linear2, decoder_faces_objects.py:262),
+ * dz16 [T*B, lddz16] mirrors dz (operand of the filter projection's backward GEMMs, dynamic.py:300). */
+int tt_dynconv_fwd_tw(const float* x, const float* z, long long z_tb_stride, float* out, float* probs,
+                      int T, int B, int C, int H, int K, int softmax, float p_drop,
+                      unsigned long long seed, void* out16, void* stream);
+int tt_dynconv_bwd_tw(const float* dout, const float* x, const float* probs, float* dx, float* dz,
+                      int T, int B, int C, int H, int K, int softmax, float p_drop,
+                      unsigned long long seed, void* dz16, long long lddz16, void* stream);
+int tt_dynconv_step_tw(float* window, const float* x_new, const float* z, long long z_b_stride,
+                       float* out, int B, int C, int H, int K, int softmax, void* out16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cross-attention core, tell/modules/attention/multi_head.py:355-466 (static_kv=True path).
@@ -298,6 +364,9 @@ typedef struct {
   float* dbias_v;
   const int* kv_len;           /* optional [B]: keys j >= kv_len[b] of sample b are all padding (mask = 1): the
                                 * kernels skip those rows / whole key tiles (results identical) */
+  void* out16;                 /* optional bf16 twin of out [T*B, ldo16]: the operand of out_proj (multi_head.py:476) */
+  void* dq16;                  /* optional bf16 twin of dq [T*B, ldq16]: the operand of in_proj_q's backward */
+  long long ldo16, ldq16;
 } TtAttnCtx;
 int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
                          int kv16, void* stream);

@@ -2,6 +2,7 @@
 // cross-attention kernels.
 #pragma once
 #include <stdint.h>
+#include <cuda_bf16.h>
 
 namespace tt {
 
@@ -34,6 +35,11 @@ struct AttnArgs {
   long long kv_j_stride, kv_b_stride, kv_h_stride;
   int Lp;               // decode kernel: padded key count of THIS context (scores row pitch in smem)
   const int* kv_len;    // decode kernel, optional [B]: keys j >= kv_len[b] are all padding (not loaded)
+  // optional bf16 twins (tensor-core kernels only): out16 mirrors out (operand of out_proj),
+  // dq16 mirrors dq (operand of the query projection's backward GEMMs); row pitches in elements
+  __nv_bfloat16* out16;
+  __nv_bfloat16* dq16;
+  long long ldo16, ldq16;
 };
 
 // Up to four contexts per launch (image / article / faces / objects of one decoder layer,

@@ -303,12 +303,20 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnArgsN args) {
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int col = h * TC_D + n * 8 + 2 * tg;
-    if (t0 < a.T)
+    if (t0 < a.T) {
       *reinterpret_cast<float2*>(a.out + (static_cast<long long>(t0) * a.B + b) * a.ldo + col) =
           make_float2(o[n][0] * i0, o[n][1] * i0);
-    if (t1 < a.T)
+      if (a.out16)
+        *reinterpret_cast<uint32_t*>(a.out16 + (static_cast<long long>(t0) * a.B + b) * a.ldo16 + col) =
+            pack_bf16(o[n][0] * i0, o[n][1] * i0);
+    }
+    if (t1 < a.T) {
       *reinterpret_cast<float2*>(a.out + (static_cast<long long>(t1) * a.B + b) * a.ldo + col) =
           make_float2(o[n][2] * i1, o[n][3] * i1);
+      if (a.out16)
+        *reinterpret_cast<uint32_t*>(a.out16 + (static_cast<long long>(t1) * a.B + b) * a.ldo16 + col) =
+            pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    }
   }
   if (tg == 0 && a.lse) {
     if (t0 < a.T) a.lse[static_cast<long long>(bh) * a.T + t0] = m0 + logf(l0);
@@ -416,12 +424,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int col = h * TC_D + n * 8 + 2 * tg;
-    if (t0 < a.T)
+    if (t0 < a.T) {
       *reinterpret_cast<float2*>(a.dq + (static_cast<long long>(t0) * a.B + b) * a.ldq + col) =
           make_float2(dq[n][0], dq[n][1]);
-    if (t1 < a.T)
+      if (a.dq16)
+        *reinterpret_cast<uint32_t*>(a.dq16 + (static_cast<long long>(t0) * a.B + b) * a.ldq16 + col) =
+            pack_bf16(dq[n][0], dq[n][1]);
+    }
+    if (t1 < a.T) {
       *reinterpret_cast<float2*>(a.dq + (static_cast<long long>(t1) * a.B + b) * a.ldq + col) =
           make_float2(dq[n][2], dq[n][3]);
+      if (a.dq16)
+        *reinterpret_cast<uint32_t*>(a.dq16 + (static_cast<long long>(t1) * a.B + b) * a.ldq16 + col) =
+            pack_bf16(dq[n][2], dq[n][3]);
+    }
   }
 }
 
@@ -689,6 +705,14 @@ attn_decode_kernel(const __grid_constant__ AttnArgsN args) {
     float4* op = reinterpret_cast<float4*>(a.out + static_cast<long long>(b) * a.ldo + h * TC_D + c8 * 8);
     op[0] = make_float4((o[0] + bvv[0]) * inv, (o[1] + bvv[1]) * inv, (o[2] + bvv[2]) * inv, (o[3] + bvv[3]) * inv);
     op[1] = make_float4((o[4] + bvv[4]) * inv, (o[5] + bvv[5]) * inv, (o[6] + bvv[6]) * inv, (o[7] + bvv[7]) * inv);
+    if (a.out16) {
+      uint4 u;
+      u.x = pack_bf16((o[0] + bvv[0]) * inv, (o[1] + bvv[1]) * inv);
+      u.y = pack_bf16((o[2] + bvv[2]) * inv, (o[3] + bvv[3]) * inv);
+      u.z = pack_bf16((o[4] + bvv[4]) * inv, (o[5] + bvv[5]) * inv);
+      u.w = pack_bf16((o[6] + bvv[6]) * inv, (o[7] + bvv[7]) * inv);
+      *reinterpret_cast<uint4*>(a.out16 + static_cast<long long>(b) * a.ldo16 + h * TC_D + c8 * 8) = u;
+    }
   }
   if (lane == 0 && a.lse) a.lse[b * a.H + h] = base + logf(sum);
 }
@@ -905,7 +929,13 @@ static int fill_ctx(AttnArgs& a, const TtAttnCtx& c, int T, int B, int H, int D,
   a.p_drop = p_drop; a.seed = c.seed; a.step_ptr = rng_step_ptr();
   a.kv_j_stride = static_cast<long long>(B) * c.ldkv; a.kv_b_stride = c.ldkv; a.kv_h_stride = TC_D;
   a.kv_len = c.kv_len;
+  TT_REQUIRE(c.out16 == nullptr || (c.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(c.out16) & 15) == 0),
+             "%s: out16 must be 16-byte aligned with a row pitch that is a multiple of 8", who);
+  a.out16 = reinterpret_cast<__nv_bfloat16*>(c.out16); a.ldo16 = c.ldo16;
   if (backward) {
+    TT_REQUIRE(c.dq16 == nullptr || (c.ldq16 % 2 == 0 && (reinterpret_cast<uintptr_t>(c.dq16) & 3) == 0),
+               "%s: dq16 must be 4-byte aligned with an even row pitch", who);
+    a.dq16 = reinterpret_cast<__nv_bfloat16*>(c.dq16); a.ldq16 = c.ldq16;
     TT_REQUIRE(c.dout && c.dq && (c.S == 0 || (c.dk && c.dv)), "%s: null dout/dq/dk/dv", who);
     a.dout = c.dout; a.dq = c.dq; a.dk = reinterpret_cast<float*>(c.dk); a.dv = reinterpret_cast<float*>(c.dv);
     a.dbias_k = c.dbias_k; a.dbias_v = c.dbias_v;
@@ -986,6 +1016,9 @@ extern "C" int tt_attn_decode_hm_multi(const TtAttnCtx* ctx, int n, int B, int H
     a.kv_j_stride = TC_D; a.kv_b_stride = static_cast<long long>(H) * c.S * TC_D;
     a.kv_h_stride = static_cast<long long>(c.S) * TC_D;
     a.kv_len = c.kv_len;
+    TT_REQUIRE(c.out16 == nullptr || (c.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(c.out16) & 15) == 0),
+               "tt_attn_decode_hm_multi: out16 must be 16-byte aligned with a row pitch that is a multiple of 8");
+    a.out16 = reinterpret_cast<__nv_bfloat16*>(c.out16); a.ldo16 = c.ldo16;
     const int L = c.S + (c.bias_k ? 1 : 0) + (zero_row ? 1 : 0);
     TT_REQUIRE(L > 0, "tt_attn_decode_hm_multi: empty key set");
     a.Lp = (L + 3) & ~3;

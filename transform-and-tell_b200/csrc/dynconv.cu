@@ -29,6 +29,7 @@ struct DynConvArgs {
   float p_drop;
   unsigned long long seed;
   const unsigned long long* step_ptr;
+  __nv_bfloat16* out16;   // optional bf16 twin of out (the GEMM operand of linear2), same layout
 };
 
 __global__ void __launch_bounds__(256)
@@ -78,7 +79,10 @@ dynconv_fwd_kernel(DynConvArgs a) {
       const int cc = c < R ? c : 0;
       float acc = 0.f;
       for (int k = 0; k < K; ++k) acc += __shfl_sync(0xffffffffu, wk, k) * xs[tt + k][cc];
-      if (c < R) a.out[tb * a.C + h * R + c] = acc;
+      if (c < R) {
+        a.out[tb * a.C + h * R + c] = acc;
+        if (a.out16) a.out16[tb * a.C + h * R + c] = __float2bfloat16_rn(acc);
+      }
     }
   }
 }
@@ -91,8 +95,8 @@ dynconv_fwd_kernel(DynConvArgs a) {
 // convolution are one pass over the window (HBM-bound: (K-1)*B*C*8 bytes per step).
 __global__ void __launch_bounds__(256)
 dynconv_step_kernel(float* __restrict__ window, const float* __restrict__ x_new,
-                    const float* __restrict__ z, long long z_b_stride, float* __restrict__ out, int B,
-                    int C, int H, int K, int softmax) {
+                    const float* __restrict__ z, long long z_b_stride, float* __restrict__ out,
+                    __nv_bfloat16* __restrict__ out16, int B, int C, int H, int K, int softmax) {
   pdl_prologue();
   const long long BC = static_cast<long long>(B) * C;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -136,6 +140,7 @@ dynconv_step_kernel(float* __restrict__ window, const float* __restrict__ x_new,
     if (k == K - 1) acc += w[k] * xn;
   if (K > 1) window[(K - 2) * BC + idx] = xn;
   out[idx] = acc;
+  if (out16) out16[idx] = __float2bfloat16_rn(acc);
 }
 
 // Same step for heads of 64 channels (every shipped decoder: C 1024 / 16 heads): ONE WARP per (b, h).
@@ -145,8 +150,8 @@ dynconv_step_kernel(float* __restrict__ window, const float* __restrict__ x_new,
 // and the tap weights are broadcast by shuffle while the window is read, shifted and appended.
 __global__ void __launch_bounds__(256)
 dynconv_step_warp_kernel(float* __restrict__ window, const float* __restrict__ x_new,
-                         const float* __restrict__ z, long long z_b_stride, float* __restrict__ out, int B,
-                         int C, int H, int K, int softmax) {
+                         const float* __restrict__ z, long long z_b_stride, float* __restrict__ out,
+                         __nv_bfloat16* __restrict__ out16, int B, int C, int H, int K, int softmax) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -181,6 +186,7 @@ dynconv_step_warp_kernel(float* __restrict__ window, const float* __restrict__ x
   acc.y = fmaf(wl, xn.y, acc.y);
   if (K > 1) *reinterpret_cast<float2*>(window + (K - 2) * BC + idx) = xn;
   *reinterpret_cast<float2*>(out + idx) = acc;
+  if (out16) *reinterpret_cast<uint32_t*>(out16 + idx) = pack_bf16(acc.x, acc.y);
 }
 
 struct DynConvBwdArgs {
@@ -194,6 +200,8 @@ struct DynConvBwdArgs {
   float p_drop;
   unsigned long long seed;
   const unsigned long long* step_ptr;
+  __nv_bfloat16* dz16;  // optional bf16 twin of dz (operand of the filter projection's backward GEMMs)
+  long long lddz16;     // its row pitch (>= H*K, multiple of 8)
 };
 
 // dp[t,h,k] = sum_c dout[t,c] x[t-K+1+k,c];  dz = softmax_bwd(dp * mask/(1-q));
@@ -256,7 +264,10 @@ dynconv_bwd_kernel(DynConvBwdArgs a) {
       const float dot = warp_sum(lane < K ? pk * dw : 0.f);
       dzk = pk * (dw - dot);
     }
-    if (lane < K) a.dz[widx] = dzk;
+    if (lane < K) {
+      a.dz[widx] = dzk;
+      if (a.dz16) a.dz16[tb * a.lddz16 + h * K + lane] = __float2bfloat16_rn(dzk);
+    }
     // ---- dx for time s = t
     for (int c = lane; c < R; c += 32) {
       float acc = 0.f;
@@ -281,34 +292,51 @@ static int dynconv_check(int T, int B, int C, int H, int K) {
   return TT_OK;
 }
 
-extern "C" int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_stride, float* out,
-                              float* probs, int T, int B, int C, int H, int K, int softmax,
-                              float p_drop, unsigned long long seed, void* stream) {
+extern "C" int tt_dynconv_fwd_tw(const float* x, const float* z, long long z_tb_stride, float* out,
+                                 float* probs, int T, int B, int C, int H, int K, int softmax,
+                                 float p_drop, unsigned long long seed, void* out16, void* stream) {
   TT_REQUIRE(x && z && out, "tt_dynconv_fwd: null pointer");
   int rc = dynconv_check(T, B, C, H, K);
   if (rc != TT_OK) return rc;
   if (T == 0) return TT_OK;
-  DynConvArgs a{x, z, z_tb_stride, out, probs, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
+  DynConvArgs a{x, z, z_tb_stride, out, probs, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr(),
+                reinterpret_cast<__nv_bfloat16*>(out16)};
   dim3 grid(B * H, ceil_div(T, DC_TT));
   launch_k(dynconv_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("dynconv_fwd_kernel");
 }
-
-extern "C" int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float* dx,
-                              float* dz, int T, int B, int C, int H, int K, int softmax,
+extern "C" int tt_dynconv_fwd(const float* x, const float* z, long long z_tb_stride, float* out,
+                              float* probs, int T, int B, int C, int H, int K, int softmax,
                               float p_drop, unsigned long long seed, void* stream) {
+  return tt_dynconv_fwd_tw(x, z, z_tb_stride, out, probs, T, B, C, H, K, softmax, p_drop, seed, nullptr,
+                           stream);
+}
+
+extern "C" int tt_dynconv_bwd_tw(const float* dout, const float* x, const float* probs, float* dx,
+                                 float* dz, int T, int B, int C, int H, int K, int softmax,
+                                 float p_drop, unsigned long long seed, void* dz16, long long lddz16,
+                                 void* stream) {
   TT_REQUIRE(dout && x && probs && dx && dz, "tt_dynconv_bwd: null pointer");
+  TT_REQUIRE(dz16 == nullptr || lddz16 >= static_cast<long long>(H) * K, "tt_dynconv_bwd: lddz16 < H*K");
   int rc = dynconv_check(T, B, C, H, K);
   if (rc != TT_OK) return rc;
   if (T == 0) return TT_OK;
-  DynConvBwdArgs a{dout, x, probs, dx, dz, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr()};
+  DynConvBwdArgs a{dout, x, probs, dx, dz, T, B, C, H, K, softmax, p_drop, seed, rng_step_ptr(),
+                   reinterpret_cast<__nv_bfloat16*>(dz16), lddz16};
   dim3 grid(B * H, ceil_div(T, DC_TT));
   launch_k(dynconv_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("dynconv_bwd_kernel");
 }
+extern "C" int tt_dynconv_bwd(const float* dout, const float* x, const float* probs, float* dx,
+                              float* dz, int T, int B, int C, int H, int K, int softmax,
+                              float p_drop, unsigned long long seed, void* stream) {
+  return tt_dynconv_bwd_tw(dout, x, probs, dx, dz, T, B, C, H, K, softmax, p_drop, seed, nullptr, 0, stream);
+}
 
-extern "C" int tt_dynconv_step(float* window, const float* x_new, const float* z, long long z_b_stride,
-                               float* out, int B, int C, int H, int K, int softmax, void* stream) {
+extern "C" int tt_dynconv_step_tw(float* window, const float* x_new, const float* z, long long z_b_stride,
+                                  float* out, int B, int C, int H, int K, int softmax, void* out16v,
+                                  void* stream) {
+  __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(out16v);
   TT_REQUIRE(x_new && z && out && (window || K == 1), "tt_dynconv_step: null pointer");
   int rc = dynconv_check(1, B, C, H, K);
   if (rc != TT_OK) return rc;
@@ -318,10 +346,14 @@ extern "C" int tt_dynconv_step(float* window, const float* x_new, const float* z
       (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (reinterpret_cast<uintptr_t>(window) & 7) == 0) {
     const long long warps = static_cast<long long>(B) * H;
     launch_k(dynconv_step_warp_kernel, dim3(static_cast<unsigned>(ceil_div_ll(warps, 8))), dim3(256), 0,
-             (cudaStream_t)stream, window, x_new, z, z_b_stride, out, B, C, H, K, softmax);
+             (cudaStream_t)stream, window, x_new, z, z_b_stride, out, out16, B, C, H, K, softmax);
     return check_launch("dynconv_step_warp_kernel");
   }
   launch_k(dynconv_step_kernel, dim3(static_cast<unsigned>(ceil_div_ll(BC, 256))), dim3(256), 0,
-           (cudaStream_t)stream, window, x_new, z, z_b_stride, out, B, C, H, K, softmax);
+           (cudaStream_t)stream, window, x_new, z, z_b_stride, out, out16, B, C, H, K, softmax);
   return check_launch("dynconv_step_kernel");
+}
+extern "C" int tt_dynconv_step(float* window, const float* x_new, const float* z, long long z_b_stride,
+                               float* out, int B, int C, int H, int K, int softmax, void* stream) {
+  return tt_dynconv_step_tw(window, x_new, z, z_b_stride, out, B, C, H, K, softmax, nullptr, stream);
 }

@@ -388,6 +388,12 @@ extern "C" int tt_ln_fwd(float* h, const float* res, const float* gamma, const f
         h, res, gamma, beta, y, ldy, mean, rstd, N, eps, p_drop, seed, rng_step_ptr());
     return check_launch("ln_fwd_row_kernel");
   }
+  if (E < 1024) {       // same CTA-per-row arithmetic at every width (twin.cu), so that the single and
+    TtLnFwdMulti a{};   // the multi-context launches agree bit for bit
+    a.h[0] = h; a.gamma[0] = gamma; a.beta[0] = beta; a.mean[0] = mean; a.rstd[0] = rstd; a.seed[0] = seed;
+    a.res = res; a.y = y; a.ldy = ldy; a.n = 1; a.N = N; a.E = E; a.eps = eps; a.p_drop = p_drop;
+    return tt_ln_fwd_multi(&a, stream);
+  }
   launch_k(ln_fwd_kernel, dim3(row_grid(N)), dim3(ROW_WARPS * 32), 0, (cudaStream_t)stream, 
       h, res, gamma, beta, y, ldy, mean, rstd, N, E, eps, p_drop, seed, rng_step_ptr());
   return check_launch("ln_fwd_kernel");

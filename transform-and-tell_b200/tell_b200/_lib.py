@@ -40,7 +40,26 @@ class TtAttnCtx(ctypes.Structure):
                 ('bias_v', c_void_p), ('mask', c_void_p), ('out', c_void_p), ('lse', c_void_p),
                 ('S', c_int), ('ldq', c_ll), ('ldkv', c_ll), ('ldo', c_ll),
                 ('seed', ctypes.c_ulonglong), ('dout', c_void_p), ('dq', c_void_p), ('dk', c_void_p),
-                ('dv', c_void_p), ('dbias_k', c_void_p), ('dbias_v', c_void_p), ('kv_len', c_void_p)]
+                ('dv', c_void_p), ('dbias_k', c_void_p), ('dbias_v', c_void_p), ('kv_len', c_void_p),
+                ('out16', c_void_p), ('dq16', c_void_p), ('ldo16', c_ll), ('ldq16', c_ll)]
+
+
+_P4 = c_void_p * 4
+_U4 = ctypes.c_ulonglong * 4
+
+
+class TtLnFwdMulti(ctypes.Structure):
+    _fields_ = [('h', _P4), ('gamma', _P4), ('beta', _P4), ('mean', _P4), ('rstd', _P4), ('seed', _U4),
+                ('res', c_void_p), ('y', c_void_p), ('ldy', c_ll), ('y16', c_void_p), ('ldy16', c_ll),
+                ('n', c_int), ('N', c_int), ('E', c_int), ('eps', ctypes.c_float),
+                ('p_drop', ctypes.c_float)]
+
+
+class TtLnBwdMulti(ctypes.Structure):
+    _fields_ = [('x', _P4), ('mean', _P4), ('rstd', _P4), ('gamma', _P4), ('dgamma', _P4),
+                ('dbeta', _P4), ('dh', _P4), ('seed', _U4), ('dy', c_void_p), ('lddy', c_ll),
+                ('dx', c_void_p), ('dh16', c_void_p), ('lddh16', c_ll), ('n', c_int), ('N', c_int),
+                ('E', c_int), ('p_drop', ctypes.c_float)]
 
 
 _lib = None

@@ -26,6 +26,9 @@ attn_multi = os.environ.get('TT_ATTN_MULTI', '1') == '1'
 attn_skip_padding = os.environ.get('TT_ATTN_SKIP_PADDING', '1') == '1'
 # same-shape GEMMs of one layer (the four out-projections, their dX and dW) as ONE batched launch
 gemm_batched = os.environ.get('TT_GEMM_BATCHED', '1') == '1'
+# producers write the bf16 operand of the consuming GEMM beside their fp32 result (twin.py, csrc/twin.cu):
+# no standalone cast launches between row kernels and GEMMs; the context LayerNorms of a layer as one launch
+twins = os.environ.get('TT_TWINS', '1') == '1'
 wgrad_stream = 0        # 0 off, 1 bank dL/dw only (deferred join), 2 + function-local forks
 
 # NVTX ranges around the phases of Model.forward / generate (encoders, decoder, loss, decode steps):

@@ -7,7 +7,7 @@ the ones the reference leaves to torch autograd.
 import torch
 from torch.autograd import Function
 
-from . import config, ops, weight_bank
+from . import config, ops, twin, weight_bank
 
 
 def operand(x, side, transpose=False):
@@ -15,6 +15,10 @@ def operand(x, side, transpose=False):
     'b' (weights/right); in bf16x3 mode the two sides get complementary hi/lo patterns."""
     if config.precision == 'bf16':
         split = 0
+        if side == 'a' and not transpose and config.twins:
+            t16 = twin.get(x)                       # written by the kernel that produced x
+            if t16 is not None:
+                return t16
         if side == 'b' and not transpose and weight_bank.ACTIVE is not None:
             hit = weight_bank.ACTIVE.single(x)      # prepared by the step's one weight_prep launch
             if hit is not None:
@@ -117,6 +121,11 @@ def _as_operand(d):
     return d if d.dtype == torch.bfloat16 else operand(d, 'a')
 
 
+def _tw():
+    """Producers emit bf16 operand twins (throughput mode only: bf16x3 operands are hi/lo splits)."""
+    return config.precision == 'bf16' and config.twins
+
+
 def _fast():
     """bf16 throughput mode: backward GEMMs read the forward's bf16 operands in place through
     MN-major UMMA descriptors (trans_a / trans_b) -- no transposed copies, no weight re-casts.
@@ -129,10 +138,15 @@ class LinearFn(Function):
     """y = act(alpha * (x @ w^T + bias)); x [M,K], w [N,K] (F.linear / GehringLinear / in_proj)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, alpha=1.0, act=ops.ACT_NONE):
+    def forward(ctx, x, w, bias, alpha=1.0, act=ops.ACT_NONE, twin_out=False):
         a16 = operand(x, 'a')
         b16 = operand(w, 'b')
-        y = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act)
+        if twin_out and _tw() and w.shape[0] % 8 == 0:
+            # the consumer of y is another GEMM: its bf16 operand comes out of this epilogue
+            y, y16 = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act, want16=True)
+            twin.put(y, y16)
+        else:
+            y = ops.gemm_tn(a16, b16, bias=bias, alpha=alpha, act=act)
         ctx.alpha, ctx.act, ctx.has_bias, ctx.fast = alpha, act, bias is not None, _fast()
         ctx.bank, ctx.wkey = weight_bank.ACTIVE, w.data_ptr()
         keep_y = y if act != ops.ACT_NONE else None
@@ -146,13 +160,18 @@ class LinearFn(Function):
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         dy = _c(dy)
+        dy16 = None
         if ctx.act == ops.ACT_RELU:
-            dy = ops.relu_bwd(dy, y)
+            if ctx.fast and _tw() and dy.shape[1] % 8 == 0:
+                dy, dy16 = ops.relu_bwd_tw(dy, y)        # the masked gradient and its operand twin
+            else:
+                dy = ops.relu_bwd(dy, y)
         elif ctx.act != ops.ACT_NONE:
             raise NotImplementedError('backward of fused GELU is not needed on this path')
         dx = dw = db = None
         if ctx.fast:
-            dy16 = operand(dy, 'a')                      # [M, N]: K-major for dx, MN-major for dw
+            if dy16 is None:
+                dy16 = operand(dy, 'a')                  # [M, N]: K-major for dx, MN-major for dw
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(dy16, w, alpha=ctx.alpha, trans_b=True)          # dy . W
             if ctx.needs_input_grad[1]:
@@ -175,7 +194,7 @@ class LinearFn(Function):
                                  alpha=ctx.alpha)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy, scale=ctx.alpha)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class KVProjFn(Function):
@@ -358,7 +377,14 @@ class ResidualLayerNormFn(Function):
 
     @staticmethod
     def forward(ctx, h, res, gamma, beta, p, seed, eps=1e-5):
-        y, mean, rstd = ops.ln_fwd(h, res, gamma, beta, eps, p, seed)
+        ctx.tw = _tw() and h.shape[1] % 8 == 0 and h.shape[1] <= 1024 and h.is_contiguous() and \
+            (res is None or res.is_contiguous())
+        if ctx.tw:
+            y, y16, means, rstds = ops.ln_fwd_multi([h], res, [gamma], [beta], eps, p, [seed])
+            mean, rstd = means[0], rstds[0]
+            twin.put(y, y16)
+        else:
+            y, mean, rstd = ops.ln_fwd(h, res, gamma, beta, eps, p, seed)
         ctx.p, ctx.seed, ctx.has_res = p, seed, res is not None
         ctx.save_for_backward(h, mean, rstd, gamma)
         return y
@@ -367,6 +393,14 @@ class ResidualLayerNormFn(Function):
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
         dgamma, dbeta = ops.zeros_f32(gamma.shape, gamma), ops.zeros_f32(gamma.shape, gamma)
+        if ctx.tw:
+            drop = ctx.p > 0
+            dx, dhs, dh16 = ops.ln_bwd_multi(_c(dy), [x], [mean], [rstd], [gamma], ctx.p, [ctx.seed],
+                                             want_dx=ctx.has_res or not drop, want_dh32=drop,
+                                             dgammas=[dgamma], dbetas=[dbeta])
+            dh = dhs[0] if drop else dx
+            twin.put(dh, dh16)                     # dh feeds the backward GEMMs of the branch's last Linear
+            return dh, (dx if ctx.has_res else None), dgamma, dbeta, None, None, None
         if ctx.p > 0:
             dx, dh = ops.ln_bwd(_c(dy), x, mean, rstd, gamma, ctx.p, ctx.seed,
                                 want_dx=ctx.has_res, dgamma=dgamma, dbeta=dbeta)
@@ -442,23 +476,40 @@ class GLUFn(Function):
     @staticmethod
     def forward(ctx, h):
         ctx.save_for_backward(h)
+        ctx.tw = _tw() and h.is_contiguous() and (h.shape[1] // 2) % 8 == 0
+        if ctx.tw:
+            out, out16 = ops.glu_fwd_tw(h)
+            twin.put(out, out16)                   # operand of the DynamicConv filter projection
+            return out
         return ops.glu_fwd(h)
 
     @staticmethod
     def backward(ctx, dout):
         (h,) = ctx.saved_tensors
+        if ctx.tw:
+            dh, dh16 = ops.glu_bwd_tw(_c(dout), h)
+            twin.put(dh, dh16)                     # operand of linear1's backward GEMMs
+            return dh
         return ops.glu_bwd(_c(dout), h)
 
 
 class DropoutFn(Function):
+    """F.dropout; x [N,C].  twin_out: the consumer is a GEMM (input dropout -> linear1, relu dropout
+    -> fc2), so the bf16 operand is written by the same pass."""
+
     @staticmethod
-    def forward(ctx, x, p, seed):
+    def forward(ctx, x, p, seed, twin_out=False):
         ctx.p, ctx.seed = p, seed
-        return ops.dropout(_c(x), p, seed)
+        x = _c(x)
+        if twin_out and _tw() and x.dim() == 2 and x.shape[1] % 8 == 0:
+            y, y16 = ops.dropout_tw(x, p, seed)
+            twin.put(y, y16)
+            return y
+        return ops.dropout(x, p, seed)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.dropout(_c(dy), ctx.p, ctx.seed), None, None
+        return ops.dropout(_c(dy), ctx.p, ctx.seed), None, None, None
 
 
 class DynConvFn(Function):
@@ -466,7 +517,12 @@ class DynConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, z, H, K, softmax, p, seed):
-        out, probs = ops.dynconv_fwd(x, z, H, K, softmax, p, seed)
+        ctx.tw = _tw() and x.shape[2] % 8 == 0
+        if ctx.tw:
+            out, probs, out16 = ops.dynconv_fwd(x, z, H, K, softmax, p, seed, twin=True)
+            twin.put(out.view(-1, x.shape[2]), out16)   # operand of linear2 (which sees out as [T*B, C])
+        else:
+            out, probs = ops.dynconv_fwd(x, z, H, K, softmax, p, seed)
         ctx.cfg = (H, K, softmax, p, seed)
         ctx.save_for_backward(x, probs)
         return out
@@ -475,8 +531,13 @@ class DynConvFn(Function):
     def backward(ctx, dout):
         x, probs = ctx.saved_tensors
         H, K, softmax, p, seed = ctx.cfg
-        dx, dz = ops.dynconv_bwd(_c(dout), x, probs, H, K, softmax, p, seed)
         T, B, _ = x.shape
+        if ctx.tw:
+            dx, dz, dz16 = ops.dynconv_bwd(_c(dout), x, probs, H, K, softmax, p, seed, twin=True)
+            dz2 = dz.view(T * B, H * K)
+            twin.put(dz2, dz16)                    # operand of the filter projection's backward GEMMs
+            return dx, dz.view(T, B, H * K), None, None, None, None, None
+        dx, dz = ops.dynconv_bwd(_c(dout), x, probs, H, K, softmax, p, seed)
         return dx, dz.view(T, B, H * K), None, None, None, None, None
 
 
@@ -618,6 +679,8 @@ class MultiCtxAttentionFn(Function):
         out_all = torch.empty_like(q_all)
         lses, weights, Ss = [], [], []
         multi = tc and n <= 4 and config.attn_multi      # one launch for all contexts of the layer
+        tw = multi and _tw() and E % 8 == 0
+        out16_all = torch.empty(q_all.shape, dtype=torch.bfloat16, device=q_all.device) if tw else None
         items = []
         for c in range(n):
             kv = kvs[c]
@@ -630,7 +693,8 @@ class MultiCtxAttentionFn(Function):
                 lse = torch.empty((B, H, T), dtype=torch.float32, device=q_all.device)
                 items.append(dict(q=q, k=kv[:, :E] if S > 0 else None, v=kv[:, E:] if S > 0 else None,
                                   bias_k=bk, bias_v=bv, mask=masks[c], out=out_all[:, c * E:(c + 1) * E],
-                                  lse=lse, S=S, seed=seeds[c], kv_len=ctx.kv_lens[c]))
+                                  lse=lse, S=S, seed=seeds[c], kv_len=ctx.kv_lens[c],
+                                  out16=out16_all[:, c * E:(c + 1) * E] if tw else None))
             else:
                 _, lse = ops.attn_fwd(q, kv[:, :E] if S > 0 else None, kv[:, E:] if S > 0 else None, bk, bv,
                                       masks[c] if S > 0 else None, T, B, S, H, D, zero_row, p, seeds[c],
@@ -638,6 +702,8 @@ class MultiCtxAttentionFn(Function):
             lses.append(lse)
         if multi:
             ops.attn_fwd_tc_multi(items, T, B, H, D, zero_row, p)
+            if tw:
+                twin.put(out_all, out16_all)        # operand of the out-projections
         for c in range(n):
             kv, S = kvs[c], Ss[c]
             q = q_all[:, c * E:(c + 1) * E]
@@ -662,6 +728,8 @@ class MultiCtxAttentionFn(Function):
         E = H * D
         dout_all = _c(dout_all)
         dq_all = torch.empty_like(q_all)
+        tw = multi and _tw() and E % 8 == 0
+        dq16_all = torch.empty(q_all.shape, dtype=torch.bfloat16, device=q_all.device) if tw else None
         dkvs, dbks, dbvs = [], [], []
         items = []
         for c in range(n):
@@ -680,7 +748,8 @@ class MultiCtxAttentionFn(Function):
                                   mask=masks[c], out=out_all[:, sl], lse=lses[c], S=S, seed=seeds[c],
                                   dout=dout_all[:, sl], dq=dq_all[:, sl],
                                   dk=dkv[:, :E] if S > 0 else None, dv=dkv[:, E:] if S > 0 else None,
-                                  dbias_k=dbk, dbias_v=dbv, kv_len=ctx.kv_lens[c]))
+                                  dbias_k=dbk, dbias_v=dbv, kv_len=ctx.kv_lens[c],
+                                  dq16=dq16_all[:, sl] if tw else None))
             else:
                 ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
                              kv[:, E:] if S > 0 else None,
@@ -694,6 +763,8 @@ class MultiCtxAttentionFn(Function):
             dbvs.append(dbv)
         if multi:
             ops.attn_bwd_tc_multi(items, T, B, H, D, zero_row, p)
+            if tw:
+                twin.put(dq_all, dq16_all)          # operand of the query projection's backward GEMMs
         return (dq_all,) + (None,) * 8 + tuple(dkvs) + tuple(dbks) + tuple(dbvs) + (None,) * n \
             + (None,) * max(0, len(ctx.needs_input_grad) - (9 + 4 * n))
 
@@ -783,6 +854,65 @@ class FusedOutProjFn(Function):
                 dbs.append(ops.colsum(dh) if has_bias else None)
         wgrad_join(local=True)
         return (da_all, None) + tuple(dws) + tuple(dbs)
+
+
+class OutProjContextLNFn(Function):
+    """FusedOutProjFn + ContextLayerNormFn as one autograd node (throughput mode): the n attention
+    outputs side by side in a_all [N, n*E] go through their out-projections (ONE batched GEMM launch,
+    multi_head.py:476), then Y[:, cE:(c+1)E] = LN_c(X + dropout_c(h_c)) for all contexts in ONE launch
+    that also writes the bf16 operand of context_fc (decoder_faces_objects.py:272-354).  Backward: ONE
+    LayerNorm launch that writes dL/dh of all contexts straight as the bf16 operand of the batched dX
+    and dW GEMMs and sums the residual gradients; no fp32 dL/dh is materialised."""
+
+    @staticmethod
+    def usable(a_all, n, ws):
+        E = a_all.shape[1] // n
+        return _fast() and _tw() and config.gemm_batched and 1 < n <= 4 and E % 64 == 0 and E <= 1024 \
+            and all(w.shape == (E, E) for w in ws)
+
+    @staticmethod
+    def forward(ctx, a_all, X, p, seeds, eps, n, *args):
+        ws, bs, gammas, betas = args[:n], args[n:2 * n], args[2 * n:3 * n], args[3 * n:4 * n]
+        N, E = X.shape
+        a16 = operand(a_all, 'a')
+        w16 = concat_rows_operand(list(ws), 'b', a_all.device)          # [n*E, E]
+        has_bias = bs[0] is not None
+        bias = torch.cat([b.reshape(-1) for b in bs]) if has_bias else None
+        hs = torch.empty((n, N, E), dtype=torch.float32, device=a_all.device)
+        ops.gemm_tn_batched(a16, w16, n, N, E, E, hs.view(n * N, E), N * E, a_off=(E, 0), b_off=(0, E),
+                            bias=bias, bias_off=E)
+        Y, Y16, means, rstds = ops.ln_fwd_multi([hs[c] for c in range(n)], _c(X), gammas, betas, eps, p,
+                                                seeds)
+        twin.put(Y, Y16)
+        ctx.cfg = (n, E, p, seeds, has_bias)
+        ctx.save_for_backward(a16, w16, hs, *means, *rstds, *gammas)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        n, E, p, seeds, has_bias = ctx.cfg
+        sv = ctx.saved_tensors
+        a16, w16, hs = sv[:3]
+        means, rstds, gammas = sv[3:3 + n], sv[3 + n:3 + 2 * n], sv[3 + 2 * n:3 + 3 * n]
+        N = hs.shape[1]
+        dev = dY.device
+        dgb = ops.zeros_f32((2 * n, E), dY)
+        dX, _, d16 = ops.ln_bwd_multi(_c(dY), [hs[c] for c in range(n)], means, rstds, gammas, p, seeds,
+                                      want_dx=True, want_dh32=False, want_dh16=True,
+                                      dgammas=[dgb[c] for c in range(n)],
+                                      dbetas=[dgb[n + c] for c in range(n)])
+        da_all = torch.empty((N, n * E), dtype=torch.float32, device=dev)
+        ops.gemm_tn_batched(d16, w16, n, N, E, E, da_all, E, a_off=(E, 0), b_off=(0, E), trans_b=True)
+        dW = torch.empty((n * E, E), dtype=torch.float32, device=dev)
+        ops.gemm_tn_batched(d16, a16, n, E, E, N, dW, E * E, a_off=(E, 0), b_off=(E, 0), trans_a=True,
+                            trans_b=True)
+        dws = tuple(dW[c * E:(c + 1) * E] for c in range(n))
+        dbs = (None,) * n
+        if has_bias:
+            db = ops.colsum(d16)
+            dbs = tuple(db[c * E:(c + 1) * E] for c in range(n))
+        return (da_all, dX, None, None, None, None) + dws + dbs + tuple(dgb[c] for c in range(n)) + \
+            tuple(dgb[n + c] for c in range(n))
 
 
 def _rep():

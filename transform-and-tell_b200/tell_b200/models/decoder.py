@@ -13,6 +13,7 @@ import torch.nn as nn
 from .. import config
 from .. import functional as Fn
 from .. import ops
+from .. import twin
 from .. import weight_bank
 from ..modules import (AdaptiveEmbedding, AdaptiveSoftmax, DynamicConv1dTBC, GehringLinear,
                        LayerNorm, LightweightConv1dTBC, MultiHeadAttention, TextFieldEmbedder)
@@ -92,7 +93,7 @@ class DynamicConvDecoderLayer(DecoderLayer):
         X2 = X.reshape(N, E)
         # ---- conv block (decoder_faces_objects.py:256-266)
         p_in = self._p(self.input_dropout)
-        h = Fn.DropoutFn.apply(X2, p_in, self._seed(p_in)) if p_in > 0 else X2
+        h = Fn.DropoutFn.apply(X2, p_in, self._seed(p_in), True) if p_in > 0 else X2
         h = self.linear1(h)
         if self.glu:
             h = Fn.GLUFn.apply(h)
@@ -135,6 +136,8 @@ class DynamicConvDecoderLayer(DecoderLayer):
                 all(h_ is not None or kv is None for h_, kv in zip(hm, kvs)) and any(h_ is not None for h_ in hm):
             # incremental decoding over the head-major K|V cache (built once by the generate loop)
             A_all = torch.empty_like(Q_all)
+            tw = Fn._tw()
+            A16 = torch.empty(Q_all.shape, dtype=torch.bfloat16, device=Q_all.device) if tw else None
             if config.attn_multi and n <= 4 and mhas[0].head_dim == 64:
                 # all contexts of the layer in ONE launch (blockIdx.z walks them)
                 items = []
@@ -146,8 +149,11 @@ class DynamicConvDecoderLayer(DecoderLayer):
                                       bias_k=mha.bias_k.view(-1) if mha.bias_k is not None else None,
                                       bias_v=mha.bias_v.view(-1) if mha.bias_v is not None else None,
                                       mask=masks[c], out=A_all[:, sl], lse=None, S=S_c,
-                                      kv_len=kv_cache.get(names[c] + '/len')))
+                                      kv_len=kv_cache.get(names[c] + '/len'),
+                                      out16=A16[:, sl] if tw else None))
                 ops.attn_decode_hm_multi(items, B, mhas[0].num_heads, mhas[0].head_dim, mhas[0].add_zero_attn)
+                if tw:
+                    twin.put(A_all, A16)
             else:
                 for c, (mha, kv) in enumerate(zip(mhas, kvs)):
                     sl = slice(c * E_, (c + 1) * E_)
@@ -167,18 +173,24 @@ class DynamicConvDecoderLayer(DecoderLayer):
                                                *masks, *extra)
             A_all = res[0]
             attns = {nm: w for nm, w in zip(names, res[1:])} if need_w else {}
-        hs = Fn.FusedOutProjFn.apply(A_all, n, *[m.out_proj.weight for m in mhas],
-                                     *[m.out_proj.bias for m in mhas])
         lns = [self.context_attn_lns[nm] for nm in names]
         seeds = tuple(self._seed(p) for _ in range(n))
-        Xc = Fn.ContextLayerNormFn.apply(X2, p, seeds, lns[0].eps, n, *hs,
-                                         *[l.weight for l in lns], *[l.bias for l in lns])
+        out_ws = [m.out_proj.weight for m in mhas]
+        if Fn.OutProjContextLNFn.usable(A_all, n, out_ws):
+            # out-projections (one batched GEMM) + the n residual LayerNorms (one launch) as one node
+            Xc = Fn.OutProjContextLNFn.apply(A_all, X2, p, seeds, lns[0].eps, n, *out_ws,
+                                             *[m.out_proj.bias for m in mhas],
+                                             *[l.weight for l in lns], *[l.bias for l in lns])
+        else:
+            hs = Fn.FusedOutProjFn.apply(A_all, n, *out_ws, *[m.out_proj.bias for m in mhas])
+            Xc = Fn.ContextLayerNormFn.apply(X2, p, seeds, lns[0].eps, n, *hs,
+                                             *[l.weight for l in lns], *[l.bias for l in lns])
         # ---- context_fc + FFN (:354-364)
-        X2 = self.context_fc(Xc)
-        h = self.fc1(X2, act=ops.ACT_RELU)
+        X2 = self.context_fc(Xc, twin_out=True)            # fc1 reads it as a GEMM operand
         p_relu = self._p(self.relu_dropout)
+        h = self.fc1(X2, act=ops.ACT_RELU, twin_out=p_relu == 0)
         if p_relu > 0:
-            h = Fn.DropoutFn.apply(h, p_relu, self._seed(p_relu))
+            h = Fn.DropoutFn.apply(h, p_relu, self._seed(p_relu), True)
         h = self.fc2(h)
         X2 = Fn.ResidualLayerNormFn.apply(h, X2, self.final_layer_norm.weight,
                                           self.final_layer_norm.bias, p, self._seed(p),
@@ -347,6 +359,7 @@ class _DynamicConvDecoderBase(Decoder):
         return built
 
     def _forward_tbc(self, prev_target, contexts, incremental_state=None, use_layers=None):
+        twin.clear()                         # operand twins never outlive one forward + backward
         for layer in self.layers:            # parameter splits belong to one forward's autograd graph
             for mha in layer.context_attns.values():
                 mha.begin_step()

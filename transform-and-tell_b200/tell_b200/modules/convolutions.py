@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .. import config, ops
+from .. import config, ops, twin
 from .. import functional as Fn
 from ..utils import get_incremental_state, set_incremental_state
 from .linear import linear
@@ -83,8 +83,13 @@ class DynamicConv1dTBC(nn.Module):
             x_new = X[0].contiguous()
             window = _step_window(self, incremental_state, X)
             z = linear(x_new, self.weight_linear.weight, self.weight_linear.bias)
-            out = ops.dynconv_step(window, x_new, z.contiguous(), self.num_heads, self.kernel_size,
-                                   self.weight_softmax)
+            if Fn._tw() and C % 8 == 0:
+                out, out16 = ops.dynconv_step(window, x_new, z.contiguous(), self.num_heads,
+                                              self.kernel_size, self.weight_softmax, twin=True)
+                twin.put(out, out16)               # operand of linear2
+            else:
+                out = ops.dynconv_step(window, x_new, z.contiguous(), self.num_heads, self.kernel_size,
+                                       self.weight_softmax)
             return out.view(1, B, C)
         prev = None
         if incremental_state is not None:

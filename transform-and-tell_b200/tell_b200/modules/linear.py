@@ -8,10 +8,11 @@ from .. import functional as Fn
 from .. import ops, weight_bank
 
 
-def linear(x, weight, bias=None, alpha=1.0, act=ops.ACT_NONE):
-    """F.linear over the last dim through the tcgen05 GEMM."""
+def linear(x, weight, bias=None, alpha=1.0, act=ops.ACT_NONE, twin_out=False):
+    """F.linear over the last dim through the tcgen05 GEMM.  twin_out: the result feeds another GEMM,
+    so the epilogue also writes its bf16 operand (tell_b200/twin.py)."""
     shape = x.shape
-    y = Fn.LinearFn.apply(x.reshape(-1, shape[-1]), weight, bias, alpha, act)
+    y = Fn.LinearFn.apply(x.reshape(-1, shape[-1]), weight, bias, alpha, act, twin_out)
     return y.view(*shape[:-1], weight.shape[0])
 
 
@@ -57,8 +58,8 @@ class GehringLinear(nn.Module):
             return Fn.WeightNormFn.apply(self.weight_v, self.weight_g)
         return self.weight
 
-    def forward(self, x, act=ops.ACT_NONE):
-        return linear(x, self.effective_weight(), self.bias, 1.0, act)
+    def forward(self, x, act=ops.ACT_NONE, twin_out=False):
+        return linear(x, self.effective_weight(), self.bias, 1.0, act, twin_out)
 
 
 class TiedLinear(nn.Module):

@@ -210,6 +210,106 @@ def glu_bwd(dout, h):
     return dh
 
 
+def bf16_like(rows, cols, device):
+    """Uninitialised bf16 [rows, cols] view whose row pitch is a multiple of 8 elements (TMA); the pad
+    columns lie outside every TMA extent and are zeroed only when they exist."""
+    ld = (cols + 7) // 8 * 8
+    if ld == cols:
+        return torch.empty((rows, cols), dtype=torch.bfloat16, device=device)
+    return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)[:, :cols]
+
+
+def dropout_tw(x, p, seed, want32=True):
+    """dropout with the bf16 operand twin: x [N,C] contiguous -> (y fp32 or None, y16)."""
+    assert x.is_contiguous() and x.dim() == 2 and x.shape[1] % 8 == 0
+    y = torch.empty_like(x) if want32 else None
+    y16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call('tt_dropout_tw', _ptr(x), _ptr(y), _ptr(y16), c_ll(x.numel()), c_float(p), _ull(seed),
+              _stream())
+    return y, y16
+
+
+def relu_bwd_tw(dy, y):
+    assert dy.is_contiguous() and y.is_contiguous() and dy.shape == y.shape and dy.shape[-1] % 8 == 0
+    dx = torch.empty_like(dy)
+    dx16 = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    _lib.call('tt_relu_bwd_tw', _ptr(dy), _ptr(y), _ptr(dx), _ptr(dx16), c_ll(dy.numel()), _stream())
+    return dx, dx16
+
+
+def glu_fwd_tw(h):
+    N, C2 = h.shape
+    assert h.is_contiguous() and (C2 // 2) % 8 == 0
+    out = _f32(N, C2 // 2, like=h)
+    out16 = torch.empty((N, C2 // 2), dtype=torch.bfloat16, device=h.device)
+    _lib.call('tt_glu_fwd_tw', _ptr(h), _ptr(out), _ptr(out16), c_ll(N), c_int(C2 // 2), _stream())
+    return out, out16
+
+
+def glu_bwd_tw(dout, h):
+    N, C2 = h.shape
+    assert dout.is_contiguous() and h.is_contiguous() and (C2 // 2) % 8 == 0
+    dh = torch.empty_like(h)
+    dh16 = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device)
+    _lib.call('tt_glu_bwd_tw', _ptr(dout), _ptr(h), _ptr(dh), _ptr(dh16), c_ll(N), c_int(C2 // 2),
+              _stream())
+    return dh, dh16
+
+
+def ln_fwd_multi(hs, res, gammas, betas, eps=1e-5, p=0.0, seeds=None, want32=True, want16=True):
+    """n <= 4 LayerNorms sharing the residual `res` in one launch: hs[c] [N,E] is overwritten with
+    res + dropout_c(hs[c]); returns (Y fp32 [N,n*E] or None, Y16 bf16 [N,n*E] or None, means, rstds)."""
+    n = len(hs)
+    N, E = hs[0].shape
+    _check_cuda(*hs, res)
+    assert 1 <= n <= 4 and E % 8 == 0 and all(h.is_contiguous() and h.shape == (N, E) for h in hs)
+    assert res is None or (res.is_contiguous() and res.shape == (N, E))
+    dev = hs[0].device
+    Y = torch.empty((N, n * E), dtype=torch.float32, device=dev) if want32 else None
+    Y16 = torch.empty((N, n * E), dtype=torch.bfloat16, device=dev) if want16 else None
+    stats = torch.empty((2 * n, N), dtype=torch.float32, device=dev)
+    means, rstds = [stats[2 * c] for c in range(n)], [stats[2 * c + 1] for c in range(n)]
+    a = _lib.TtLnFwdMulti()
+    for c in range(n):
+        a.h[c], a.gamma[c], a.beta[c] = hs[c].data_ptr(), gammas[c].data_ptr(), betas[c].data_ptr()
+        a.mean[c], a.rstd[c] = means[c].data_ptr(), rstds[c].data_ptr()
+        a.seed[c] = (int(seeds[c]) if seeds is not None else 0) & 0xFFFFFFFFFFFFFFFF
+    a.res = _dp(res)
+    a.y, a.ldy = _dp(Y), (n * E)
+    a.y16, a.ldy16 = _dp(Y16), (n * E)
+    a.n, a.N, a.E, a.eps, a.p_drop = n, N, E, eps, p
+    _lib.call('tt_ln_fwd_multi', ctypes.byref(a), _stream())
+    return Y, Y16, means, rstds
+
+
+def ln_bwd_multi(dY, xs, means, rstds, gammas, p=0.0, seeds=None, want_dx=True, want_dh32=False,
+                 want_dh16=True, dgammas=None, dbetas=None):
+    """Backward of ln_fwd_multi in one launch.  dY [N, n*E] (row stride free).  Returns
+    (dX [N,E] = sum_c dx_c or None, [dh_c fp32] or None, dh16 [N, n*E] bf16 or None)."""
+    n = len(xs)
+    N, E = xs[0].shape
+    _check_cuda(dY, *xs)
+    assert dY.stride(1) == 1 and dY.shape == (N, n * E)
+    dev = dY.device
+    dX = torch.empty((N, E), dtype=torch.float32, device=dev) if want_dx else None
+    dhs = [torch.empty((N, E), dtype=torch.float32, device=dev) for _ in range(n)] if want_dh32 else None
+    dh16 = torch.empty((N, n * E), dtype=torch.bfloat16, device=dev) if want_dh16 else None
+    a = _lib.TtLnBwdMulti()
+    for c in range(n):
+        a.x[c], a.mean[c], a.rstd[c] = xs[c].data_ptr(), means[c].data_ptr(), rstds[c].data_ptr()
+        a.gamma[c] = gammas[c].data_ptr()
+        a.dgamma[c] = _dp(dgammas[c]) if dgammas is not None else None
+        a.dbeta[c] = _dp(dbetas[c]) if dbetas is not None else None
+        a.dh[c] = dhs[c].data_ptr() if dhs is not None else None
+        a.seed[c] = (int(seeds[c]) if seeds is not None else 0) & 0xFFFFFFFFFFFFFFFF
+    a.dy, a.lddy = dY.data_ptr(), dY.stride(0)
+    a.dx = _dp(dX)
+    a.dh16, a.lddh16 = _dp(dh16), n * E
+    a.n, a.N, a.E, a.p_drop = n, N, E, p
+    _lib.call('tt_ln_bwd_multi', ctypes.byref(a), _stream())
+    return dX, dhs, dh16
+
+
 def dropout(x, p, seed):
     assert x.is_contiguous()
     y = torch.empty_like(x)
@@ -307,37 +407,49 @@ def layer_mix_bwd(hiddens, w, dout):
 
 
 # --------------------------------------------------------------------------- dynamic conv
-def dynconv_fwd(x, z, H, K, softmax=True, p=0.0, seed=0, broadcast=False):
+def dynconv_fwd(x, z, H, K, softmax=True, p=0.0, seed=0, broadcast=False, twin=False):
+    """twin=True: also returns out16 (bf16 [T*B, C]), the operand of the following linear2."""
     T, B, C = x.shape
     out = torch.empty_like(x)
     probs = _f32(T, B, H, K, like=x)
-    _lib.call('tt_dynconv_fwd', _ptr(x), _ptr(z), c_ll(0 if broadcast else H * K), _ptr(out),
+    out16 = torch.empty((T * B, C), dtype=torch.bfloat16, device=x.device) if twin and C % 8 == 0 else None
+    _lib.call('tt_dynconv_fwd_tw', _ptr(x), _ptr(z), c_ll(0 if broadcast else H * K), _ptr(out),
               _ptr(probs), c_int(T), c_int(B), c_int(C), c_int(H), c_int(K),
-              c_int(1 if softmax else 0), c_float(p), _ull(seed), _stream())
+              c_int(1 if softmax else 0), c_float(p), _ull(seed), _ptr(out16), _stream())
+    if twin:
+        return out, probs, out16
     return out, probs
 
 
-def dynconv_step(window, x_new, z, H, K, softmax=True, broadcast=False):
+def dynconv_step(window, x_new, z, H, K, softmax=True, broadcast=False, twin=False):
     """One incremental step: window [K-1,B,C] (updated in place), x_new [B,C], z [B,H*K] (or [H,K]
-    with broadcast) -> out [B,C]."""
+    with broadcast) -> out [B,C] (twin=True: (out, out16))."""
     _check_cuda(window, x_new, z)
     B, C = x_new.shape
     assert x_new.is_contiguous() and z.is_contiguous()
     assert K == 1 or (window.is_contiguous() and window.shape == (K - 1, B, C))
     out = torch.empty_like(x_new)
-    _lib.call('tt_dynconv_step', _ptr(window if K > 1 else None), _ptr(x_new), _ptr(z),
+    out16 = torch.empty((B, C), dtype=torch.bfloat16, device=x_new.device) if twin and C % 8 == 0 else None
+    _lib.call('tt_dynconv_step_tw', _ptr(window if K > 1 else None), _ptr(x_new), _ptr(z),
               c_ll(0 if broadcast else H * K), _ptr(out), c_int(B), c_int(C), c_int(H), c_int(K),
-              c_int(1 if softmax else 0), _stream())
+              c_int(1 if softmax else 0), _ptr(out16), _stream())
+    if twin:
+        return out, out16
     return out
 
 
-def dynconv_bwd(dout, x, probs, H, K, softmax=True, p=0.0, seed=0):
+def dynconv_bwd(dout, x, probs, H, K, softmax=True, p=0.0, seed=0, twin=False):
+    """twin=True: also returns dz16 (bf16 [T*B, H*K] view), the operand of the filter projection's
+    backward GEMMs."""
     T, B, C = x.shape
     dx = torch.empty_like(x)
     dz = _f32(T, B, H, K, like=x)
-    _lib.call('tt_dynconv_bwd', _ptr(dout), _ptr(x), _ptr(probs), _ptr(dx), _ptr(dz), c_int(T),
+    dz16 = bf16_like(T * B, H * K, x.device) if twin else None
+    _lib.call('tt_dynconv_bwd_tw', _ptr(dout), _ptr(x), _ptr(probs), _ptr(dx), _ptr(dz), c_int(T),
               c_int(B), c_int(C), c_int(H), c_int(K), c_int(1 if softmax else 0), c_float(p),
-              _ull(seed), _stream())
+              _ull(seed), _ptr(dz16), c_ll(dz16.stride(0) if dz16 is not None else 0), _stream())
+    if twin:
+        return dx, dz, dz16
     return dx, dz
 
 
@@ -400,6 +512,10 @@ def _attn_ctx_array(items, E):
         c.ldkv = it['k'].stride(0) if (S > 0 and it['k'].dim() == 2) else E
         c.seed = int(it.get('seed', 0)) & 0xFFFFFFFFFFFFFFFF
         c.kv_len = _dp(it.get('kv_len')) if S > 0 else None
+        if it.get('out16') is not None:
+            c.out16, c.ldo16 = _dp(it['out16']), it['out16'].stride(0)
+        if it.get('dq16') is not None:
+            c.dq16, c.ldq16 = _dp(it['dq16']), it['dq16'].stride(0)
         if it.get('dout') is not None:
             c.dout, c.dq = _dp(it['dout']), _dp(it['dq'])
             c.dk, c.dv = (_dp(it['dk']), _dp(it['dv'])) if S > 0 else (None, None)
