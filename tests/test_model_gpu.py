@@ -291,6 +291,32 @@ def test_graphed_decode_equals_eager_decode(precision):
             assert ids1.shape == (4, 24)
 
 
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+def test_decode_graph_reused_across_calls_equals_fresh_capture(precision):
+    """The captured decode step is kept across generate() calls of one shape: a second call with
+    DIFFERENT inputs (other article / faces / objects / start tokens, other padding) copies its step-0
+    state into the captured buffers and replays -- same tokens and log-probs as the eager loop; a
+    call with another shape captures anew."""
+    from tell_b200 import synth
+    cfg, sd, model = _tiny_model(precision, _StubResNet(None), _StubRoberta(None, 24))
+    model.eval()
+    model.gen_len = 17
+    timing = {}
+    object.__setattr__(model, 'decode_timing', timing)
+    runs = []
+    for seed, (B, S) in [(7, (4, 11)), (8, (4, 11)), (9, (4, 11)), (10, (3, 13)), (11, (3, 13))]:
+        cap, ctx = synth.decoder_inputs(cfg, B, 9, S, 3, 4, 5, seed=seed)
+        cctx = {k: v.cuda() for k, v in ctx.items()}
+        model.decode_graph = False
+        lp0, ids0, _ = model._generate(cap[:, 0:1].cuda(), cctx, early_exit=False)
+        model.decode_graph = True
+        lp1, ids1, _ = model._generate(cap[:, 0:1].cuda(), cctx, early_exit=False)
+        runs.append(bool(timing['graph_reused']))
+        assert torch.equal(ids0, ids1), (seed, runs)
+        assert (lp0 - lp1).abs().max().item() < 1e-5
+    assert runs == [False, True, True, False, True], runs
+
+
 def test_dynconv_decode_step_matches_full_convolution():
     """tt_dynconv_step over T single steps == the full causal convolution (DynamicConv and
     Lightweight), including the in-place shift of the [K-1,B,C] buffer."""

@@ -30,6 +30,9 @@ config.manual_seed(1234)
 model = bench.build_model(dev).eval()
 model.gen_len = args.steps
 model.decode_graph = not args.eager
+phases = {}
+if os.environ.get('TT_DECODE_PHASES') == '1':
+    object.__setattr__(model, 'decode_timing', phases)
 B = args.batch
 host = bench.make_batch(B)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -57,6 +60,6 @@ print(json.dumps({'metric': 'greedy decode latency', 'batch': B, 'steps': args.s
                   'captions_per_s_decode_only': round(B / (dec_ms * 1e-3), 1),
                   'captions_per_s_incl_encoders': round(B / ((dec_ms + ctx_ms) * 1e-3), 1),
                   'decode_ms_min': round(min(r[1] for r in res), 2),
-                  'decode_graph': bool(model.decode_graph), 'decode_ms_reps': [round(r[1], 1) for r in res],
+                  'phases': {k: round(v, 2) for k, v in phases.items()}, 'decode_graph': bool(model.decode_graph), 'decode_ms_reps': [round(r[1], 1) for r in res],
                   'note': 'steps 0-1 eager (one-off K|V projections of the four contexts, graph capture), '
                           'steps 2.. replay one captured decode step'}))
