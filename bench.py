@@ -267,6 +267,7 @@ def run_b200(args):
             self.grads = None
             self.enc_done = torch.cuda.Event()
             self.train_done = torch.cuda.Event()
+            self.copied = torch.cuda.Event()
             self.busy = False
 
         def restore(self):
@@ -318,17 +319,32 @@ def run_b200(args):
     sets[0].fwd_bwd()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count()
+    green = None
+    if args.green_dec_sms > 0 and not args.no_graph and args.pipeline:
+        # two disjoint SM partitions (CUDA green contexts): decoder stage / frozen-encoder stage; each
+        # graph is captured on a stream of its partition and keeps it when replayed
+        from tell_b200 import green as green_mod
+        from tell_b200.models import transformer as _tr
+        (n_dec, mk_dec), (n_enc, mk_enc) = green_mod.sm_partition(dev.index, args.green_dec_sms)
+        green = {'s_enc': mk_enc(), 's_train': mk_dec(), 'cap_enc': mk_enc(), 'cap_dec': mk_dec(),
+                 'n_dec': n_dec, 'n_enc': n_enc}
+        _tr._SIDE[(dev.type, dev.index)] = mk_enc()      # the ResNet branch of Model.encode
+        config.encoder_sm_cap = min(int(args.enc_sms), n_enc) if int(args.enc_sms) > 0 else n_enc
     if not args.no_graph:
         for st in sets:
             st.g1, st.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             st.restore()
-            with torch.cuda.graph(st.g1):
+            with torch.cuda.graph(st.g1, stream=green['cap_enc'] if green else None):
                 st.encode()
-            with torch.cuda.graph(st.g2, pool=st.g1.pool()):
+            with torch.cuda.graph(st.g2, pool=st.g1.pool(), stream=green['cap_dec'] if green else None):
                 st.train_part()
             torch.cuda.synchronize()
     graph = sets[0].g1
-    s_enc, s_train = torch.cuda.Stream(), torch.cuda.Stream()      # encoder / train pipeline stages
+    if green is None:
+        s_enc, s_train = torch.cuda.Stream(), torch.cuda.Stream()      # encoder / train pipeline stages
+    else:
+        s_enc, s_train = green['s_enc'], green['s_train']
+    s_copy = torch.cuda.Stream()                                   # H2D input prefetch (e2e measurement)
     s_ar = torch.cuda.Stream() if world > 1 else None
     ev_bwd, ev_ar = torch.cuda.Event(), torch.cuda.Event()
     ar_pending = [False]
@@ -339,12 +355,20 @@ def run_b200(args):
         counter[0] += 1
         # stage 1 (stream s_enc): inputs + frozen encoders of this step.  With two sets this runs
         # while the previous step's stage 2 is still executing on s_train.
+        if e2e:
+            # the step's inputs come from pinned host memory: H2D on a copy stream as soon as the set
+            # is free, so the transfer of step i+1 runs under the encoders of step i (input prefetch)
+            with torch.cuda.stream(s_copy):
+                if st.busy:
+                    s_copy.wait_event(st.train_done)
+                for k in st.static:
+                    st.static[k].copy_(pinned[k], non_blocking=True)
+                st.copied.record(s_copy)
         with torch.cuda.stream(s_enc):
             if st.busy:
                 s_enc.wait_event(st.train_done)   # the step that last used this set has finished
             if e2e:
-                for k in st.static:
-                    st.static[k].copy_(pinned[k], non_blocking=True)
+                s_enc.wait_event(st.copied)
             else:
                 st.restore()
             if st.g1 is not None:
@@ -378,6 +402,7 @@ def run_b200(args):
 
     def drain():
         main = torch.cuda.current_stream()
+        main.wait_stream(s_copy)
         main.wait_stream(s_enc)
         main.wait_stream(s_train)
         if ar_pending[0]:
@@ -397,6 +422,7 @@ def run_b200(args):
         s.record(main)                    # the pipeline is empty here: every timed step's encoders
         s_enc.wait_event(s)               # AND train part run inside [s, e]
         s_train.wait_event(s)
+        s_copy.wait_event(s)              # ... and so does every H2D copy of the e2e measurement
         for _ in range(steps):
             step(e2e)
         drain()
@@ -601,6 +627,9 @@ def run_b200(args):
                    'cuda_graph': graph is not None, 'wgrad_stream': args.wgrad,
                    'encoder_overlap': bool(args.encoder_overlap),
                    'encoder_sm_cap': config.encoder_sm_cap, 'gemm_occupancy_weight': occ_w,
+                   'sm_partition': (None if green is None else
+                                    {'decoder_sms': green['n_dec'], 'encoder_sms': green['n_enc'],
+                                     'how': 'CUDA green contexts, one per pipeline stage'}),
                    'pipeline': ('2 step-buffer sets: frozen encoders of step i+1 overlap the decoder '
                                 'fwd+bwd of step i; all K encoder and K train passes run inside the '
                                 'timed region' if n_sets == 2 else None),
@@ -788,6 +817,9 @@ def main():
     ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
                     help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
                          "model.train()) or 'running' statistics folded into the convolutions (eval())")
+    ap.add_argument('--green-dec-sms', type=int, default=0,
+                    help='> 0: split the SMs into two CUDA green contexts -- this many (rounded by the '
+                         'driver) for the decoder stage, the rest for the frozen-encoder stage')
     ap.add_argument('--skip-parity-mode', action='store_true',
                     help='skip the bf16x3 (1e-3-parity precision) throughput measurement')
     ap.add_argument('--skip-extras', action='store_true',
