@@ -32,6 +32,11 @@ def cast_bf16(x, transpose=False, split=0, out=None, seg_stride=0):
     """fp32 [R,C] -> bf16 GEMM operand ([R,C*rep] or [C,R*rep] when transposed); see tt_cast_bf16."""
     _check_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    from . import weight_bank
+    for bank in weight_bank.LIVE:
+        if bank.is_unwritten_handle(x):
+            raise _lib.TtError('cast of a weight-bank handle: the fp32 effective weights are not materialised '
+                               '(WeightBank.write_w32 = False); the bf16 operand must come from the bank')
     rows, cols = x.shape
     rep = 1 if split == 0 else 3
     shape = (cols, rows * rep) if transpose else (rows, cols * rep)

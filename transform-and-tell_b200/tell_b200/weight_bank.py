@@ -16,6 +16,8 @@ Only the throughput mode ('bf16') uses the bank; the parity mode ('bf16x3') keep
 """
 import ctypes
 
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -51,8 +53,12 @@ class _WN:
     __slots__ = ('v', 'g', 'w32', 'norm', 'b16', 'dw', 'dv', 'dg')
 
 
+LIVE = weakref.WeakSet()      # every bank alive in this process (ops.cast_bf16 guards their handles)
+
+
 class WeightBank:
     def __init__(self, module):
+        LIVE.add(self)
         from .modules.linear import GehringLinear
         self.module = module
         self.device = next(module.parameters()).device
@@ -98,6 +104,7 @@ class WeightBank:
         self.current = None    # {id(weight_v): effective weight} of the running forward
         self.claimed = set()
         self.prepared_once = False
+        self.write_w32 = False
         self._build_tables()
 
     # ------------------------------------------------------------------ tables
@@ -114,7 +121,10 @@ class WeightBank:
         self.map = {}
         for e in self.wn:
             O, I = e.v.shape
-            add(e.v, e.g, e.w32, e.norm, e.b16, O, I, I, I)
+            # the fp32 effective weight is only a HANDLE here (autograd node output, lookup key): every
+            # consumer takes the bf16 operand from the table, so its 4 bytes per element are not
+            # written (write_w32 = True restores them; functional.operand refuses to cast the handle)
+            add(e.v, e.g, e.w32 if self.write_w32 else None, e.norm, e.b16, O, I, I, I)
             self.map[('s', e.w32.data_ptr(), (O, I))] = e.b16
         for kind, tensors, buf, key in self.extra:
             if kind == 's':
@@ -196,6 +206,10 @@ class WeightBank:
             self.prepare()
             ws = [e.w32 for e in self.wn]
         return {id(e.v): w for e, w in zip(self.wn, ws)}
+
+    def is_unwritten_handle(self, t):
+        """True for a view of the fp32 effective-weight buffer whose contents are not maintained."""
+        return (not self.write_w32) and t.untyped_storage().data_ptr() == self._w32.untyped_storage().data_ptr()
 
     # ------------------------------------------------------------------ lookups (forward only)
     def _backed(self, t):
