@@ -367,6 +367,8 @@ typedef struct {
   void* out16;                 /* optional bf16 twin of out [T*B, ldo16]: the operand of out_proj (multi_head.py:476) */
   void* dq16;                  /* optional bf16 twin of dq [T*B, ldq16]: the operand of in_proj_q's backward */
   long long ldo16, ldq16;
+  float* dsum;                 /* backward, optional scratch [B,H,T]: D = rowsum(dO * O), written by the dQ kernel and
+                                * read by the dK|dV kernel instead of recomputing it in every key-tile CTA */
 } TtAttnCtx;
 int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
                          int kv16, void* stream);

@@ -40,6 +40,10 @@ struct AttnArgs {
   __nv_bfloat16* out16;
   __nv_bfloat16* dq16;
   long long ldo16, ldq16;
+  // backward, optional [B,H,T]: D = rowsum(dO * O), written by the dQ kernel and read by the dK|dV
+  // kernel (which would otherwise recompute it in every key-tile CTA: 2 x 16 KB of fp32 per CTA)
+  float* dsum;
+  int dkv_tpc;          // dK|dV kernel: consecutive key tiles per CTA (set by the launcher)
 };
 
 // Up to four contexts per launch (image / article / faces / objects of one decoder layer,

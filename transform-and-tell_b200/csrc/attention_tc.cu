@@ -15,6 +15,9 @@
 
 namespace tt {
 
+#ifndef TT_ATTN_MINB
+#define TT_ATTN_MINB 2      // CTAs per SM the tensor-core attention kernels are compiled for (3 / 4 spill: measured slower)
+#endif
 constexpr int TC_BM = 64, TC_BN = 64, TC_D = 64, TC_LD = TC_D + 8;
 
 constexpr int TC_THREADS = 128;   // every kernel here runs 4 warps
@@ -215,7 +218,7 @@ struct TileWalk {
 
 // ------------------------------------------------------------------------------------------ forward
 template <bool KV16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TT_ATTN_MINB)
 attn_fwd_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
   AttnArgs a = args.a[blockIdx.z];
@@ -327,6 +330,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnArgsN args) {
 // D[t] = sum_c dO[t,c] * O[t,c] and lse[t] for the 64 queries q0.. into shared memory.
 // Thread pair (2r, 2r+1) owns row r, 32 columns each: 16 independent float4 loads per thread, one
 // round of memory latency (the previous warp-per-row loop paid 16 dependent rounds per warp).
+template <bool WRITE = false>
 __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h, int bh, int q0,
                                                 float* sD, float* sLse) {
   const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
@@ -347,12 +351,22 @@ __device__ __forceinline__ void stage_row_stats(const AttnArgs& a, int b, int h,
   if (half == 0) {
     sD[r] = d;
     sLse[r] = t < a.T ? a.lse[static_cast<long long>(bh) * a.T + t] : INFINITY;  // p := 0 beyond T
+    if (WRITE && a.dsum != nullptr && t < a.T) a.dsum[static_cast<long long>(bh) * a.T + t] = d;
+  }
+}
+// The same two row vectors when the dQ kernel (launched just before) has left D in a.dsum.
+__device__ __forceinline__ void stage_row_stats_cached(const AttnArgs& a, int bh, int q0, float* sD, float* sLse) {
+  if (threadIdx.x < 64) {
+    const int t = q0 + threadIdx.x;
+    const bool ok = t < a.T;
+    sD[threadIdx.x] = ok ? __ldg(a.dsum + static_cast<long long>(bh) * a.T + t) : 0.f;
+    sLse[threadIdx.x] = ok ? a.lse[static_cast<long long>(bh) * a.T + t] : INFINITY;
   }
 }
 
 // ------------------------------------------------------------------------------------------ dQ
 template <bool KV16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TT_ATTN_MINB)
 attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
   AttnArgs a = args.a[blockIdx.z];
@@ -376,7 +390,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
     store_tile(qreg, sQ);
     store_tile(doreg, sdO);
   }
-  stage_row_stats(a, b, h, bh, q0, sD, sLse);
+  stage_row_stats<true>(a, b, h, bh, q0, sD, sLse);
   store_kv(nxt, sK, sV, sMask);
   __syncthreads();
   uint32_t qf[4][4], dof[4][4];
@@ -442,8 +456,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
 }
 
 // ------------------------------------------------------------------------------------------ dK, dV
+// CTA = (b, h, a.dkv_tpc consecutive key tiles).  The query side of the problem (Q, dO, lse, D) is the
+// same for every key tile of a (b, h): it is staged once per CTA and, when the whole query range fits
+// one tile (T <= 64: every training shape), reused for all a.dkv_tpc key tiles -- the query-side loads
+// were 4x the key-side bytes of a one-tile CTA.  D = rowsum(dO * O) comes from the dQ kernel (a.dsum).
+// Key tiles per CTA: enough CTAs for two rounds of the resident slots (2 CTAs x 148 SMs), at most 9.
+static inline int dkv_tiles_per_cta(int L, int BH) {
+  const long long tiles = static_cast<long long>(ceil_div(L, TC_BN)) * BH;
+  long long t = (tiles + 295) / 592;
+  return static_cast<int>(t < 1 ? 1 : (t > 9 ? 9 : t));
+}
 template <bool KV16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TT_ATTN_MINB)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnArgsN args) {
   pdl_prologue();
   AttnArgs a = args.a[blockIdx.z];
@@ -454,116 +478,130 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnArgsN args) {
   __shared__ __align__(16) __nv_bfloat16 sV[64][TC_LD];
   __shared__ float sMask[64], sD[64], sLse[64];
   const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
-  const int j0 = blockIdx.y * TC_BN;
-  if (j0 >= a.S + (a.bias_k ? 1 : 0) + (a.zero_row ? 1 : 0)) return;   // grid.y covers the longest context
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const bool has_bias = a.bias_k != nullptr;
   const int L = a.S + (has_bias ? 1 : 0) + (a.zero_row ? 1 : 0);
+  const int jbeg = blockIdx.y * (a.dkv_tpc * TC_BN);
+  if (jbeg >= L) return;                                                // grid.y covers the longest context
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const float inv_keep = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  if (TileWalk(a, b).skipped(j0)) {
-    // a tile of trailing padding: every probability is 0, so dK = dV = 0 (the rows are still written:
-    // the projection's dW GEMM reads the whole slab)
-    for (int i = threadIdx.x; i < 64 * 8; i += 128) {
-      const int r = i >> 3, c8 = i & 7;
-      const long long off = (static_cast<long long>(j0 + r) * a.B + b) * a.ldkv + h * TC_D + c8 * 8;
-      if (KV16) {
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = make_uint4(0, 0, 0, 0);
-      } else {
-        *reinterpret_cast<float4*>(a.dk + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a.dk + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a.dv + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a.dv + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const TileWalk walk(a, b);
+  bool q_staged = false;        // sQ / sdO / sD / sLse hold query tile 0 (valid across key tiles when T <= 64)
+  for (int tile = 0; tile < a.dkv_tpc; ++tile) {
+    const int j0 = jbeg + tile * TC_BN;
+    if (j0 >= L) break;                                                 // CTA-uniform
+    if (walk.skipped(j0)) {
+      // a tile of trailing padding: every probability is 0, so dK = dV = 0 (the rows are still written:
+      // the projection's dW GEMM reads the whole slab)
+      for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+        const int r = i >> 3, c8 = i & 7;
+        const long long off = (static_cast<long long>(j0 + r) * a.B + b) * a.ldkv + h * TC_D + c8 * 8;
+        if (KV16) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = make_uint4(0, 0, 0, 0);
+        } else {
+          *reinterpret_cast<float4*>(a.dk + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.dk + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.dv + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.dv + off + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
+      continue;
     }
-    return;
-  }
-  {
-    KvRegs<KV16> kv;
-    float4 qreg[TC_ST], doreg[TC_ST];
-    load_kv(a, b, h, j0, L, kv);                      // all loads of the first round in flight
-    load_tile(a.q, a.ldq, a.B, b, h, 0, a.T, qreg);
-    load_tile(a.dout, a.ldo, a.B, b, h, 0, a.T, doreg);
-    store_kv(kv, sK, sV, sMask);
-    store_tile(qreg, sQ);
-    store_tile(doreg, sdO);
-  }
-  stage_row_stats(a, b, h, bh, 0, sD, sLse);
-  __syncthreads();
-  uint32_t kf[4][4], vf[4][4];
-  load_a_frags(sK, warp, lane, kf);
-  load_a_frags(sV, warp, lane, vf);
-  const int r0 = warp * 16 + g, r1 = r0 + 8;       // key rows of this thread
-  const float km0 = sMask[r0], km1 = sMask[r1];
-  float dk[8][4], dv[8][4];
-  zero_acc(dk);
-  zero_acc(dv);
-  for (int q0 = 0; q0 < a.T; q0 += TC_BM) {
-    if (q0 > 0) {
-      __syncthreads();
-      stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
-      stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
-      stage_row_stats(a, b, h, bh, q0, sD, sLse);
-      __syncthreads();
+    if (tile > 0) __syncthreads();          // the previous tile's readers of sK / sV / sQ / sdO are done
+    {
+      KvRegs<KV16> kv;
+      load_kv(a, b, h, j0, L, kv);                      // all loads of the round in flight
+      if (!q_staged) {
+        float4 qreg[TC_ST], doreg[TC_ST];
+        load_tile(a.q, a.ldq, a.B, b, h, 0, a.T, qreg);
+        load_tile(a.dout, a.ldo, a.B, b, h, 0, a.T, doreg);
+        store_tile(qreg, sQ);
+        store_tile(doreg, sdO);
+      }
+      store_kv(kv, sK, sV, sMask);
     }
-    float st[8][4], dpt[8][4];      // S^T and dP^T: rows = keys, cols = queries
-    zero_acc(st);
-    zero_acc(dpt);
-    mma_a_bt(st, kf, sQ, lane);
-    mma_a_bt(dpt, vf, sdO, lane);
-    uint32_t pf[4][4], dsf[4][4];
+    if (!q_staged) {
+      if (a.dsum != nullptr) stage_row_stats_cached(a, bh, 0, sD, sLse);
+      else stage_row_stats(a, b, h, bh, 0, sD, sLse);
+    }
+    q_staged = a.T <= TC_BM;                // with more query tiles the loop below restages them
+    __syncthreads();
+    uint32_t kf[4][4], vf[4][4];
+    load_a_frags(sK, warp, lane, kf);
+    load_a_frags(sV, warp, lane, vf);
+    const int r0 = warp * 16 + g, r1 = r0 + 8;       // key rows of this thread
+    const float km0 = sMask[r0], km1 = sMask[r1];
+    float dk[8][4], dv[8][4];
+    zero_acc(dk);
+    zero_acc(dv);
+    for (int q0 = 0; q0 < a.T; q0 += TC_BM) {
+      if (q0 > 0) {
+        __syncthreads();
+        stage_tile(a.q, a.ldq, a.B, b, h, q0, a.T, sQ);
+        stage_tile(a.dout, a.ldo, a.B, b, h, q0, a.T, sdO);
+        if (a.dsum != nullptr) stage_row_stats_cached(a, bh, q0, sD, sLse);
+        else stage_row_stats(a, b, h, bh, q0, sD, sLse);
+        __syncthreads();
+      }
+      float st[8][4], dpt[8][4];      // S^T and dP^T: rows = keys, cols = queries
+      zero_acc(st);
+      zero_acc(dpt);
+      mma_a_bt(st, kf, sQ, lane);
+      mma_a_bt(dpt, vf, sdO, lane);
+      uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int tt = n * 8 + 2 * tg;             // query column (and tt+1)
+        const float lse_a = sLse[tt], lse_b = sLse[tt + 1], Da = sD[tt], Db = sD[tt + 1];
+        float sc0 = 1.f, sc1 = 1.f, sc2 = 1.f, sc3 = 1.f;
+        if (a.p_drop > 0.f) {
+          const unsigned long long ba = (static_cast<unsigned long long>(bh) * a.T + q0 + tt) * L;
+          const unsigned long long bb = ba + L;
+          sc0 = dropout_scale(a.seed, ba + j0 + r0, a.p_drop, inv_keep);
+          sc1 = dropout_scale(a.seed, bb + j0 + r0, a.p_drop, inv_keep);
+          sc2 = dropout_scale(a.seed, ba + j0 + r1, a.p_drop, inv_keep);
+          sc3 = dropout_scale(a.seed, bb + j0 + r1, a.p_drop, inv_keep);
+        }
+        const float p0 = __expf(st[n][0] + km0 - lse_a), p1 = __expf(st[n][1] + km0 - lse_b);
+        const float p2 = __expf(st[n][2] + km1 - lse_a), p3 = __expf(st[n][3] + km1 - lse_b);
+        pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * sc0, p1 * sc1);
+        pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * sc2, p3 * sc3);
+        dsf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * (dpt[n][0] * sc0 - Da), p1 * (dpt[n][1] * sc1 - Db));
+        dsf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * (dpt[n][2] * sc2 - Da), p3 * (dpt[n][3] * sc3 - Db));
+      }
+      mma_p_b(dv, pf, sdO, lane);
+      mma_p_b(dk, dsf, sQ, lane);
+    }
+    const int ja = j0 + r0, jb = j0 + r1;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const int tt = n * 8 + 2 * tg;             // query column (and tt+1)
-      const float lse_a = sLse[tt], lse_b = sLse[tt + 1], Da = sD[tt], Db = sD[tt + 1];
-      float sc0 = 1.f, sc1 = 1.f, sc2 = 1.f, sc3 = 1.f;
-      if (a.p_drop > 0.f) {
-        const unsigned long long ba = (static_cast<unsigned long long>(bh) * a.T + q0 + tt) * L;
-        const unsigned long long bb = ba + L;
-        sc0 = dropout_scale(a.seed, ba + j0 + r0, a.p_drop, inv_keep);
-        sc1 = dropout_scale(a.seed, bb + j0 + r0, a.p_drop, inv_keep);
-        sc2 = dropout_scale(a.seed, ba + j0 + r1, a.p_drop, inv_keep);
-        sc3 = dropout_scale(a.seed, bb + j0 + r1, a.p_drop, inv_keep);
+      const int c = n * 8 + 2 * tg;
+      if (ja < a.S) {
+        const long long off = (static_cast<long long>(ja) * a.B + b) * a.ldkv + h * TC_D + c;
+        if (KV16) {
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][0], dk[n][1]);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][0], dv[n][1]);
+        } else {
+          *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][0], dk[n][1]);
+          *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][0], dv[n][1]);
+        }
+      } else if (has_bias && ja == a.S) {
+        if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][0]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][1]); }
+        if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][0]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][1]); }
       }
-      const float p0 = __expf(st[n][0] + km0 - lse_a), p1 = __expf(st[n][1] + km0 - lse_b);
-      const float p2 = __expf(st[n][2] + km1 - lse_a), p3 = __expf(st[n][3] + km1 - lse_b);
-      pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * sc0, p1 * sc1);
-      pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * sc2, p3 * sc3);
-      dsf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0 * (dpt[n][0] * sc0 - Da), p1 * (dpt[n][1] * sc1 - Db));
-      dsf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2 * (dpt[n][2] * sc2 - Da), p3 * (dpt[n][3] * sc3 - Db));
-    }
-    mma_p_b(dv, pf, sdO, lane);
-    mma_p_b(dk, dsf, sQ, lane);
-  }
-  const int ja = j0 + r0, jb = j0 + r1;
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int c = n * 8 + 2 * tg;
-    if (ja < a.S) {
-      const long long off = (static_cast<long long>(ja) * a.B + b) * a.ldkv + h * TC_D + c;
-      if (KV16) {
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][0], dk[n][1]);
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][0], dv[n][1]);
-      } else {
-        *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][0], dk[n][1]);
-        *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][0], dv[n][1]);
+      if (jb < a.S) {
+        const long long off = (static_cast<long long>(jb) * a.B + b) * a.ldkv + h * TC_D + c;
+        if (KV16) {
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][2], dk[n][3]);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][2], dv[n][3]);
+        } else {
+          *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][2], dk[n][3]);
+          *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][2], dv[n][3]);
+        }
+      } else if (has_bias && jb == a.S) {
+        if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][2]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][3]); }
+        if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][2]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][3]); }
       }
-    } else if (has_bias && ja == a.S) {
-      if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][0]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][1]); }
-      if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][0]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][1]); }
-    }
-    if (jb < a.S) {
-      const long long off = (static_cast<long long>(jb) * a.B + b) * a.ldkv + h * TC_D + c;
-      if (KV16) {
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dk) + off) = pack_bf16(dk[n][2], dk[n][3]);
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dv) + off) = pack_bf16(dv[n][2], dv[n][3]);
-      } else {
-        *reinterpret_cast<float2*>(a.dk + off) = make_float2(dk[n][2], dk[n][3]);
-        *reinterpret_cast<float2*>(a.dv + off) = make_float2(dv[n][2], dv[n][3]);
-      }
-    } else if (has_bias && jb == a.S) {
-      if (a.dbias_k) { atomicAdd(a.dbias_k + h * TC_D + c, dk[n][2]); atomicAdd(a.dbias_k + h * TC_D + c + 1, dk[n][3]); }
-      if (a.dbias_v) { atomicAdd(a.dbias_v + h * TC_D + c, dv[n][2]); atomicAdd(a.dbias_v + h * TC_D + c + 1, dv[n][3]); }
     }
   }
 }
@@ -818,7 +856,8 @@ static int attn_bwd_tc_impl(const float* dout, const float* q, const void* k, co
   else launch_k(attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, an);
   rc = check_launch("attn_bwd_dq_tc_kernel");
   if (rc != TT_OK) return rc;
-  dim3 grid2(B * H, ceil_div(L, TC_BN));
+  an.a[0].dkv_tpc = dkv_tiles_per_cta(L, B * H);
+  dim3 grid2(B * H, ceil_div(L, TC_BN * an.a[0].dkv_tpc));
   if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, an);
   else launch_k(attn_bwd_dkv_tc_kernel<false>, dim3(grid2), dim3(128), 0, (cudaStream_t)stream, an);
   return check_launch("attn_bwd_dkv_tc_kernel");
@@ -936,6 +975,7 @@ static int fill_ctx(AttnArgs& a, const TtAttnCtx& c, int T, int B, int H, int D,
     TT_REQUIRE(c.dq16 == nullptr || (c.ldq16 % 2 == 0 && (reinterpret_cast<uintptr_t>(c.dq16) & 3) == 0),
                "%s: dq16 must be 4-byte aligned with an even row pitch", who);
     a.dq16 = reinterpret_cast<__nv_bfloat16*>(c.dq16); a.ldq16 = c.ldq16;
+    a.dsum = c.dsum;
     TT_REQUIRE(c.dout && c.dq && (c.S == 0 || (c.dk && c.dv)), "%s: null dout/dq/dk/dv", who);
     a.dout = c.dout; a.dq = c.dq; a.dk = reinterpret_cast<float*>(c.dk); a.dv = reinterpret_cast<float*>(c.dv);
     a.dbias_k = c.dbias_k; a.dbias_v = c.dbias_v;
@@ -991,7 +1031,9 @@ extern "C" int tt_attn_bwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, i
   else launch_k(attn_bwd_dq_tc_kernel<false>, grid, dim3(128), 0, (cudaStream_t)stream, an);
   int rc = check_launch("attn_bwd_dq_tc_kernel");
   if (rc != TT_OK) return rc;
-  const dim3 grid2(B * H, ceil_div(Lmax, TC_BN), n);
+  const int tpc = dkv_tiles_per_cta(Lmax, B * H);
+  for (int i = 0; i < n; ++i) an.a[i].dkv_tpc = tpc;
+  const dim3 grid2(B * H, ceil_div(Lmax, TC_BN * tpc), n);
   if (kv16) launch_k(attn_bwd_dkv_tc_kernel<true>, grid2, dim3(128), 0, (cudaStream_t)stream, an);
   else launch_k(attn_bwd_dkv_tc_kernel<false>, grid2, dim3(128), 0, (cudaStream_t)stream, an);
   return check_launch("attn_bwd_dkv_tc_kernel");

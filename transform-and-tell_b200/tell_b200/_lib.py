@@ -41,7 +41,8 @@ class TtAttnCtx(ctypes.Structure):
                 ('S', c_int), ('ldq', c_ll), ('ldkv', c_ll), ('ldo', c_ll),
                 ('seed', ctypes.c_ulonglong), ('dout', c_void_p), ('dq', c_void_p), ('dk', c_void_p),
                 ('dv', c_void_p), ('dbias_k', c_void_p), ('dbias_v', c_void_p), ('kv_len', c_void_p),
-                ('out16', c_void_p), ('dq16', c_void_p), ('ldo16', c_ll), ('ldq16', c_ll)]
+                ('out16', c_void_p), ('dq16', c_void_p), ('ldo16', c_ll), ('ldq16', c_ll),
+                ('dsum', c_void_p)]
 
 
 _P4 = c_void_p * 4

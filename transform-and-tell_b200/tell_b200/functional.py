@@ -732,6 +732,8 @@ class MultiCtxAttentionFn(Function):
         dq16_all = torch.empty(q_all.shape, dtype=torch.bfloat16, device=q_all.device) if tw else None
         dkvs, dbks, dbvs = [], [], []
         items = []
+        # D = rowsum(dO * O) of every context: written by the dQ kernel, read by the dK|dV kernel
+        dsum = torch.empty((n, B * H * T), dtype=torch.float32, device=q_all.device) if multi else None
         for c in range(n):
             S, kv = Ss[c], kvs[c]
             if S > 0 and ctx.slabs[c] is not None:
@@ -749,7 +751,7 @@ class MultiCtxAttentionFn(Function):
                                   dout=dout_all[:, sl], dq=dq_all[:, sl],
                                   dk=dkv[:, :E] if S > 0 else None, dv=dkv[:, E:] if S > 0 else None,
                                   dbias_k=dbk, dbias_v=dbv, kv_len=ctx.kv_lens[c],
-                                  dq16=dq16_all[:, sl] if tw else None))
+                                  dq16=dq16_all[:, sl] if tw else None, dsum=dsum[c]))
             else:
                 ops.attn_bwd(dout_all[:, sl], q_all[:, sl], kv[:, :E] if S > 0 else None,
                              kv[:, E:] if S > 0 else None,

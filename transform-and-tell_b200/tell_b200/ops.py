@@ -521,6 +521,8 @@ def _attn_ctx_array(items, E):
             c.out16, c.ldo16 = _dp(it['out16']), it['out16'].stride(0)
         if it.get('dq16') is not None:
             c.dq16, c.ldq16 = _dp(it['dq16']), it['dq16'].stride(0)
+        if it.get('dsum') is not None:
+            c.dsum = _dp(it['dsum'])
         if it.get('dout') is not None:
             c.dout, c.dq = _dp(it['dout']), _dp(it['dq'])
             c.dk, c.dv = (_dp(it['dk']), _dp(it['dv'])) if S > 0 else (None, None)
