@@ -14,6 +14,8 @@ tc5 = (sys.argv[1] if len(sys.argv) > 1 else '1') == '1'
 rs = np.random.RandomState(1234)
 B, S, H, D = 16, 512, 16, 64
 lens = rs.randint(256, 513, size=B)
+if os.environ.get('TT_LEN'):
+    lens = np.full(B, int(os.environ['TT_LEN']))
 cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device='cuda')
 qkv = (torch.randn(B * S, 3 * H * D, device='cuda') * 0.5).to(torch.bfloat16)
 for _ in range(3):
