@@ -31,6 +31,40 @@ def test_library_exports_every_declared_symbol():
     assert lib.tt_last_error() is not None
 
 
+def test_ctypes_argument_blocks_match_the_header(tmp_path):
+    """Every struct that crosses the C ABI by pointer (TtGemmParams, TtAttnCtx, TtLnFwdMulti, TtLnBwdMulti,
+    ...) has the size and the field offsets the header gives it: compiled from include/tt_b200.h with gcc
+    and compared with the ctypes mirrors in tell_b200/_lib.py, so a field added on one side only fails
+    here instead of corrupting arguments on the GPU."""
+    import subprocess
+    from tell_b200 import _lib, optim, weight_bank
+    structs = {'TtGemmParams': _lib.TtGemmParams, 'TtAttnCtx': _lib.TtAttnCtx,
+               'TtLnFwdMulti': _lib.TtLnFwdMulti, 'TtLnBwdMulti': _lib.TtLnBwdMulti,
+               'TtPrepSeg': weight_bank.TtPrepSeg, 'TtWnormBwdSeg': weight_bank.TtWnormBwdSeg,
+               'TtAdamSeg': optim.TtAdamSeg, 'TtAdamHyper': optim.TtAdamHyper}
+    hdr = open(os.path.join(ROOT, 'include', 'tt_b200.h')).read()
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tt_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        assert re.search(r'\}\s*%s\s*;' % name, hdr), '%s is not declared in the header' % name
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'abi.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        a, b, c = ln.split()
+        got[(a, b)] = int(c)
+    for name, cls in structs.items():
+        assert got[(name, 'size')] == ctypes.sizeof(cls), (name, got[(name, 'size')], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert got[(name, fname)] == getattr(cls, fname).offset, (name, fname)
+
+
 def test_invalid_arguments_fail_loudly_without_a_gpu():
     _ensure_built()
     from tell_b200 import _lib
