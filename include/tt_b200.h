@@ -375,6 +375,9 @@ int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D
 int tt_attn_bwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row, float p_drop,
                          int kv16, void* stream);
 int tt_attn_decode_hm_multi(const TtAttnCtx* ctx, int n, int B, int H, int D, int zero_row, void* stream);
+/* Key tiles (of 64 keys) one CTA of the dK|dV kernel walks with the query side staged once; 0 = chosen from
+ * the problem size (the default).  Results do not depend on it (tests force 1 / 2 / 5). */
+void tt_attn_set_dkv_tiles_per_cta(int n);
 /* Incremental decoding (transformer_faces_objects.py:399-494 recomputes every K|V projection per
  * step; here they are projected once and cached).  tt_kv_repack_heads turns the token-major bf16
  * projection ([S*B, ldkv] rows, key j of batch b at row j*B+b) into head-major K, V [B,H,S,64];

@@ -319,6 +319,58 @@ def test_attention_bf16_keys_values(T, B, S):
     assert (got - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize('T,B,S,p', [(50, 2, 300, 0.0), (50, 3, 512, 0.1), (70, 1, 200, 0.0), (130, 2, 129, 0.1)])
+def test_attention_dkv_tiles_per_cta_do_not_change_results(T, B, S, p):
+    """The dK|dV kernel walks several key tiles per CTA with the query side staged once and takes
+    D = rowsum(dO * O) from the dQ kernel (TtAttnCtx.dsum): dq / dk / dv / dbias are bit-identical for
+    1, 2, 5 and 9 tiles per CTA, with and without the handed-over D, for one and for several query
+    tiles (T > 64), with trailing padding skipped (kv_len) and with dropout."""
+    import ctypes
+    from tell_b200 import _lib, ops
+    torch.manual_seed(T * 1000 + S)
+    H, D = 4, 64
+    E = H * D
+    q = cuda(torch.randn(T * B, E) * D ** -0.5)
+    kv = cuda(torch.randn(S * B, 2 * E)).to(torch.bfloat16)
+    do = cuda(torch.randn(T * B, E))
+    bk, bv = cuda(torch.randn(E) * 0.5), cuda(torch.randn(E) * 0.5)
+    mask = torch.zeros(B, S, dtype=torch.uint8)
+    lens = []
+    for b in range(B):                      # trailing padding of different lengths per sample
+        n_valid = S - (b * 97) % (S - 1)
+        mask[b, n_valid:] = 1
+        lens.append(n_valid)
+    mask = cuda(mask)
+    kv_len = cuda(torch.tensor(lens, dtype=torch.int32))
+
+    def run(tpc, with_dsum):
+        _lib.lib().tt_attn_set_dkv_tiles_per_cta(ctypes.c_int(tpc))
+        out = torch.empty_like(q)
+        lse = torch.empty(B * H * T, device='cuda')
+        item = dict(q=q, k=kv[:, :E], v=kv[:, E:], bias_k=bk, bias_v=bv, mask=mask, out=out, lse=lse, S=S,
+                    seed=11, kv_len=kv_len)
+        ops.attn_fwd_tc_multi([item], T, B, H, D, True, p)
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        dbk, dbv = torch.zeros(E, device='cuda'), torch.zeros(E, device='cuda')
+        item.update(dout=do, dq=dq, dk=dkv[:, :E], dv=dkv[:, E:], dbias_k=dbk, dbias_v=dbv,
+                    dsum=torch.empty(B * H * T, device='cuda') if with_dsum else None)
+        ops.attn_bwd_tc_multi([item], T, B, H, D, True, p)
+        torch.cuda.synchronize()
+        return dq, dkv, dbk, dbv
+
+    try:
+        ref = run(1, False)
+        for tpc, with_dsum in [(1, True), (2, True), (5, True), (9, False), (0, True)]:
+            got = run(tpc, with_dsum)
+            assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), (tpc, with_dsum)
+            # the bias-row gradients are atomics over heads' CTAs: same addends, order may differ
+            assert torch.allclose(got[2], ref[2], rtol=1e-5, atol=1e-5)
+            assert torch.allclose(got[3], ref[3], rtol=1e-5, atol=1e-5)
+    finally:
+        _lib.lib().tt_attn_set_dkv_tiles_per_cta(ctypes.c_int(0))
+
+
 def test_attention_strided_and_dropout():
     from tell_b200 import ops
     torch.manual_seed(5)

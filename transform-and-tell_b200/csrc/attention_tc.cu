@@ -461,7 +461,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnArgsN args) {
 // one tile (T <= 64: every training shape), reused for all a.dkv_tpc key tiles -- the query-side loads
 // were 4x the key-side bytes of a one-tile CTA.  D = rowsum(dO * O) comes from the dQ kernel (a.dsum).
 // Key tiles per CTA: enough CTAs for two rounds of the resident slots (2 CTAs x 148 SMs), at most 9.
+static int g_dkv_tpc = 0;       // tt_attn_set_dkv_tiles_per_cta: 0 = automatic
 static inline int dkv_tiles_per_cta(int L, int BH) {
+  if (g_dkv_tpc > 0) return g_dkv_tpc;
   const long long tiles = static_cast<long long>(ceil_div(L, TC_BN)) * BH;
   long long t = (tiles + 295) / 592;
   return static_cast<int>(t < 1 ? 1 : (t > 9 ? 9 : t));
@@ -983,6 +985,8 @@ static int fill_ctx(AttnArgs& a, const TtAttnCtx& c, int T, int B, int H, int D,
   return tc_check(a, D, kv16 && c.S > 0);
 }
 }  // namespace tt
+
+extern "C" void tt_attn_set_dkv_tiles_per_cta(int n) { tt::g_dkv_tpc = n > 0 ? (n > 64 ? 64 : n) : 0; }
 
 extern "C" int tt_attn_fwd_tc_multi(const TtAttnCtx* ctx, int n, int T, int B, int H, int D, int zero_row,
                                     float p_drop, int kv16, void* stream) {
