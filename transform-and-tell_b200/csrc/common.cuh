@@ -312,13 +312,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn =
 
 // ---------------------------------------------------------------- counter-based dropout RNG
 // Stateless: the keep/drop decision is a pure function of (seed, element index), so the backward
-// pass regenerates the forward mask instead of storing it.  splitmix64 finaliser.
+// pass regenerates the forward mask instead of storing it.  Two 32-bit multiply-xorshift rounds
+// (the "lowbias32" finaliser) keyed by both words of the 64-bit seed, the high index word folded in:
+// ~10 integer instructions per element.  (The splitmix64 finaliser it replaces costs ~30 with its 64-bit
+// multiplies, and the attention kernels draw one number per score: a third of their issue slots.)
 __device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 32);
+  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t x = static_cast<uint32_t>(idx) ^ s0;
+  x += static_cast<uint32_t>(idx >> 32) * 0x9E3779B9u;
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= s1;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
 // Effective seed = call seed mixed with an optional device-resident step counter, so a captured
 // CUDA graph draws fresh masks on every replay.
