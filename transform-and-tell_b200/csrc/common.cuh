@@ -338,8 +338,9 @@ __device__ __forceinline__ unsigned long long mix_seed(unsigned long long seed,
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx,
                                                float p, float inv_keep) {
   if (p <= 0.f) return 1.f;
-  const float u = static_cast<float>(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.f;
+  // keep iff hash >= p * 2^32 (integer compare: the threshold is loop-invariant, no conversion per element)
+  const uint32_t thr = static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f));
+  return hash_u32(seed, idx) >= thr ? inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------- warp-level bf16 MMA (mma.sync) helpers

@@ -215,9 +215,11 @@ ln_fwd_multi_kernel(const __grid_constant__ LnFwdMultiArgs a) {
 //   dx_c = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dY[:, cE:(c+1)E] * gamma_c
 //   dh_c = dx_c * dropmask_c/(1-p)   -> fp32 dh[c] (optional) and bf16 dh16[:, cE:(c+1)E] (optional)
 //   dX   = sum_c dx_c                (the residual gradient; replaces n-1 axpby launches)
-// A warp owns a row for every context in turn (c outer, rows inner) so dX accumulates race-free
-// through global memory (same thread re-reads what it wrote); dgamma_c / dbeta_c leave per context
-// through the CTA reduction + one atomic per column per CTA.
+// The 8 warps of a CTA work on 8/n rows x n contexts at a time (warp = (row slot, context)): the n
+// contexts of a row run side by side instead of one after the other, the n dx rows meet in shared
+// memory and are summed in context order (bit-identical to adding separately stored dx_c one by one).
+// dgamma_c / dbeta_c: register accumulators per warp (fixed context), CTA reduction, one atomic per
+// column per CTA.
 struct LnBwdMultiArgs {
   const float* x[LN_MAX];
   const float* mean[LN_MAX];
@@ -245,27 +247,31 @@ ln_bwd_multi_kernel(const __grid_constant__ LnBwdMultiArgs a) {
   pdl_prologue();
   extern __shared__ float lnm_red[];   // [LNB_WARPS][E]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warp_global = blockIdx.x * LNB_WARPS + warp;
-  const int nwarps = gridDim.x * LNB_WARPS;
+  const int n = a.n;
+  const int rpi = LNB_WARPS / n;             // rows per CTA iteration (n = 3: two warps idle)
+  const int rs = warp / n, ctx = warp - rs * n;
+  const bool warp_on = warp < rpi * n;
   const int E = a.E, E4 = E >> 2;
   const float p = a.p;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  for (int ctx = 0; ctx < a.n; ++ctx) {
-    const unsigned long long seed = mix_seed(a.seed[ctx], a.step_ptr);
-    const float* __restrict__ xc = a.x[ctx];
-    const float* __restrict__ gamma = a.gamma[ctx];
-    float* dh = a.dh[ctx];
-    float4 acc_g[MAXC], acc_b[MAXC];
+  const unsigned long long seed = mix_seed(a.seed[ctx], a.step_ptr);
+  const float* __restrict__ xc = a.x[ctx];
+  const float* __restrict__ gamma = a.gamma[ctx];
+  float* dh = a.dh[ctx];
+  float4 acc_g[MAXC], acc_b[MAXC];
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int r = warp_global; r < a.N; r += nwarps) {
+  for (int i = 0; i < MAXC; ++i) {
+    acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int base = blockIdx.x * rpi; base < a.N; base += gridDim.x * rpi) {      // CTA-uniform trip count
+    const int r = base + rs;
+    const bool on = warp_on && r < a.N;
+    if (on) {
       const float4* dyr = reinterpret_cast<const float4*>(a.dy + static_cast<long long>(r) * a.lddy +
                                                           static_cast<long long>(ctx) * E);
       const float4* xr = reinterpret_cast<const float4*>(xc + static_cast<long long>(r) * E);
-      const float mu = a.mean[ctx][r], rs = a.rstd[ctx][r];
+      const float mu = a.mean[ctx][r], rstd = a.rstd[ctx][r];
       float s1 = 0.f, s2 = 0.f;
       float4 g4[MAXC], xh4[MAXC];
 #pragma unroll
@@ -276,8 +282,8 @@ ln_bwd_multi_kernel(const __grid_constant__ LnBwdMultiArgs a) {
           const float4 xv = __ldg(xr + c);
           const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
           float4 xh, g;
-          xh.x = (xv.x - mu) * rs; xh.y = (xv.y - mu) * rs;
-          xh.z = (xv.z - mu) * rs; xh.w = (xv.w - mu) * rs;
+          xh.x = (xv.x - mu) * rstd; xh.y = (xv.y - mu) * rstd;
+          xh.z = (xv.z - mu) * rstd; xh.w = (xv.w - mu) * rstd;
           g.x = d.x * gm.x; g.y = d.y * gm.y; g.z = d.z * gm.z; g.w = d.w * gm.w;
           s1 += (g.x + g.y) + (g.z + g.w);
           s2 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
@@ -294,26 +300,20 @@ ln_bwd_multi_kernel(const __grid_constant__ LnBwdMultiArgs a) {
         const int c = lane + 32 * i;
         if (c < E4) {
           float4 o;
-          o.x = rs * (g4[i].x - s1 - xh4[i].x * s2);
-          o.y = rs * (g4[i].y - s1 - xh4[i].y * s2);
-          o.z = rs * (g4[i].z - s1 - xh4[i].z * s2);
-          o.w = rs * (g4[i].w - s1 - xh4[i].w * s2);
+          o.x = rstd * (g4[i].x - s1 - xh4[i].x * s2);
+          o.y = rstd * (g4[i].y - s1 - xh4[i].y * s2);
+          o.z = rstd * (g4[i].z - s1 - xh4[i].z * s2);
+          o.w = rstd * (g4[i].w - s1 - xh4[i].w * s2);
           if (a.dx) {
-            float4* dxp = reinterpret_cast<float4*>(a.dx + static_cast<long long>(r) * E) + c;
-            float4 t = o;
-            if (ctx > 0) {
-              const float4 prev = *dxp;     // plain adds (no FMA contraction with the products above):
-              t.x = __fadd_rn(o.x, prev.x); t.y = __fadd_rn(o.y, prev.y);   // bit-identical to summing
-              t.z = __fadd_rn(o.z, prev.z); t.w = __fadd_rn(o.w, prev.w);   // separately stored dx_c
-            }
-            *dxp = t;
+            if (n == 1) reinterpret_cast<float4*>(a.dx + static_cast<long long>(r) * E)[c] = o;
+            else reinterpret_cast<float4*>(lnm_red + static_cast<long long>(warp) * E)[c] = o;
           }
           if (p > 0.f) {
-            const unsigned long long base = static_cast<unsigned long long>(r) * E + 4ull * c;
-            o.x *= dropout_scale(seed, base, p, inv_keep);
-            o.y *= dropout_scale(seed, base + 1, p, inv_keep);
-            o.z *= dropout_scale(seed, base + 2, p, inv_keep);
-            o.w *= dropout_scale(seed, base + 3, p, inv_keep);
+            const unsigned long long bidx = static_cast<unsigned long long>(r) * E + 4ull * c;
+            o.x *= dropout_scale(seed, bidx, p, inv_keep);
+            o.y *= dropout_scale(seed, bidx + 1, p, inv_keep);
+            o.z *= dropout_scale(seed, bidx + 2, p, inv_keep);
+            o.w *= dropout_scale(seed, bidx + 3, p, inv_keep);
           }
           if (dh) reinterpret_cast<float4*>(dh + static_cast<long long>(r) * E)[c] = o;
           if (a.dh16)
@@ -321,23 +321,46 @@ ln_bwd_multi_kernel(const __grid_constant__ LnBwdMultiArgs a) {
         }
       }
     }
+    if (n > 1 && a.dx) {
+      // dX[row] = ((dx_0 + dx_1) + dx_2) + dx_3: plain adds in context order
+      __syncthreads();
+      for (int i = threadIdx.x; i < rpi * E4; i += blockDim.x) {
+        const int row = i / E4, c = i - row * E4;
+        if (base + row < a.N) {
+          const float4* src = reinterpret_cast<const float4*>(lnm_red + static_cast<long long>(row * n) * E) + c;
+          float4 t = src[0];
+          for (int k = 1; k < n; ++k) {
+            const float4 v = src[static_cast<long long>(k) * E4];
+            t.x = __fadd_rn(v.x, t.x); t.y = __fadd_rn(v.y, t.y);
+            t.z = __fadd_rn(v.z, t.z); t.w = __fadd_rn(v.w, t.w);
+          }
+          reinterpret_cast<float4*>(a.dx + static_cast<long long>(base + row) * E)[c] = t;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- dgamma / dbeta: the warps of one context add their register accumulators through shared
+  //      memory, one global atomic per column per CTA and context
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float* dst = q == 0 ? a.dgamma[ctx] : a.dbeta[ctx];
-      if (dst == nullptr) continue;       // CTA-uniform
+  for (int q = 0; q < 2; ++q) {
+    __syncthreads();
+    if (warp_on) {
 #pragma unroll
       for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
-        if (c < E4) reinterpret_cast<float4*>(lnm_red + warp * E)[c] = q == 0 ? acc_g[i] : acc_b[i];
+        if (c < E4) reinterpret_cast<float4*>(lnm_red + static_cast<long long>(warp) * E)[c] = q == 0 ? acc_g[i] : acc_b[i];
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    for (int c = 0; c < n; ++c) {
+      float* dst = q == 0 ? a.dgamma[c] : a.dbeta[c];
+      if (dst == nullptr) continue;        // CTA-uniform
       for (int i = threadIdx.x; i < E; i += blockDim.x) {
         float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < LNB_WARPS; ++w) t += lnm_red[w * E + i];
+        for (int k = 0; k < rpi; ++k) t += lnm_red[static_cast<long long>(k * n + c) * E + i];
         atomicAdd(dst + i, t);
       }
-      __syncthreads();
     }
   }
 }
@@ -433,7 +456,7 @@ extern "C" int tt_ln_bwd_multi(const TtLnBwdMulti* p, void* stream) {
   a.dy = p->dy; a.lddy = p->lddy; a.dx = p->dx;
   a.dh16 = reinterpret_cast<__nv_bfloat16*>(p->dh16); a.lddh16 = p->lddh16;
   a.N = p->N; a.E = p->E; a.n = p->n; a.p = p->p_drop; a.step_ptr = rng_step_ptr();
-  long long g = ceil_div_ll(p->N, LNB_WARPS);
+  long long g = ceil_div_ll(p->N, LNB_WARPS / p->n);
   if (g > num_sms()) g = num_sms();
   const int grid = static_cast<int>(g > 0 ? g : 1);
   const size_t smem = LNB_WARPS * static_cast<size_t>(p->E) * sizeof(float);
