@@ -12,4 +12,13 @@ for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 0 --print-limit 20 \
     python -m pytest tests/test_ops_gpu.py -q -x -k "$SEL_OPS" > gpurun_out/sanitizer_${tool}_ops.log 2>&1
 done
+# round-2 additions: operand-twin kernels (twin.cu), multi-tile dK|dV, the warp-specialised flash kernel is in SEL_OPS
+SEL_TWIN='test_elementwise_twins or test_layernorm_multi or test_dynconv_twins'
+SEL_DKV='test_attention_dkv_tiles_per_cta'
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 0 --print-limit 20 \
+    python -m pytest tests/test_twin_gpu.py -q -x -k "$SEL_TWIN" > gpurun_out/sanitizer_${tool}_twin.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 0 --print-limit 20 \
+    python -m pytest tests/test_ops_gpu.py -q -x -k "$SEL_DKV" > gpurun_out/sanitizer_${tool}_dkv.log 2>&1
+done
 for f in gpurun_out/sanitizer_*.log; do echo "== $f"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error" $f | tail -4; done
