@@ -124,6 +124,11 @@ void tt_gemm_set_sm_cap(int sms);
  * launch; w > 0 = cost * (fraction of SMs held)^w, w = 1 being SMs x time -- for steps whose streams
  * share the machine (throughput bound by SM occupancy, not by one chain's latency).  Results identical. */
 void tt_gemm_set_occupancy_weight(float w);
+/* Programmatic dependent launch for every kernel of the library (also env TT_PDL; default off): the next
+ * kernel's CTAs are scheduled while the current one still runs and wait at their first instruction.  Worth
+ * it for single latency-bound chains (decoder forward/backward graph, decode step); graphs with parallel
+ * branches lose.  Returns the previous setting.  Results identical. */
+int tt_set_pdl(int on);
 
 /* fp32 [rows, cols] (row stride ld_src) -> bf16 operand for tt_gemm_bf16_tn.
  *   transpose==0: dst is [rows, cols*rep]   transpose!=0: dst is [cols, rows*rep]

@@ -18,6 +18,7 @@ int make_tmap_bf16_2d_sw(CUtensorMap* m, const void* ptr, uint64_t inner, uint64
 // Kernel launch helper; TT_PDL=1 turns on programmatic dependent launch (measured neutral under
 // CUDA-graph replay, so off by default).
 bool pdl_enabled();
+void set_pdl(int on);
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                      Args&&... args) {

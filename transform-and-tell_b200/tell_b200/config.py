@@ -70,6 +70,25 @@ def set_gemm_occupancy_weight(w):
     _lib.lib().tt_gemm_set_occupancy_weight(ctypes.c_float(float(w)))
 
 
+class pdl:
+    """`with config.pdl():` -- kernels launched (or captured) inside use programmatic dependent launch
+    (tt_set_pdl): the next kernel is scheduled while the current one still runs.  For single-chain graphs
+    (the decoder forward/backward, the decode step); a graph with parallel branches gets slower."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        from . import _lib
+        self.prev = _lib.lib().tt_set_pdl(1 if self.on else 0)
+        return self
+
+    def __exit__(self, *exc):
+        from . import _lib
+        _lib.lib().tt_set_pdl(self.prev)
+        return False
+
+
 class gemm_sm_cap:
     """`with config.gemm_sm_cap(64):` -- large GEMMs launched (or captured) inside use at most that many
     SMs (tt_gemm_set_sm_cap), so that kernels of concurrent streams are not queued behind persistent

@@ -7,6 +7,8 @@ constructed randomly initialised (or injected through the extra `resnet=` / `rob
 their state dicts use torchvision's / fairseq's key names so real checkpoints load unchanged."""
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -245,6 +247,8 @@ class _CaptionModelBase(Model):
     decode_graph = True
 
     decode_graph_reuse = True      # keep the captured decode step across generate() calls of one shape
+    # capture the decode step (one chain, nothing beside it) with programmatic dependent launch
+    decode_pdl = os.environ.get('TT_DECODE_PDL', '1') == '1'
 
     def _decode_setup(self, caption_ids, contexts):
         """Static device buffers of one greedy decode + the step function that updates them in place."""
@@ -364,7 +368,7 @@ class _CaptionModelBase(Model):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(cur)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side), dec.weight_scope(refresh=False):
+            with torch.cuda.stream(side), dec.weight_scope(refresh=False), config.pdl(self.decode_pdl):
                 run.one_step()
                 # one allocator pool for every decode graph of this model: the blocks of a replaced
                 # graph are reused by the next capture instead of cudaMalloc / cudaFree per capture
