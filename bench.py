@@ -300,7 +300,11 @@ def run_b200(args):
             self.encode()
             self.train_part()
 
-    n_sets = 2 if (args.pipeline and not args.no_graph) else 1
+    # two sets make the software pipeline (encoders of step i+1 beside the decoder pass of step i); a third
+    # one lets the end-to-end measurement copy the inputs of step i+1 from pinned host memory while both
+    # other sets are still in flight (with two, the copy could only start when the decoder pass of step
+    # i-1 had finished: a ~0.5 ms bubble in front of every encoder graph)
+    n_sets = int(args.sets) if (args.pipeline and not args.no_graph) else 1
     sets = [StepSet() for _ in range(n_sets)]
 
     # ---- warm-up (eager): lazy weight folding, cudaFuncSetAttribute, allocator pools
@@ -635,9 +639,10 @@ def run_b200(args):
                    'sm_partition': (None if green is None else
                                     {'decoder_sms': green['n_dec'], 'encoder_sms': green['n_enc'],
                                      'how': 'CUDA green contexts, one per pipeline stage'}),
-                   'pipeline': ('2 step-buffer sets: frozen encoders of step i+1 overlap the decoder '
-                                'fwd+bwd of step i; all K encoder and K train passes run inside the '
-                                'timed region' if n_sets == 2 else None),
+                   'pipeline': ('%d step-buffer sets: frozen encoders of step i+1 overlap the decoder '
+                                'fwd+bwd of step i (and, end to end, the H2D copy of step i+1 runs under '
+                                'step i); all K encoder and K train passes run inside the timed region'
+                                % n_sets if n_sets >= 2 else None),
                    'grad_allreduce': (None if world == 1 else args.grad_dtype + ' payload, one flat buffer: '
                                       'converting pack + ONE NCCL all-reduce (AVG) on a side stream, '
                                       'overlapped with the next step\'s frozen-encoder forward'),
@@ -822,6 +827,7 @@ def main():
     ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
                     help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
                          "model.train()) or 'running' statistics folded into the convolutions (eval())")
+    ap.add_argument('--sets', type=int, default=3, choices=[2, 3, 4], help='step-buffer sets of the pipeline')
     ap.add_argument('--pdl-decoder', type=int, default=0, choices=[0, 1],
                     help='programmatic dependent launch for the captured decoder forward/backward graph '
                          '(measured: the graph alone 4.97 -> 4.93 ms, the overlapped step 9.58 -> 10.1 ms: off)')
