@@ -304,7 +304,9 @@ def run_b200(args):
     # one lets the end-to-end measurement copy the inputs of step i+1 from pinned host memory while both
     # other sets are still in flight (with two, the copy could only start when the decoder pass of step
     # i-1 had finished: a ~0.5 ms bubble in front of every encoder graph)
-    n_sets = int(args.sets) if (args.pipeline and not args.no_graph) else 1
+    # (auto: 3 on one GPU, 2 with the gradient all-reduce between the decoder passes -- the configuration the
+    # multi-GPU numbers were measured with)
+    n_sets = (int(args.sets) or (3 if world == 1 else 2)) if (args.pipeline and not args.no_graph) else 1
     sets = [StepSet() for _ in range(n_sets)]
 
     # ---- warm-up (eager): lazy weight folding, cudaFuncSetAttribute, allocator pools
@@ -827,7 +829,8 @@ def main():
     ap.add_argument('--bn-mode', default='batch', choices=['batch', 'running'],
                     help="frozen ResNet BatchNorm: 'batch' statistics (the reference's training step, "
                          "model.train()) or 'running' statistics folded into the convolutions (eval())")
-    ap.add_argument('--sets', type=int, default=3, choices=[2, 3, 4], help='step-buffer sets of the pipeline')
+    ap.add_argument('--sets', type=int, default=0, choices=[0, 2, 3, 4],
+                    help='step-buffer sets of the pipeline (0 = auto: 3 on one GPU, 2 with data parallelism)')
     ap.add_argument('--pdl-decoder', type=int, default=0, choices=[0, 1],
                     help='programmatic dependent launch for the captured decoder forward/backward graph '
                          '(measured: the graph alone 4.97 -> 4.93 ms, the overlapped step 9.58 -> 10.1 ms: off)')
