@@ -372,7 +372,8 @@ def run_b200(args):
                 if st.busy:
                     s_copy.wait_event(st.train_done)
                 for k in st.static:
-                    st.static[k].copy_(pinned[k], non_blocking=True)
+                    if os.environ.get('TT_E2E_NO_H2D') != '1':          # (experiment switch)
+                        st.static[k].copy_(pinned[k], non_blocking=True)
                 st.copied.record(s_copy)
         with torch.cuda.stream(s_enc):
             if st.busy:
@@ -396,7 +397,7 @@ def run_b200(args):
                 st.g2.replay()
             else:
                 st.train_part()
-            if e2e:
+            if e2e and os.environ.get('TT_E2E_NO_D2H') != '1':       # (experiment switch)
                 loss_host.copy_(out_loss, non_blocking=True)
             st.train_done.record(s_train)
             st.busy = True
