@@ -310,7 +310,12 @@ class _CaptionModelBase(Model):
             return all(_CaptionModelBase._copy_tree(d, s_) for d, s_ in zip(dst, src))
         if isinstance(dst, (set, frozenset)):
             return isinstance(src, (set, frozenset)) and len(dst) == len(src)
-        return dst == src or (dst is None) == (src is None)
+        if dst is None or src is None:
+            return dst is None and src is None
+        try:
+            return bool(dst == src)              # scalar state (batch size, flags) must agree
+        except Exception:
+            return False
 
     def _generate_graphed(self, caption_ids, contexts, early_exit, sync_every):
         """The greedy loop with ONE captured decode step replayed gen_len-1 times.
